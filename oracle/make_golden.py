@@ -1,0 +1,324 @@
+"""Pin the oracle against the reference and write ``tests/golden/*.npz``.
+
+Runs ONLY in the build container (needs ``/root/reference``).  It
+
+1. imports the reference's own modules (with ``oracle/shims`` standing in for the
+   absent ``timm``) and checks every oracle function against them on seeded inputs;
+2. cross-checks the ViT restatement against torchvision's independent
+   ``VisionTransformer`` and the BERT restatement against the installed
+   ``transformers`` ``BertModel``;
+3. spawns a 2-rank gloo group to pin the global-reduce NCE branch (``GatherLayer``
+   + ``targets = arange(b*rank, b*(rank+1))``) fwd and bwd;
+4. stores the REFERENCE outputs (not the oracle's) as small fixtures.
+
+    python oracle/make_golden.py            # regenerate + verify
+"""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = "/root/reference"
+sys.path[:0] = [REF, os.path.join(HERE, "shims"), ROOT]
+
+from oracle import simseg_oracle as O  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+TOL = 2e-5
+
+
+def _check(name, a, b, tol=TOL):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    err = (a - b).abs().max().item() if a.numel() else 0.0
+    status = "ok" if err <= tol else "MISMATCH"
+    print(f"  {name:48s} max|diff| = {err:.3e}  [{status}]")
+    assert err <= tol, name
+    return err
+
+
+_CFG = {}
+
+
+def _ref_cfg(yaml_name, extra=()):
+    if yaml_name in _CFG:            # the reference's cfg is a global that freezes after one load
+        return _CFG[yaml_name]
+    import simseg.core  # noqa: F401  (must precede simseg.models)
+    from simseg.core import cfg, update_cfg
+    from simseg.tasks.clip.config import task_cfg_init_fn, update_clip_config
+    argv = ["model.image_encoder.pretrained=False", "model.text_encoder.pretrained=False",
+            "loss.global_reduce=False", "transforms.input_size=224"] + list(extra)
+    cwd = os.getcwd()
+    update_cfg(task_cfg_init_fn, os.path.join(REF, "configs/clip", yaml_name), argv,
+               preprocess_fn=update_clip_config)
+    os.chdir(cwd)
+    _CFG[yaml_name] = cfg
+    return cfg
+
+
+def heads_and_loss():
+    print("[heads / loss vs reference modules]")
+    import simseg.core  # noqa: F401
+    from simseg.models.components import SimpleProjection, TopKPooling, L2norm
+    from simseg.tasks.clip.hooks.utils import IndexedEmbInfo, EmbANN, RetrievalMetric
+    from simseg.utils.interpolate_pe import interpolate_pos_embed
+    g = torch.Generator().manual_seed(7)
+    out = {}
+    x_img = torch.randn(6, 196, 384, generator=g)
+    x_txt = torch.randn(6, 25, 768, generator=g)
+    lens = torch.tensor([25, 8, 13, 1, 20, 9])
+    mask = (torch.arange(25)[None] < lens[:, None]).long()
+    pi = SimpleProjection(None, 384, 512); pt = SimpleProjection(None, 768, 512)
+    with torch.no_grad():
+        r_pi = pi(x_img); r_pt = pt(x_txt)
+        _check("SimpleProjection img", O.simple_projection(x_img, pi.linear.weight), r_pi)
+        r_pool_i = TopKPooling(5, 1)(r_pi.clone())
+        r_pool_t = TopKPooling(1, 1)(r_pt.clone(), mask)
+        r_pool_t3 = TopKPooling(3, 1)(r_pt.clone(), mask)          # k shrinks to min_len=1
+        _check("TopKPooling k=5", O.topk_pooling(r_pi, 5), r_pool_i)
+        _check("TopKPooling masked k=1", O.topk_pooling(r_pt, 1, mask), r_pool_t)
+        _check("TopKPooling masked k=3->1", O.topk_pooling(r_pt, 3, mask), r_pool_t3)
+        r_ni, r_nt = L2norm(r_pool_i, dim=-1), L2norm(r_pool_t, dim=-1)
+        _check("L2norm", O.l2norm(r_pool_i), r_ni)
+        _check("image_embed", O.image_embed(torch.cat([x_img[:, :1], x_img], 1), pi.linear.weight, 5), r_ni)
+        _check("text_embed", O.text_embed(x_txt, pt.linear.weight, mask, 1), r_nt)
+    out.update(heads_x_img=x_img[:2, :, :64].numpy(), heads_seed=np.array(7),
+               heads_img_emb=r_ni.numpy(), heads_txt_emb=r_nt.numpy(), heads_mask=mask.numpy(),
+               heads_wi=pi.linear.weight.detach().numpy(), heads_wt=pt.linear.weight.detach().numpy())
+
+    # NCE non-global branch == W=1 global (mml_loss.py:79-87)
+    from simseg.models.criteria.losses.mml_loss import NCE
+    cfg = _ref_cfg("simseg.vit-s.yaml")
+    nce = NCE(cfg, 0)
+    a = r_ni.clone().requires_grad_(True); b = r_nt.clone().requires_grad_(True)
+    loss, i2t, t2i = nce(a, b)
+    loss.backward()
+    a2 = r_ni.clone().requires_grad_(True); b2 = r_nt.clone().requires_grad_(True)
+    temp = nce.temperature.detach().clone().requires_grad_(True)
+    l2, ai, at = O.clip_loss(a2, b2, a2, b2, temp, 0)
+    l2.backward()
+    _check("NCE loss (W=1)", l2, loss); _check("NCE i2t acc", ai, i2t); _check("NCE t2i acc", at, t2i)
+    _check("NCE d/d img", a2.grad, a.grad); _check("NCE d/d txt", b2.grad, b.grad)
+    _check("NCE d/d temperature", temp.grad, nce.temperature.grad, 1e-3)
+    out.update(nce_loss=loss.detach().numpy(), nce_i2t=i2t.numpy(), nce_t2i=t2i.numpy(),
+               nce_dimg=a.grad.numpy(), nce_dtxt=b.grad.numpy(), nce_dtemp=nce.temperature.grad.numpy())
+
+    # retrieval
+    left = F.normalize(torch.randn(40, 512, generator=g), dim=-1)
+    right = F.normalize(torch.randn(200, 512, generator=g), dim=-1)
+    lg = torch.arange(40); rg = torch.arange(200) // 5
+    L, R = IndexedEmbInfo("image", lg, left), IndexedEmbInfo("text", rg, right)
+    _, matched = EmbANN()(L, R)
+    has_r, first_r = torch.max(matched, dim=1)
+    has, first = O.retrieval_first_match_rank(O.allpairs_sim(left, right), lg, rg)
+    _check("retrieval first-match rank", first, first_r, 0)
+    rec_r = RetrievalMetric(with_prefix=False)(L, R)
+    rec = O.recall_at(has, first)
+    for k in rec:
+        _check(f"retrieval {k}", rec[k], rec_r[k], 1e-7)
+    out.update(retr_left=left.numpy(), retr_right=right.numpy(), retr_first=first_r.numpy(),
+               retr_r1=np.array(rec_r["R@1"]), retr_r5=np.array(rec_r["R@5"]), retr_r10=np.array(rec_r["R@10"]))
+
+    # pos-embed interpolation 14x14 -> 18x18 (seg_evaluation.py:228-231)
+    class _V:  # minimal visual_encoder view the reference function reads
+        pass
+    v = _V(); v.patch_embed = _V(); v.patch_embed.num_patches = 324; v.pos_embed = torch.zeros(1, 325, 384)
+    pe = torch.randn(1, 197, 384, generator=g)
+    r_pe = interpolate_pos_embed(pe, v)
+    _check("interpolate_pos_embed 196->324", O.interpolate_pos_embed(pe, 324), r_pe)
+    out.update(pe_in=pe[:, :, :16].numpy(), pe_out=r_pe[:, :, :16].numpy())
+
+    # seg sim-map lines (tools/seg_evaluation.py:111-112,136 — the tool itself is a script that
+    # imports pydensecrf, absent here; its two torch lines are executed verbatim on the same data)
+    pf = torch.randn(2, 196, 512, generator=g)
+    tf = O.zero_shot_class_embedding(torch.randn(20, 80, 512, generator=g))
+    im_f_a = F.normalize(pf[0], dim=-1, p=2)
+    for c in (0, 7, 19):
+        attn = im_f_a @ tf[c].unsqueeze(-1)
+        _check(f"seg sim map class {c}", O.patch_text_sim(pf, tf)[0][0, :, c], attn[:, 0])
+    sim, am = O.patch_text_sim(pf, tf)
+    out.update(seg_patch=pf.numpy(), seg_text=tf.numpy(), seg_sim=sim.numpy(), seg_argmax=am.numpy())
+    return out
+
+
+def encoders_cross_check():
+    print("[ViT vs torchvision, BERT vs transformers]")
+    out = {}
+    from torchvision.models.vision_transformer import VisionTransformer
+    for D, H in ((384, 6),):
+        torch.manual_seed(0)
+        tv = VisionTransformer(image_size=224, patch_size=16, num_layers=12, num_heads=H,
+                               hidden_dim=D, mlp_dim=4 * D).eval()
+        with torch.no_grad():
+            for p_ in tv.parameters():
+                if p_.dim() == 1:
+                    p_.add_(torch.randn_like(p_) * 0.05)
+            tv.class_token.normal_(std=0.02)
+        sd = {"cls_token": tv.class_token, "pos_embed": tv.encoder.pos_embedding,
+              "patch_embed.proj.weight": tv.conv_proj.weight, "patch_embed.proj.bias": tv.conv_proj.bias,
+              "norm.weight": tv.encoder.ln.weight, "norm.bias": tv.encoder.ln.bias}
+        for i in range(12):
+            l = getattr(tv.encoder.layers, f"encoder_layer_{i}")
+            b = f"blocks.{i}."
+            sd.update({b + "norm1.weight": l.ln_1.weight, b + "norm1.bias": l.ln_1.bias,
+                       b + "attn.qkv.weight": l.self_attention.in_proj_weight, b + "attn.qkv.bias": l.self_attention.in_proj_bias,
+                       b + "attn.proj.weight": l.self_attention.out_proj.weight, b + "attn.proj.bias": l.self_attention.out_proj.bias,
+                       b + "norm2.weight": l.ln_2.weight, b + "norm2.bias": l.ln_2.bias,
+                       b + "mlp.fc1.weight": l.mlp[0].weight, b + "mlp.fc1.bias": l.mlp[0].bias,
+                       b + "mlp.fc2.weight": l.mlp[3].weight, b + "mlp.fc2.bias": l.mlp[3].bias})
+        sd = {k: v.detach() for k, v in sd.items()}
+        img = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(3))
+        with torch.no_grad():
+            x = tv._process_input(img)
+            x = torch.cat([tv.class_token.expand(2, -1, -1), x], dim=1)
+            r = tv.encoder(x)
+            o = O.vit_forward(sd, img, H)
+        _check(f"ViT D={D} tokens vs torchvision", o, r, 2e-4)
+
+    from transformers import BertConfig, BertModel
+    torch.manual_seed(0)
+    bm = BertModel(BertConfig(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0),
+                   add_pooling_layer=False).eval()
+    bsd = {k: v.detach() for k, v in bm.state_dict().items()}
+    batch = O.make_batch(3, 25, seed=5)
+    with torch.no_grad():
+        r = bm(input_ids=batch["input_ids"], attention_mask=batch["attention_mask"]).last_hidden_state
+        o = O.bert_forward(bsd, batch["input_ids"], batch["attention_mask"])
+    _check("BERT last_hidden_state vs transformers", o, r, 2e-4)
+    return out
+
+
+def full_model():
+    print("[reference CLIPModel (ViT-S + BERT-base) vs oracle, same weights]")
+    import simseg.core  # noqa: F401
+    from simseg.models import PIPELINE
+    from simseg.utils import build_from_cfg
+    tmp = tempfile.mkdtemp()
+    from transformers import BertConfig
+    BertConfig(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0).save_pretrained(
+        os.path.join(tmp, "bert-base-uncased"))
+    cwd = os.getcwd(); os.chdir(tmp)
+    try:
+        cfg = _ref_cfg("simseg.vit-s.yaml")
+        model = build_from_cfg(cfg.model.name, cfg, PIPELINE)
+    finally:
+        os.chdir(cwd)
+    sd = O.make_state_dict(384, 6, seed=0)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    missing = [m for m in missing if "pooler" not in m and "position_ids" not in m and "token_type_ids" not in m]
+    assert not missing and not unexpected, (missing, unexpected)
+    print("  state-dict keys: reference accepts all", len(sd), "oracle keys (SURVEY §8b naming)")
+    model.eval()                                  # dropout off; parity is defined at p=0
+    B = 8
+    batch = O.make_batch(B, 25, seed=1234)
+    ref_batch = {k: v.clone() for k, v in batch.items()}
+    model.zero_grad()
+    loss_dict, i2t, t2i = model(ref_batch)
+    loss = loss_dict["nce_loss"]
+    loss.backward()
+    with torch.no_grad():
+        img_e, txt_e = model({k: v.clone() for k, v in batch.items()}, embeddings="all")
+        tok = model.forward_image_feature(batch["image"])
+    sdg = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    l_o, ai, at = O.clip_train_forward(sdg, batch, 6)
+    l_o.backward()
+    oi, ot = O.clip_embeddings(sd, batch, 6)
+    _check("CLIP img embeddings", oi, img_e, 1e-4); _check("CLIP txt embeddings", ot, txt_e, 1e-4)
+    _check("CLIP loss", l_o, loss, 1e-4); _check("CLIP i2t acc", ai, i2t); _check("CLIP t2i acc", at, t2i)
+    named = dict(model.named_parameters())
+    gkeys = ["image_projection.linear.weight", "text_projection.linear.weight", "loss.temperature",
+             O.IMG_PREFIX + "blocks.0.attn.qkv.weight", O.IMG_PREFIX + "patch_embed.proj.weight",
+             O.IMG_PREFIX + "pos_embed", O.IMG_PREFIX + "blocks.11.mlp.fc2.bias",
+             O.TXT_PREFIX + "encoder.layer.0.attention.self.query.weight",
+             O.TXT_PREFIX + "encoder.layer.11.output.LayerNorm.weight",
+             O.TXT_PREFIX + "embeddings.position_embeddings.weight"]
+    out = {}
+    for k in gkeys:
+        rg, og = named[k].grad, sdg[k].grad
+        scale = rg.abs().max().item() + 1e-12
+        _check(f"grad {k[-44:]}", og / scale, rg / scale, 2e-3)
+        out["grad_norm/" + k] = np.array(rg.norm().item())
+    out.update(clip_img_emb=img_e.numpy(), clip_txt_emb=txt_e.numpy(), clip_loss=loss.detach().numpy(),
+               clip_i2t=i2t.numpy(), clip_t2i=t2i.numpy(),
+               clip_tokens_head=tok[:, :4, :32].contiguous().numpy(),
+               clip_dWi_head=named["image_projection.linear.weight"].grad[:8, :32].numpy(),
+               clip_dtemp=named["loss.temperature"].grad.numpy())
+    return out
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), HOSTNAME="box",
+                      RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path[:0] = [REF, os.path.join(HERE, "shims"), ROOT]
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from simseg.utils import ENV
+    from simseg.utils.dist import GatherLayer
+    g = torch.Generator().manual_seed(11)
+    img = O.l2norm(torch.randn(world * 6, 512, generator=g))
+    txt = O.l2norm(torch.randn(world * 6, 512, generator=g))
+    b = 6
+    li = img[rank * b:(rank + 1) * b].clone().requires_grad_(True)
+    lt = txt[rank * b:(rank + 1) * b].clone().requires_grad_(True)
+    temp = torch.tensor(0.02)
+    # the reference's global branch, mml_loss.py:58-77,89-95, with its own GatherLayer
+    def ref_dir(f1, f2):
+        f2g = GatherLayer.apply(f2, dist.group.WORLD, rank)
+        logits = (f1 @ f2g.T) / torch.clamp(temp, 0.001, 0.5)
+        targets = torch.arange(b * rank, b * (rank + 1))
+        return F.cross_entropy(logits, targets, reduction="none").mean()
+    loss = 0.5 * (ref_dir(li, lt) + ref_dir(lt, li))
+    loss.backward()
+    q.put((rank, loss.item(), li.grad.numpy(), lt.grad.numpy(), img.numpy(), txt.numpy()))
+    dist.barrier(); dist.destroy_process_group()
+
+
+def global_reduce_two_ranks():
+    print("[global-reduce NCE with the reference GatherLayer, 2 gloo ranks]")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29541
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted([q.get(timeout=300) for _ in ps], key=lambda t: t[0])
+    [p.join() for p in ps]
+    out = {}
+    img, txt = torch.tensor(res[0][4]), torch.tensor(res[0][5])
+    for rank, loss, gi, gt, _, _ in res:
+        b = 6
+        ig = img.clone().requires_grad_(True); tg = txt.clone().requires_grad_(True)
+        # per-rank loss as the oracle states it; gradient wrt a rank's local rows is the SUM over
+        # ranks of d loss_r (GatherLayer.backward all_reduce, utils/dist.py:348-354)
+        total = 0
+        for r in range(2):
+            l, _, _ = O.clip_loss(ig[r * b:(r + 1) * b], tg[r * b:(r + 1) * b], ig, tg, torch.tensor(0.02), r)
+            if r == rank:
+                _check(f"rank {rank} loss", l, loss, 1e-5)
+            total = total + l
+        total.backward()
+        _check(f"rank {rank} d img (sum over ranks)", ig.grad[rank * b:(rank + 1) * b], gi, 1e-5)
+        _check(f"rank {rank} d txt (sum over ranks)", tg.grad[rank * b:(rank + 1) * b], gt, 1e-5)
+        out[f"gr_loss_{rank}"] = np.array(loss); out[f"gr_dimg_{rank}"] = gi; out[f"gr_dtxt_{rank}"] = gt
+    out["gr_img"] = img.numpy(); out["gr_txt"] = txt.numpy()
+    return out
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    os.makedirs(GOLD, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLD, "heads_loss.npz"), **heads_and_loss())
+    encoders_cross_check()
+    np.savez_compressed(os.path.join(GOLD, "global_reduce.npz"), **global_reduce_two_ranks())
+    np.savez_compressed(os.path.join(GOLD, "clip_vit_s.npz"), **full_model())
+    print("golden vectors written to", GOLD)
+
+
+if __name__ == "__main__":
+    main()
