@@ -1,0 +1,201 @@
+/* libsimseg_b200 — C ABI of the B200-native SimSeg hot path.
+ *
+ * The reference (muyangyi/SimSeg) is 100% Python; it has no FFI of its own.  Its boundary for
+ * this path is the nn.Module contract of simseg/models/pipelines/clip.py:13-229.  This header
+ * is the C ABI we put UNDER that contract: each entry point names the reference call it
+ * replaces (paths relative to the reference root).  The Python mirror of the reference
+ * interface (package simseg_b200) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *  - every function returns 0 on success, <0 on error (simseg_last_error() gives the text,
+ *    thread-local);
+ *  - tensors are raw DEVICE pointers + explicit sizes; row-major unless stated; the caller
+ *    owns every buffer including workspaces (no hidden allocation, no host sync);
+ *  - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised;
+ *  - dtype enum: SIMSEG_F32 = 0, SIMSEG_BF16 = 1;
+ *  - one simseg_ctx per process/GPU; calls on one ctx are not thread-safe.
+ */
+#ifndef SIMSEG_B200_H_
+#define SIMSEG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIMSEG_OK 0
+#define SIMSEG_ERR_INVALID (-1)
+#define SIMSEG_ERR_CUDA (-2)
+#define SIMSEG_ERR_UNSUPPORTED (-3)
+
+#define SIMSEG_F32 0
+#define SIMSEG_BF16 1
+
+typedef struct simseg_ctx simseg_ctx;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int simseg_version(void);
+const char* simseg_last_error(void);
+int simseg_ctx_create(int device, simseg_ctx** out);
+int simseg_ctx_destroy(simseg_ctx* ctx);
+/* number of kernels launched through this ctx since creation / last reset */
+int64_t simseg_ctx_launch_count(simseg_ctx* ctx, int reset);
+
+/* ---- GEMM engine (tcgen05 + TMA) ---------------------------------------------------------- */
+/* Replaces every nn.Linear on the path: timm Block qkv/proj/fc1/fc2 driven by
+ * simseg/models/backbones/mml/vit_builder.py:18, HF BertLayer dense layers
+ * (huggingface_builder.py:16-17), SimpleProjection (components/projection.py:45-46), the
+ * patch-embed conv as GEMM (vit_builder.py:14), and their dgrad / wgrad in backward.
+ *
+ *   D[M,N] = epilogue( sum_k A[m,k] * B[n,k] )       bf16 operands, fp32 accumulation in TMEM
+ *
+ * a_major / b_major: 0 = K-major  (A stored [M,K] row-major, B stored [N,K] row-major, i.e. x @ W^T)
+ *                    1 = MN-major (A stored [K,M] row-major, B stored [K,N] row-major)
+ * lda / ldb / ldd / ld_aux / ld_res: leading dimension in elements of the respective storage. */
+#define SIMSEG_EPI_NONE 0          /* D = acc (+bias)                                     */
+#define SIMSEG_EPI_BIAS_GELU 1     /* aux(bf16, optional) = acc+bias ; D = gelu_erf(acc+bias) */
+#define SIMSEG_EPI_BIAS_RESIDUAL 2 /* D = acc + bias + residual(f32 or bf16, dtype res_dtype) */
+#define SIMSEG_EPI_DGELU 3         /* D = acc * gelu_erf'(aux[m,n])   (aux = saved pre-activation) */
+#define SIMSEG_EPI_ROWSCALE 4      /* D = acc * row_scale[m]                              */
+
+typedef struct simseg_gemm_args {
+  const void* a;
+  const void* b;
+  void* d;
+  int64_t M, N, K;
+  int64_t lda, ldb, ldd;
+  int32_t a_major, b_major;
+  int32_t in_dtype;       /* SIMSEG_BF16 (tcgen05 kind::f16) or SIMSEG_F32 (kind::tf32) */
+  int32_t out_dtype;      /* SIMSEG_F32 or SIMSEG_BF16 */
+  int32_t epilogue;       /* SIMSEG_EPI_* */
+  int32_t accumulate;     /* !=0: D += result (wgrad accumulation across micro-batches; out f32 only) */
+  const float* bias;      /* [N] fp32 or NULL */
+  const void* residual;   /* [M,N] or NULL */
+  int64_t ld_res;
+  int32_t res_dtype;
+  void* aux;              /* [M,N] bf16: out for BIAS_GELU (may be NULL), in for DGELU */
+  int64_t ld_aux;
+  const float* row_scale; /* [M] for ROWSCALE */
+  float* col_sum;         /* optional [N] fp32: atomically accumulates column sums of the fp32
+                             epilogue result (bias gradients) ; NULL = off */
+  int32_t tile_n;         /* 0 = auto; else 64/128/192/256 */
+  int32_t reserved;
+} simseg_gemm_args;
+
+int simseg_gemm(simseg_ctx* ctx, const simseg_gemm_args* args, void* stream);
+
+/* ---- elementwise / normalisation ----------------------------------------------------------- */
+/* fp32 -> bf16 cast, optionally also writing the transpose ([rows,cols] -> [cols,rows]). */
+int simseg_cast_bf16(simseg_ctx* ctx, const float* src, void* dst, void* dst_t, int64_t rows, int64_t cols,
+                     void* stream);
+/* bf16/f32 column sums: out[n] (+)= sum_m x[m,n]   (bias gradients) */
+int simseg_colsum(simseg_ctx* ctx, const void* x, int dtype, int64_t M, int64_t N, int64_t ldx, float* out,
+                  int accumulate, void* stream);
+/* a = gelu_erf(h)  (recomputed in backward instead of being stored) */
+int simseg_gelu_fwd(simseg_ctx* ctx, const void* h, void* a, int64_t n, void* stream);
+
+/* LayerNorm over the last dim (timm LayerNorm eps 1e-6, HF BERT LayerNorm eps 1e-12).
+ * x: [M,D] f32 or bf16; writes y_bf16 and/or y_f32 (either may be NULL), mean/rstd [M] (may be NULL). */
+int simseg_layernorm_fwd(simseg_ctx* ctx, const void* x, int x_dtype, const float* gamma, const float* beta,
+                         float eps, int64_t M, int D, void* y_bf16, float* y_f32, float* mean, float* rstd,
+                         void* stream);
+/* dx[M,D] (f32) = LN backward ; if dx_accumulate, dx += (residual-gradient accumulation);
+ * dgamma/dbeta [D] fp32 are ACCUMULATED atomically (zero them first).
+ * dy: f32 or bf16; optional second upstream gradient dy2 (f32, may be NULL) is added to dy first.
+ * dx_colsum [D] (may be NULL): ACCUMULATES the column sums of the final dx — the bias gradient of the
+ * residual-branch Linear that produced x's summand. */
+int simseg_layernorm_bwd(simseg_ctx* ctx, const void* dy, int dy_dtype, const float* dy2, const void* x,
+                         int x_dtype, const float* gamma, const float* mean, const float* rstd, int64_t M, int D,
+                         float* dx, int dx_accumulate, void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum,
+                         void* stream);
+
+/* ---- attention (timm Attention.forward; HF BertSelfAttention) ------------------------------- */
+/* q,k,v: bf16 with element strides (batch, token, head); head_dim = 64 contiguous.
+ * ViT packs qkv as [B,S,3,H,64] (vit_builder.py:18 -> timm Attention); BERT has three [B,T,H*64].
+ * key_len: optional int32 [B] — keys >= key_len[b] are masked (BERT additive mask from a
+ * left-aligned attention_mask); NULL = no mask.
+ * out: bf16 [B,S,H*64]; lse: fp32 [B,H,S] (log-sum-exp of scaled scores, saved for backward). */
+int simseg_attention_fwd(simseg_ctx* ctx, const void* q, const void* k, const void* v, int64_t stride_b,
+                         int64_t stride_s, int64_t stride_h, int B, int H, int S, const int32_t* key_len,
+                         float scale, void* out, float* lse, void* stream);
+/* dq,dk,dv written with the same strides as q,k,v (so a packed dqkv buffer works). */
+int simseg_attention_bwd(simseg_ctx* ctx, const void* q, const void* k, const void* v, const void* out,
+                         const void* dout, const float* lse, int64_t stride_b, int64_t stride_s, int64_t stride_h,
+                         int B, int H, int S, const int32_t* key_len, float scale, void* dq, void* dk, void* dv,
+                         void* stream);
+
+/* ---- ViT / BERT embedding stages ------------------------------------------------------------ */
+/* image [B,3,Hi,Wi] f32 NCHW -> patches bf16 [B*N, 768] (k = c*256 + py*16 + px), the im2col of the
+ * stride-16 conv in timm PatchEmbed (vit_builder.py:14). */
+int simseg_im2col16(simseg_ctx* ctx, const float* image, int B, int Hi, int Wi, void* patches, void* stream);
+/* x[b,0,:] = cls + pos[0]; x[b,1+n,:] = patch[b*N+n,:] + pos[1+n]   (vit_builder.py:15-17) */
+int simseg_vit_tokens_fwd(simseg_ctx* ctx, const void* patch, int patch_dtype, const float* cls,
+                          const float* pos, int B, int N, int D, float* x, void* stream);
+/* dpatch(bf16)[b*N+n] = dx[b,1+n]; dpos += sum_b dx[b]; dcls += sum_b dx[b,0]  (accumulating) */
+int simseg_vit_tokens_bwd(simseg_ctx* ctx, const float* dx, int B, int N, int D, void* dpatch, float* dpos,
+                          float* dcls, void* stream);
+/* e[b,t,:] = word[ids[b,t]] + pos[t] + type[0]   (HF BertEmbeddings) */
+int simseg_bert_embed_fwd(simseg_ctx* ctx, const int64_t* ids, const float* word, const float* pos,
+                          const float* type0, int B, int T, int D, float* e, void* stream);
+/* scatter-add of de into dword / dpos / dtype0 (accumulating, fp32 atomics) */
+int simseg_bert_embed_bwd(simseg_ctx* ctx, const int64_t* ids, const float* de, int B, int T, int D,
+                          float* dword, float* dpos, float* dtype0, void* stream);
+
+/* ---- heads ----------------------------------------------------------------------------------- */
+/* TopKPooling (components/pooling.py:42-65): per (sample, channel) mean of the top-k values over
+ * tokens [tok_begin, tok_begin+ntok) of x[B,S,E] (row stride given); masked variant: tokens with
+ * attention_mask==0 are replaced by -10000 (pooling.py:60).  k <= 8.  Saves the selected token
+ * indices int32 [B,k,E] for backward.  Fused with L2norm (components/normalization.py:6-11) when
+ * emb != NULL: emb = pooled / (||pooled|| + eps).  pooled f32 [B,E] always written. */
+int simseg_topk_pool_l2norm_fwd(simseg_ctx* ctx, const void* x, int x_dtype, int B, int S, int E, int tok_begin,
+                                int ntok, int k, const int64_t* attention_mask, int mask_ld, float eps,
+                                float* pooled, float* emb, int32_t* sel_idx, void* stream);
+/* backward of the fused head: demb [B,E] -> dx [B,S,E] (bf16, ZEROED then the k selected tokens of
+ * every channel get dpooled/k). */
+int simseg_topk_pool_l2norm_bwd(simseg_ctx* ctx, const float* demb, const float* pooled, const int32_t* sel_idx,
+                                int B, int S, int E, int tok_begin, int k, float eps, int has_l2norm, void* dx,
+                                void* stream);
+
+/* ---- InfoNCE (criteria/losses/mml_loss.py:51-96, driven twice by clip.py:123-149) ------------ */
+#define SIMSEG_PREC_FP32 0 /* exact fp32 FFMA products                       */
+#define SIMSEG_PREC_TF32 1 /* tcgen05 kind::tf32 products, fp32 accumulation */
+/* feat1 [b,E] fp32 local rows, feat2g [Bg,E] fp32 gathered columns, temperature: device scalar
+ * (clamped to [0.001,0.5] inside, mml_loss.py:56), target of row i = row_offset + i (:75).
+ * cos_ws [b,Bg] fp32 (caller-owned): receives feat1 @ feat2g^T and must be handed unchanged to
+ * simseg_infonce_bwd.  Outputs: loss_rows[b] = CE_i ; lse[b] ; argmax[b] (int32, first max, for the
+ * top-1 accuracy of utils/misc.py:462-477, may be NULL) ; logits_out [b,Bg] optional. */
+int simseg_infonce_fwd(simseg_ctx* ctx, const float* feat1, const float* feat2g, int b, int Bg, int E,
+                       const float* temperature, int row_offset, int precision, float* cos_ws, float* logits_out,
+                       float* loss_rows, float* lse, int32_t* argmax, void* stream);
+/* grad_scale = dLoss/d(CE_i) (0.5/b for clip.py:140 with the mean of :89-91).  cos_ws is consumed
+ * (overwritten by dLoss/dcos).  dfeat1 [b,E] written; dfeat2g [Bg,E] ACCUMULATED (GatherLayer.backward
+ * sums over ranks, utils/dist.py:348-354); dtemp scalar ACCUMULATED (zero outside the clamp range). */
+int simseg_infonce_bwd(simseg_ctx* ctx, const float* feat1, const float* feat2g, int b, int Bg, int E,
+                       const float* temperature, int row_offset, int precision, const float* lse, float grad_scale,
+                       float* cos_ws, float* dfeat1, float* dfeat2g, float* dtemp, void* stream);
+
+/* ---- dense patch-text similarity map (tools/seg_evaluation.py:111-112,136-139) -------------- */
+/* patches [rows,E] (rows = B*N projected patch tokens; f32 or bf16), text [C,E] same dtype
+ * (class embeddings, already unit norm — seg_evaluation.py:71-72).
+ * sim[rows,C] fp32 = (patch / max(||patch||,1e-12)) . text ; argmax[rows] int32 optional.
+ * normalize = 0 skips the row normalisation (plain patches @ text^T). */
+int64_t simseg_patch_text_sim_workspace_bytes(int64_t rows);
+int simseg_patch_text_sim(simseg_ctx* ctx, const void* patches, int dtype, int64_t rows, int E, const void* text,
+                          int C, int normalize, float* sim, int32_t* argmax, void* workspace, int64_t workspace_bytes,
+                          void* stream);
+
+/* ---- all-pairs retrieval similarity (tasks/clip/hooks/utils.py:36) --------------------------- */
+/* out[M,Nr] fp32 = left[M,E] @ right[Nr,E]^T  (fp32 in, fp32 accumulate; precision = SIMSEG_PREC_*). */
+int simseg_allpairs_sim(simseg_ctx* ctx, const float* left, const float* right, int M, int Nr, int E, int precision,
+                        float* out, void* stream);
+/* rank of the first right item whose gid matches the row's gid under a stable descending sort of
+ * the similarities (tasks/clip/hooks/utils.py:37-42,63-65) without materialising the sort:
+ * rank[i] = #{j : s_ij > s*_i} + #{j < j* : s_ij == s*_i}, (s*,j*) = best matching item. -1 if none. */
+int simseg_retrieval_rank(simseg_ctx* ctx, const float* sim, int M, int Nr, const int64_t* left_gid,
+                          const int64_t* right_gid, int32_t* rank, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMSEG_B200_H_ */

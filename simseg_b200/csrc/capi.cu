@@ -1,0 +1,234 @@
+// extern "C" surface of libsimseg_b200 (see include/simseg_b200.h).  Thin argument checks + dispatch.
+#include "common.cuh"
+
+#include <cstring>
+
+namespace simseg {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// implemented in the kernel translation units
+int gemm_impl(Ctx*, const simseg_gemm_args*, cudaStream_t);
+int cast_bf16_impl(Ctx*, const float*, void*, void*, int64_t, int64_t, cudaStream_t);
+int colsum_impl(Ctx*, const void*, int, int64_t, int64_t, int64_t, float*, int, cudaStream_t);
+int gelu_fwd_impl(Ctx*, const void*, void*, int64_t, cudaStream_t);
+int layernorm_fwd_impl(Ctx*, const void*, int, const float*, const float*, float, int64_t, int, void*, float*, float*, float*, cudaStream_t);
+int layernorm_bwd_impl(Ctx*, const void*, int, const float*, const void*, int, const float*, const float*, const float*, int64_t, int, float*, int, void*, float*, float*, float*, cudaStream_t);
+int attention_fwd_impl(Ctx*, const void*, const void*, const void*, int64_t, int64_t, int64_t, int, int, int, const int32_t*, float, void*, float*, cudaStream_t);
+int attention_bwd_impl(Ctx*, const void*, const void*, const void*, const void*, const void*, const float*, int64_t, int64_t, int64_t, int, int, int, const int32_t*, float, void*, void*, void*, cudaStream_t);
+int im2col16_impl(Ctx*, const float*, int, int, int, void*, cudaStream_t);
+int vit_tokens_fwd_impl(Ctx*, const void*, int, const float*, const float*, int, int, int, float*, cudaStream_t);
+int vit_tokens_bwd_impl(Ctx*, const float*, int, int, int, void*, float*, float*, cudaStream_t);
+int bert_embed_fwd_impl(Ctx*, const int64_t*, const float*, const float*, const float*, int, int, int, float*, cudaStream_t);
+int bert_embed_bwd_impl(Ctx*, const int64_t*, const float*, int, int, int, float*, float*, float*, cudaStream_t);
+int topk_pool_l2norm_fwd_impl(Ctx*, const void*, int, int, int, int, int, int, int, const int64_t*, int, float, float*, float*, int32_t*, cudaStream_t);
+int topk_pool_l2norm_bwd_impl(Ctx*, const float*, const float*, const int32_t*, int, int, int, int, float, int, void*, cudaStream_t);
+int sgemm_impl(Ctx*, const float*, const float*, float*, int, int, int, int64_t, int64_t, int64_t, int, int, int, cudaStream_t);
+int nce_rows_fwd_impl(Ctx*, const float*, int, int, int64_t, const float*, int, float*, float*, float*, int32_t*, cudaStream_t);
+int nce_rows_bwd_impl(Ctx*, float*, int, int, int64_t, const float*, int, const float*, float, float*, cudaStream_t);
+int row_inv_norm_impl(Ctx*, const void*, int, int64_t, int, float*, cudaStream_t);
+int row_argmax_impl(Ctx*, const float*, int64_t, int, int32_t*, cudaStream_t);
+int retrieval_rank_impl(Ctx*, const float*, int, int, const int64_t*, const int64_t*, int32_t*, cudaStream_t);
+
+// fp32 product in the requested precision: C[M,N] (+)= A(m,k) B(n,k)
+static int fp32_matmul(Ctx* c, const float* A, const float* B, float* C, int M, int N, int K, int64_t lda, int64_t ldb,
+                       int64_t ldc, int a_major, int b_major, int accumulate, int precision, cudaStream_t st) {
+  if (precision == SIMSEG_PREC_FP32) return sgemm_impl(c, A, B, C, M, N, K, lda, ldb, ldc, a_major, b_major, accumulate, st);
+  simseg_gemm_args g;
+  memset(&g, 0, sizeof(g));
+  g.a = A; g.b = B; g.d = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldd = ldc;
+  g.a_major = a_major; g.b_major = b_major; g.in_dtype = SIMSEG_F32; g.out_dtype = SIMSEG_F32;
+  g.epilogue = SIMSEG_EPI_NONE; g.accumulate = accumulate;
+  return gemm_impl(c, &g, st);
+}
+
+}  // namespace simseg
+
+using namespace simseg;
+
+struct simseg_ctx { Ctx c; };
+#define CTX_OR_FAIL()                                   \
+  if (ctx == nullptr) { set_error("null ctx"); return SIMSEG_ERR_INVALID; } \
+  Ctx* c = &ctx->c;                                     \
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" {
+
+int simseg_version(void) { return 100; }
+const char* simseg_last_error(void) { return g_err; }
+
+int simseg_ctx_create(int device, simseg_ctx** out) {
+  if (!out) { set_error("null out"); return SIMSEG_ERR_INVALID; }
+  cudaDeviceProp prop;
+  SIMSEG_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; libsimseg_b200 carries sm_100a code only", device, prop.major, prop.minor);
+    return SIMSEG_ERR_UNSUPPORTED;
+  }
+  SIMSEG_CUDA(cudaSetDevice(device));
+  simseg_ctx* x = new simseg_ctx();
+  x->c.device = device;
+  x->c.num_sms = prop.multiProcessorCount;
+  x->c.launches = 0;
+  *out = x;
+  return SIMSEG_OK;
+}
+int simseg_ctx_destroy(simseg_ctx* ctx) { delete ctx; return SIMSEG_OK; }
+int64_t simseg_ctx_launch_count(simseg_ctx* ctx, int reset) {
+  if (!ctx) return -1;
+  const int64_t n = ctx->c.launches;
+  if (reset) ctx->c.launches = 0;
+  return n;
+}
+
+int simseg_gemm(simseg_ctx* ctx, const simseg_gemm_args* args, void* stream) {
+  CTX_OR_FAIL();
+  if (!args) { set_error("null args"); return SIMSEG_ERR_INVALID; }
+  return gemm_impl(c, args, st);
+}
+int simseg_cast_bf16(simseg_ctx* ctx, const float* src, void* dst, void* dst_t, int64_t rows, int64_t cols, void* stream) {
+  CTX_OR_FAIL();
+  return cast_bf16_impl(c, src, dst, dst_t, rows, cols, st);
+}
+int simseg_colsum(simseg_ctx* ctx, const void* x, int dtype, int64_t M, int64_t N, int64_t ldx, float* out, int accumulate, void* stream) {
+  CTX_OR_FAIL();
+  return colsum_impl(c, x, dtype, M, N, ldx, out, accumulate, st);
+}
+int simseg_gelu_fwd(simseg_ctx* ctx, const void* h, void* a, int64_t n, void* stream) {
+  CTX_OR_FAIL();
+  return gelu_fwd_impl(c, h, a, n, st);
+}
+int simseg_layernorm_fwd(simseg_ctx* ctx, const void* x, int x_dtype, const float* gamma, const float* beta, float eps,
+                         int64_t M, int D, void* y_bf16, float* y_f32, float* mean, float* rstd, void* stream) {
+  CTX_OR_FAIL();
+  return layernorm_fwd_impl(c, x, x_dtype, gamma, beta, eps, M, D, y_bf16, y_f32, mean, rstd, st);
+}
+int simseg_layernorm_bwd(simseg_ctx* ctx, const void* dy, int dy_dtype, const float* dy2, const void* x, int x_dtype,
+                         const float* gamma, const float* mean, const float* rstd, int64_t M, int D, float* dx,
+                         int dx_accumulate, void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, void* stream) {
+  CTX_OR_FAIL();
+  return layernorm_bwd_impl(c, dy, dy_dtype, dy2, x, x_dtype, gamma, mean, rstd, M, D, dx, dx_accumulate, dx_bf16, dgamma,
+                            dbeta, dx_colsum, st);
+}
+int simseg_attention_fwd(simseg_ctx* ctx, const void* q, const void* k, const void* v, int64_t stride_b, int64_t stride_s,
+                         int64_t stride_h, int B, int H, int S, const int32_t* key_len, float scale, void* out, float* lse,
+                         void* stream) {
+  CTX_OR_FAIL();
+  return attention_fwd_impl(c, q, k, v, stride_b, stride_s, stride_h, B, H, S, key_len, scale, out, lse, st);
+}
+int simseg_attention_bwd(simseg_ctx* ctx, const void* q, const void* k, const void* v, const void* out, const void* dout,
+                         const float* lse, int64_t stride_b, int64_t stride_s, int64_t stride_h, int B, int H, int S,
+                         const int32_t* key_len, float scale, void* dq, void* dk, void* dv, void* stream) {
+  CTX_OR_FAIL();
+  return attention_bwd_impl(c, q, k, v, out, dout, lse, stride_b, stride_s, stride_h, B, H, S, key_len, scale, dq, dk, dv, st);
+}
+int simseg_im2col16(simseg_ctx* ctx, const float* image, int B, int Hi, int Wi, void* patches, void* stream) {
+  CTX_OR_FAIL();
+  return im2col16_impl(c, image, B, Hi, Wi, patches, st);
+}
+int simseg_vit_tokens_fwd(simseg_ctx* ctx, const void* patch, int patch_dtype, const float* cls, const float* pos, int B,
+                          int N, int D, float* x, void* stream) {
+  CTX_OR_FAIL();
+  return vit_tokens_fwd_impl(c, patch, patch_dtype, cls, pos, B, N, D, x, st);
+}
+int simseg_vit_tokens_bwd(simseg_ctx* ctx, const float* dx, int B, int N, int D, void* dpatch, float* dpos, float* dcls,
+                          void* stream) {
+  CTX_OR_FAIL();
+  return vit_tokens_bwd_impl(c, dx, B, N, D, dpatch, dpos, dcls, st);
+}
+int simseg_bert_embed_fwd(simseg_ctx* ctx, const int64_t* ids, const float* word, const float* pos, const float* type0,
+                          int B, int T, int D, float* e, void* stream) {
+  CTX_OR_FAIL();
+  return bert_embed_fwd_impl(c, ids, word, pos, type0, B, T, D, e, st);
+}
+int simseg_bert_embed_bwd(simseg_ctx* ctx, const int64_t* ids, const float* de, int B, int T, int D, float* dword,
+                          float* dpos, float* dtype0, void* stream) {
+  CTX_OR_FAIL();
+  return bert_embed_bwd_impl(c, ids, de, B, T, D, dword, dpos, dtype0, st);
+}
+int simseg_topk_pool_l2norm_fwd(simseg_ctx* ctx, const void* x, int x_dtype, int B, int S, int E, int tok_begin, int ntok,
+                                int k, const int64_t* attention_mask, int mask_ld, float eps, float* pooled, float* emb,
+                                int32_t* sel_idx, void* stream) {
+  CTX_OR_FAIL();
+  return topk_pool_l2norm_fwd_impl(c, x, x_dtype, B, S, E, tok_begin, ntok, k, attention_mask, mask_ld, eps, pooled, emb,
+                                   sel_idx, st);
+}
+int simseg_topk_pool_l2norm_bwd(simseg_ctx* ctx, const float* demb, const float* pooled, const int32_t* sel_idx, int B,
+                                int S, int E, int tok_begin, int k, float eps, int has_l2norm, void* dx, void* stream) {
+  CTX_OR_FAIL();
+  (void)tok_begin;   // sel_idx already holds absolute token positions
+  return topk_pool_l2norm_bwd_impl(c, demb, pooled, sel_idx, B, S, E, k, eps, has_l2norm, dx, st);
+}
+
+int simseg_infonce_fwd(simseg_ctx* ctx, const float* feat1, const float* feat2g, int b, int Bg, int E,
+                       const float* temperature, int row_offset, int precision, float* cos_ws, float* logits_out,
+                       float* loss_rows, float* lse, int32_t* argmax, void* stream) {
+  CTX_OR_FAIL();
+  SIMSEG_CHECK_ARG(cos_ws != nullptr, "infonce_fwd: cos_ws workspace required");
+  int rc = fp32_matmul(c, feat1, feat2g, cos_ws, b, Bg, E, E, E, Bg, 0, 0, 0, precision, st);
+  if (rc) return rc;
+  return nce_rows_fwd_impl(c, cos_ws, b, Bg, Bg, temperature, row_offset, logits_out, loss_rows, lse, argmax, st);
+}
+int simseg_infonce_bwd(simseg_ctx* ctx, const float* feat1, const float* feat2g, int b, int Bg, int E,
+                       const float* temperature, int row_offset, int precision, const float* lse, float grad_scale,
+                       float* cos_ws, float* dfeat1, float* dfeat2g, float* dtemp, void* stream) {
+  CTX_OR_FAIL();
+  SIMSEG_CHECK_ARG(cos_ws != nullptr, "infonce_bwd: cos_ws workspace required");
+  int rc = nce_rows_bwd_impl(c, cos_ws, b, Bg, Bg, temperature, row_offset, lse, grad_scale, dtemp, st);
+  if (rc) return rc;
+  // dfeat1[b,E] = G[b,Bg] @ feat2g[Bg,E]          (A K-major, B stored [K,N])
+  if (dfeat1) {
+    rc = fp32_matmul(c, cos_ws, feat2g, dfeat1, b, E, Bg, Bg, E, E, 0, 1, 0, precision, st);
+    if (rc) return rc;
+  }
+  // dfeat2g[Bg,E] += G^T[Bg,b] @ feat1[b,E]       (A stored [K,M], B stored [K,N])
+  if (dfeat2g) {
+    rc = fp32_matmul(c, cos_ws, feat1, dfeat2g, Bg, E, b, Bg, E, E, 1, 1, 1, precision, st);
+    if (rc) return rc;
+  }
+  return SIMSEG_OK;
+}
+
+int64_t simseg_patch_text_sim_workspace_bytes(int64_t rows) { return ((rows * 4 + 255) / 256) * 256; }
+
+int simseg_patch_text_sim(simseg_ctx* ctx, const void* patches, int dtype, int64_t rows, int E, const void* text, int C,
+                          int normalize, float* sim, int32_t* argmax, void* workspace, int64_t workspace_bytes,
+                          void* stream) {
+  CTX_OR_FAIL();
+  SIMSEG_CHECK_ARG(rows > 0 && C > 0 && E > 0, "patch_text_sim: empty");
+  simseg_gemm_args g;
+  memset(&g, 0, sizeof(g));
+  g.a = patches; g.b = text; g.d = sim; g.M = rows; g.N = C; g.K = E; g.lda = E; g.ldb = E; g.ldd = C;
+  g.in_dtype = dtype; g.out_dtype = SIMSEG_F32; g.epilogue = SIMSEG_EPI_NONE;
+  int rc;
+  if (normalize) {
+    SIMSEG_CHECK_ARG(workspace != nullptr && workspace_bytes >= rows * 4, "patch_text_sim: workspace too small");
+    rc = row_inv_norm_impl(c, patches, dtype, rows, E, reinterpret_cast<float*>(workspace), st);
+    if (rc) return rc;
+    g.epilogue = SIMSEG_EPI_ROWSCALE;
+    g.row_scale = reinterpret_cast<const float*>(workspace);
+  }
+  rc = gemm_impl(c, &g, st);
+  if (rc) return rc;
+  if (argmax) return row_argmax_impl(c, sim, rows, C, argmax, st);
+  return SIMSEG_OK;
+}
+
+int simseg_allpairs_sim(simseg_ctx* ctx, const float* left, const float* right, int M, int Nr, int E, int precision,
+                        float* out, void* stream) {
+  CTX_OR_FAIL();
+  return fp32_matmul(c, left, right, out, M, Nr, E, E, E, Nr, 0, 0, 0, precision, st);
+}
+int simseg_retrieval_rank(simseg_ctx* ctx, const float* sim, int M, int Nr, const int64_t* left_gid,
+                          const int64_t* right_gid, int32_t* rank, void* stream) {
+  CTX_OR_FAIL();
+  return retrieval_rank_impl(c, sim, M, Nr, left_gid, right_gid, rank, st);
+}
+
+}  // extern "C"

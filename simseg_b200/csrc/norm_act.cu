@@ -1,0 +1,347 @@
+// Bandwidth-bound row / elementwise kernels: casts, column sums, GELU recompute, LayerNorm fwd/bwd.
+// All use 128-bit global accesses; LayerNorm keeps a whole row in the registers of one warp.
+#include "common.cuh"
+
+namespace simseg {
+
+// ------------------------------------------------------------------------------------------------
+// fp32 -> bf16 cast (+ optional transposed copy) for weights.  32x32 smem tile, coalesced both ways.
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                 __nv_bfloat16* __restrict__ dst_t, int64_t rows, int64_t cols) {
+  __shared__ float tile[32][33];
+  const int64_t c = blockIdx.x * 32 + threadIdx.x;
+  const int64_t r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int64_t r = r0 + i;
+    float v = 0.f;
+    if (r < rows && c < cols) {
+      v = src[r * cols + c];
+      if (dst) dst[r * cols + c] = __float2bfloat16(v);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  if (!dst_t) return;
+  __syncthreads();
+  const int64_t tr = blockIdx.x * 32;     // transposed: row index = original column
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int64_t oc = tr + i;            // original column
+    const int64_t orow = r0 + threadIdx.x;
+    if (oc < cols && orow < rows) dst_t[oc * rows + orow] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+
+int cast_bf16_impl(Ctx* ctx, const float* src, void* dst, void* dst_t, int64_t rows, int64_t cols, cudaStream_t st) {
+  SIMSEG_CHECK_ARG(rows > 0 && cols > 0, "cast_bf16: empty");
+  dim3 grid(static_cast<unsigned>(cdiv(cols, 32)), static_cast<unsigned>(cdiv(rows, 32)));
+  cast_bf16_kernel<<<grid, dim3(32, 8), 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst),
+                                                 reinterpret_cast<__nv_bfloat16*>(dst_t), rows, cols);
+  ctx->launches++;
+  SIMSEG_LAUNCH_CHECK();
+  return SIMSEG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums: out[n] += sum_m x[m,n].  Block = 32 column-lanes x 8 row-lanes, each lane owns 4 columns.
+template <bool BF16>
+__global__ void colsum_kernel(const void* __restrict__ x, int64_t M, int64_t N, int64_t ldx, float* __restrict__ out,
+                              int64_t rows_per_block) {
+  const int64_t c0 = (static_cast<int64_t>(blockIdx.x) * 32 + threadIdx.x) * 4;
+  const int64_t r_begin = blockIdx.y * rows_per_block;
+  const int64_t r_end = min(M, r_begin + rows_per_block);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (c0 < N) {
+    const bool full = c0 + 4 <= N;
+    for (int64_t r = r_begin + threadIdx.y; r < r_end; r += 8) {
+      if (BF16) {
+        const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(x) + r * ldx + c0;
+        if (full) {
+          const uint2 u = *reinterpret_cast<const uint2*>(p);
+          a0 += bf16_lo(u.x); a1 += bf16_hi(u.x); a2 += bf16_lo(u.y); a3 += bf16_hi(u.y);
+        } else {
+          a0 += __bfloat162float(p[0]);
+          if (c0 + 1 < N) a1 += __bfloat162float(p[1]);
+          if (c0 + 2 < N) a2 += __bfloat162float(p[2]);
+        }
+      } else {
+        const float* p = reinterpret_cast<const float*>(x) + r * ldx + c0;
+        if (full) {
+          const float4 f = *reinterpret_cast<const float4*>(p);
+          a0 += f.x; a1 += f.y; a2 += f.z; a3 += f.w;
+        } else {
+          a0 += p[0];
+          if (c0 + 1 < N) a1 += p[1];
+          if (c0 + 2 < N) a2 += p[2];
+        }
+      }
+    }
+  }
+  __shared__ float red[8][32][4];
+  red[threadIdx.y][threadIdx.x][0] = a0; red[threadIdx.y][threadIdx.x][1] = a1;
+  red[threadIdx.y][threadIdx.x][2] = a2; red[threadIdx.y][threadIdx.x][3] = a3;
+  __syncthreads();
+  if (threadIdx.y == 0 && c0 < N) {
+    for (int j = 0; j < 4; ++j) {
+      float s = 0.f;
+      for (int y = 0; y < 8; ++y) s += red[y][threadIdx.x][j];
+      if (c0 + j < N) atomicAdd(out + c0 + j, s);
+    }
+  }
+}
+
+int colsum_impl(Ctx* ctx, const void* x, int dtype, int64_t M, int64_t N, int64_t ldx, float* out, int accumulate,
+                cudaStream_t st) {
+  SIMSEG_CHECK_ARG(M > 0 && N > 0, "colsum: empty");
+  const int eb = dtype == SIMSEG_BF16 ? 2 : 4;
+  SIMSEG_CHECK_ARG((ldx * eb) % 16 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "colsum: rows must be 16B aligned");
+  if (!accumulate) SIMSEG_CUDA(cudaMemsetAsync(out, 0, N * sizeof(float), st));
+  const int64_t col_blocks = cdiv(N, 128);
+  int64_t row_blocks = cdiv(static_cast<int64_t>(ctx->num_sms) * 8, col_blocks);
+  const int64_t max_rb = cdiv(M, 64);
+  if (row_blocks > max_rb) row_blocks = max_rb;
+  if (row_blocks < 1) row_blocks = 1;
+  const int64_t rpb = cdiv(M, row_blocks);
+  dim3 grid(static_cast<unsigned>(col_blocks), static_cast<unsigned>(cdiv(M, rpb)));
+  if (dtype == SIMSEG_BF16) colsum_kernel<true><<<grid, dim3(32, 8), 0, st>>>(x, M, N, ldx, out, rpb);
+  else colsum_kernel<false><<<grid, dim3(32, 8), 0, st>>>(x, M, N, ldx, out, rpb);
+  ctx->launches++;
+  SIMSEG_LAUNCH_CHECK();
+  return SIMSEG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void gelu_fwd_kernel(const uint4* __restrict__ h, uint4* __restrict__ a, int64_t n8) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint4 u = ldg_nc_v4(h + i);
+    uint4 o;
+    o.x = pack_bf16(gelu_erf(bf16_lo(u.x)), gelu_erf(bf16_hi(u.x)));
+    o.y = pack_bf16(gelu_erf(bf16_lo(u.y)), gelu_erf(bf16_hi(u.y)));
+    o.z = pack_bf16(gelu_erf(bf16_lo(u.z)), gelu_erf(bf16_hi(u.z)));
+    o.w = pack_bf16(gelu_erf(bf16_lo(u.w)), gelu_erf(bf16_hi(u.w)));
+    a[i] = o;
+  }
+}
+
+int gelu_fwd_impl(Ctx* ctx, const void* h, void* a, int64_t n, cudaStream_t st) {
+  SIMSEG_CHECK_ARG(n > 0 && n % 8 == 0, "gelu_fwd: n must be a positive multiple of 8");
+  const int64_t n8 = n / 8;
+  const int grid = static_cast<int>(imin64(cdiv(n8, 256), static_cast<int64_t>(ctx->num_sms) * 16));
+  gelu_fwd_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(h), reinterpret_cast<uint4*>(a), n8);
+  ctx->launches++;
+  SIMSEG_LAUNCH_CHECK();
+  return SIMSEG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm.  One warp per row; lane owns V float4 groups: columns (g*32 + lane)*4 .. +3, g < V (D = 128 V).
+template <int V, bool XBF16>
+__device__ __forceinline__ void load_row(const void* x, int64_t row, int D, int lane, float (&v)[V][4]) {
+#pragma unroll
+  for (int g = 0; g < V; ++g) {
+    const int c = (g * 32 + lane) * 4;
+    if (XBF16) {
+      const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + row * D + c);
+      v[g][0] = bf16_lo(u.x); v[g][1] = bf16_hi(u.x); v[g][2] = bf16_lo(u.y); v[g][3] = bf16_hi(u.y);
+    } else {
+      const float4 f = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + row * D + c);
+      v[g][0] = f.x; v[g][1] = f.y; v[g][2] = f.z; v[g][3] = f.w;
+    }
+  }
+}
+
+template <int V, bool XBF16>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps, int64_t M,
+                                                            __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32,
+                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  constexpr int D = V * 128;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  float g[V][4], b[V][4];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float4 gg = *reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4);
+    const float4 bb = *reinterpret_cast<const float4*>(beta + (i * 32 + lane) * 4);
+    g[i][0] = gg.x; g[i][1] = gg.y; g[i][2] = gg.z; g[i][3] = gg.w;
+    b[i][0] = bb.x; b[i][1] = bb.y; b[i][2] = bb.z; b[i][3] = bb.w;
+  }
+  for (int64_t row = warp_global; row < M; row += nwarps) {
+    float v[V][4];
+    load_row<V, XBF16>(x, row, D, lane, v);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+    const float mu = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float d = v[i][j] - mu; q += d * d; }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mu;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = (v[i][j] - mu) * rstd * g[i][j] + b[i][j];
+      if (y_bf16) {
+        uint2 u; u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]);
+        *reinterpret_cast<uint2*>(y_bf16 + row * D + c) = u;
+      }
+      if (y_f32) *reinterpret_cast<float4*>(y_f32 + row * D + c) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+template <int V, bool XBF16, bool DYBF16>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(
+    const void* __restrict__ dy, const float* __restrict__ dy2, const void* __restrict__ x, const float* __restrict__ gamma,
+    const float* __restrict__ mean, const float* __restrict__ rstd, int64_t M, float* __restrict__ dx, int dx_accumulate,
+    __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dx_colsum) {
+  constexpr int D = V * 128;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  float g[V][4];
+  float acc_g[V][4], acc_b[V][4], acc_x[V][4];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float4 gg = *reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4);
+    g[i][0] = gg.x; g[i][1] = gg.y; g[i][2] = gg.z; g[i][3] = gg.w;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc_g[i][j] = 0.f; acc_b[i][j] = 0.f; acc_x[i][j] = 0.f; }
+  }
+  for (int64_t row = warp_global; row < M; row += nwarps) {
+    float xv[V][4], dv[V][4];
+    load_row<V, XBF16>(x, row, D, lane, xv);
+    load_row<V, DYBF16>(dy, row, D, lane, dv);
+    if (dy2) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float4 f = *reinterpret_cast<const float4*>(dy2 + row * D + (i * 32 + lane) * 4);
+        dv[i][0] += f.x; dv[i][1] += f.y; dv[i][2] += f.z; dv[i][3] += f.w;
+      }
+    }
+    const float mu = mean[row], rs = rstd[row];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xh = (xv[i][j] - mu) * rs;
+        const float gy = dv[i][j] * g[i][j];
+        c1 += gy; c2 += gy * xh;
+        acc_g[i][j] += dv[i][j] * xh;
+        acc_b[i][j] += dv[i][j];
+        xv[i][j] = xh;
+        dv[i][j] = gy;
+      }
+    c1 = warp_sum(c1) * (1.0f / D);
+    c2 = warp_sum(c2) * (1.0f / D);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = rs * (dv[i][j] - c1 - xv[i][j] * c2);
+      if (dx_accumulate) {
+        const float4 f = *reinterpret_cast<const float4*>(dx + row * D + c);
+        o[0] += f.x; o[1] += f.y; o[2] += f.z; o[3] += f.w;
+      }
+      if (dx) *reinterpret_cast<float4*>(dx + row * D + c) = make_float4(o[0], o[1], o[2], o[3]);
+      if (dx_bf16) {
+        uint2 u; u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]);
+        *reinterpret_cast<uint2*>(dx_bf16 + row * D + c) = u;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc_x[i][j] += o[j];
+    }
+  }
+  // block reduction of the per-column partials, then one atomic per column per block
+  __shared__ float red[8][128 * V];
+  auto reduce_store = [&](float (&a)[V][4], float* out) {
+    if (out == nullptr) return;            // uniform across the block
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[warp][(i * 32 + lane) * 4 + j] = a[i][j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][c];
+      atomicAdd(out + c, s);
+    }
+  };
+  reduce_store(acc_g, dgamma);
+  reduce_store(acc_b, dbeta);
+  reduce_store(acc_x, dx_colsum);
+}
+
+static int ln_grid(Ctx* ctx, int64_t M) {
+  const int64_t want = cdiv(M, 8);
+  const int64_t cap = static_cast<int64_t>(ctx->num_sms) * 8;
+  return static_cast<int>(want < cap ? want : cap);
+}
+
+int layernorm_fwd_impl(Ctx* ctx, const void* x, int x_dtype, const float* gamma, const float* beta, float eps, int64_t M,
+                       int D, void* y_bf16, float* y_f32, float* mean, float* rstd, cudaStream_t st) {
+  SIMSEG_CHECK_ARG(M > 0, "layernorm_fwd: empty");
+  SIMSEG_CHECK_ARG(D == 384 || D == 768 || D == 512 || D == 128 || D == 256, "layernorm: D=%d unsupported (128/256/384/512/768)", D);
+  const int grid = ln_grid(ctx, M);
+  auto* yb = reinterpret_cast<__nv_bfloat16*>(y_bf16);
+#define LN_FWD(V)                                                                                             \
+  if (x_dtype == SIMSEG_BF16) layernorm_fwd_kernel<V, true><<<grid, 256, 0, st>>>(x, gamma, beta, eps, M, yb, y_f32, mean, rstd); \
+  else layernorm_fwd_kernel<V, false><<<grid, 256, 0, st>>>(x, gamma, beta, eps, M, yb, y_f32, mean, rstd)
+  switch (D / 128) {
+    case 1: LN_FWD(1); break;
+    case 2: LN_FWD(2); break;
+    case 3: LN_FWD(3); break;
+    case 4: LN_FWD(4); break;
+    default: LN_FWD(6); break;
+  }
+#undef LN_FWD
+  ctx->launches++;
+  SIMSEG_LAUNCH_CHECK();
+  return SIMSEG_OK;
+}
+
+int layernorm_bwd_impl(Ctx* ctx, const void* dy, int dy_dtype, const float* dy2, const void* x, int x_dtype,
+                       const float* gamma, const float* mean, const float* rstd, int64_t M, int D, float* dx,
+                       int dx_accumulate, void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, cudaStream_t st) {
+  SIMSEG_CHECK_ARG(M > 0, "layernorm_bwd: empty");
+  SIMSEG_CHECK_ARG(D == 384 || D == 768 || D == 512 || D == 128 || D == 256, "layernorm: D=%d unsupported", D);
+  SIMSEG_CHECK_ARG(!(dx_accumulate && dx == nullptr), "layernorm_bwd: dx_accumulate needs dx");
+  const int grid = ln_grid(ctx, M);
+  auto* db = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
+#define LN_BWD(V)                                                                                                   \
+  do {                                                                                                              \
+    if (x_dtype == SIMSEG_BF16) {                                                                                   \
+      if (dy_dtype == SIMSEG_BF16) layernorm_bwd_kernel<V, true, true><<<grid, 256, 0, st>>>(dy, dy2, x, gamma, mean, rstd, M, dx, dx_accumulate, db, dgamma, dbeta, dx_colsum); \
+      else layernorm_bwd_kernel<V, true, false><<<grid, 256, 0, st>>>(dy, dy2, x, gamma, mean, rstd, M, dx, dx_accumulate, db, dgamma, dbeta, dx_colsum); \
+    } else {                                                                                                        \
+      if (dy_dtype == SIMSEG_BF16) layernorm_bwd_kernel<V, false, true><<<grid, 256, 0, st>>>(dy, dy2, x, gamma, mean, rstd, M, dx, dx_accumulate, db, dgamma, dbeta, dx_colsum); \
+      else layernorm_bwd_kernel<V, false, false><<<grid, 256, 0, st>>>(dy, dy2, x, gamma, mean, rstd, M, dx, dx_accumulate, db, dgamma, dbeta, dx_colsum); \
+    }                                                                                                               \
+  } while (0)
+  switch (D / 128) {
+    case 1: LN_BWD(1); break;
+    case 2: LN_BWD(2); break;
+    case 3: LN_BWD(3); break;
+    case 4: LN_BWD(4); break;
+    default: LN_BWD(6); break;
+  }
+#undef LN_BWD
+  ctx->launches++;
+  SIMSEG_LAUNCH_CHECK();
+  return SIMSEG_OK;
+}
+
+}  // namespace simseg

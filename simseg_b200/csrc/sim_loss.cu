@@ -1,0 +1,368 @@
+// fp32 similarity / loss kernels: exact-fp32 tiled GEMM (all-pairs cosine, InfoNCE logits and their
+// gradients), row-wise softmax cross-entropy forward/backward over a similarity matrix, patch-map row
+// norms + argmax, retrieval first-match rank.
+#include "common.cuh"
+
+namespace simseg {
+
+// ------------------------------------------------------------------------------------------------
+// C[M,N] (+)= sum_k A(m,k) * B(n,k), fp32 FFMA, 128x128x16 tiles, 8x8 register micro-tiles.
+// A_KMAJOR: A stored [M,K] (k contiguous) else stored [K,M] (m contiguous).  Same for B with N.
+constexpr int SG_BM = 128, SG_BN = 128, SG_BK = 16;
+
+template <bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(256) sgemm_nt_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                       float* __restrict__ C, int M, int N, int K, int64_t lda,
+                                                       int64_t ldb, int64_t ldc, int accumulate) {
+  __shared__ __align__(16) float As[SG_BK][SG_BM + 4];
+  __shared__ __align__(16) float Bs[SG_BK][SG_BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
+  const int tx = tid & 15, ty = tid >> 4;          // 16 x 16 threads, each 8 rows x 8 cols (strided by 16... see below)
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += SG_BK) {
+    // ---- load A tile (128 x 16) into As[k][m]
+    if (A_KMAJOR) {
+      // 128 rows x 4 float4 = 512 float4, 2 per thread
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int f = tid + it * 256;
+        const int r = f >> 2, c4 = (f & 3) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m0 + r < M && k0 + c4 < K) v = *reinterpret_cast<const float4*>(A + static_cast<int64_t>(m0 + r) * lda + k0 + c4);
+        As[c4][r] = v.x; As[c4 + 1][r] = v.y; As[c4 + 2][r] = v.z; As[c4 + 3][r] = v.w;
+      }
+    } else {
+      // 16 k-rows x 32 float4 along m
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int f = tid + it * 256;
+        const int kr = f >> 5, c4 = (f & 31) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + kr < K && m0 + c4 < M) {
+          const float* p = A + static_cast<int64_t>(k0 + kr) * lda + m0 + c4;
+          if (m0 + c4 + 3 < M) v = *reinterpret_cast<const float4*>(p);
+          else { v.x = p[0]; if (m0 + c4 + 1 < M) v.y = p[1]; if (m0 + c4 + 2 < M) v.z = p[2]; }
+        }
+        *reinterpret_cast<float4*>(&As[kr][c4]) = v;
+      }
+    }
+    if (B_KMAJOR) {
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int f = tid + it * 256;
+        const int r = f >> 2, c4 = (f & 3) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n0 + r < N && k0 + c4 < K) v = *reinterpret_cast<const float4*>(B + static_cast<int64_t>(n0 + r) * ldb + k0 + c4);
+        Bs[c4][r] = v.x; Bs[c4 + 1][r] = v.y; Bs[c4 + 2][r] = v.z; Bs[c4 + 3][r] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int f = tid + it * 256;
+        const int kr = f >> 5, c4 = (f & 31) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + kr < K && n0 + c4 < N) {
+          const float* p = B + static_cast<int64_t>(k0 + kr) * ldb + n0 + c4;
+          if (n0 + c4 + 3 < N) v = *reinterpret_cast<const float4*>(p);
+          else { v.x = p[0]; if (n0 + c4 + 1 < N) v.y = p[1]; if (n0 + c4 + 2 < N) v.z = p[2]; }
+        }
+        *reinterpret_cast<float4*>(&Bs[kr][c4]) = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SG_BK; ++kk) {
+      // thread owns rows ty*4..+3 and 64+ty*4..+3 ; cols tx*4..+3 and 64+tx*4..+3 (two float4 each)
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (r >= M) continue;
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      const int c = n0 + jh * 64 + tx * 4;
+      float* p = C + static_cast<int64_t>(r) * ldc + c;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (c + j < N) {
+          const float v = acc[i][jh * 4 + j];
+          p[j] = accumulate ? p[j] + v : v;
+        }
+      }
+    }
+  }
+}
+
+// layout flags: a_major / b_major as in simseg_gemm (0 = K-major, 1 = MN-major)
+int sgemm_impl(Ctx* ctx, const float* A, const float* B, float* C, int M, int N, int K, int64_t lda, int64_t ldb,
+               int64_t ldc, int a_major, int b_major, int accumulate, cudaStream_t st) {
+  SIMSEG_CHECK_ARG(M > 0 && N > 0 && K > 0, "sgemm: empty");
+  SIMSEG_CHECK_ARG(lda % 4 == 0 && ldb % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+                   "sgemm: operands need 16-byte aligned rows");
+  if (!a_major) SIMSEG_CHECK_ARG(K % 4 == 0, "sgemm: K must be a multiple of 4 for K-major A");
+  if (!b_major) SIMSEG_CHECK_ARG(K % 4 == 0, "sgemm: K must be a multiple of 4 for K-major B");
+  dim3 grid(static_cast<unsigned>(cdiv(N, SG_BN)), static_cast<unsigned>(cdiv(M, SG_BM)));
+  if (!a_major && !b_major) sgemm_nt_kernel<true, true><<<grid, 256, 0, st>>>(A, B, C, M, N, K, lda, ldb, ldc, accumulate);
+  else if (!a_major && b_major) sgemm_nt_kernel<true, false><<<grid, 256, 0, st>>>(A, B, C, M, N, K, lda, ldb, ldc, accumulate);
+  else if (a_major && !b_major) sgemm_nt_kernel<false, true><<<grid, 256, 0, st>>>(A, B, C, M, N, K, lda, ldb, ldc, accumulate);
+  else sgemm_nt_kernel<false, false><<<grid, 256, 0, st>>>(A, B, C, M, N, K, lda, ldb, ldc, accumulate);
+  ctx->launches++;
+  SIMSEG_LAUNCH_CHECK();
+  return SIMSEG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row-wise InfoNCE over a cosine matrix S[b,Bg]: logits = S / clamp(temp); CE against column row_offset+i.
+__device__ __forceinline__ float clamp_temp(float t) { return fminf(fmaxf(t, 0.001f), 0.5f); }
+
+__global__ void __launch_bounds__(256) nce_rows_fwd_kernel(const float* __restrict__ S, int Bg, int64_t lds,
+                                                           const float* __restrict__ temperature, int row_offset,
+                                                           float* __restrict__ logits_out, int64_t ldl,
+                                                           float* __restrict__ loss_rows, float* __restrict__ lse_out,
+                                                           int32_t* __restrict__ argmax_out) {
+  const int i = blockIdx.x;
+  const float inv_t = 1.0f / clamp_temp(*temperature);
+  const float* row = S + static_cast<int64_t>(i) * lds;
+  float m = -INFINITY, l = 0.f;
+  float best = -INFINITY;
+  int besti = 0x7fffffff;
+  for (int j = threadIdx.x; j < Bg; j += blockDim.x) {
+    const float z = row[j] * inv_t;
+    if (logits_out) logits_out[static_cast<int64_t>(i) * ldl + j] = z;
+    if (z > best) { best = z; besti = j; }
+    if (z > m) { l = l * __expf(m - z) + 1.0f; m = z; }
+    else l += __expf(z - m);
+  }
+  // combine (m,l) and (best,besti) across the block
+  __shared__ float sm[8], sl[8], sb[8];
+  __shared__ int si[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), l2 = __shfl_xor_sync(0xffffffffu, l, o);
+    const float b2 = __shfl_xor_sync(0xffffffffu, best, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, besti, o);
+    const float mm = fmaxf(m, m2);
+    l = (mm == -INFINITY) ? 0.f : l * __expf(m - mm) + l2 * __expf(m2 - mm);
+    m = mm;
+    if (b2 > best || (b2 == best && i2 < besti)) { best = b2; besti = i2; }
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { sm[w] = m; sl[w] = l; sb[w] = best; si[w] = besti; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < (blockDim.x >> 5); ++k) {
+      const float mm = fmaxf(m, sm[k]);
+      l = (mm == -INFINITY) ? 0.f : l * __expf(m - mm) + sl[k] * __expf(sm[k] - mm);
+      m = mm;
+      if (sb[k] > best || (sb[k] == best && si[k] < besti)) { best = sb[k]; besti = si[k]; }
+    }
+    const float lse = m + logf(l);
+    const float zt = row[row_offset + i] * inv_t;
+    loss_rows[i] = lse - zt;
+    lse_out[i] = lse;
+    if (argmax_out) argmax_out[i] = besti;
+  }
+}
+
+// In place: S <- G = grad_scale * (softmax(S/t) - onehot) / t ; dtemp += -(1/t) sum_ij G_ij S_ij (inside clamp range)
+__global__ void __launch_bounds__(256) nce_rows_bwd_kernel(float* __restrict__ S, int Bg, int64_t lds,
+                                                           const float* __restrict__ temperature, int row_offset,
+                                                           const float* __restrict__ lse, float grad_scale,
+                                                           float* __restrict__ dtemp) {
+  const int i = blockIdx.x;
+  const float traw = *temperature;
+  const float t = clamp_temp(traw);
+  const float inv_t = 1.0f / t;
+  float* row = S + static_cast<int64_t>(i) * lds;
+  const float L = lse[i];
+  const int tgt = row_offset + i;
+  float dsum = 0.f;
+  for (int j = threadIdx.x; j < Bg; j += blockDim.x) {
+    const float s = row[j];
+    float p = __expf(s * inv_t - L);
+    if (j == tgt) p -= 1.0f;
+    const float g = grad_scale * p * inv_t;
+    row[j] = g;
+    dsum += g * s;
+  }
+  if (dtemp == nullptr) return;
+  __shared__ float red[8];
+  dsum = warp_sum(dsum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int k = 0; k < (blockDim.x >> 5); ++k) tot += red[k];
+    if (traw >= 0.001f && traw <= 0.5f) atomicAdd(dtemp, -tot * inv_t);
+  }
+}
+
+int nce_rows_fwd_impl(Ctx* ctx, const float* S, int b, int Bg, int64_t lds, const float* temperature, int row_offset,
+                      float* logits_out, float* loss_rows, float* lse, int32_t* argmax, cudaStream_t st) {
+  SIMSEG_CHECK_ARG(b > 0 && Bg > 0 && row_offset >= 0 && row_offset + b <= Bg, "nce_rows_fwd: bad shape b=%d Bg=%d off=%d", b, Bg, row_offset);
+  nce_rows_fwd_kernel<<<b, 256, 0, st>>>(S, Bg, lds, temperature, row_offset, logits_out, Bg, loss_rows, lse, argmax);
+  ctx->launches++;
+  SIMSEG_LAUNCH_CHECK();
+  return SIMSEG_OK;
+}
+
+int nce_rows_bwd_impl(Ctx* ctx, float* S, int b, int Bg, int64_t lds, const float* temperature, int row_offset,
+                      const float* lse, float grad_scale, float* dtemp, cudaStream_t st) {
+  SIMSEG_CHECK_ARG(b > 0 && Bg > 0 && row_offset >= 0 && row_offset + b <= Bg, "nce_rows_bwd: bad shape");
+  nce_rows_bwd_kernel<<<b, 256, 0, st>>>(S, Bg, lds, temperature, row_offset, lse, grad_scale, dtemp);
+  ctx->launches++;
+  SIMSEG_LAUNCH_CHECK();
+  return SIMSEG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// patch map helpers: inverse row norms (F.normalize eps rule: x / max(||x||, 1e-12)) and row argmax.
+template <bool BF16>
+__global__ void row_inv_norm_kernel(const void* __restrict__ x, int64_t rows, int E, float* __restrict__ inv) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r = warp_global; r < rows; r += nwarps) {
+    float ss = 0.f;
+    if (BF16) {
+      const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + r * E);
+      for (int i = lane; i < E / 8; i += 32) {
+        const uint4 u = ldg_nc_v4(p + i);
+        float a;
+        a = bf16_lo(u.x); ss += a * a; a = bf16_hi(u.x); ss += a * a; a = bf16_lo(u.y); ss += a * a; a = bf16_hi(u.y); ss += a * a;
+        a = bf16_lo(u.z); ss += a * a; a = bf16_hi(u.z); ss += a * a; a = bf16_lo(u.w); ss += a * a; a = bf16_hi(u.w); ss += a * a;
+      }
+    } else {
+      const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + r * E);
+      for (int i = lane; i < E / 4; i += 32) {
+        const float4 f = p[i];
+        ss += f.x * f.x + f.y * f.y + f.z * f.z + f.w * f.w;
+      }
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) inv[r] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  }
+}
+
+int row_inv_norm_impl(Ctx* ctx, const void* x, int dtype, int64_t rows, int E, float* inv, cudaStream_t st) {
+  SIMSEG_CHECK_ARG(rows > 0 && E % 8 == 0, "row_inv_norm: E must be a multiple of 8");
+  const int grid = static_cast<int>(imin64(cdiv(rows, 8), static_cast<int64_t>(ctx->num_sms) * 8));
+  if (dtype == SIMSEG_BF16) row_inv_norm_kernel<true><<<grid, 256, 0, st>>>(x, rows, E, inv);
+  else row_inv_norm_kernel<false><<<grid, 256, 0, st>>>(x, rows, E, inv);
+  ctx->launches++;
+  SIMSEG_LAUNCH_CHECK();
+  return SIMSEG_OK;
+}
+
+__global__ void row_argmax_kernel(const float* __restrict__ x, int64_t rows, int C, int32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r = warp_global; r < rows; r += nwarps) {
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int c = lane; c < C; c += 32) {
+      const float v = x[r * C + c];
+      if (v > best) { best = v; bi = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float b2 = __shfl_xor_sync(0xffffffffu, best, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (b2 > best || (b2 == best && i2 < bi)) { best = b2; bi = i2; }
+    }
+    if (lane == 0) out[r] = bi;
+  }
+}
+
+int row_argmax_impl(Ctx* ctx, const float* x, int64_t rows, int C, int32_t* out, cudaStream_t st) {
+  SIMSEG_CHECK_ARG(rows > 0 && C > 0, "row_argmax: empty");
+  const int grid = static_cast<int>(imin64(cdiv(rows, 8), static_cast<int64_t>(ctx->num_sms) * 8));
+  row_argmax_kernel<<<grid, 256, 0, st>>>(x, rows, C, out);
+  ctx->launches++;
+  SIMSEG_LAUNCH_CHECK();
+  return SIMSEG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// retrieval: rank of the best-scoring right item that shares the row's group id (stable descending order).
+__global__ void __launch_bounds__(256) retrieval_rank_kernel(const float* __restrict__ sim, int Nr,
+                                                             const int64_t* __restrict__ left_gid,
+                                                             const int64_t* __restrict__ right_gid,
+                                                             int32_t* __restrict__ rank) {
+  const int i = blockIdx.x;
+  const float* row = sim + static_cast<int64_t>(i) * Nr;
+  const int64_t gid = left_gid[i];
+  float best = -INFINITY;
+  int bj = 0x7fffffff;
+  for (int j = threadIdx.x; j < Nr; j += blockDim.x) {
+    if (right_gid[j] == gid) {
+      const float v = row[j];
+      if (v > best || (v == best && j < bj)) { best = v; bj = j; }
+    }
+  }
+  __shared__ float sb[8];
+  __shared__ int sj[8];
+  __shared__ int cnt[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float b2 = __shfl_xor_sync(0xffffffffu, best, o);
+    const int j2 = __shfl_xor_sync(0xffffffffu, bj, o);
+    if (j2 != 0x7fffffff && (bj == 0x7fffffff || b2 > best || (b2 == best && j2 < bj))) { best = b2; bj = j2; }
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { sb[w] = best; sj[w] = bj; }
+  __syncthreads();
+  best = sb[0]; bj = sj[0];
+  for (int k = 1; k < 8; ++k) {
+    if (sj[k] != 0x7fffffff && (bj == 0x7fffffff || sb[k] > best || (sb[k] == best && sj[k] < bj))) { best = sb[k]; bj = sj[k]; }
+  }
+  if (bj == 0x7fffffff) {
+    if (threadIdx.x == 0) rank[i] = -1;
+    return;
+  }
+  int c = 0;
+  for (int j = threadIdx.x; j < Nr; j += blockDim.x) {
+    const float v = row[j];
+    c += (v > best || (v == best && j < bj)) ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) cnt[w] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int k = 0; k < 8; ++k) tot += cnt[k];
+    rank[i] = tot;
+  }
+}
+
+int retrieval_rank_impl(Ctx* ctx, const float* sim, int M, int Nr, const int64_t* left_gid, const int64_t* right_gid,
+                        int32_t* rank, cudaStream_t st) {
+  SIMSEG_CHECK_ARG(M > 0 && Nr > 0, "retrieval_rank: empty");
+  retrieval_rank_kernel<<<M, 256, 0, st>>>(sim, Nr, left_gid, right_gid, rank);
+  ctx->launches++;
+  SIMSEG_LAUNCH_CHECK();
+  return SIMSEG_OK;
+}
+
+}  // namespace simseg

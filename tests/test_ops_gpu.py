@@ -1,0 +1,237 @@
+"""Per-op parity of the CUDA kernels (through the C ABI) against plain fp32 torch math on the same inputs.
+
+Tolerances: bf16-input tensor-core ops are compared with an fp32 reference computed from the SAME bf16-rounded
+inputs, so the only differences are accumulation order and the final bf16 rounding of the output
+(<= 2^-8 relative); fp32 ops are held to 1e-5..1e-4.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from simseg_b200 import ops
+    return ops
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-12)).item()
+
+
+def gelu(x):
+    return 0.5 * x * (1 + torch.erf(x / math.sqrt(2)))
+
+
+@pytest.mark.parametrize("M,N,K,tile_n", [(256, 128, 64, 128), (128, 256, 128, 256), (300, 384, 384, 0),
+                                          (1000, 1152, 384, 192), (777, 512, 768, 0), (4096, 1536, 384, 0),
+                                          (130, 171, 512, 192), (64, 20, 512, 0)])
+def test_gemm_kk_plain(cuda, M, N, K, tile_n):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device=cuda, generator=g).bfloat16()
+    b = torch.randn(N, K, device=cuda, generator=g).bfloat16()
+    bias = torch.randn(N, device=cuda, generator=g)
+    ref = a.float() @ b.float().T + bias
+    out = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, out_dtype=torch.float32, tile_n=tile_n)
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 2e-5
+    out16 = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, out_dtype=torch.bfloat16, tile_n=tile_n)
+    assert _rel(out16, ref) < 6e-3
+
+
+@pytest.mark.parametrize("a_major,b_major", [(0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("M,N,K", [(256, 128, 128), (333, 384, 200), (384, 1536, 3000), (512, 768, 64)])
+def test_gemm_majors(cuda, a_major, b_major, M, N, K):
+    ops = _ops()
+    K8 = (K + 7) // 8 * 8
+    g = torch.Generator(device="cuda").manual_seed(7 * M + N + K)
+    A = torch.randn(M, K8, device=cuda, generator=g).bfloat16()
+    Bm = torch.randn(N, K8, device=cuda, generator=g).bfloat16()
+    ref = A.float() @ Bm.float().T
+    M8, N8 = (M + 7) // 8 * 8, (N + 7) // 8 * 8
+    if a_major:                                   # store as [K, M] with 16-byte aligned rows
+        a_st = torch.zeros(K8, M8, device=cuda, dtype=torch.bfloat16); a_st[:, :M] = A.T
+    else:
+        a_st = A
+    if b_major:
+        b_st = torch.zeros(K8, N8, device=cuda, dtype=torch.bfloat16); b_st[:, :N] = Bm.T
+    else:
+        b_st = Bm
+    out = ops.gemm(a_st, b_st, M=M, N=N, K=K8, a_major=a_major, b_major=b_major, out_dtype=torch.float32)
+    assert _rel(out, ref) < 2e-5
+
+
+def test_gemm_splitk_accumulate(cuda):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    T, Do, Di = 20000, 384, 384                     # wgrad shape: K = tokens
+    dy = torch.randn(T, Do, device=cuda, generator=g).bfloat16()
+    x = torch.randn(T, Di, device=cuda, generator=g).bfloat16()
+    ref = dy.float().T @ x.float()
+    out = torch.empty(Do, Di, device=cuda)
+    ops.linear_wgrad(dy, x, out)
+    assert _rel(out, ref) < 1e-4
+    ops.linear_wgrad(dy, x, out, accumulate=True)
+    assert _rel(out, 2 * ref) < 1e-4
+
+
+def test_gemm_epilogues(cuda):
+    ops = _ops()
+    from simseg_b200._lib import EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU, EPI_ROWSCALE
+    g = torch.Generator(device="cuda").manual_seed(11)
+    M, N, K = 1000, 1536, 384
+    a = (torch.randn(M, K, device=cuda, generator=g) * 0.5).bfloat16()
+    b = (torch.randn(N, K, device=cuda, generator=g) * 0.1).bfloat16()
+    bias = torch.randn(N, device=cuda, generator=g) * 0.1
+    pre = a.float() @ b.float().T + bias
+    # GELU: pre-activation saved in bf16, activation computed from the rounded value
+    aux = torch.empty(M, N, device=cuda, dtype=torch.bfloat16)
+    act = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, epilogue=EPI_BIAS_GELU, aux=aux)
+    assert _rel(aux, pre) < 6e-3
+    assert (act.float() - gelu(aux.float())).abs().max().item() < 2e-2
+    assert _rel(act, gelu(pre)) < 1e-2
+    # residual (fp32 stream)
+    res = torch.randn(M, N, device=cuda, generator=g)
+    out = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, epilogue=EPI_BIAS_RESIDUAL, residual=res, out_dtype=torch.float32)
+    assert _rel(out, pre + res) < 2e-5
+    # dGELU + column sums
+    cs = torch.zeros(N, device=cuda)
+    dh = ops.gemm(a, b, M=M, N=N, K=K, epilogue=EPI_DGELU, aux=aux, col_sum=cs, out_dtype=torch.float32)
+    h = aux.float().requires_grad_(True)
+    gelu(h).backward(pre - bias)
+    assert _rel(dh, h.grad) < 1e-4
+    assert _rel(cs, h.grad.sum(0)) < 1e-4
+    # row scale
+    rs = torch.rand(M, device=cuda, generator=g) + 0.5
+    o = ops.gemm(a, b, M=M, N=N, K=K, epilogue=EPI_ROWSCALE, row_scale=rs, out_dtype=torch.float32)
+    assert _rel(o, (pre - bias) * rs[:, None]) < 2e-5
+
+
+def test_gemm_tf32(cuda):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, K = 500, 700, 512
+    a = torch.nn.functional.normalize(torch.randn(M, K, device=cuda, generator=g), dim=-1)
+    b = torch.nn.functional.normalize(torch.randn(N, K, device=cuda, generator=g), dim=-1)
+    out = ops.gemm(a, b, M=M, N=N, K=K, out_dtype=torch.float32)
+    assert (out - a @ b.T).abs().max().item() < 1e-3
+    bt = b.T.contiguous()
+    out2 = ops.gemm(a, bt, M=M, N=N, K=K, b_major=1, out_dtype=torch.float32)
+    assert (out2 - a @ b.T).abs().max().item() < 1e-3
+    at = a.T.contiguous()
+    out3 = ops.gemm(at, bt, M=M, N=N, K=K, a_major=1, b_major=1, out_dtype=torch.float32)
+    assert (out3 - a @ b.T).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("D", [384, 768, 512])
+@pytest.mark.parametrize("xdt", [torch.float32, torch.bfloat16])
+def test_layernorm(cuda, D, xdt):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(D)
+    M = 1003
+    x = (torch.randn(M, D, device=cuda, generator=g) * 2 + 0.3).to(xdt)
+    gamma = 1 + 0.1 * torch.randn(D, device=cuda, generator=g)
+    beta = 0.1 * torch.randn(D, device=cuda, generator=g)
+    eps = 1e-6
+    yb, yf, mean, rstd = ops.layernorm_fwd(x, gamma, beta, eps, want_f32=True)
+    xr = x.float().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (D,), gamma, beta, eps)
+    assert (yf - ref).abs().max().item() < 2e-5
+    assert _rel(yb, ref) < 6e-3
+    dy = torch.randn(M, D, device=cuda, generator=g)
+    dy2 = torch.randn(M, D, device=cuda, generator=g)
+    gr = gamma.clone().requires_grad_(True); br = beta.clone().requires_grad_(True)
+    torch.nn.functional.layer_norm(xr, (D,), gr, br, eps).backward(dy + dy2)
+    prev = torch.randn(M, D, device=cuda, generator=g)
+    dx = prev.clone()
+    dxb = torch.empty(M, D, device=cuda, dtype=torch.bfloat16)
+    dgam = torch.zeros(D, device=cuda); dbet = torch.zeros(D, device=cuda); dcs = torch.zeros(D, device=cuda)
+    ops.layernorm_bwd(dy, x, gamma, mean, rstd, dy2=dy2, dx=dx, dx_accumulate=True, dx_bf16=dxb, dgamma=dgam, dbeta=dbet,
+                      dx_colsum=dcs)
+    assert (dx - (prev + xr.grad)).abs().max().item() < 1e-4
+    assert _rel(dxb, prev + xr.grad) < 6e-3
+    assert _rel(dgam, gr.grad) < 1e-4 and _rel(dbet, br.grad) < 1e-4
+    assert _rel(dcs, (prev + xr.grad).sum(0)) < 1e-3
+
+
+@pytest.mark.parametrize("B,H,S,masked", [(3, 6, 197, False), (2, 12, 325, False), (5, 12, 25, True), (4, 12, 77, True),
+                                          (2, 2, 16, False), (2, 3, 64, True)])
+def test_attention(cuda, B, H, S, masked):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(S)
+    D = H * 64
+    qkv = (torch.randn(B, S, 3, H, 64, device=cuda, generator=g)).bfloat16()
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    strides = (S * 3 * D, 3 * D, 64)
+    klen = None
+    if masked:
+        klen = torch.randint(1, S + 1, (B,), device=cuda, generator=g, dtype=torch.int32)
+        klen[0] = S
+    scale = 0.125
+    out, lse = ops.attention_fwd(q, k, v, B, H, S, strides, klen, scale)
+    qf, kf, vf = [t.float().permute(0, 2, 1, 3).detach().requires_grad_(True) for t in (q, k, v)]
+    s = (qf @ kf.transpose(-1, -2)) * scale
+    if masked:
+        km = torch.arange(S, device=cuda)[None] >= klen[:, None]
+        s = s.masked_fill(km[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ vf)
+    ref_o = ref.permute(0, 2, 1, 3).reshape(B, S, D)
+    assert (out.float() - ref_o).abs().max().item() < 3e-2
+    assert (lse - torch.logsumexp(s, -1)).abs().max().item() < 2e-3
+    dout = torch.randn(B, S, D, device=cuda, generator=g).bfloat16()
+    ref_o.backward(dout.float())
+    dqkv = torch.empty_like(qkv)
+    ops.attention_bwd(q, k, v, out, dout, lse, B, H, S, strides, klen, scale, dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2])
+    for i, (name, t) in enumerate((("dq", qf), ("dk", kf), ("dv", vf))):
+        r = t.grad.permute(0, 2, 1, 3)
+        assert _rel(dqkv[:, :, i], r) < 2.5e-2, name
+
+
+def test_embeddings(cuda):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    B, D = 3, 384
+    img = torch.randn(B, 3, 224, 224, device=cuda, generator=g)
+    w = torch.randn(D, 3, 16, 16, device=cuda, generator=g) * 0.02
+    patches = ops.im2col16(img)
+    ref = torch.nn.functional.conv2d(img.bfloat16().float(), w.bfloat16().float(), stride=16).flatten(2).transpose(1, 2)
+    out = ops.gemm(patches, w.reshape(D, 768).bfloat16(), M=B * 196, N=D, K=768, out_dtype=torch.float32)
+    assert _rel(out.reshape(B, 196, D), ref) < 1e-4
+    cls = torch.randn(D, device=cuda, generator=g); pos = torch.randn(197, D, device=cuda, generator=g)
+    x = ops.vit_tokens_fwd(out, cls, pos, B, 196, D)
+    refx = torch.cat([cls.expand(B, 1, D), out.reshape(B, 196, D)], 1) + pos
+    assert (x - refx).abs().max().item() < 1e-6
+    dx = torch.randn(B, 197, D, device=cuda, generator=g)
+    dpos = torch.zeros(197, D, device=cuda); dcls = torch.zeros(D, device=cuda)
+    dpatch = ops.vit_tokens_bwd(dx, B, 196, D, dpos, dcls)
+    assert _rel(dpatch.reshape(B, 196, D), dx[:, 1:]) < 5e-3
+    assert (dpos - dx.sum(0)).abs().max().item() < 1e-5 and (dcls - dx[:, 0].sum(0)).abs().max().item() < 1e-5
+    # BERT embeddings
+    T, V, H = 25, 1000, 768
+    ids = torch.randint(0, V, (B, T), device=cuda, generator=g); ids[:, 0] = 101
+    word = torch.randn(V, H, device=cuda, generator=g); pe = torch.randn(512, H, device=cuda, generator=g)
+    te = torch.randn(2, H, device=cuda, generator=g)
+    e = ops.bert_embed_fwd(ids, word, pe, te)
+    assert (e - (word[ids] + pe[:T] + te[0])).abs().max().item() < 1e-6
+    de = torch.randn(B, T, H, device=cuda, generator=g)
+    dword = torch.zeros_like(word); dpe = torch.zeros_like(pe); dte = torch.zeros_like(te)
+    ops.bert_embed_bwd(ids, de, dword, dpe, dte[0])
+    rw = torch.zeros_like(word).index_add_(0, ids.reshape(-1), de.reshape(-1, H))
+    assert (dword - rw).abs().max().item() < 1e-5
+    assert (dpe[:T] - de.sum(0)).abs().max().item() < 1e-5 and (dte[0] - de.sum((0, 1))).abs().max().item() < 1e-4
+
+
+def test_misc_elementwise(cuda):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    w = torch.randn(300, 77, device=cuda, generator=g)
+    wb, wt = ops.cast_bf16(w, transpose_too=True)
+    assert torch.equal(wb, w.bfloat16()) and torch.equal(wt, w.bfloat16().T.contiguous())
+    x = torch.randn(5000, 1152, device=cuda, generator=g)
+    assert _rel(ops.colsum(x), x.sum(0)) < 1e-5
+    assert _rel(ops.colsum(x.bfloat16()), x.bfloat16().float().sum(0)) < 1e-5
+    h = torch.randn(64, 1536, device=cuda, generator=g).bfloat16()
+    assert (ops.gelu_fwd(h).float() - gelu(h.float())).abs().max().item() < 2e-2
