@@ -39,7 +39,10 @@ int retrieval_rank_impl(Ctx*, const float*, int, int, const int64_t*, const int6
 // fp32 product in the requested precision: C[M,N] (+)= A(m,k) B(n,k)
 static int fp32_matmul(Ctx* c, const float* A, const float* B, float* C, int M, int N, int K, int64_t lda, int64_t ldb,
                        int64_t ldc, int a_major, int b_major, int accumulate, int precision, cudaStream_t st) {
-  if (precision == SIMSEG_PREC_FP32) return sgemm_impl(c, A, B, C, M, N, K, lda, ldb, ldc, a_major, b_major, accumulate, st);
+  // tensor-core path: K-major tf32 operands with 16-byte aligned rows; everything else runs exact fp32 FFMA
+  const bool tc_ok = precision == SIMSEG_PREC_TF32 && !a_major && !b_major && lda % 4 == 0 && ldb % 4 == 0 &&
+                     (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0;
+  if (!tc_ok) return sgemm_impl(c, A, B, C, M, N, K, lda, ldb, ldc, a_major, b_major, accumulate, st);
   simseg_gemm_args g;
   memset(&g, 0, sizeof(g));
   g.a = A; g.b = B; g.d = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldd = ldc;

@@ -452,6 +452,11 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
                    (long long)a->N, (long long)a->K);
   SIMSEG_CHECK_ARG(a->in_dtype == SIMSEG_BF16 || a->in_dtype == SIMSEG_F32, "gemm: bad in_dtype %d", a->in_dtype);
   const int eb = a->in_dtype == SIMSEG_BF16 ? 2 : 4;
+  if (a->in_dtype == SIMSEG_F32 && (a->a_major || a->b_major)) {
+    // 32-bit MN-major operands need the 128B_BASE32B shared-memory layout, which this engine does not stage
+    set_error("gemm: tf32 operands must be K-major");
+    return SIMSEG_ERR_UNSUPPORTED;
+  }
   SIMSEG_CHECK_ARG((a->lda * eb) % 16 == 0 && (a->ldb * eb) % 16 == 0, "gemm: lda/ldb rows must be 16-byte multiples");
   SIMSEG_CHECK_ARG((reinterpret_cast<uintptr_t>(a->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->b) & 15) == 0,
                    "gemm: A/B must be 16-byte aligned");

@@ -10,10 +10,24 @@ namespace simseg {
 // A_KMAJOR: A stored [M,K] (k contiguous) else stored [K,M] (m contiguous).  Same for B with N.
 constexpr int SG_BM = 128, SG_BN = 128, SG_BK = 16;
 
+// Element-wise tile load for operands whose rows are not 16-byte aligned (ragged batch sizes).
+template <bool KMAJOR>
+__device__ __forceinline__ void load_tile_scalar(float (&Ts)[SG_BK][SG_BM + 4], const float* __restrict__ P, int mn0,
+                                                 int k0, int MN, int K, int64_t ld, int tid) {
+  for (int f = tid; f < SG_BK * SG_BM; f += 256) {
+    int kk, mm;
+    if (KMAJOR) { kk = f % SG_BK; mm = f / SG_BK; } else { mm = f % SG_BM; kk = f / SG_BM; }
+    float v = 0.f;
+    if (mn0 + mm < MN && k0 + kk < K)
+      v = KMAJOR ? P[static_cast<int64_t>(mn0 + mm) * ld + k0 + kk] : P[static_cast<int64_t>(k0 + kk) * ld + mn0 + mm];
+    Ts[kk][mm] = v;
+  }
+}
+
 template <bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(256) sgemm_nt_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                        float* __restrict__ C, int M, int N, int K, int64_t lda,
-                                                       int64_t ldb, int64_t ldc, int accumulate) {
+                                                       int64_t ldb, int64_t ldc, int accumulate, int a_vec, int b_vec) {
   __shared__ __align__(16) float As[SG_BK][SG_BM + 4];
   __shared__ __align__(16) float Bs[SG_BK][SG_BN + 4];
   const int tid = threadIdx.x;
@@ -27,7 +41,9 @@ __global__ void __launch_bounds__(256) sgemm_nt_kernel(const float* __restrict__
 
   for (int k0 = 0; k0 < K; k0 += SG_BK) {
     // ---- load A tile (128 x 16) into As[k][m]
-    if (A_KMAJOR) {
+    if (!a_vec) {
+      load_tile_scalar<A_KMAJOR>(As, A, m0, k0, M, K, lda, tid);
+    } else if (A_KMAJOR) {
       // 128 rows x 4 float4 = 512 float4, 2 per thread
 #pragma unroll
       for (int it = 0; it < 2; ++it) {
@@ -52,7 +68,9 @@ __global__ void __launch_bounds__(256) sgemm_nt_kernel(const float* __restrict__
         *reinterpret_cast<float4*>(&As[kr][c4]) = v;
       }
     }
-    if (B_KMAJOR) {
+    if (!b_vec) {
+      load_tile_scalar<B_KMAJOR>(Bs, B, n0, k0, N, K, ldb, tid);
+    } else if (B_KMAJOR) {
 #pragma unroll
       for (int it = 0; it < 2; ++it) {
         const int f = tid + it * 256;
@@ -115,16 +133,14 @@ __global__ void __launch_bounds__(256) sgemm_nt_kernel(const float* __restrict__
 int sgemm_impl(Ctx* ctx, const float* A, const float* B, float* C, int M, int N, int K, int64_t lda, int64_t ldb,
                int64_t ldc, int a_major, int b_major, int accumulate, cudaStream_t st) {
   SIMSEG_CHECK_ARG(M > 0 && N > 0 && K > 0, "sgemm: empty");
-  SIMSEG_CHECK_ARG(lda % 4 == 0 && ldb % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
-                       (reinterpret_cast<uintptr_t>(B) & 15) == 0,
-                   "sgemm: operands need 16-byte aligned rows");
-  if (!a_major) SIMSEG_CHECK_ARG(K % 4 == 0, "sgemm: K must be a multiple of 4 for K-major A");
-  if (!b_major) SIMSEG_CHECK_ARG(K % 4 == 0, "sgemm: K must be a multiple of 4 for K-major B");
+  // 128-bit loads need 16-byte aligned rows (and K % 4 == 0 for K-major operands); otherwise element-wise loads
+  const int a_vec = (lda % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (a_major || K % 4 == 0)) ? 1 : 0;
+  const int b_vec = (ldb % 4 == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 && (b_major || K % 4 == 0)) ? 1 : 0;
   dim3 grid(static_cast<unsigned>(cdiv(N, SG_BN)), static_cast<unsigned>(cdiv(M, SG_BM)));
-  if (!a_major && !b_major) sgemm_nt_kernel<true, true><<<grid, 256, 0, st>>>(A, B, C, M, N, K, lda, ldb, ldc, accumulate);
-  else if (!a_major && b_major) sgemm_nt_kernel<true, false><<<grid, 256, 0, st>>>(A, B, C, M, N, K, lda, ldb, ldc, accumulate);
-  else if (a_major && !b_major) sgemm_nt_kernel<false, true><<<grid, 256, 0, st>>>(A, B, C, M, N, K, lda, ldb, ldc, accumulate);
-  else sgemm_nt_kernel<false, false><<<grid, 256, 0, st>>>(A, B, C, M, N, K, lda, ldb, ldc, accumulate);
+  if (!a_major && !b_major) sgemm_nt_kernel<true, true><<<grid, 256, 0, st>>>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, a_vec, b_vec);
+  else if (!a_major && b_major) sgemm_nt_kernel<true, false><<<grid, 256, 0, st>>>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, a_vec, b_vec);
+  else if (a_major && !b_major) sgemm_nt_kernel<false, true><<<grid, 256, 0, st>>>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, a_vec, b_vec);
+  else sgemm_nt_kernel<false, false><<<grid, 256, 0, st>>>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, a_vec, b_vec);
   ctx->launches++;
   SIMSEG_LAUNCH_CHECK();
   return SIMSEG_OK;

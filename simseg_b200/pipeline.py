@@ -1,0 +1,553 @@
+"""Host-side mirror of the reference's model interface for the hot path.
+
+Same class / method / parameter names as ``simseg/models/pipelines/clip.py:13-229`` and the components it
+builds (``SimpleProjection`` components/projection.py:29-46, ``TopKPooling`` components/pooling.py:42-65,
+``NCE`` criteria/losses/mml_loss.py:12-103, ``ViTModel`` backbones/mml/vit_builder.py:6-21,
+``HuggingFaceModel`` backbones/mml/huggingface_builder.py:6-17), the same state-dict keys and
+the same error behaviour (``NotImplementedError`` for unknown projection / pool / temperature kinds) — but every
+tensor op runs in ``libsimseg_b200.so``.  The modules here only own parameters and sequence kernels; autograd
+sees five coarse ``torch.autograd.Function`` nodes whose backward passes are hand-written.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import dist as sdist
+from . import ops, towers
+from ._lib import PREC_FP32
+
+Tensor = torch.Tensor
+
+_VIT_TAGS = {
+    "vit_small_patch16_224_in21k": dict(dim=384, heads=6),
+    "vit_base_patch16_224_in21k": dict(dim=768, heads=12),
+    "vit_small_patch16_224": dict(dim=384, heads=6),
+    "vit_base_patch16_224": dict(dim=768, heads=12),
+}
+
+
+def _tn(t: Tensor, std: float = 0.02) -> Tensor:
+    return nn.init.trunc_normal_(t, std=std)
+
+
+# ======================================================================================= parameter trees
+class _PatchEmbed(nn.Module):
+    def __init__(self, img_size: int, dim: int):
+        super().__init__()
+        self.img_size = (img_size, img_size)
+        self.num_patches = (img_size // 16) ** 2          # read by utils/interpolate_pe.py:7
+        self.proj = nn.Conv2d(3, dim, kernel_size=16, stride=16)
+
+
+class _Attn(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.qkv = nn.Linear(dim, 3 * dim)
+        self.proj = nn.Linear(dim, dim)
+
+
+class _Mlp(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, 4 * dim)
+        self.fc2 = nn.Linear(4 * dim, dim)
+
+
+class _Block(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.attn = _Attn(dim)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = _Mlp(dim)
+
+
+class VisionTransformer(nn.Module):
+    """Parameter tree with timm 0.6.13 ``VisionTransformer`` names."""
+
+    def __init__(self, dim: int, heads: int, img_size: int = 224, depth: int = 12):
+        super().__init__()
+        self.embed_dim, self.num_heads = dim, heads
+        self.patch_embed = _PatchEmbed(img_size, dim)
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, self.patch_embed.num_patches + 1, dim))
+        self.blocks = nn.ModuleList([_Block(dim) for _ in range(depth)])
+        self.norm = nn.LayerNorm(dim, eps=1e-6)
+        _tn(self.pos_embed)
+        nn.init.normal_(self.cls_token, std=1e-6)
+        for mod in self.modules():
+            if isinstance(mod, nn.Linear):
+                _tn(mod.weight)
+                nn.init.zeros_(mod.bias)
+
+
+class _BertSelfAttention(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.query, self.key, self.value = nn.Linear(d, d), nn.Linear(d, d), nn.Linear(d, d)
+
+
+class _BertSelfOutput(nn.Module):
+    def __init__(self, d_in, d):
+        super().__init__()
+        self.dense = nn.Linear(d_in, d)
+        self.LayerNorm = nn.LayerNorm(d, eps=1e-12)
+
+
+class _BertAttention(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.self = _BertSelfAttention(d)
+        self.output = _BertSelfOutput(d, d)
+
+
+class _BertIntermediate(nn.Module):
+    def __init__(self, d, f):
+        super().__init__()
+        self.dense = nn.Linear(d, f)
+
+
+class _BertLayer(nn.Module):
+    def __init__(self, d, f):
+        super().__init__()
+        self.attention = _BertAttention(d)
+        self.intermediate = _BertIntermediate(d, f)
+        self.output = _BertSelfOutput(f, d)
+
+
+class _BertEncoder(nn.Module):
+    def __init__(self, d, f, depth):
+        super().__init__()
+        self.layer = nn.ModuleList([_BertLayer(d, f) for _ in range(depth)])
+
+
+class _BertEmbeddings(nn.Module):
+    def __init__(self, vocab, d, max_pos):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(vocab, d)
+        self.position_embeddings = nn.Embedding(max_pos, d)
+        self.token_type_embeddings = nn.Embedding(2, d)
+        self.LayerNorm = nn.LayerNorm(d, eps=1e-12)
+
+
+class BertModel(nn.Module):
+    """Parameter tree with HF ``BertModel`` names, bert-base-uncased geometry, no pooler (appendix B.2)."""
+
+    def __init__(self, vocab=30522, dim=768, heads=12, ffn=3072, depth=12, max_pos=512):
+        super().__init__()
+        self.num_heads = heads
+        self.embeddings = _BertEmbeddings(vocab, dim, max_pos)
+        self.encoder = _BertEncoder(dim, ffn, depth)
+        for mod in self.modules():
+            if isinstance(mod, (nn.Linear, nn.Embedding)):
+                nn.init.normal_(mod.weight, std=0.02)
+                if isinstance(mod, nn.Linear):
+                    nn.init.zeros_(mod.bias)
+
+
+# ======================================================================================= autograd nodes
+class _Shared:
+    """Per-model scratch shared by the autograd nodes of one step (bf16 weight cache)."""
+
+    def __init__(self):
+        self.wc = towers.Bf16Weights()
+        self.stash = {}          # side outputs of the autograd nodes (bf16 token copies)
+
+
+class _VitFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, anchor, vit, shared, drop_cls, save):
+        tok_f32, tok_bf16, sv = towers.vit_forward(vit, image, shared.wc, save)
+        ctx.vit, ctx.shared, ctx.sv, ctx.drop_cls = vit, shared, sv, drop_cls
+        shared.stash["vit"] = tok_bf16               # full [B,S,D] bf16 copy for the projection GEMM
+        return tok_f32[:, 1:] if drop_cls else tok_f32
+
+    @staticmethod
+    def backward(ctx, g):
+        full = getattr(g, "_simseg_full", None)
+        if full is None:                              # generic upstream: rebuild the [B,S,D] gradient
+            if ctx.drop_cls:
+                full = torch.zeros((g.shape[0], g.shape[1] + 1, g.shape[2]), device=g.device, dtype=torch.float32)
+                full[:, 1:] = g
+            else:
+                full = g.contiguous().float()
+        towers.vit_backward(ctx.vit, ctx.sv, full, ctx.shared.wc)
+        ctx.sv = None
+        return None, None, None, None, None, None
+
+
+class _BertFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input_ids, attention_mask, anchor, bert, shared, save):
+        h_f32, h_bf16, sv = towers.bert_forward(bert, input_ids, attention_mask, shared.wc, save)
+        ctx.bert, ctx.shared, ctx.sv = bert, shared, sv
+        shared.stash["bert"] = h_bf16
+        return h_f32
+
+    @staticmethod
+    def backward(ctx, g):
+        towers.bert_backward(ctx.bert, ctx.sv, g.contiguous(), ctx.shared.wc)
+        ctx.sv = None
+        return None, None, None, None, None, None
+
+
+def _bf16_tokens(x: Tensor):
+    """(full bf16 [B,S,D] buffer, first token used, number of tokens used) for a token tensor."""
+    xb = getattr(x, "_simseg_bf16", None)
+    if xb is not None:
+        return xb, x._simseg_tok_begin, x.shape[1]
+    xc = x.contiguous()
+    return ops.cast_bf16(xc.reshape(-1, xc.shape[-1]).float()).view(xc.shape), 0, x.shape[1]
+
+
+class _ProjectFn(torch.autograd.Function):
+    """``SimpleProjection.forward`` on every token: (…,D) -> (…,E) fp32."""
+
+    @staticmethod
+    def forward(ctx, x, weight, shared):
+        xb, t0, nt = _bf16_tokens(x)
+        B, S, D = xb.shape
+        y = ops.linear_fwd(xb.view(B * S, D), shared.wc.get(weight), out_dtype=torch.float32).view(B, S, -1)
+        ctx.save_for_backward(xb)
+        ctx.weight, ctx.shared, ctx.t0, ctx.nt = weight, shared, t0, nt
+        return y[:, t0:t0 + nt]
+
+    @staticmethod
+    def backward(ctx, g):
+        (xb,) = ctx.saved_tensors
+        B, S, D = xb.shape
+        gf = torch.zeros((B, S, g.shape[-1]), device=g.device, dtype=torch.bfloat16)
+        gf[:, ctx.t0:ctx.t0 + ctx.nt] = g
+        return _project_backward(ctx, gf, xb)
+
+
+def _project_backward(ctx, gf_bf16: Tensor, xb: Tensor):
+    B, S, D = xb.shape
+    E = gf_bf16.shape[-1]
+    w = ctx.weight
+    if w.requires_grad:
+        ops.linear_wgrad(gf_bf16.view(B * S, E), xb.view(B * S, D), towers._grad_of(w), accumulate=True)
+    dfull = ops.linear_dgrad(gf_bf16.view(B * S, E), ctx.shared.wc.get(w), out_dtype=torch.float32).view(B, S, D)
+    dx = dfull[:, ctx.t0:ctx.t0 + ctx.nt]
+    dx._simseg_full = dfull
+    return dx, None, None
+
+
+class _ProjectPoolFn(torch.autograd.Function):
+    """projection -> TopKPooling -> L2norm fused at the kernel level (``clip.py:87-93`` / ``:111-120``)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, attention_mask, k, l2norm, shared, save):
+        xb, t0, nt = _bf16_tokens(x)
+        B, S, D = xb.shape
+        p = ops.linear_fwd(xb.view(B * S, D), shared.wc.get(weight)).view(B, S, -1)        # bf16 [B,S,E]
+        mask = None
+        if attention_mask is not None:
+            mask = attention_mask.contiguous()
+            if t0:                                   # mask columns are indexed by absolute token position
+                pad = torch.ones((B, t0), device=mask.device, dtype=mask.dtype)
+                mask = torch.cat([pad, mask], 1).contiguous()
+        pooled, emb, idx = ops.topk_pool_l2norm_fwd(p, k, t0, nt, attention_mask=mask, l2norm=l2norm, save_idx=save)
+        ctx.save_for_backward(xb, pooled, idx)
+        ctx.weight, ctx.shared, ctx.t0, ctx.nt, ctx.k, ctx.l2norm = weight, shared, t0, nt, k, l2norm
+        return emb if l2norm else pooled
+
+    @staticmethod
+    def backward(ctx, g):
+        xb, pooled, idx = ctx.saved_tensors
+        B, S, D = xb.shape
+        gp = ops.topk_pool_l2norm_bwd(g.contiguous().float(), pooled, idx, S, ctx.k, l2norm=ctx.l2norm)
+        dx, _, _ = _project_backward(ctx, gp, xb)
+        return dx, None, None, None, None, None, None
+
+
+class _NceFn(torch.autograd.Function):
+    """One ``NCE.forward`` direction (``mml_loss.py:51-96``) incl. the gather of feat2 (``utils/dist.py:323-354``)."""
+
+    @staticmethod
+    def forward(ctx, feat1, feat2, temperature, rank, group, precision):
+        f1 = feat1.contiguous().float()
+        f2g = sdist.all_gather_rows(feat2.contiguous().float(), group)
+        b = f1.shape[0]
+        loss_rows, lse, argmax, cos, _ = ops.infonce_fwd(f1, f2g, temperature.detach().reshape(()), rank * b, precision)
+        ctx.save_for_backward(f1, f2g, lse, cos)
+        ctx.temperature, ctx.rank, ctx.group, ctx.precision, ctx.b = temperature, rank, group, precision, b
+        targets = torch.arange(rank * b, (rank + 1) * b, device=f1.device, dtype=torch.int32)
+        acc = (argmax == targets).float().sum() / b
+        ctx.mark_non_differentiable(acc)
+        return loss_rows.mean(), acc
+
+    @staticmethod
+    def backward(ctx, gloss, _gacc):
+        f1, f2g, lse, cos = ctx.saved_tensors
+        t = ctx.temperature
+        dtemp = torch.zeros((), device=f1.device, dtype=torch.float32)
+        df2g = torch.zeros_like(f2g)
+        # loss = mean_i CE_i  ->  dCE_i = gloss / b   (gloss is a device scalar: fold it in afterwards)
+        df1 = ops.infonce_bwd(f1, f2g, t.detach().reshape(()), ctx.rank * ctx.b, lse, 1.0 / ctx.b, cos, df2g,
+                              dtemp if t.requires_grad else None, ctx.precision)
+        df2 = sdist.reduce_scatter_rows(df2g, ctx.rank, ctx.b, ctx.group)
+        gl = gloss.float()
+        return df1 * gl, df2 * gl, (dtemp * gl).reshape(t.shape) if t.requires_grad else None, None, None, None
+
+
+# ======================================================================================= reference-named modules
+class SimpleProjection(nn.Module):
+    """``components/projection.py:29-46``: bias-free Linear applied to every token."""
+
+    def __init__(self, cfg, embedding_dim, projection_dim, trainable=True, shared: Optional[_Shared] = None):
+        super().__init__()
+        self.projection_dim = projection_dim
+        self.linear = nn.Linear(embedding_dim, projection_dim, bias=False)
+        if not trainable:
+            for p in self.linear.parameters():
+                p.requires_grad = False
+        self._shared = shared or _Shared()
+
+    def forward(self, x):
+        squeeze = x.dim() == 2
+        if squeeze:
+            x = x.unsqueeze(0)
+        y = _ProjectFn.apply(x, self.linear.weight, self._shared)
+        return y[0] if squeeze else y
+
+
+class TopKPooling(nn.Module):
+    """``components/pooling.py:42-65`` for an already projected (B,T,E) tensor (standalone use)."""
+
+    def __init__(self, k, dim):
+        super().__init__()
+        assert dim == 1
+        self.k, self.dim = k, dim
+
+    def forward(self, x, attention_mask=None):
+        k = self.k
+        if attention_mask is not None and k > 1:
+            k = min(k, int(attention_mask.sum(1).min()))        # pooling.py:61-63 (host sync, as in the reference)
+        xc = x.contiguous()
+        pooled, _, _ = ops.topk_pool_l2norm_fwd(xc, k, 0, xc.shape[1], attention_mask=attention_mask, l2norm=False,
+                                                save_idx=False)
+        return pooled
+
+
+class AvgPooling(nn.Module):
+    """``components/pooling.py:7-19`` — not on the shipped path (pool.name = loda); kept for config parity."""
+
+    def forward(self, x, attention_mask=None):
+        raise NotImplementedError("pool.name='avg' is outside the B200 hot path (shipped configs use 'loda')")
+
+
+class NCE(nn.Module):
+    """``criteria/losses/mml_loss.py:12-103`` (NCE, smoothing = 0)."""
+
+    def __init__(self, cfg, rank):
+        super().__init__()
+        self.cfg = cfg
+        self.global_reduce = cfg.loss.global_reduce
+        self.rank, self.group = 0, None
+        if self.global_reduce and sdist.is_initialized():
+            group_size = cfg.loss.group_size
+            if group_size >= 0 and group_size != sdist.world_size():
+                raise NotImplementedError("loss.group_size sub-world gather groups are not built (one NVSwitch box = world)")
+            self.rank = sdist.rank()
+        self.gather_backward = cfg.loss.nce_loss.gather_backward
+        if cfg.loss.temperature.name == "constant":
+            self.register_buffer("temperature", torch.ones([]) * cfg.loss.temperature.value, persistent=False)
+        elif cfg.loss.temperature.name == "parameter":
+            self.temperature = nn.Parameter(torch.ones([]) * cfg.loss.temperature.value)
+        else:
+            raise NotImplementedError
+        if cfg.loss.smoothing > 0:
+            raise NotImplementedError("label smoothing is outside the B200 hot path (shipped configs use 0)")
+        self.precision = PREC_FP32
+
+    def forward(self, feat1, feat2, label=None, ignore_mask=None):
+        if ignore_mask is not None:
+            raise NotImplementedError("ignore_mask is always None on the shipped path (clip.py:171-175)")
+        use_group = self.global_reduce and sdist.is_initialized() and sdist.world_size() > 1
+        f2 = feat2 if (self.gather_backward or not use_group) else feat2.detach()
+        loss, acc = _NceFn.apply(feat1, f2, self.temperature, self.rank if use_group else 0,
+                                 sdist.WORLD if use_group else None, self.precision)
+        if self.global_reduce:
+            return loss, acc
+        # non-global branch (mml_loss.py:79-87): both directions on the local batch
+        loss2, acc2 = _NceFn.apply(feat2, feat1, self.temperature, 0, None, self.precision)
+        return 0.5 * (loss + loss2), acc, acc2
+
+
+class ViTModel(nn.Module):
+    """``backbones/mml/vit_builder.py:6-21``."""
+
+    def __init__(self, cfg, shared: _Shared, **kwargs):
+        super().__init__()
+        tag = cfg.model.image_encoder.tag
+        if tag not in _VIT_TAGS:
+            raise NotImplementedError(f"image encoder tag {tag!r}: only ViT-S/16 and ViT-B/16 are on the B200 hot path")
+        if cfg.model.image_encoder.pretrained:
+            raise RuntimeError("pretrained timm weights cannot be downloaded here: load a checkpoint with load_state_dict")
+        t = _VIT_TAGS[tag]
+        self.model = VisionTransformer(t["dim"], t["heads"], img_size=kwargs.get("img_size", 224))
+        self._shared = shared
+
+    def forward(self, x, drop_cls=False):
+        save = torch.is_grad_enabled() and self.model.cls_token.requires_grad
+        out = _VitFn.apply(x, self.model.cls_token, self.model, self._shared, drop_cls, save)
+        out._simseg_bf16 = self._shared.stash.pop("vit")        # rides along for forward_image_project
+        out._simseg_tok_begin = 1 if drop_cls else 0
+        return out
+
+
+class HuggingFaceModel(nn.Module):
+    """``backbones/mml/huggingface_builder.py:6-17`` for bert-base-uncased (no pooler)."""
+
+    def __init__(self, cfg, shared: _Shared, **kwargs):
+        super().__init__()
+        if cfg.model.text_encoder.tag != "bert-base-uncased":
+            raise NotImplementedError("text encoder: only bert-base-uncased is on the B200 hot path")
+        if cfg.model.text_encoder.pretrained:
+            raise RuntimeError("pretrained HF weights cannot be downloaded here: load a checkpoint with load_state_dict")
+        self.model = BertModel()
+        self._shared = shared
+
+    def forward(self, input_ids, attention_mask, **kwargs):
+        anchor = self.model.embeddings.LayerNorm.weight
+        save = torch.is_grad_enabled() and anchor.requires_grad
+        out = _BertFn.apply(input_ids, attention_mask, anchor, self.model, self._shared, save)
+        out._simseg_bf16 = self._shared.stash.pop("bert")
+        out._simseg_tok_begin = 0
+        return out
+
+
+class ImageEncoder(nn.Module):
+    """``pipelines/clip.py:179-204``."""
+
+    def __init__(self, cfg, shared):
+        super().__init__()
+        self.cfg = cfg
+        self.model_tag = cfg.model.image_encoder.tag
+        self.pretrained = cfg.model.image_encoder.pretrained
+        self.trainable = cfg.model.image_encoder.trainable
+        if cfg.model.image_encoder.name != "vit_modelzoo":
+            raise NotImplementedError("only the vit_modelzoo image backbone is on the B200 hot path")
+        self.model = ViTModel(cfg, shared, img_size=cfg.transforms.input_size)
+        for p in self.model.parameters():
+            p.requires_grad = self.trainable
+
+    def forward(self, x, drop_cls=False):
+        return self.model(x, drop_cls=drop_cls)
+
+
+class TextEncoder(nn.Module):
+    """``pipelines/clip.py:207-223``."""
+
+    def __init__(self, cfg, shared):
+        super().__init__()
+        self.model_tag = cfg.model.text_encoder.tag
+        self.pretrained = cfg.model.text_encoder.pretrained
+        self.trainable = cfg.model.text_encoder.trainable
+        if cfg.model.text_encoder.name != "huggingface_modelzoo":
+            raise NotImplementedError("only the huggingface_modelzoo text backbone is on the B200 hot path")
+        self.model = HuggingFaceModel(cfg, shared)
+        for p in self.model.parameters():
+            p.requires_grad = self.trainable
+
+    def forward(self, input_ids, attention_mask):
+        return self.model(input_ids=input_ids, attention_mask=attention_mask)
+
+
+class CLIPModel(nn.Module):
+    """``pipelines/clip.py:13-176`` — same constructor signature, attributes and methods."""
+
+    def __init__(self, cfg, rank=0):
+        super().__init__()
+        self.cfg = cfg
+        self._shared = _Shared()
+        self.image_encoder = ImageEncoder(cfg, self._shared)
+        self.text_encoder = TextEncoder(cfg, self._shared)
+        self.random_seed = np.random.RandomState(seed=2021)
+        if cfg.model.projection.name != "simple":
+            # 'complex' is broken in the reference itself (projection.py:4-9 vs clip.py:28-33)
+            raise NotImplementedError
+        self.image_projection = SimpleProjection(cfg, cfg.model.image_encoder.embedding_dim, cfg.model.projection.dim,
+                                                 cfg.model.projection.image_projector_trainable, self._shared)
+        self.text_projection = SimpleProjection(cfg, cfg.model.text_encoder.embedding_dim, cfg.model.projection.dim,
+                                                cfg.model.projection.text_projector_trainable, self._shared)
+        if cfg.model.pool.name == "loda":
+            self.text_pool = TopKPooling(cfg.model.pool.loda.text_k, dim=1)
+            self.image_pool = TopKPooling(cfg.model.pool.loda.image_k, dim=1)
+        else:
+            raise NotImplementedError(f"pool.name={cfg.model.pool.name!r}: only 'loda' is on the B200 hot path")
+        if cfg.loss.name != "NCE":
+            raise NotImplementedError(f"loss.name={cfg.loss.name!r}: only NCE is on the B200 hot path")
+        self.loss = NCE(cfg, rank)
+        self.global_reduce = cfg.loss.global_reduce
+        self.text_target_token_idx = cfg.model.text_encoder.target_token_idx
+        if self.text_target_token_idx != 0:
+            raise NotImplementedError("text_encoder.target_token_idx != 0")
+
+    # -- bookkeeping ---------------------------------------------------------------------------
+    def new_step(self):
+        """Drop the cached bf16 weight copies (call after every optimizer step)."""
+        self._shared.wc.clear()
+
+    # -- reference API -------------------------------------------------------------------------
+    def forward_image_feature(self, image):
+        self._maybe_refresh()
+        return self.image_encoder(image, drop_cls=True)                   # clip.py:73-76
+
+    def forward_image_project(self, image_features):
+        return _ProjectPoolFn.apply(image_features, self.image_projection.linear.weight, None,
+                                    self.image_pool.k, True, self._shared, torch.is_grad_enabled())
+
+    def forward_text_feature(self, input_ids, attention_mask):
+        self._maybe_refresh()
+        return self.text_encoder(input_ids=input_ids, attention_mask=attention_mask)   # [:, 0:, :] is the identity
+
+    def forward_text_project(self, text_features, attention_mask):
+        k = self.text_pool.k
+        if k > 1:
+            k = min(k, int(attention_mask.sum(1).min()))                  # pooling.py:61-63
+        return _ProjectPoolFn.apply(text_features, self.text_projection.linear.weight, attention_mask, k, True,
+                                    self._shared, torch.is_grad_enabled())
+
+    def forward_loss(self, image_embeddings, text_embeddings, ignore_mask=None):
+        if self.global_reduce:
+            i2t_loss, i2t_acc = self.loss(image_embeddings, text_embeddings, ignore_mask=ignore_mask)
+            t2i_loss, t2i_acc = self.loss(text_embeddings, image_embeddings, ignore_mask=ignore_mask)
+            loss = 0.5 * (i2t_loss + t2i_loss)
+        else:
+            loss, i2t_acc, t2i_acc = self.loss(image_embeddings, text_embeddings, ignore_mask=ignore_mask)
+        return {f"{self.cfg.loss.name}_loss".lower(): loss}, i2t_acc, t2i_acc
+
+    def forward(self, batch, embeddings=False):
+        if embeddings == "image":
+            return self.forward_image_feature(batch["image"])
+        if embeddings == "text":
+            return self.forward_text_feature(batch["input_ids"], batch["attention_mask"])
+        image_embeddings = self.forward_image_feature(batch["image"])
+        text_embeddings = self.forward_text_feature(batch["input_ids"], batch["attention_mask"])
+        image_embeddings = self.forward_image_project(image_embeddings)
+        text_embeddings = self.forward_text_project(text_embeddings, batch["attention_mask"])
+        if embeddings == "all":
+            return [image_embeddings, text_embeddings]
+        return self.forward_loss(image_embeddings, text_embeddings, ignore_mask=None)
+
+    # weights change under the optimizer: track a version so stale bf16 copies are never used
+    def _maybe_refresh(self):
+        v = sum(p._version for p in (self.image_projection.linear.weight, self.image_encoder.model.model.norm.weight,
+                                     self.text_encoder.model.model.embeddings.LayerNorm.weight))
+        if getattr(self, "_wver", None) != v:
+            self._shared.wc.clear()
+            self._wver = v
+
+
+def clip(cfg, rank: Optional[int] = None):
+    """Registry entry, as ``pipelines/clip.py:226-229``."""
+    return CLIPModel(cfg, sdist.rank() if rank is None else rank)
+
+
+PIPELINE: Dict[str, callable] = {"clip": clip}

@@ -1,0 +1,307 @@
+"""Hand-sequenced forward / backward of the two towers over the C-ABI kernels.
+
+Precision contract (= the reference under bf16 autocast, ``simseg/tasks/clip/clip_runner.py:226-228``):
+fp32 master weights, bf16 tensor-core GEMM operands with fp32 accumulation, fp32 residual stream,
+fp32 LayerNorm / softmax statistics.  Activations that are cheap to rebuild (LayerNorm outputs, GELU
+outputs) are recomputed in backward instead of stored; what is stored per block is listed in ``_Blk``.
+
+Gradients are written straight into ``param.grad`` (fp32, accumulated) by the wgrad GEMMs.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from ._lib import EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU, EPI_NONE
+
+Tensor = torch.Tensor
+
+
+def _grad_of(p: Tensor) -> Tensor:
+    """fp32 gradient buffer of a parameter (allocated zeroed on first touch)."""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return p.grad
+
+
+class Bf16Weights:
+    """Per-step bf16 copies of the fp32 master weights (cast once in forward, reused in backward)."""
+
+    def __init__(self):
+        self._c: Dict[int, Tensor] = {}
+
+    def get(self, p: Tensor) -> Tensor:
+        k = id(p)
+        if k not in self._c:
+            w = p.detach()
+            self._c[k] = ops.cast_bf16(w.reshape(w.shape[0], -1))
+        return self._c[k]
+
+    def packed(self, key: str, ps: List[Tensor]) -> Tensor:
+        """Row-concatenation of several [n_i, K] weights as one bf16 matrix (BERT q/k/v -> one GEMM)."""
+        if key not in self._c:
+            self._c[key] = torch.cat([self.get(p) for p in ps], 0)
+        return self._c[key]
+
+    def clear(self):
+        self._c.clear()
+
+
+# ------------------------------------------------------------------------------------------------ ViT
+@dataclass
+class _Blk:
+    x: Tensor = None          # block input, fp32 [M,D]
+    mean1: Tensor = None
+    rstd1: Tensor = None
+    qkv: Tensor = None        # bf16 [M,3D]
+    o: Tensor = None          # bf16 [M,D]  attention output
+    lse: Tensor = None        # fp32 [B,H,S]
+    x1: Tensor = None         # fp32 [M,D]  after attention residual
+    mean2: Tensor = None
+    rstd2: Tensor = None
+    h: Tensor = None          # bf16 [M,4D] fc1 pre-activation
+
+
+@dataclass
+class VitSaved:
+    B: int = 0
+    S: int = 0
+    patches: Tensor = None
+    blocks: List[_Blk] = field(default_factory=list)
+    x_last: Tensor = None
+    mean_n: Tensor = None
+    rstd_n: Tensor = None
+
+
+def vit_forward(m, image: Tensor, wc: Bf16Weights, save: bool):
+    """``ViTModel.forward`` (``simseg/models/backbones/mml/vit_builder.py:13-21``): all tokens, fp32 + bf16."""
+    B = image.shape[0]
+    D, H = m.embed_dim, m.num_heads
+    N = m.patch_embed.num_patches
+    S = N + 1
+    M = B * S
+    sv = VitSaved(B=B, S=S) if save else None
+    patches = ops.im2col16(image.contiguous().float())
+    pe = ops.linear_fwd(patches, wc.get(m.patch_embed.proj.weight), m.patch_embed.proj.bias)
+    x = ops.vit_tokens_fwd(pe, m.cls_token.reshape(-1), m.pos_embed.reshape(S, D), B, N, D).reshape(M, D)
+    if save:
+        sv.patches = patches
+    strides = (S * 3 * D, 3 * D, 64)
+    for blk in m.blocks:
+        y, _, mean1, rstd1 = ops.layernorm_fwd(x, blk.norm1.weight, blk.norm1.bias, 1e-6)
+        qkv = ops.linear_fwd(y, wc.get(blk.attn.qkv.weight), blk.attn.qkv.bias)
+        q5 = qkv.view(B, S, 3, H, 64)
+        o, lse = ops.attention_fwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], B, H, S, strides, None, 0.125)
+        o = o.view(M, D)
+        x1 = ops.linear_fwd(o, wc.get(blk.attn.proj.weight), blk.attn.proj.bias, epilogue=EPI_BIAS_RESIDUAL,
+                            residual=x, out_dtype=torch.float32)
+        y2, _, mean2, rstd2 = ops.layernorm_fwd(x1, blk.norm2.weight, blk.norm2.bias, 1e-6)
+        h = torch.empty((M, 4 * D), device=x.device, dtype=torch.bfloat16) if save else None
+        a = ops.linear_fwd(y2, wc.get(blk.mlp.fc1.weight), blk.mlp.fc1.bias, epilogue=EPI_BIAS_GELU, aux=h)
+        x2 = ops.linear_fwd(a, wc.get(blk.mlp.fc2.weight), blk.mlp.fc2.bias, epilogue=EPI_BIAS_RESIDUAL,
+                            residual=x1, out_dtype=torch.float32)
+        if save:
+            sv.blocks.append(_Blk(x, mean1, rstd1, qkv, o, lse, x1, mean2, rstd2, h))
+        x = x2
+    tok_bf16, tok_f32, mean_n, rstd_n = ops.layernorm_fwd(x, m.norm.weight, m.norm.bias, 1e-6, want_f32=True)
+    if save:
+        sv.x_last, sv.mean_n, sv.rstd_n = x, mean_n, rstd_n
+    return tok_f32.view(B, S, D), tok_bf16.view(B, S, D), sv
+
+
+def vit_backward(m, sv: VitSaved, dtok: Tensor, wc: Bf16Weights, dtok2: Optional[Tensor] = None):
+    """Backward of ``vit_forward``.  ``dtok`` [B,S,D] bf16|f32 (+ optional fp32 ``dtok2``) = dL/d tokens."""
+    B, S = sv.B, sv.S
+    D, H = m.embed_dim, m.num_heads
+    M = B * S
+    dev = dtok.device
+    strides = (S * 3 * D, 3 * D, 64)
+    dx = torch.empty((M, D), device=dev, dtype=torch.float32)
+    g = torch.empty((M, D), device=dev, dtype=torch.bfloat16)
+    nb = len(m.blocks)
+    last_fc2_bias = _grad_of(m.blocks[-1].mlp.fc2.bias) if nb else None
+    ops.layernorm_bwd(dtok.reshape(M, D), sv.x_last, m.norm.weight, sv.mean_n, sv.rstd_n,
+                      dy2=None if dtok2 is None else dtok2.reshape(M, D), dx=dx, dx_bf16=g,
+                      dgamma=_grad_of(m.norm.weight), dbeta=_grad_of(m.norm.bias), dx_colsum=last_fc2_bias)
+    sv.x_last = None
+    for i in range(nb - 1, -1, -1):
+        blk, s = m.blocks[i], sv.blocks[i]
+        # ---- MLP branch: x2 = x1 + fc2(gelu(fc1(LN2(x1))))
+        a = ops.gelu_fwd(s.h)
+        ops.linear_wgrad(g, a, _grad_of(blk.mlp.fc2.weight), accumulate=True)
+        del a
+        dh = ops.linear_dgrad(g, wc.get(blk.mlp.fc2.weight), epilogue=EPI_DGELU, aux=s.h,
+                              col_sum=_grad_of(blk.mlp.fc1.bias))
+        s.h = None
+        y2, _, _, _ = ops.layernorm_fwd(s.x1, blk.norm2.weight, blk.norm2.bias, 1e-6, want_stats=False)
+        ops.linear_wgrad(dh, y2, _grad_of(blk.mlp.fc1.weight), accumulate=True)
+        del y2
+        dy2 = ops.linear_dgrad(dh, wc.get(blk.mlp.fc1.weight))
+        del dh
+        ops.layernorm_bwd(dy2, s.x1, blk.norm2.weight, s.mean2, s.rstd2, dx=dx, dx_accumulate=True, dx_bf16=g,
+                          dgamma=_grad_of(blk.norm2.weight), dbeta=_grad_of(blk.norm2.bias),
+                          dx_colsum=_grad_of(blk.attn.proj.bias))
+        del dy2
+        s.x1 = None
+        # ---- attention branch: x1 = x + proj(attn(qkv(LN1(x))))
+        ops.linear_wgrad(g, s.o, _grad_of(blk.attn.proj.weight), accumulate=True)
+        do = ops.linear_dgrad(g, wc.get(blk.attn.proj.weight))
+        dqkv = torch.empty_like(s.qkv)
+        q5, d5 = s.qkv.view(B, S, 3, H, 64), dqkv.view(B, S, 3, H, 64)
+        ops.attention_bwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], s.o, do, s.lse, B, H, S, strides, None, 0.125,
+                          d5[:, :, 0], d5[:, :, 1], d5[:, :, 2])
+        del do
+        s.o = s.qkv = s.lse = None
+        ops.colsum(dqkv, _grad_of(blk.attn.qkv.bias), accumulate=True)
+        y, _, _, _ = ops.layernorm_fwd(s.x, blk.norm1.weight, blk.norm1.bias, 1e-6, want_stats=False)
+        ops.linear_wgrad(dqkv, y, _grad_of(blk.attn.qkv.weight), accumulate=True)
+        del y
+        dy = ops.linear_dgrad(dqkv, wc.get(blk.attn.qkv.weight))
+        del dqkv
+        prev_bias = _grad_of(m.blocks[i - 1].mlp.fc2.bias) if i > 0 else None
+        ops.layernorm_bwd(dy, s.x, blk.norm1.weight, s.mean1, s.rstd1, dx=dx, dx_accumulate=True, dx_bf16=g,
+                          dgamma=_grad_of(blk.norm1.weight), dbeta=_grad_of(blk.norm1.bias), dx_colsum=prev_bias)
+        del dy
+        s.x = None
+    N = S - 1
+    dpatch = ops.vit_tokens_bwd(dx, B, N, D, _grad_of(m.pos_embed).view(S, D), _grad_of(m.cls_token).view(D))
+    ops.linear_wgrad(dpatch, sv.patches, _grad_of(m.patch_embed.proj.weight).view(D, 768), accumulate=True)
+    ops.colsum(dpatch, _grad_of(m.patch_embed.proj.bias), accumulate=True)
+
+
+# ------------------------------------------------------------------------------------------------ BERT
+@dataclass
+class _Lyr:
+    h_in: Tensor = None       # bf16 [M,D] layer input (GEMM operand)
+    qkv: Tensor = None        # bf16 [M,3D]
+    c: Tensor = None          # bf16 [M,D]
+    lse: Tensor = None
+    s1: Tensor = None         # fp32 [M,D] attention.output pre-LN sum
+    mean1: Tensor = None
+    rstd1: Tensor = None
+    pre: Tensor = None        # bf16 [M,F] intermediate pre-activation
+    s2: Tensor = None         # fp32 [M,D] output pre-LN sum
+    mean2: Tensor = None
+    rstd2: Tensor = None
+
+
+@dataclass
+class BertSaved:
+    B: int = 0
+    T: int = 0
+    ids: Tensor = None
+    key_len: Tensor = None
+    e: Tensor = None
+    mean0: Tensor = None
+    rstd0: Tensor = None
+    layers: List[_Lyr] = field(default_factory=list)
+
+
+def _qkv_params(layer):
+    a = layer.attention.self
+    return [a.query, a.key, a.value]
+
+
+def bert_forward(m, input_ids: Tensor, attention_mask: Tensor, wc: Bf16Weights, save: bool):
+    """HF ``BertModel(...).last_hidden_state`` as called by ``huggingface_builder.py:16-17`` (dropout p = 0).
+
+    The additive ``finfo.min`` key mask of a left-aligned ``attention_mask`` is applied as a per-sample key
+    length inside the attention kernel."""
+    B, T = input_ids.shape
+    emb = m.embeddings
+    D = emb.word_embeddings.weight.shape[1]
+    H = m.num_heads
+    M = B * T
+    key_len = attention_mask.sum(1).to(torch.int32).contiguous()
+    sv = BertSaved(B=B, T=T, ids=input_ids.contiguous(), key_len=key_len) if save else None
+    e = ops.bert_embed_fwd(input_ids.contiguous(), emb.word_embeddings.weight, emb.position_embeddings.weight,
+                           emb.token_type_embeddings.weight).view(M, D)
+    hb, hf, mean0, rstd0 = ops.layernorm_fwd(e, emb.LayerNorm.weight, emb.LayerNorm.bias, 1e-12, want_f32=True)
+    if save:
+        sv.e, sv.mean0, sv.rstd0 = e, mean0, rstd0
+    strides = (T * 3 * D, 3 * D, 64)
+    for li, layer in enumerate(m.encoder.layer):
+        qp = _qkv_params(layer)
+        wqkv = wc.packed(f"bert.qkv.{li}", [p.weight for p in qp])
+        bqkv = torch.cat([p.bias.detach() for p in qp])
+        qkv = ops.linear_fwd(hb, wqkv, bqkv)
+        q5 = qkv.view(B, T, 3, H, 64)
+        c, lse = ops.attention_fwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], B, H, T, strides, key_len, 0.125)
+        c = c.view(M, D)
+        ao = layer.attention.output
+        s1 = ops.linear_fwd(c, wc.get(ao.dense.weight), ao.dense.bias, epilogue=EPI_BIAS_RESIDUAL, residual=hf,
+                            out_dtype=torch.float32)
+        h1b, h1f, mean1, rstd1 = ops.layernorm_fwd(s1, ao.LayerNorm.weight, ao.LayerNorm.bias, 1e-12, want_f32=True)
+        F = layer.intermediate.dense.weight.shape[0]
+        pre = torch.empty((M, F), device=e.device, dtype=torch.bfloat16) if save else None
+        f = ops.linear_fwd(h1b, wc.get(layer.intermediate.dense.weight), layer.intermediate.dense.bias,
+                           epilogue=EPI_BIAS_GELU, aux=pre)
+        s2 = ops.linear_fwd(f, wc.get(layer.output.dense.weight), layer.output.dense.bias, epilogue=EPI_BIAS_RESIDUAL,
+                            residual=h1f, out_dtype=torch.float32)
+        h2b, h2f, mean2, rstd2 = ops.layernorm_fwd(s2, layer.output.LayerNorm.weight, layer.output.LayerNorm.bias,
+                                                   1e-12, want_f32=True)
+        if save:
+            sv.layers.append(_Lyr(hb, qkv, c, lse, s1, mean1, rstd1, pre, s2, mean2, rstd2))
+        hb, hf = h2b, h2f
+    return hf.view(B, T, D), hb.view(B, T, D), sv
+
+
+def bert_backward(m, sv: BertSaved, dh: Tensor, wc: Bf16Weights, dh2: Optional[Tensor] = None):
+    """Backward of ``bert_forward``; ``dh`` [B,T,D] bf16|f32 (+ optional fp32 ``dh2``) = dL/d last_hidden_state."""
+    B, T = sv.B, sv.T
+    emb = m.embeddings
+    D = emb.word_embeddings.weight.shape[1]
+    H = m.num_heads
+    M = B * T
+    dev = dh.device
+    strides = (T * 3 * D, 3 * D, 64)
+    dy = dh.reshape(M, D)
+    dres = None if dh2 is None else dh2.reshape(M, D)     # fp32 residual-path gradient added to dy
+    for li in range(len(m.encoder.layer) - 1, -1, -1):
+        layer, s = m.encoder.layer[li], sv.layers[li]
+        ao = layer.attention.output
+        # h2 = LN(s2), s2 = out.dense(gelu(inter.dense(h1))) + h1
+        ds2 = torch.empty((M, D), device=dev, dtype=torch.float32)
+        g2 = torch.empty((M, D), device=dev, dtype=torch.bfloat16)
+        ops.layernorm_bwd(dy, s.s2, layer.output.LayerNorm.weight, s.mean2, s.rstd2, dy2=dres, dx=ds2, dx_bf16=g2,
+                          dgamma=_grad_of(layer.output.LayerNorm.weight), dbeta=_grad_of(layer.output.LayerNorm.bias),
+                          dx_colsum=_grad_of(layer.output.dense.bias))
+        f = ops.gelu_fwd(s.pre)
+        ops.linear_wgrad(g2, f, _grad_of(layer.output.dense.weight), accumulate=True)
+        del f
+        dpre = ops.linear_dgrad(g2, wc.get(layer.output.dense.weight), epilogue=EPI_DGELU, aux=s.pre,
+                                col_sum=_grad_of(layer.intermediate.dense.bias))
+        h1b, _, _, _ = ops.layernorm_fwd(s.s1, ao.LayerNorm.weight, ao.LayerNorm.bias, 1e-12, want_stats=False)
+        ops.linear_wgrad(dpre, h1b, _grad_of(layer.intermediate.dense.weight), accumulate=True)
+        dh1 = ops.linear_dgrad(dpre, wc.get(layer.intermediate.dense.weight))
+        del dpre, h1b
+        # h1 = LN(s1), s1 = attn.out.dense(c) + h_in ; dh1_total = dh1 + ds2
+        ds1 = torch.empty((M, D), device=dev, dtype=torch.float32)
+        g1 = g2
+        ops.layernorm_bwd(dh1, s.s1, ao.LayerNorm.weight, s.mean1, s.rstd1, dy2=ds2, dx=ds1, dx_bf16=g1,
+                          dgamma=_grad_of(ao.LayerNorm.weight), dbeta=_grad_of(ao.LayerNorm.bias),
+                          dx_colsum=_grad_of(ao.dense.bias))
+        del dh1, ds2
+        ops.linear_wgrad(g1, s.c, _grad_of(ao.dense.weight), accumulate=True)
+        dc = ops.linear_dgrad(g1, wc.get(ao.dense.weight))
+        dqkv = torch.empty_like(s.qkv)
+        q5, d5 = s.qkv.view(B, T, 3, H, 64), dqkv.view(B, T, 3, H, 64)
+        ops.attention_bwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], s.c, dc, s.lse, B, H, T, strides, sv.key_len, 0.125,
+                          d5[:, :, 0], d5[:, :, 1], d5[:, :, 2])
+        del dc
+        qp = _qkv_params(layer)
+        bsum = ops.colsum(dqkv)
+        for j, p in enumerate(qp):
+            _grad_of(p.bias).add_(bsum[j * D:(j + 1) * D])
+            ops.linear_wgrad(dqkv[:, j * D:(j + 1) * D], s.h_in, _grad_of(p.weight), accumulate=True)
+        dy = ops.linear_dgrad(dqkv, wc.packed(f"bert.qkv.{li}", [p.weight for p in qp]))
+        dres = ds1
+        sv.layers[li] = None
+    de = torch.empty((M, D), device=dev, dtype=torch.float32)
+    ops.layernorm_bwd(dy, sv.e, emb.LayerNorm.weight, sv.mean0, sv.rstd0, dy2=dres, dx=de,
+                      dgamma=_grad_of(emb.LayerNorm.weight), dbeta=_grad_of(emb.LayerNorm.bias))
+    ops.bert_embed_bwd(sv.ids, de, _grad_of(emb.word_embeddings.weight), _grad_of(emb.position_embeddings.weight),
+                       _grad_of(emb.token_type_embeddings.weight)[0])
