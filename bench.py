@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the SimSeg hot path on B200 (contract: see README / DESIGN.md §Measurement).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N>1)
+    python bench.py --impl reference --gpus N ...            # the reference's CPU path (oracle port) on host cores
+
+Workload at every N (strong scaling): BASELINE.json configs[1] — ViT-S/16 224x224 + BERT-base contrastive
+pre-training step (forward + backward + AdamW), GLOBAL batch 4096 image-text pairs, 25 text tokens, bf16
+tensor-core operands, embeddings all-gathered across ranks before the InfoNCE logits.  Synthetic inputs,
+seeded random-init weights.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "image-text pairs/sec (train)"
+UNIT = "pairs/s"
+MODELS = {"vit-s": dict(yaml="simseg.vit-s.yaml", dim=384, heads=6, fwd_gf_img=9.20),
+          "vit-b": dict(yaml="simseg.vit-b.yaml", dim=768, heads=12, fwd_gf_img=35.1)}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="vit-s", choices=list(MODELS))
+    ap.add_argument("--global-batch", type=int, default=4096)
+    ap.add_argument("--seq-len", type=int, default=25)
+    ap.add_argument("--micro-batch", type=int, default=0, help="0 = whole per-rank batch in one pass")
+    ap.add_argument("--cpu-sample", type=int, default=32, help="pairs in the CPU-baseline sample")
+    ap.add_argument("--no-extras", action="store_true", help="skip roofline / patch-sim / cpu_baseline legs")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"ViT-{a.model[-1].upper()}/16 224x224 + BERT-base contrastive train step (fwd+bwd+AdamW), "
+            f"global batch {a.global_batch}, {a.seq_len} text tokens, bf16")
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm),
+                "power_w_max": max(float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit())}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops_sustained"], d["bf16_tflops"], "measured"
+    return 6650.0, 1400.0, 1590.0, "fallback"
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def cpu_pairs_per_s(a, pairs: int, steps: int = 1, warmup: int = 0):
+    """The reference's path restated on the CPU (oracle port): fwd + bwd + AdamW on `pairs` image-text pairs."""
+    import torch
+    from oracle import simseg_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    m = MODELS[a.model]
+    sd = O.make_state_dict(m["dim"], m["heads"], seed=0)
+    params = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    opt = torch.optim.AdamW([p for p in params.values() if p.requires_grad], lr=1e-4, betas=(0.9, 0.98), eps=1e-6,
+                            weight_decay=0.001)
+    batch = O.make_batch(pairs, a.seq_len, seed=1234)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss, _, _ = O.clip_train_forward(params, batch, m["heads"])
+        loss.backward()
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return pairs / dt, dt, torch.get_num_threads()
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    v, dt, cores = cpu_pairs_per_s(a, a.cpu_sample, steps=a.steps, warmup=min(a.warmup, 1))
+    sample = f"{a.cpu_sample}-pair micro-batch fwd+bwd+AdamW per step (a {a.global_batch}-pair CPU step would take hours)"
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": min(a.warmup, 1),
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": workload_name(a), "global_batch": a.global_batch, "seq_len": a.seq_len,
+                       "parallelism": "cpu"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from simseg_b200 import ops
+    from simseg_b200.synthetic import make_batch
+    from simseg_b200.config import load_cfg
+    from simseg_b200.pipeline import PIPELINE
+    from simseg_b200.train import Trainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert a.global_batch % world == 0
+    b = a.global_batch // world
+    m = MODELS[a.model]
+    cfg = load_cfg(m["yaml"], ["model.image_encoder.pretrained=False", "model.text_encoder.pretrained=False",
+                               "transforms.input_size=224", f"data.batch_size={a.global_batch}"])
+    torch.manual_seed(0)                            # same random-init weights on every rank (DDP broadcast not needed)
+    model = PIPELINE["clip"](cfg).to(dev)
+    trainer = Trainer(model, cfg, micro_batch=a.micro_batch or None)
+
+    # synthetic per-rank shard, pinned on the host (two rotating host batches so every step copies fresh bytes)
+    host = []
+    for j in range(2):
+        hb = make_batch(b, a.seq_len, seed=1234 + 17 * rank + 1000 * j)
+        host.append({k: v.pin_memory() for k, v in hb.items()})
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+    copy_stream = torch.cuda.Stream()
+    dev_bufs = [{k: torch.empty_like(v, device=dev) for k, v in host[0].items()} for _ in range(2)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn(steps)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    # ---- resident-input loop (value): inputs already in HBM
+    for k in dev_bufs[0]:
+        dev_bufs[0][k].copy_(host[0][k])
+    last = {}
+
+    def resident(steps):
+        for _ in range(steps):
+            last["out"] = trainer.step(dev_bufs[0])
+
+    resident(a.warmup)
+    ops.launch_count(reset=True)
+    with ClockSampler(local) as cs:
+        ms_total = timed(resident, a.steps)
+    launches = ops.launch_count()
+    ms_step = ms_total / a.steps
+    value = a.global_batch / (ms_step / 1e3)
+
+    # ---- end-to-end loop: pinned host batch -> H2D (prefetched on a copy stream) -> step -> loss.item()
+    def e2e(steps):
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        done = [None, None]
+
+        def issue(i):
+            s = i % 2
+            with torch.cuda.stream(copy_stream):
+                if done[s] is not None:
+                    copy_stream.wait_event(done[s])           # the step that last read this buffer has finished
+                for k in dev_bufs[s]:
+                    dev_bufs[s][k].copy_(host[s][k], non_blocking=True)
+                ready[s].record(copy_stream)
+        issue(0)
+        for i in range(steps):
+            s = i % 2
+            if i + 1 < steps:
+                issue(i + 1)
+            torch.cuda.current_stream().wait_event(ready[s])
+            loss, _, _ = trainer.step(dev_bufs[s])
+            done[s] = torch.cuda.Event()
+            done[s].record()
+            last["loss"] = loss.item()                        # D2H read of the step result
+    e2e(1)
+    ms_e2e = timed(e2e, a.steps) / a.steps
+    e2e_value = a.global_batch / (ms_e2e / 1e3)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": workload_name(a), "global_batch": a.global_batch, "per_gpu_batch": b,
+                       "seq_len": a.seq_len, "parallelism": f"dp{world}", "micro_batch": a.micro_batch or b,
+                       "l2": "per-step working set (>10 GB of activations) is far larger than the 126 MB L2"},
+            "clocks": cs.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": 4 * world,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches),
+            "loss": float(last.get("loss", float("nan")))}
+
+    if rank == 0 and not a.no_extras:
+        hbm, tf_sus, tf_burst, how = peaks()
+        line["roofline"] = gemm_roofline(trainer, dev_bufs[0], tf_sus, how)
+        line["train_flops"] = train_flops(a, m, ms_step, tf_sus)
+        line["patch_sim"] = patch_sim_bench(hbm, how)
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        if world == 1 and not a.no_extras:
+            v, dt, cores = cpu_pairs_per_s(a, a.cpu_sample)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"one {a.cpu_sample}-pair micro-batch fwd+bwd+AdamW of the same model, fp32, {dt:.1f} s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def train_flops(a, m, ms_step, tf_peak):
+    """Whole-step algorithmic FLOPs per SURVEY.md §8d (train = 3x forward)."""
+    T = a.seq_len
+    fwd_pair = m["fwd_gf_img"] + T * 12 * (24 * 768 ** 2 + 4 * T * 768) / 1e9 + (2 * 196 * m["dim"] * 512 + 2 * T * 768 * 512) / 1e9
+    tf = 3 * fwd_pair * a.global_batch / 1e3 / (ms_step / 1e3)
+    return {"gflop_per_pair_train": 3 * fwd_pair, "achieved_tflops_all_gpus": tf}
+
+
+def gemm_roofline(trainer, batch, tf_peak, how):
+    """Dominant kernel = the tcgen05 GEMM engine: algorithmic FLOPs of every GEMM launch of one step divided by the
+    summed CUDA-event durations of those launches (events on the launching stream, separate pass after the timed run)."""
+    import torch
+    from simseg_b200 import ops
+    rec = []
+    orig = ops.gemm
+
+    def timed_gemm(a, b, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = orig(a, b, **kw)
+        e1.record()
+        rec.append((2.0 * kw["M"] * kw["N"] * kw["K"], e0, e1))
+        return out
+    ops.gemm = timed_gemm
+    try:
+        trainer.step(batch)
+        torch.cuda.synchronize()
+    finally:
+        ops.gemm = orig
+    fl = sum(r[0] for r in rec)
+    ms = sum(r[1].elapsed_time(r[2]) for r in rec)
+    ach = fl / (ms / 1e3) / 1e12
+    return {"kernel": "simseg::gemm_kernel (tcgen05+TMA)", "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
+            "frac": ach / tf_peak, "traffic": None, "peak_source": f"{how} sustained bf16", "launches_per_step": len(rec),
+            "gemm_ms_per_step": ms}
+
+
+def patch_sim_bench(hbm_peak, how):
+    """BASELINE.json configs[3]: 64 images x 196 patches x 171 classes, bf16 patch embeddings in HBM -> fp32 map + argmax.
+    16 distinct input/output sets (>= 370 MB) are cycled so no launch finds its operands in L2."""
+    import torch
+    from simseg_b200 import ops
+    B, N, C, E = 64, 196, 171, 512
+    nset = 16
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ps = [torch.randn(B, N, E, device="cuda", generator=g).bfloat16() for _ in range(nset)]
+    t = torch.nn.functional.normalize(torch.randn(C, E, device="cuda", generator=g), dim=-1).bfloat16()
+    for i in range(nset):
+        ops.patch_text_sim(ps[i], t)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        for i in range(nset):
+            ops.patch_text_sim(ps[i], t)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (reps * nset)
+    bytes_per_map = N * E * 2 + N * C * 4 + N * 4
+    ach = B * bytes_per_map / (ms / 1e3) / 1e9
+    return {"workload": "ViT-B seg inference map: 64 x 196 patches x 171 classes, bf16 in, fp32 map + argmax",
+            "value": B / (ms / 1e3), "unit": "maps/s", "ms_per_batch": ms,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                         "traffic": None, "peak_source": how, "algorithmic_bytes_per_map": bytes_per_map}}
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -156,6 +156,7 @@ class _Shared:
     def __init__(self):
         self.wc = towers.Bf16Weights()
         self.stash = {}          # side outputs of the autograd nodes (bf16 token copies)
+        self.tower_done = None   # optional callback(name) fired when a tower's backward has been enqueued
 
 
 class _VitFn(torch.autograd.Function):
@@ -177,6 +178,8 @@ class _VitFn(torch.autograd.Function):
                 full = g.contiguous().float()
         towers.vit_backward(ctx.vit, ctx.sv, full, ctx.shared.wc)
         ctx.sv = None
+        if ctx.shared.tower_done is not None:
+            ctx.shared.tower_done("vit")
         return None, None, None, None, None, None
 
 
@@ -192,6 +195,8 @@ class _BertFn(torch.autograd.Function):
     def backward(ctx, g):
         towers.bert_backward(ctx.bert, ctx.sv, g.contiguous(), ctx.shared.wc)
         ctx.sv = None
+        if ctx.shared.tower_done is not None:
+            ctx.shared.tower_done("bert")
         return None, None, None, None, None, None
 
 
