@@ -1,0 +1,147 @@
+"""CPU: the oracle (oracle/simseg_oracle.py) against the committed golden fixtures.
+
+The fixtures under tests/golden/ hold outputs of the REFERENCE's own modules (``oracle/make_golden.py`` imported
+them from /root/reference in the build container); nothing here reads /root/reference.  These tests keep the
+oracle pinned so that the ``-m gpu`` parity tests compare the CUDA path with a checked checker.
+"""
+import os
+
+import numpy as np
+import torch
+
+from oracle import simseg_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _max(a, b):
+    return (torch.as_tensor(a).double() - torch.as_tensor(b).double()).abs().max().item()
+
+
+def _heads_inputs():
+    """Regenerate the seeded inputs of oracle/make_golden.py:heads_and_loss (generator seed 7, same draw order)."""
+    g = torch.Generator().manual_seed(7)
+    x_img = torch.randn(6, 196, 384, generator=g)
+    x_txt = torch.randn(6, 25, 768, generator=g)
+    return x_img, x_txt
+
+
+def test_heads_vs_reference_fixture():
+    z = np.load(os.path.join(GOLD, "heads_loss.npz"))
+    x_img, x_txt = _heads_inputs()
+    assert _max(x_img[:2, :, :64], z["heads_x_img"]) == 0.0           # the regenerated inputs ARE the fixture's
+    wi, wt, mask = torch.tensor(z["heads_wi"]), torch.tensor(z["heads_wt"]), torch.tensor(z["heads_mask"])
+    img = O.image_embed(torch.cat([x_img[:, :1], x_img], 1), wi, 5)   # drop-CLS + project + top-5 mean + L2norm
+    txt = O.text_embed(x_txt, wt, mask, 1)
+    assert _max(img, z["heads_img_emb"]) < 2e-5
+    assert _max(txt, z["heads_txt_emb"]) < 2e-5
+
+
+def test_topk_pooling_edge_cases():
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(3, 7, 16, generator=g)
+    # k shrinks to the shortest caption (pooling.py:61-63); a length-1 caption makes every k behave as k=1
+    mask = torch.tensor([[1] * 7, [1] + [0] * 6, [1, 1, 1, 0, 0, 0, 0]])
+    got = O.topk_pooling(x, 3, mask)
+    want = torch.stack([x[0].max(0)[0], x[1, 0], x[2, :3].max(0)[0]])
+    assert _max(got, want) == 0.0
+    # k == ntok -> plain mean
+    assert _max(O.topk_pooling(x, 7), x.mean(1)) < 1e-6
+    # zero vector: L2norm adds eps after the sqrt (normalization.py:9-10) -> 0, not NaN
+    assert torch.equal(O.l2norm(torch.zeros(2, 8)), torch.zeros(2, 8))
+
+
+def test_nce_vs_reference_fixture():
+    z = np.load(os.path.join(GOLD, "heads_loss.npz"))
+    a = torch.tensor(z["heads_img_emb"]).requires_grad_(True)
+    b = torch.tensor(z["heads_txt_emb"]).requires_grad_(True)
+    t = torch.tensor(0.02, requires_grad=True)
+    loss, i2t, t2i = O.clip_loss(a, b, a, b, t, 0)
+    loss.backward()
+    assert _max(loss, z["nce_loss"]) < 2e-5
+    assert _max(i2t, z["nce_i2t"]) == 0 and _max(t2i, z["nce_t2i"]) == 0
+    assert _max(a.grad, z["nce_dimg"]) < 2e-5 and _max(b.grad, z["nce_dtxt"]) < 2e-5
+    assert _max(t.grad, z["nce_dtemp"]) < 1e-3
+
+
+def test_nce_temperature_clamp():
+    g = torch.Generator().manual_seed(2)
+    a, b = O.l2norm(torch.randn(5, 32, generator=g)), O.l2norm(torch.randn(5, 32, generator=g))
+    for raw, eff in ((1e-5, 0.001), (3.0, 0.5)):                      # mml_loss.py:56
+        l1, _, lg1, _ = O.nce_direction(a, b, torch.tensor(raw))
+        l2, _, lg2, _ = O.nce_direction(a, b, torch.tensor(eff))
+        assert _max(l1, l2) == 0 and _max(lg1, lg2) == 0
+
+
+def test_global_reduce_two_rank_fixture():
+    """Global-reduce branch (GatherLayer + targets = arange(b*rank, b*(rank+1))) against the reference run on 2 gloo ranks."""
+    z = np.load(os.path.join(GOLD, "global_reduce.npz"))
+    img, txt = torch.tensor(z["gr_img"]), torch.tensor(z["gr_txt"])
+    b = 6
+    for rank in range(2):
+        ig, tg = img.clone().requires_grad_(True), txt.clone().requires_grad_(True)
+        total = 0
+        for r in range(2):
+            l, _, _ = O.clip_loss(ig[r * b:(r + 1) * b], tg[r * b:(r + 1) * b], ig, tg, torch.tensor(0.02), r)
+            if r == rank:
+                assert _max(l, z[f"gr_loss_{rank}"]) < 1e-5
+            total = total + l
+        total.backward()
+        assert _max(ig.grad[rank * b:(rank + 1) * b], z[f"gr_dimg_{rank}"]) < 1e-5
+        assert _max(tg.grad[rank * b:(rank + 1) * b], z[f"gr_dtxt_{rank}"]) < 1e-5
+
+
+def test_retrieval_vs_reference_fixture():
+    z = np.load(os.path.join(GOLD, "heads_loss.npz"))
+    left, right = torch.tensor(z["retr_left"]), torch.tensor(z["retr_right"])
+    lg, rg = torch.arange(40), torch.arange(200) // 5
+    has, first = O.retrieval_first_match_rank(O.allpairs_sim(left, right), lg, rg)
+    assert bool(has.all()) and torch.equal(first, torch.tensor(z["retr_first"]))
+    rec = O.recall_at(has, first)
+    for k, key in (("R@1", "retr_r1"), ("R@5", "retr_r5"), ("R@10", "retr_r10")):
+        assert abs(rec[k] - float(z[key])) < 1e-7
+
+
+def test_seg_map_vs_reference_fixture():
+    z = np.load(os.path.join(GOLD, "heads_loss.npz"))
+    sim, am = O.patch_text_sim(torch.tensor(z["seg_patch"]), torch.tensor(z["seg_text"]))
+    assert _max(sim, z["seg_sim"]) < 2e-6
+    assert torch.equal(am, torch.tensor(z["seg_argmax"]))
+    # an all-zero patch row: F.normalize clamps the norm at 1e-12 -> similarity 0 everywhere, argmax = class 0
+    p = torch.tensor(z["seg_patch"]).clone()
+    p[0, 3] = 0
+    s2, a2 = O.patch_text_sim(p, torch.tensor(z["seg_text"]))
+    assert float(s2[0, 3].abs().max()) == 0.0 and int(a2[0, 3]) == 0
+
+
+def test_pos_embed_interpolation_vs_reference_fixture():
+    z = np.load(os.path.join(GOLD, "heads_loss.npz"))
+    out = O.interpolate_pos_embed(torch.tensor(z["pe_in"]), 324)      # bicubic is per channel: a 16-channel slice suffices
+    assert out.shape == (1, 325, 16)
+    assert _max(out, z["pe_out"]) < 2e-5
+    assert O.interpolate_pos_embed(torch.tensor(z["pe_in"]), 196) is not None
+
+
+def test_full_clip_vit_s_vs_reference_fixture():
+    """Whole ViT-S + BERT-base + heads + NCE forward/backward (B = 8) against the reference CLIPModel's outputs."""
+    z = np.load(os.path.join(GOLD, "clip_vit_s.npz"))
+    torch.set_num_threads(os.cpu_count())
+    sd = O.make_state_dict(384, 6, seed=0)
+    batch = O.make_batch(8, 25, seed=1234)
+    sdg = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    loss, i2t, t2i = O.clip_train_forward(sdg, batch, 6)
+    loss.backward()
+    assert _max(loss, z["clip_loss"]) < 1e-4
+    assert _max(i2t, z["clip_i2t"]) == 0 and _max(t2i, z["clip_t2i"]) == 0
+    with torch.no_grad():
+        img, txt = O.clip_embeddings(sd, batch, 6)
+        tok = O.vit_forward(sd, batch["image"], 6, O.IMG_PREFIX)[:, 1:]
+    assert _max(img, z["clip_img_emb"]) < 1e-4 and _max(txt, z["clip_txt_emb"]) < 1e-4
+    assert _max(tok[:, :4, :32], z["clip_tokens_head"]) < 2e-4
+    assert _max(sdg["image_projection.linear.weight"].grad[:8, :32], z["clip_dWi_head"]) < 2e-4 * max(
+        1.0, float(np.abs(z["clip_dWi_head"]).max()))
+    assert abs(float(sdg["loss.temperature"].grad) - float(z["clip_dtemp"])) < 2e-3 * max(1.0, abs(float(z["clip_dtemp"])))
+    for key in z.files:
+        if key.startswith("grad_norm/"):
+            g = sdg[key[len("grad_norm/"):]].grad
+            assert abs(g.norm().item() - float(z[key])) <= 2e-3 * float(z[key]) + 1e-9, key
