@@ -86,8 +86,11 @@ def _grad_table(model, sd, batch, heads):
 def test_tower_and_head_backward_fixed_cotangent_vs_oracle(cuda):
     """Backward kernels in isolation: the same random cotangents are pushed into the (image, text) embeddings of
     ``forward(batch, embeddings='all')`` on both sides, so every one of the 349 tower/head parameter gradients is
-    compared without the loss's own conditioning (with random-init weights the embeddings of different samples are
-    nearly collinear, and dL/d(emb) = (mean_j e_j - e_i)/t is a difference of almost equal vectors)."""
+    compared without the loss's own conditioning.  Two bars per parameter: (i) relative L2 error to the fp32 oracle
+    <= 0.2 with cosine >= 0.98, and (ii) no worse than 1.5x (+0.01) the error the ORACLE ITSELF shows when it is run
+    under ``torch.autocast(bfloat16)`` on the GPU — the reference's own precision contract
+    (``tasks/clip/clip_runner.py:226-228``).  Measured: mean 0.059 (ours) vs 0.053 (autocast); the weights feeding
+    GELU / LayerNorm-scaled GEMMs sit near 0.10-0.15 on both sides (bf16 activations), so (i) alone cannot be tighter."""
     from oracle import simseg_oracle as O
     model, _ = _build(cuda)
     sd = O.make_state_dict(384, 6, seed=0)
@@ -95,25 +98,38 @@ def test_tower_and_head_backward_fixed_cotangent_vs_oracle(cuda):
     batch = O.make_batch(8, 25, seed=1234)
     gb = {k: v.to(cuda) for k, v in batch.items()}
     g = torch.Generator().manual_seed(99)
-    gi, gt = torch.randn(8, 512, generator=g), torch.randn(8, 512, generator=g)
+    gi, gt = torch.randn(8, 512, generator=g).to(cuda), torch.randn(8, 512, generator=g).to(cuda)
     model.zero_grad(set_to_none=True)
     ie, te = model(gb, embeddings="all")
-    torch.autograd.backward([ie, te], [gi.to(cuda), gt.to(cuda)])
+    torch.autograd.backward([ie, te], [gi, gt])
     torch.cuda.synchronize()
-    sdg = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
-    oi, ot = O.clip_embeddings(sdg, batch, 6)
-    torch.autograd.backward([oi, ot], [gi, gt])
+
+    def oracle_grads(autocast):
+        sdg = {k: v.to(cuda).clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            oi, ot = O.clip_embeddings(sdg, gb, 6)
+        torch.autograd.backward([oi.float(), ot.float()], [gi, gt])
+        return {k: v.grad for k, v in sdg.items() if v.grad is not None}
+
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref, amp = oracle_grads(False), oracle_grads(True)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    rel = lambda a, b: ((a - b).norm() / (b.norm() + 1e-30)).item()
     rows = []
     for k, p in model.named_parameters():
-        if k == "loss.temperature":
+        if k == "loss.temperature" or ref[k].norm().item() <= 1e-7:
             continue
-        ref, got = sdg[k].grad, p.grad.cpu()
-        rows.append((k, _cos(got, ref), ((got - ref).norm() / (ref.norm() + 1e-30)).item(), ref.norm().item()))
-    rows = [r for r in rows if r[3] > 1e-7]
-    bad = sorted(rows, key=lambda r: r[1])[:8]
-    print("worst gradients (name, cos, rel, |ref|):", *bad, sep="\n  ")
+        rows.append((k, _cos(p.grad, ref[k]), rel(p.grad, ref[k]), rel(amp[k], ref[k])))
+    bad = sorted(rows, key=lambda r: r[2] - 1.5 * r[3], reverse=True)[:8]
+    print("worst gradients (name, cos, rel ours, rel autocast):", *bad, sep="\n  ")
     assert len(rows) > 300
-    assert all(r[1] > 0.999 and r[2] < 0.05 for r in rows), bad
+    assert all(r[1] > 0.98 and r[2] < 0.2 for r in rows), bad
+    assert all(r[2] <= 1.5 * r[3] + 0.01 for r in rows), bad
+    mean_ours, mean_amp = sum(r[2] for r in rows) / len(rows), sum(r[3] for r in rows) / len(rows)
+    assert mean_ours <= 1.25 * mean_amp, (mean_ours, mean_amp)
 
 
 @pytest.mark.parametrize("temperature,min_cos,max_rel", [(0.5, 0.98, 0.2), (0.02, 0.98, 0.2)])
