@@ -35,6 +35,7 @@ int nce_rows_bwd_impl(Ctx*, float*, int, int, int64_t, const float*, int, const 
 int row_inv_norm_impl(Ctx*, const void*, int, int64_t, int, float*, cudaStream_t);
 int row_argmax_impl(Ctx*, const float*, int64_t, int, int32_t*, cudaStream_t);
 int retrieval_rank_impl(Ctx*, const float*, int, int, const int64_t*, const int64_t*, int32_t*, cudaStream_t);
+int patch_sim_fused_impl(Ctx*, const void*, int64_t, int, const void*, int, int, float*, int32_t*, cudaStream_t);
 
 // fp32 product in the requested precision: C[M,N] (+)= A(m,k) B(n,k)
 static int fp32_matmul(Ctx* c, const float* A, const float* B, float* C, int M, int N, int K, int64_t lda, int64_t ldb,
@@ -205,6 +206,11 @@ int simseg_patch_text_sim(simseg_ctx* ctx, const void* patches, int dtype, int64
                           void* stream) {
   CTX_OR_FAIL();
   SIMSEG_CHECK_ARG(rows > 0 && C > 0 && E > 0, "patch_text_sim: empty");
+  if (dtype == SIMSEG_BF16) {
+    // single-pass fused kernel (patch_sim.cu); shapes it does not cover take the generic 3-kernel sequence below
+    const int frc = patch_sim_fused_impl(c, patches, rows, E, text, C, normalize, sim, argmax, st);
+    if (frc != SIMSEG_ERR_UNSUPPORTED) return frc;
+  }
   simseg_gemm_args g;
   memset(&g, 0, sizeof(g));
   g.a = patches; g.b = text; g.d = sim; g.M = rows; g.N = C; g.K = E; g.lda = E; g.ldb = E; g.ldd = C;

@@ -43,6 +43,8 @@ struct GemmParams {
   const float* row_scale;
   float* col_sum;
   int32_t vec_ok;          // 16-byte aligned rows for d / residual / aux
+  int32_t a_3d, b_3d;      // MN-major operand loaded with one 3-D TMA box per k-block
+  int32_t dbg;             // bench-only: 1 = no TMA after the ring is primed, 2 = no MMA (results are garbage)
 };
 
 template <int BN>
@@ -116,6 +118,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
+          if (p.dbg == 1 && (phase != 0 || tile != static_cast<int>(blockIdx.x))) {
+            mbar_arrive(&full_bar[stage]);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           const int k0 = kb * k_elems;
           if (!p.a_mn) {
@@ -125,7 +132,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const int mn_atom = kSwizzleBytes / p.elem_bytes;          // 64 bf16 / 32 tf32 elements
             const int nbox = kBM / mn_atom;
             const int box_bytes = Cfg::kABytes / nbox;
-            for (int j = 0; j < nbox; ++j) tma_load_2d(sa + j * box_bytes, &tmap_a, &full_bar[stage], m0 + j * mn_atom, k0);
+            if (p.a_3d) tma_load_3d(sa, &tmap_a, &full_bar[stage], 0, k0, m0 / mn_atom);
+            else
+              for (int j = 0; j < nbox; ++j) tma_load_2d(sa + j * box_bytes, &tmap_a, &full_bar[stage], m0 + j * mn_atom, k0);
           }
           if (!p.b_mn) {
             tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
@@ -133,7 +142,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const int mn_atom = kSwizzleBytes / p.elem_bytes;
             const int nbox = BN / mn_atom;
             const int box_bytes = Cfg::kBBytes / nbox;
-            for (int j = 0; j < nbox; ++j) tma_load_2d(sb + j * box_bytes, &tmap_b, &full_bar[stage], n0 + j * mn_atom, k0);
+            if (p.b_3d) tma_load_3d(sb, &tmap_b, &full_bar[stage], 0, k0, n0 / mn_atom);
+            else
+              for (int j = 0; j < nbox; ++j) tma_load_2d(sb + j * box_bytes, &tmap_b, &full_bar[stage], n0 + j * mn_atom, k0);
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
@@ -169,6 +180,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
+          if (p.dbg == 2 && kb > kb0) {
+            mbar_arrive(&empty_bar[stage]);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
 #pragma unroll
           for (int kk = 0; kk < kk_steps; ++kk) {
             const uint64_t adesc = make_smem_desc_sw128(sa + kk * a_step, a_lbo, 1024);
@@ -398,8 +414,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D row-major tensor [rows, cols] (cols contiguous, leading dim ld elements); box = {box_cols, box_rows}
-static int make_tmap(CUtensorMap* m, const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld,
-                     int box_cols, int box_rows) {
+int make_tmap(CUtensorMap* m, const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld,
+              int box_cols, int box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled not available (driver entry point lookup failed)"); return SIMSEG_ERR_CUDA; }
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
@@ -412,6 +428,26 @@ static int make_tmap(CUtensorMap* m, const void* ptr, int elem_bytes, int64_t ro
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p rows=%lld cols=%lld ld=%lld box=%dx%d", static_cast<int>(r), ptr,
               static_cast<long long>(rows), static_cast<long long>(cols), static_cast<long long>(ld), box_cols, box_rows);
+    return SIMSEG_ERR_CUDA;
+  }
+  return SIMSEG_OK;
+}
+
+int make_tmap_mn3d(CUtensorMap* m, const void* ptr, int elem_bytes, int64_t k_rows, int64_t mn_cols, int64_t ld, int box_k,
+                   int box_atoms) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled not available (driver entry point lookup failed)"); return SIMSEG_ERR_CUDA; }
+  const int atom = kSwizzleBytes / elem_bytes;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(atom), static_cast<cuuint64_t>(k_rows), static_cast<cuuint64_t>(mn_cols / atom)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * elem_bytes, static_cast<cuuint64_t>(kSwizzleBytes)};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(atom), static_cast<cuuint32_t>(box_k), static_cast<cuuint32_t>(box_atoms)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d) failed (%d): ptr=%p k_rows=%lld mn=%lld ld=%lld box_k=%d atoms=%d", static_cast<int>(r),
+              ptr, static_cast<long long>(k_rows), static_cast<long long>(mn_cols), static_cast<long long>(ld), box_k, box_atoms);
     return SIMSEG_ERR_CUDA;
   }
   return SIMSEG_OK;
@@ -485,15 +521,24 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
   p.n_tiles = static_cast<int>(cdiv(a->N, bn));
   const int k_elems = kSwizzleBytes / eb;
   p.kb_total = static_cast<int>(cdiv(a->K, k_elems));
-  // split-K only for plain fp32 accumulation outputs with few output tiles (wgrad: K = all tokens)
+  // split-K only for plain fp32 accumulation outputs with few output tiles (wgrad: K = all tokens).
+  // The split count is chosen for wave efficiency: work items (tiles x splits) should fill whole waves of
+  // num_sms persistent CTAs; among equally efficient choices the smallest split count wins (fewer atomics).
   int splits = 1;
   const int tiles_mn = p.m_tiles * p.n_tiles;
   const bool can_split = a->epilogue == SIMSEG_EPI_NONE && a->out_dtype == SIMSEG_F32 && a->col_sum == nullptr;
-  if (can_split && tiles_mn < ctx->num_sms && p.kb_total >= 64) {
-    splits = static_cast<int>(cdiv(ctx->num_sms, tiles_mn));
-    const int max_splits = p.kb_total / 16;
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
+  if (can_split && p.kb_total >= 32) {
+    const int max_splits = p.kb_total / 8 < 64 ? p.kb_total / 8 : 64;
+    double best_eff = 0.0;
+    for (int s = 1; s <= max_splits; ++s) {
+      const int kbs = static_cast<int>(cdiv(p.kb_total, s));
+      const int s_eff = static_cast<int>(cdiv(p.kb_total, kbs));
+      const int64_t items = static_cast<int64_t>(tiles_mn) * s_eff;
+      const int64_t waves = cdiv(items, ctx->num_sms);
+      // time ~ waves * (k-blocks per item + fixed per-item cost of ~6 k-blocks for prologue/epilogue)
+      const double eff = static_cast<double>(tiles_mn) * p.kb_total / (static_cast<double>(waves) * ctx->num_sms * (kbs + 6.0));
+      if (eff > best_eff * 1.02) { best_eff = eff; splits = s_eff; }
+    }
   }
   p.kb_per_split = static_cast<int>(cdiv(p.kb_total, splits));
   p.splits = static_cast<int>(cdiv(p.kb_total, p.kb_per_split));
@@ -508,6 +553,7 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
   if (a->aux) vec = vec && (a->ld_aux * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0;
   if (a->bias) vec = vec && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0;
   p.vec_ok = vec ? 1 : 0;
+  p.dbg = a->reserved & 3;
 
   if (p.splits > 1 && !a->accumulate) {
     // split-K partial sums are reduced with atomics: start from zero
@@ -517,10 +563,17 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
   CUtensorMap ta, tb;
   const int mn_atom = kSwizzleBytes / eb;
   int rc;
+  // MN-major operands whose MN extent is a whole number of 128-byte atoms take ONE 3-D box per k-block
+  // (atoms past the matrix edge are zero-filled by TMA); ragged extents keep one 2-D box per atom.
+  const bool no3d = (a->reserved & 4) != 0;
+  p.a_3d = (p.a_mn && a->M % mn_atom == 0 && !no3d) ? 1 : 0;
+  p.b_3d = (p.b_mn && a->N % mn_atom == 0 && !no3d) ? 1 : 0;
   if (!p.a_mn) rc = make_tmap(&ta, a->a, eb, a->M, a->K, a->lda, k_elems, kBM);
+  else if (p.a_3d) rc = make_tmap_mn3d(&ta, a->a, eb, a->K, a->M, a->lda, k_elems, kBM / mn_atom);
   else rc = make_tmap(&ta, a->a, eb, a->K, a->M, a->lda, mn_atom, k_elems);
   if (rc) return rc;
   if (!p.b_mn) rc = make_tmap(&tb, a->b, eb, a->N, a->K, a->ldb, k_elems, bn);
+  else if (p.b_3d) rc = make_tmap_mn3d(&tb, a->b, eb, a->K, a->N, a->ldb, k_elems, bn / mn_atom);
   else rc = make_tmap(&tb, a->b, eb, a->K, a->N, a->ldb, mn_atom, k_elems);
   if (rc) return rc;
 

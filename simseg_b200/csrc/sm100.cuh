@@ -84,6 +84,14 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorM
       "l"(policy)
       : "memory");
 }
+// 3-D tiled load (used for MN-major operands: {64 mn elements, k rows, mn atoms} in ONE instruction)
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1,
+                                            int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 // 2-D tiled store shared -> global (bulk async group)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -192,4 +200,14 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t ab_format, uint32_t a
 }
 
 }  // namespace sm100
+
+// host: 2-D row-major tensor [rows, cols] (cols contiguous, leading dim ld elements), SWIZZLE_128B,
+// box = {box_cols, box_rows}; elem_bytes 2 = bf16, 4 = fp32.  Defined in gemm_sm100.cu.
+int make_tmap(CUtensorMap* m, const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+              int box_rows);
+// host: MN-major operand stored [k_rows, mn_cols] row-major viewed as {atom = 128 B of mn, k_rows, mn_cols/atom}:
+// one box = {atom, box_k, box_atoms} lands in smem as [atom index][k][128 B] — the canonical UMMA MN-major SW128 tile.
+// Requires mn_cols * elem_bytes % 128 == 0.
+int make_tmap_mn3d(CUtensorMap* m, const void* ptr, int elem_bytes, int64_t k_rows, int64_t mn_cols, int64_t ld, int box_k,
+                   int box_atoms);
 }  // namespace simseg

@@ -63,7 +63,7 @@ def gemm(a: Tensor, b: Tensor, *, M: int, N: int, K: int, a_major: int = 0, b_ma
          out: Optional[Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, epilogue: int = EPI_NONE,
          bias: Optional[Tensor] = None, residual: Optional[Tensor] = None, aux: Optional[Tensor] = None,
          row_scale: Optional[Tensor] = None, col_sum: Optional[Tensor] = None, accumulate: bool = False,
-         tile_n: int = 0) -> Tensor:
+         tile_n: int = 0, _dbg: int = 0) -> Tensor:
     """D[M,N] = epilogue(sum_k A(m,k) B(n,k)).  a_major/b_major: 0 = operand stored [MN,K], 1 = stored [K,MN]."""
     lda, ldb = _rowmajor2d(a), _rowmajor2d(b)
     assert a.dtype == b.dtype
@@ -90,6 +90,7 @@ def gemm(a: Tensor, b: Tensor, *, M: int, N: int, K: int, a_major: int = 0, b_ma
         assert col_sum.dtype == torch.float32 and col_sum.numel() == N
         g.col_sum = col_sum.data_ptr()
     g.tile_n = tile_n
+    g.reserved = _dbg
     check(_lib.load().simseg_gemm(ctx(), C.byref(g), _stream()), "simseg_gemm")
     return out
 

@@ -145,6 +145,44 @@ def test_patch_text_sim_shapes_vs_oracle(cuda, B, N, C, dtype):
     assert torch.equal(am.long(), sim.argmax(-1))
 
 
+@pytest.mark.parametrize("rows,C,E", [(588, 171, 512), (1, 1, 512), (129, 255, 512), (4097, 256, 512), (300, 16, 256),
+                                      (77, 300, 512), (640, 33, 1024)])
+def test_patch_text_sim_fused_ragged_bf16(cuda, rows, C, E):
+    """Edge shapes of the single-pass fused kernel (ragged last tile, C = 1 / 255 / 256, other E) and of the generic
+    sequence it defers to (C > 256); an all-zero patch row must give similarity 0 and argmax 0 (F.normalize eps rule)."""
+    ops, O = _ops(), _O()
+    g = torch.Generator().manual_seed(rows * 7 + C)
+    p = torch.randn(rows, E, generator=g).bfloat16()
+    p[rows // 2] = 0
+    t = torch.nn.functional.normalize(torch.randn(C, E, generator=g), dim=-1).bfloat16()
+    sim, am = ops.patch_text_sim(p.to(cuda), t.to(cuda))
+    ref, _ = O.patch_text_sim(p[None], t)
+    assert sim.shape == (rows, C) and am.shape == (rows,)
+    assert (sim.cpu() - ref[0]).abs().max().item() < 1e-2
+    assert torch.equal(am.long(), sim.argmax(-1))
+    assert float(sim[rows // 2].abs().max()) == 0.0 and int(am[rows // 2]) == 0
+    # normalize=False is the plain projection product
+    raw, _ = ops.patch_text_sim(p.to(cuda), t.to(cuda), normalize=False, want_argmax=False)
+    assert (raw.cpu() - p.float() @ t.float().T).abs().max().item() < 0.15
+
+
+def test_patch_text_sim_large_batch_properties(cuda):
+    """Full-size property check (4096 maps x 196 patches x 171 classes — far beyond what the CPU oracle is run on):
+    scale invariance of the cosine map, |sim| <= 1, argmax consistency, and agreement with a sampled oracle subset."""
+    ops, O = _ops(), _O()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    p = torch.randn(4096 * 196, 512, device=cuda, generator=g).bfloat16()
+    t = torch.nn.functional.normalize(torch.randn(171, 512, device=cuda, generator=g), dim=-1).bfloat16()
+    sim, am = ops.patch_text_sim(p, t)
+    assert float(sim.abs().max()) <= 1.0 + 1e-3
+    assert torch.equal(am.long(), sim.argmax(-1))
+    sim2, am2 = ops.patch_text_sim(p * 4, t)                       # power-of-two scale: bf16-exact, cosine unchanged
+    assert float((sim2 - sim).abs().max()) < 1e-6 and torch.equal(am2, am)
+    idx = torch.randint(0, p.shape[0], (2048,), device=cuda, generator=g)
+    ref, _ = O.patch_text_sim(p[idx].cpu()[None], t.cpu())
+    assert (sim[idx].cpu() - ref[0]).abs().max().item() < 1e-2
+
+
 def test_retrieval_golden(cuda):
     ops, O = _ops(), _O()
     gold = np.load(os.path.join(GOLD, "heads_loss.npz"))

@@ -1,0 +1,96 @@
+"""GEMM-engine microbenchmark over the shapes of one training step (run on the GPU box).
+   python tools/gemm_bench.py [vit-s|vit-b|bert|all] [reps]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from simseg_b200 import ops
+from simseg_b200._lib import EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU, EPI_NONE
+
+dev = "cuda"
+
+
+def t_ms(fn, reps):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def bench(tag, M, N, K, a_major=0, b_major=0, epi=EPI_NONE, out_dtype=torch.bfloat16, reps=10, tile_ns=(0,), accumulate=False, dbg=0):
+    bf = torch.bfloat16
+    A = torch.randn((K, M) if a_major else (M, K), device=dev, dtype=bf)
+    B = torch.randn((K, N) if b_major else (N, K), device=dev, dtype=bf)
+    kw = dict(M=M, N=N, K=K, a_major=a_major, b_major=b_major, epilogue=epi, out_dtype=out_dtype)
+    out = torch.empty((M, N), device=dev, dtype=out_dtype)
+    kw["out"] = out
+    if epi in (EPI_BIAS_GELU, EPI_BIAS_RESIDUAL):
+        kw["bias"] = torch.randn(N, device=dev)
+    if epi == EPI_BIAS_RESIDUAL:
+        kw["residual"] = torch.randn(M, N, device=dev)
+    if epi == EPI_BIAS_GELU:
+        kw["aux"] = torch.empty(M, N, device=dev, dtype=bf)
+    if epi == EPI_DGELU:
+        kw["aux"] = torch.randn(M, N, device=dev, dtype=bf)
+        kw["col_sum"] = torch.zeros(N, device=dev)
+    if accumulate:
+        kw["accumulate"] = True
+    if dbg:
+        kw["_dbg"] = dbg
+    res = []
+    for tn in tile_ns:
+        ms = t_ms(lambda: ops.gemm(A, B, tile_n=tn, **kw), reps)
+        res.append(f"bn={tn}: {ms:7.3f} ms {2.0 * M * N * K / ms / 1e9:7.1f} TF/s")
+    # cuBLAS reference point for the same math (library call, only as a yardstick)
+    if not dbg:
+        Ao, Bo = (A.t() if a_major else A), (B if b_major else B.t())
+        ms = t_ms(lambda: torch.matmul(Ao, Bo), reps)
+        res.append(f"cublas {ms:7.3f} ms {2.0 * M * N * K / ms / 1e9:7.1f} TF/s")
+    print(f"{tag:34s} M={M:7d} N={N:5d} K={K:7d} | " + " | ".join(res), flush=True)
+
+
+def tower(name, M, D, F, reps):
+    f32 = torch.float32
+    tn = (0, 128, 192, 256)
+    bench(f"{name} qkv fwd", M, 3 * D, D, reps=reps, tile_ns=tn)
+    bench(f"{name} proj fwd +res(f32)", M, D, D, epi=EPI_BIAS_RESIDUAL, out_dtype=f32, reps=reps, tile_ns=tn)
+    bench(f"{name} fc1 fwd gelu+aux", M, F, D, epi=EPI_BIAS_GELU, reps=reps, tile_ns=tn)
+    bench(f"{name} fc2 fwd +res(f32)", M, D, F, epi=EPI_BIAS_RESIDUAL, out_dtype=f32, reps=reps, tile_ns=tn)
+    bench(f"{name} fc2 dgrad dgelu+colsum", M, F, D, b_major=1, epi=EPI_DGELU, reps=reps, tile_ns=tn)
+    bench(f"{name} fc1 dgrad", M, D, F, b_major=1, reps=reps, tile_ns=tn)
+    bench(f"{name} qkv dgrad", M, D, 3 * D, b_major=1, reps=reps, tile_ns=tn)
+    bench(f"{name} proj dgrad", M, D, D, b_major=1, reps=reps, tile_ns=tn)
+    bench(f"{name} fc2 wgrad", D, F, M, a_major=1, b_major=1, out_dtype=f32, reps=reps, tile_ns=tn, accumulate=True)
+    bench(f"{name} fc1 wgrad", F, D, M, a_major=1, b_major=1, out_dtype=f32, reps=reps, tile_ns=tn, accumulate=True)
+    bench(f"{name} qkv wgrad", 3 * D, D, M, a_major=1, b_major=1, out_dtype=f32, reps=reps, tile_ns=tn, accumulate=True)
+    bench(f"{name} proj wgrad", D, D, M, a_major=1, b_major=1, out_dtype=f32, reps=reps, tile_ns=tn, accumulate=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which == "one":      # one M N K a_major b_major epi out(bf16|f32) tile_n [accumulate]
+        M, N, K, am, bm, epi = (int(x) for x in sys.argv[2:8])
+        od = torch.float32 if sys.argv[8] == "f32" else torch.bfloat16
+        bench("one", M, N, K, a_major=am, b_major=bm, epi=epi, out_dtype=od, reps=2, tile_ns=(int(sys.argv[9]),),
+              accumulate=len(sys.argv) > 10)
+        sys.exit(0)
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+    if which == "layouts":
+        for (am, bm) in ((0, 0), (0, 1), (1, 0), (1, 1)):
+            for (M, N, K) in ((8192, 8192, 4096), (4096, 4096, 65536)):
+                bench(f"layout a_major={am} b_major={bm}", M, N, K, a_major=am, b_major=bm, reps=reps, tile_ns=(128, 256))
+                for dbg in (1, 2, 4, 6):
+                    bench(f"   dbg={dbg} ({ {1: 'no TMA', 2: 'no MMA', 4: '2-D boxes', 6: 'no MMA, 2-D boxes'}[dbg] })", M, N, K, a_major=am, b_major=bm, reps=reps,
+                          tile_ns=(256,), dbg=dbg)
+        sys.exit(0)
+    if which in ("vit-s", "all"):
+        tower("vit-s b=4096", 4096 * 197, 384, 1536, reps)
+    if which in ("bert", "all"):
+        tower("bert b=4096 T=25", 4096 * 25, 768, 3072, reps)
+    if which in ("vit-b", "all"):
+        tower("vit-b b=1024", 1024 * 197, 768, 3072, reps)
