@@ -1,0 +1,404 @@
+// tcgen05 attention backward for head_dim 64 and S <= 256 (ViT: 197 tokens; BERT: 25 / 77).
+//
+// One (batch, head) per work item, persistent CTAs (one per SM), 10 warps:
+//   warp 0      TMA producer: Q, dO (two 128-row query tiles, resident for the whole item) and K, V (128-key tiles,
+//               double buffered) land in 128B-swizzled smem through 4-D tensor maps {d, head, token, batch} — rows past S
+//               are zero-filled by TMA, so no tile ever reads a neighbouring batch element.
+//   warp 1      one elected thread issues every tcgen05.mma (all accumulators live in TMEM, 512 columns):
+//                 S  = Q_qt K_kt^T   [128 q x 128 keys]  cols   0..127      dP = dO_qt V_kt^T         cols 128..255
+//                 dV_kt += P^T dO_qt [128 keys x 64]     cols 256..319      dK_kt += dS^T Q_qt        cols 320..383
+//                 dQ_qt += dS K_kt   [128 q x 64]        cols 384 + 64 qt
+//   warps 2..9  elementwise: tcgen05.ld S and dP, P = exp2(S*scale*log2e - lse*log2e), dS = P * (dP - D), written as bf16
+//               into smem in the [key atom][q row][128 B] swizzled layout that serves BOTH as the K-major A operand of
+//               dQ = dS K and as the MN-major A operand of dK = dS^T Q / dV = P^T dO (no transposes anywhere);
+//               the same warps drain dK/dV after the last query tile of a key tile and dQ after the last key tile.
+//   D_i = sum_d dO[i,d] O[i,d] is computed in-kernel from the dO tile in smem and one 128-byte global read of O per row.
+// Loop order: key tile outer, query tile inner, so dK/dV accumulate in TMEM over the inner loop and dQ over the outer one;
+// nothing is ever re-read from HBM and S x S never exists outside TMEM/smem.
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace simseg {
+
+using namespace sm100;
+
+constexpr int kAbThreads = 320;
+constexpr int kTile = 128;                 // query rows / key rows per tile
+constexpr int kTileBytes = kTile * 128;    // [128 rows][64 bf16]
+constexpr int kPBytes = 2 * kTileBytes;    // P or dS: [2 key atoms][128 q rows][128 B]
+
+struct AttnBwdParams {
+  int32_t B, H, S, nqt, nkt, items;
+  float scale, scale_log2e;
+  const int32_t* key_len;
+  const float* lse;                 // [B,H,S]
+  const __nv_bfloat16* out;         // [B,S,H*64]
+  __nv_bfloat16 *dq, *dk, *dv;      // strides as q/k/v
+  int64_t sb, ss, sh;
+};
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1,
+                                            int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ int ceil16(int x) { return (x + 15) & ~15; }
+
+__global__ void __launch_bounds__(kAbThreads, 1)
+attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                        const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                        const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                          // [2][16 KB]
+  uint8_t* sdO = sQ + 2 * kTileBytes;          // [2][16 KB]
+  uint8_t* sK = sdO + 2 * kTileBytes;          // [2 buffers][16 KB]
+  uint8_t* sV = sK + 2 * kTileBytes;           // [2 buffers][16 KB]
+  uint8_t* sP = sV + 2 * kTileBytes;           // 32 KB
+  uint8_t* sdS = sP + kPBytes;                 // 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + kPBytes);
+  uint64_t* qdo_full = bars;          // [2]
+  uint64_t* qdo_empty = bars + 2;     // [2]
+  uint64_t* kv_full = bars + 4;       // [2]
+  uint64_t* kv_empty = bars + 6;      // [2]
+  uint64_t* sdp_full = bars + 8;      // MMA -> EW : S and dP are in TMEM
+  uint64_t* ew_done = bars + 9;       // EW -> MMA : S/dP consumed, P/dS written to smem        (8 warps)
+  uint64_t* pds_free = bars + 10;     // MMA -> EW : the MMAs reading P/dS have completed
+  uint64_t* dkv_full = bars + 11;     // MMA -> EW : dK/dV of a key tile complete
+  uint64_t* dkv_free = bars + 12;     // EW -> MMA : dK/dV drained                               (8 warps)
+  uint64_t* dq_full = bars + 13;
+  uint64_t* dq_free = bars + 14;      //                                                          (8 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_q); prefetch_tmap(&tm_k); prefetch_tmap(&tm_v); prefetch_tmap(&tm_do);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1);
+      mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(sdp_full, 1); mbar_init(ew_done, 8); mbar_init(pds_free, 1);
+    mbar_init(dkv_full, 1); mbar_init(dkv_free, 8); mbar_init(dq_full, 1); mbar_init(dq_free, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320, tdQ = tmem_base + 384;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      uint32_t kvc = 0, it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        const int b = item / p.H, h = item - b * p.H;
+        for (int kt = 0; kt < p.nkt; ++kt, ++kvc) {
+          const uint32_t buf = kvc & 1, ph = (kvc >> 1) & 1;
+          mbar_wait(&kv_empty[buf], ph ^ 1);
+          mbar_arrive_expect_tx(&kv_full[buf], 2 * kTileBytes);
+          tma_load_4d(sK + buf * kTileBytes, &tm_k, &kv_full[buf], 0, h, kt * kTile, b);
+          tma_load_4d(sV + buf * kTileBytes, &tm_v, &kv_full[buf], 0, h, kt * kTile, b);
+          if (kt == 0) {
+            for (int qt = 0; qt < p.nqt; ++qt) {
+              mbar_wait(&qdo_empty[qt], (it & 1) ^ 1);
+              mbar_arrive_expect_tx(&qdo_full[qt], 2 * kTileBytes);
+              tma_load_4d(sQ + qt * kTileBytes, &tm_q, &qdo_full[qt], 0, h, qt * kTile, b);
+              tma_load_4d(sdO + qt * kTileBytes, &tm_do, &qdo_full[qt], 0, h, qt * kTile, b);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      uint32_t kvc = 0, it = 0, g = 0, drains = 0;
+      const uint32_t id_sdp_base = make_idesc(1u, 0u, 0u, kTile, 16u) & ~(0x3Fu << 17);     // N filled per key tile
+      const uint32_t id_dkv = make_idesc(1u, 1u, 1u, kTile, 64u);                           // A, B MN-major
+      const uint32_t id_dq = make_idesc(1u, 0u, 1u, kTile, 64u);                            // A K-major, B MN-major
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        for (int kt = 0; kt < p.nkt; ++kt, ++kvc) {
+          const uint32_t buf = kvc & 1;
+          const int nkc = min(kTile, ceil16(p.S - kt * kTile));               // key columns of this tile (multiple of 16)
+          const uint32_t id_sdp = id_sdp_base | (static_cast<uint32_t>(nkc >> 3) << 17);
+          mbar_wait(&kv_full[buf], (kvc >> 1) & 1);
+          const uint32_t aK = smem_u32(sK + buf * kTileBytes), aV = smem_u32(sV + buf * kTileBytes);
+          for (int qt = 0; qt < p.nqt; ++qt, ++g) {
+            if (kt == 0) mbar_wait(&qdo_full[qt], it & 1);
+            tc_fence_after();
+            const uint32_t aQ = smem_u32(sQ + qt * kTileBytes), adO = smem_u32(sdO + qt * kTileBytes);
+            // ---- S = Q K^T, dP = dO V^T   (K = d = 64: four K-steps inside one 128-byte swizzle row)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16(tS, make_smem_desc_sw128(aQ + kk * 32, 16, 1024), make_smem_desc_sw128(aK + kk * 32, 16, 1024), id_sdp,
+                       kk > 0 ? 1u : 0u);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16(tdP, make_smem_desc_sw128(adO + kk * 32, 16, 1024), make_smem_desc_sw128(aV + kk * 32, 16, 1024), id_sdp,
+                       kk > 0 ? 1u : 0u);
+            umma_commit(sdp_full);
+            // ---- wait for P / dS
+            mbar_wait(ew_done, g & 1);
+            tc_fence_after();
+            if (qt == 0 && drains > 0) mbar_wait(dkv_free, (drains - 1) & 1);
+            if (kt == 0 && qt == 0 && it > 0) mbar_wait(dq_free, (it - 1) & 1);
+            tc_fence_after();
+            const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
+            const int qsteps = min(kTile, ceil16(p.S - qt * kTile)) >> 4;      // K-steps over query rows
+            const int ksteps = nkc >> 4;                                       // K-steps over keys
+            // dV += P^T dO ; dK += dS^T Q      (A MN-major: key atoms 16 KB apart; K-step = 16 q rows = 2048 B)
+            for (int ks = 0; ks < qsteps; ++ks)
+              umma_f16(tdV, make_smem_desc_sw128(aP + ks * 2048, 16384, 1024), make_smem_desc_sw128(adO + ks * 2048, 16384, 1024),
+                       id_dkv, (qt > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < qsteps; ++ks)
+              umma_f16(tdK, make_smem_desc_sw128(adS + ks * 2048, 16384, 1024), make_smem_desc_sw128(aQ + ks * 2048, 16384, 1024),
+                       id_dkv, (qt > 0 || ks > 0) ? 1u : 0u);
+            // dQ += dS K                        (A K-major: 4 K-steps per 64-key atom; B MN-major: K-step = 16 key rows)
+            for (int ks = 0; ks < ksteps; ++ks)
+              umma_f16(tdQ + 64 * qt, make_smem_desc_sw128(adS + (ks >> 2) * kTileBytes + (ks & 3) * 32, 16, 1024),
+                       make_smem_desc_sw128(aK + ks * 2048, 16384, 1024), id_dq, (kt > 0 || ks > 0) ? 1u : 0u);
+            umma_commit(pds_free);
+            if (qt == p.nqt - 1) {
+              umma_commit(dkv_full);
+              umma_commit(&kv_empty[buf]);
+              ++drains;
+            }
+            if (kt == p.nkt - 1) {
+              umma_commit(&qdo_empty[qt]);
+              if (qt == p.nqt - 1) umma_commit(dq_full);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // =============================== elementwise + drains ===============================
+    const int ew = warp - 2;                   // 0..7
+    const int quarter = warp & 3;              // TMEM lane quarter
+    const int half = ew >> 2;                  // column half
+    const int r = quarter * 32 + lane;         // row inside a tile
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const int sw = r & 7;
+    uint32_t it = 0, g = 0, drains = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const int b = item / p.H, h = item - b * p.H;
+      const int klen = p.key_len ? min(max(p.key_len[b], 1), p.S) : p.S;
+      const int64_t base = static_cast<int64_t>(b) * p.sb + static_cast<int64_t>(h) * p.sh;
+      float Dv[2] = {0.f, 0.f}, L2v[2] = {0.f, 0.f};
+      for (int kt = 0; kt < p.nkt; ++kt) {
+        const int nkc = min(kTile, ceil16(p.S - kt * kTile));
+        for (int qt = 0; qt < p.nqt; ++qt, ++g) {
+          const int qrow = qt * kTile + r;
+          const bool q_ok = qrow < p.S;
+          if (kt == 0) {
+            // D = rowsum(dO * O), lse in log2 units — once per (item, query tile)
+            mbar_wait(&qdo_full[qt], it & 1);
+            float d = 0.f, l2 = 0.f;
+            if (q_ok) {
+              const uint8_t* dorow = sdO + qt * kTileBytes + r * 128;
+              const uint4* orow = reinterpret_cast<const uint4*>(p.out + (static_cast<int64_t>(b) * p.S + qrow) * (p.H * 64) + h * 64);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint4 a = *reinterpret_cast<const uint4*>(dorow + ((j ^ sw) << 4));
+                const uint4 o = __ldg(orow + j);
+                d += bf16_lo(a.x) * bf16_lo(o.x) + bf16_hi(a.x) * bf16_hi(o.x) + bf16_lo(a.y) * bf16_lo(o.y) + bf16_hi(a.y) * bf16_hi(o.y) +
+                     bf16_lo(a.z) * bf16_lo(o.z) + bf16_hi(a.z) * bf16_hi(o.z) + bf16_lo(a.w) * bf16_lo(o.w) + bf16_hi(a.w) * bf16_hi(o.w);
+              }
+              l2 = p.lse[(static_cast<int64_t>(b) * p.H + h) * p.S + qrow] * 1.44269504088896341f;
+            }
+            if (qt == 0) { Dv[0] = d; L2v[0] = l2; } else { Dv[1] = d; L2v[1] = l2; }
+          }
+          const float Dq = qt == 0 ? Dv[0] : Dv[1];
+          const float Lq = qt == 0 ? L2v[0] : L2v[1];
+          mbar_wait(sdp_full, g & 1);
+          tc_fence_after();
+          bool waited_free = (g == 0);
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            const int col0 = half * 64 + c * 32;
+            if (col0 >= nkc) break;                                   // warp-uniform: nothing of this chunk is ever read
+            uint32_t sr[32], dr[32];
+            tmem_ld_32x32(tS + lane_off + col0, sr);
+            tmem_ld_32x32(tdP + lane_off + col0, dr);
+            tmem_ld_wait();
+            uint32_t pp[16], dd[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const int key = kt * kTile + col0 + j;
+              float p0 = exp2f(__uint_as_float(sr[j]) * p.scale_log2e - Lq);
+              float p1 = exp2f(__uint_as_float(sr[j + 1]) * p.scale_log2e - Lq);
+              p0 = (q_ok && key < klen) ? p0 : 0.f;
+              p1 = (q_ok && key + 1 < klen) ? p1 : 0.f;
+              const float d0 = p0 * (__uint_as_float(dr[j]) - Dq);
+              const float d1 = p1 * (__uint_as_float(dr[j + 1]) - Dq);
+              pp[j >> 1] = pack_bf16(p0, p1);
+              dd[j >> 1] = pack_bf16(d0, d1);
+            }
+            if (!waited_free) { mbar_wait(pds_free, (g - 1) & 1); waited_free = true; }
+            // 32 keys = four 16-byte chunks of this row inside key atom (col0 / 64)
+            const uint32_t rowoff = (col0 >> 6) * kTileBytes + r * 128;
+            const int ch0 = (col0 & 63) >> 3;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const uint32_t off = rowoff + (((ch0 + q4) ^ sw) << 4);
+              *reinterpret_cast<uint4*>(sP + off) = make_uint4(pp[4 * q4], pp[4 * q4 + 1], pp[4 * q4 + 2], pp[4 * q4 + 3]);
+              *reinterpret_cast<uint4*>(sdS + off) = make_uint4(dd[4 * q4], dd[4 * q4 + 1], dd[4 * q4 + 2], dd[4 * q4 + 3]);
+            }
+          }
+          if (!waited_free) mbar_wait(pds_free, (g - 1) & 1);         // keep every waiter in phase lock-step
+          tc_fence_before();
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ew_done);
+
+          if (qt == p.nqt - 1) {
+            // ---- drain dV, dK of key tile kt: thread = key row, this warp's 32 of the 64 d-columns
+            mbar_wait(dkv_full, drains & 1);
+            tc_fence_after();
+            uint32_t a[32], c2[32];
+            tmem_ld_32x32(tdV + lane_off + half * 32, a);
+            tmem_ld_32x32(tdK + lane_off + half * 32, c2);
+            tmem_ld_wait();
+            const int key = kt * kTile + r;
+            if (key < p.S) {
+              __nv_bfloat16* pv = p.dv + base + static_cast<int64_t>(key) * p.ss + half * 32;
+              __nv_bfloat16* pk = p.dk + base + static_cast<int64_t>(key) * p.ss + half * 32;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 u, w;
+                u.x = pack_bf16(__uint_as_float(a[8 * j]), __uint_as_float(a[8 * j + 1]));
+                u.y = pack_bf16(__uint_as_float(a[8 * j + 2]), __uint_as_float(a[8 * j + 3]));
+                u.z = pack_bf16(__uint_as_float(a[8 * j + 4]), __uint_as_float(a[8 * j + 5]));
+                u.w = pack_bf16(__uint_as_float(a[8 * j + 6]), __uint_as_float(a[8 * j + 7]));
+                w.x = pack_bf16(__uint_as_float(c2[8 * j]) * p.scale, __uint_as_float(c2[8 * j + 1]) * p.scale);
+                w.y = pack_bf16(__uint_as_float(c2[8 * j + 2]) * p.scale, __uint_as_float(c2[8 * j + 3]) * p.scale);
+                w.z = pack_bf16(__uint_as_float(c2[8 * j + 4]) * p.scale, __uint_as_float(c2[8 * j + 5]) * p.scale);
+                w.w = pack_bf16(__uint_as_float(c2[8 * j + 6]) * p.scale, __uint_as_float(c2[8 * j + 7]) * p.scale);
+                reinterpret_cast<uint4*>(pv)[j] = u;
+                reinterpret_cast<uint4*>(pk)[j] = w;
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dkv_free);
+            ++drains;
+            if (kt == p.nkt - 1) {
+              // ---- drain dQ of both query tiles
+              mbar_wait(dq_full, it & 1);
+              tc_fence_after();
+              for (int t = 0; t < p.nqt; ++t) {
+                uint32_t a2[32];
+                tmem_ld_32x32(tdQ + 64 * t + lane_off + half * 32, a2);
+                tmem_ld_wait();
+                const int qr = t * kTile + r;
+                if (qr < p.S) {
+                  __nv_bfloat16* pq = p.dq + base + static_cast<int64_t>(qr) * p.ss + half * 32;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    uint4 u;
+                    u.x = pack_bf16(__uint_as_float(a2[8 * j]) * p.scale, __uint_as_float(a2[8 * j + 1]) * p.scale);
+                    u.y = pack_bf16(__uint_as_float(a2[8 * j + 2]) * p.scale, __uint_as_float(a2[8 * j + 3]) * p.scale);
+                    u.z = pack_bf16(__uint_as_float(a2[8 * j + 4]) * p.scale, __uint_as_float(a2[8 * j + 5]) * p.scale);
+                    u.w = pack_bf16(__uint_as_float(a2[8 * j + 6]) * p.scale, __uint_as_float(a2[8 * j + 7]) * p.scale);
+                    reinterpret_cast<uint4*>(pq)[j] = u;
+                  }
+                }
+              }
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(dq_free);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn4)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// {64 d, H heads, S tokens, B batch} bf16 view of a (batch, token, head)-strided tensor; box = 128 tokens of one head
+static int make_tmap_bshd(CUtensorMap* m, const void* ptr, int B, int H, int S, int64_t sb, int64_t ss, int64_t sh) {
+  static EncodeTiledFn4 enc = nullptr;
+  if (!enc) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled not available");
+      return SIMSEG_ERR_CUDA;
+    }
+    enc = reinterpret_cast<EncodeTiledFn4>(f);
+  }
+  cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(sh) * 2, static_cast<cuuint64_t>(ss) * 2, static_cast<cuuint64_t>(sb) * 2};
+  cuuint32_t box[4] = {64, 1, kTile, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4d) failed (%d): ptr=%p B=%d H=%d S=%d sb=%lld ss=%lld sh=%lld", static_cast<int>(r), ptr, B, H, S,
+              static_cast<long long>(sb), static_cast<long long>(ss), static_cast<long long>(sh));
+    return SIMSEG_ERR_CUDA;
+  }
+  return SIMSEG_OK;
+}
+
+// SIMSEG_ERR_UNSUPPORTED => caller uses the mma.sync kernel (S > 256, unaligned pointers, H == 1 with odd strides ...)
+int attention_bwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v, const void* out, const void* dout,
+                          const float* lse, int64_t sb, int64_t ss, int64_t sh, int B, int H, int S, const int32_t* key_len,
+                          float scale, void* dq, void* dk, void* dv, cudaStream_t st) {
+  if (S > 256 || S < 1) return SIMSEG_ERR_UNSUPPORTED;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+                       reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dq) |
+                       reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv);
+  if ((al & 15) || sb % 8 || ss % 8 || sh % 8) return SIMSEG_ERR_UNSUPPORTED;
+  if ((H > 1 && sh * 2 >= (int64_t(1) << 40)) || ss * 2 >= (int64_t(1) << 40)) return SIMSEG_ERR_UNSUPPORTED;
+  CUtensorMap tq, tk, tv, tdo;
+  int rc;
+  if ((rc = make_tmap_bshd(&tq, q, B, H, S, sb, ss, sh))) return rc;
+  if ((rc = make_tmap_bshd(&tk, k, B, H, S, sb, ss, sh))) return rc;
+  if ((rc = make_tmap_bshd(&tv, v, B, H, S, sb, ss, sh))) return rc;
+  if ((rc = make_tmap_bshd(&tdo, dout, B, H, S, static_cast<int64_t>(S) * H * 64, static_cast<int64_t>(H) * 64, 64))) return rc;
+  AttnBwdParams p{};
+  p.B = B; p.H = H; p.S = S;
+  p.nqt = (S + kTile - 1) / kTile; p.nkt = p.nqt;
+  p.items = B * H;
+  p.scale = scale; p.scale_log2e = scale * 1.44269504088896341f;
+  p.key_len = key_len; p.lse = lse; p.out = reinterpret_cast<const __nv_bfloat16*>(out);
+  p.dq = reinterpret_cast<__nv_bfloat16*>(dq); p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dv = reinterpret_cast<__nv_bfloat16*>(dv);
+  p.sb = sb; p.ss = ss; p.sh = sh;
+  const int smem_bytes = 1024 + 8 * kTileBytes + 2 * kPBytes + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SIMSEG_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_set = true;
+  }
+  const int grid = p.items < ctx->num_sms ? p.items : ctx->num_sms;
+  attention_bwd_tc_kernel<<<grid, kAbThreads, smem_bytes, st>>>(tq, tk, tv, tdo, p);
+  ctx->launches++;
+  SIMSEG_LAUNCH_CHECK();
+  return SIMSEG_OK;
+}
+
+}  // namespace simseg

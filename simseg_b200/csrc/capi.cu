@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <cstring>
+#include <cstdlib>
 
 namespace simseg {
 
@@ -35,6 +36,7 @@ int nce_rows_bwd_impl(Ctx*, float*, int, int, int64_t, const float*, int, const 
 int row_inv_norm_impl(Ctx*, const void*, int, int64_t, int, float*, cudaStream_t);
 int row_argmax_impl(Ctx*, const float*, int64_t, int, int32_t*, cudaStream_t);
 int retrieval_rank_impl(Ctx*, const float*, int, int, const int64_t*, const int64_t*, int32_t*, cudaStream_t);
+int attention_bwd_tc_impl(Ctx*, const void*, const void*, const void*, const void*, const void*, const float*, int64_t, int64_t, int64_t, int, int, int, const int32_t*, float, void*, void*, void*, cudaStream_t);
 int patch_sim_fused_impl(Ctx*, const void*, int64_t, int, const void*, int, int, float*, int32_t*, cudaStream_t);
 
 // fp32 product in the requested precision: C[M,N] (+)= A(m,k) B(n,k)
@@ -130,6 +132,14 @@ int simseg_attention_bwd(simseg_ctx* ctx, const void* q, const void* k, const vo
                          const float* lse, int64_t stride_b, int64_t stride_s, int64_t stride_h, int B, int H, int S,
                          const int32_t* key_len, float scale, void* dq, void* dk, void* dv, void* stream) {
   CTX_OR_FAIL();
+  // tcgen05 kernel for S <= 256 (attention_sm100.cu); longer sequences and shapes it rejects run the mma.sync kernel.
+  // SIMSEG_ATTN_BWD=mma|tc overrides the choice (tests exercise both).
+  const char* force = getenv("SIMSEG_ATTN_BWD");
+  const bool want_tc = force ? (force[0] == 't') : (S >= 96);
+  if (want_tc) {
+    const int rc = attention_bwd_tc_impl(c, q, k, v, out, dout, lse, stride_b, stride_s, stride_h, B, H, S, key_len, scale, dq, dk, dv, st);
+    if (rc != SIMSEG_ERR_UNSUPPORTED) return rc;
+  }
   return attention_bwd_impl(c, q, k, v, out, dout, lse, stride_b, stride_s, stride_h, B, H, S, key_len, scale, dq, dk, dv, st);
 }
 int simseg_im2col16(simseg_ctx* ctx, const float* image, int B, int Hi, int Wi, void* patches, void* stream) {

@@ -188,6 +188,44 @@ def test_attention(cuda, B, H, S, masked):
         assert _rel(dqkv[:, :, i], r) < 2.5e-2, name
 
 
+@pytest.mark.parametrize("impl", ["tc", "mma"])
+@pytest.mark.parametrize("B,H,S,masked", [(3, 6, 197, False), (2, 12, 256, True), (7, 12, 25, True), (4, 12, 77, True),
+                                          (2, 2, 129, True), (40, 6, 197, False), (3, 1, 128, False)])
+def test_attention_bwd_both_kernels(cuda, impl, B, H, S, masked):
+    """Backward through the tcgen05 kernel (S <= 256) and through the mma.sync kernel, selected explicitly; more work
+    items than SMs (40 x 6 heads) exercises the persistent loop, the buffer recycling and every barrier phase."""
+    import os
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(S + B)
+    D = H * 64
+    qkv = (torch.randn(B, S, 3, H, 64, device=cuda, generator=g)).bfloat16()
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    strides = (S * 3 * D, 3 * D, 64)
+    klen = None
+    if masked:
+        klen = torch.randint(1, S + 1, (B,), device=cuda, generator=g, dtype=torch.int32)
+        klen[0] = S
+    out, lse = ops.attention_fwd(q, k, v, B, H, S, strides, klen, 0.125)
+    qf, kf, vf = [t.float().permute(0, 2, 1, 3).detach().requires_grad_(True) for t in (q, k, v)]
+    s = (qf @ kf.transpose(-1, -2)) * 0.125
+    if masked:
+        km = torch.arange(S, device=cuda)[None] >= klen[:, None]
+        s = s.masked_fill(km[:, None, None, :], float("-inf"))
+    ref_o = (torch.softmax(s, -1) @ vf).permute(0, 2, 1, 3).reshape(B, S, D)
+    dout = torch.randn(B, S, D, device=cuda, generator=g).bfloat16()
+    ref_o.backward(dout.float())
+    dqkv = torch.full_like(qkv, float("nan"))
+    os.environ["SIMSEG_ATTN_BWD"] = impl
+    try:
+        ops.attention_bwd(q, k, v, out, dout, lse, B, H, S, strides, klen, 0.125, dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2])
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("SIMSEG_ATTN_BWD", None)
+    assert torch.isfinite(dqkv.float()).all()
+    for i, (name, t) in enumerate((("dq", qf), ("dk", kf), ("dv", vf))):
+        assert _rel(dqkv[:, :, i], t.grad.permute(0, 2, 1, 3)) < 2.5e-2, name
+
+
 def test_embeddings(cuda):
     ops = _ops()
     g = torch.Generator(device="cuda").manual_seed(1)
