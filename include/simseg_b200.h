@@ -56,7 +56,7 @@ int64_t simseg_ctx_launch_count(simseg_ctx* ctx, int reset);
 #define SIMSEG_EPI_NONE 0          /* D = acc (+bias)                                     */
 #define SIMSEG_EPI_BIAS_GELU 1     /* aux(bf16, optional) = acc+bias ; D = gelu_erf(acc+bias) */
 #define SIMSEG_EPI_BIAS_RESIDUAL 2 /* D = acc + bias + residual(f32 or bf16, dtype res_dtype) */
-#define SIMSEG_EPI_DGELU 3         /* D = acc * gelu_erf'(aux[m,n])   (aux = saved pre-activation) */
+#define SIMSEG_EPI_DGELU 3         /* D = acc * gelu_erf'(aux[m,n])   (aux = saved pre-activation) ; aux2 = gelu_erf(aux) */
 #define SIMSEG_EPI_ROWSCALE 4      /* D = acc * row_scale[m]                              */
 
 typedef struct simseg_gemm_args {
@@ -79,8 +79,11 @@ typedef struct simseg_gemm_args {
   const float* row_scale; /* [M] for ROWSCALE */
   float* col_sum;         /* optional [N] fp32: atomically accumulates column sums of the fp32
                              epilogue result (bias gradients) ; NULL = off */
-  int32_t tile_n;         /* 0 = auto; else 64/128/192/256 */
+  int32_t tile_n;         /* 0 = auto; else 128/192/256 */
   int32_t reserved;
+  void* aux2;             /* DGELU only, optional [M,N] bf16 out: gelu_erf(aux) (the activation the following
+                             wgrad needs), produced by the same epilogue instead of a separate recompute pass */
+  int64_t ld_aux2;
 } simseg_gemm_args;
 
 int simseg_gemm(simseg_ctx* ctx, const simseg_gemm_args* args, void* stream);
@@ -100,6 +103,12 @@ int simseg_gelu_fwd(simseg_ctx* ctx, const void* h, void* a, int64_t n, void* st
 int simseg_layernorm_fwd(simseg_ctx* ctx, const void* x, int x_dtype, const float* gamma, const float* beta,
                          float eps, int64_t M, int D, void* y_bf16, float* y_f32, float* mean, float* rstd,
                          void* stream);
+/* Residual add fused with the LayerNorm that follows it (timm Block: x + attn(..) -> norm2, x + mlp(..) -> next norm1;
+ * HF BertSelfOutput / BertOutput: LayerNorm(dense(..) + input)):  s = x (f32) + add (bf16 output of the Linear, exactly
+ * what the reference's autocast produces) ; sum_out (f32, optional) = s ; y = LayerNorm(s). */
+int simseg_add_layernorm_fwd(simseg_ctx* ctx, const float* x, const void* add_bf16, const float* gamma, const float* beta,
+                             float eps, int64_t M, int D, float* sum_out, void* y_bf16, float* y_f32, float* mean, float* rstd,
+                             void* stream);
 /* dx[M,D] (f32) = LN backward ; if dx_accumulate, dx += (residual-gradient accumulation);
  * dgamma/dbeta [D] fp32 are ACCUMULATED atomically (zero them first).
  * dy: f32 or bf16; optional second upstream gradient dy2 (f32, may be NULL) is added to dy first.

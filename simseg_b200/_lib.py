@@ -24,7 +24,7 @@ class GemmArgs(C.Structure):
                 ("in_dtype", i32), ("out_dtype", i32), ("epilogue", i32), ("accumulate", i32),
                 ("bias", vp), ("residual", vp), ("ld_res", i64), ("res_dtype", i32),
                 ("aux", vp), ("ld_aux", i64), ("row_scale", vp), ("col_sum", vp),
-                ("tile_n", i32), ("reserved", i32)]
+                ("tile_n", i32), ("reserved", i32), ("aux2", vp), ("ld_aux2", i64)]
 
 
 # name -> (restype, argtypes); every symbol include/simseg_b200.h declares
@@ -39,6 +39,7 @@ PROTOTYPES = {
     "simseg_colsum": (i32, [vp, vp, i32, i64, i64, i64, vp, i32, vp]),
     "simseg_gelu_fwd": (i32, [vp, vp, vp, i64, vp]),
     "simseg_layernorm_fwd": (i32, [vp, vp, i32, vp, vp, f32, i64, i32, vp, vp, vp, vp, vp]),
+    "simseg_add_layernorm_fwd": (i32, [vp, vp, vp, vp, vp, f32, i64, i32, vp, vp, vp, vp, vp, vp]),
     "simseg_layernorm_bwd": (i32, [vp, vp, i32, vp, vp, i32, vp, vp, vp, i64, i32, vp, i32, vp, vp, vp, vp, vp]),
     "simseg_attention_fwd": (i32, [vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp, f32, vp, vp, vp]),
     "simseg_attention_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp, f32, vp, vp, vp, vp]),

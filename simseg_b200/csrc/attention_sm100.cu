@@ -46,6 +46,11 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
 }
 
 __device__ __forceinline__ int ceil16(int x) { return (x + 15) & ~15; }
+__device__ __forceinline__ float ex2_approx(float x) {       // MUFU.EX2, 2 ulp; arguments here are <= 0 up to rounding
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __global__ void __launch_bounds__(kAbThreads, 1)
 attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -201,20 +206,28 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           const int qrow = qt * kTile + r;
           const bool q_ok = qrow < p.S;
           if (kt == 0) {
-            // D = rowsum(dO * O), lse in log2 units — once per (item, query tile)
-            mbar_wait(&qdo_full[qt], it & 1);
-            float d = 0.f, l2 = 0.f;
+            // D = rowsum(dO * O), lse in log2 units — once per (item, query tile).  The O row and lse are fetched from
+            // global BEFORE waiting for the dO tile so their latency overlaps the TMA wait.
+            uint4 o[8];
+            float l2 = 0.f;
             if (q_ok) {
-              const uint8_t* dorow = sdO + qt * kTileBytes + r * 128;
               const uint4* orow = reinterpret_cast<const uint4*>(p.out + (static_cast<int64_t>(b) * p.S + qrow) * (p.H * 64) + h * 64);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const uint4 a = *reinterpret_cast<const uint4*>(dorow + ((j ^ sw) << 4));
-                const uint4 o = __ldg(orow + j);
-                d += bf16_lo(a.x) * bf16_lo(o.x) + bf16_hi(a.x) * bf16_hi(o.x) + bf16_lo(a.y) * bf16_lo(o.y) + bf16_hi(a.y) * bf16_hi(o.y) +
-                     bf16_lo(a.z) * bf16_lo(o.z) + bf16_hi(a.z) * bf16_hi(o.z) + bf16_lo(a.w) * bf16_lo(o.w) + bf16_hi(a.w) * bf16_hi(o.w);
-              }
-              l2 = p.lse[(static_cast<int64_t>(b) * p.H + h) * p.S + qrow] * 1.44269504088896341f;
+              for (int j = 0; j < 8; ++j) o[j] = __ldg(orow + j);
+              l2 = __ldg(p.lse + (static_cast<int64_t>(b) * p.H + h) * p.S + qrow) * 1.44269504088896341f;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = make_uint4(0, 0, 0, 0);
+            }
+            mbar_wait(&qdo_full[qt], it & 1);
+            float d = 0.f;
+            const uint8_t* dorow = sdO + qt * kTileBytes + r * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 a = *reinterpret_cast<const uint4*>(dorow + ((j ^ sw) << 4));
+              d += bf16_lo(a.x) * bf16_lo(o[j].x) + bf16_hi(a.x) * bf16_hi(o[j].x) + bf16_lo(a.y) * bf16_lo(o[j].y) +
+                   bf16_hi(a.y) * bf16_hi(o[j].y) + bf16_lo(a.z) * bf16_lo(o[j].z) + bf16_hi(a.z) * bf16_hi(o[j].z) +
+                   bf16_lo(a.w) * bf16_lo(o[j].w) + bf16_hi(a.w) * bf16_hi(o[j].w);
             }
             if (qt == 0) { Dv[0] = d; L2v[0] = l2; } else { Dv[1] = d; L2v[1] = l2; }
           }
@@ -235,8 +248,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               const int key = kt * kTile + col0 + j;
-              float p0 = exp2f(__uint_as_float(sr[j]) * p.scale_log2e - Lq);
-              float p1 = exp2f(__uint_as_float(sr[j + 1]) * p.scale_log2e - Lq);
+              float p0 = ex2_approx(fmaf(__uint_as_float(sr[j]), p.scale_log2e, -Lq));
+              float p1 = ex2_approx(fmaf(__uint_as_float(sr[j + 1]), p.scale_log2e, -Lq));
               p0 = (q_ok && key < klen) ? p0 : 0.f;
               p1 = (q_ok && key + 1 < klen) ? p1 : 0.f;
               const float d0 = p0 * (__uint_as_float(dr[j]) - Dq);

@@ -19,7 +19,7 @@ int gemm_impl(Ctx*, const simseg_gemm_args*, cudaStream_t);
 int cast_bf16_impl(Ctx*, const float*, void*, void*, int64_t, int64_t, cudaStream_t);
 int colsum_impl(Ctx*, const void*, int, int64_t, int64_t, int64_t, float*, int, cudaStream_t);
 int gelu_fwd_impl(Ctx*, const void*, void*, int64_t, cudaStream_t);
-int layernorm_fwd_impl(Ctx*, const void*, int, const float*, const float*, float, int64_t, int, void*, float*, float*, float*, cudaStream_t);
+int layernorm_fwd_impl(Ctx*, const void*, int, const float*, const float*, float, int64_t, int, void*, float*, float*, float*, const void*, float*, cudaStream_t);
 int layernorm_bwd_impl(Ctx*, const void*, int, const float*, const void*, int, const float*, const float*, const float*, int64_t, int, float*, int, void*, float*, float*, float*, cudaStream_t);
 int attention_fwd_impl(Ctx*, const void*, const void*, const void*, int64_t, int64_t, int64_t, int, int, int, const int32_t*, float, void*, float*, cudaStream_t);
 int attention_bwd_impl(Ctx*, const void*, const void*, const void*, const void*, const void*, const float*, int64_t, int64_t, int64_t, int, int, int, const int32_t*, float, void*, void*, void*, cudaStream_t);
@@ -113,7 +113,14 @@ int simseg_gelu_fwd(simseg_ctx* ctx, const void* h, void* a, int64_t n, void* st
 int simseg_layernorm_fwd(simseg_ctx* ctx, const void* x, int x_dtype, const float* gamma, const float* beta, float eps,
                          int64_t M, int D, void* y_bf16, float* y_f32, float* mean, float* rstd, void* stream) {
   CTX_OR_FAIL();
-  return layernorm_fwd_impl(c, x, x_dtype, gamma, beta, eps, M, D, y_bf16, y_f32, mean, rstd, st);
+  return layernorm_fwd_impl(c, x, x_dtype, gamma, beta, eps, M, D, y_bf16, y_f32, mean, rstd, nullptr, nullptr, st);
+}
+int simseg_add_layernorm_fwd(simseg_ctx* ctx, const float* x, const void* add_bf16, const float* gamma, const float* beta,
+                             float eps, int64_t M, int D, float* sum_out, void* y_bf16, float* y_f32, float* mean, float* rstd,
+                             void* stream) {
+  CTX_OR_FAIL();
+  SIMSEG_CHECK_ARG(x != nullptr && add_bf16 != nullptr, "add_layernorm_fwd: x and add are required");
+  return layernorm_fwd_impl(c, x, SIMSEG_F32, gamma, beta, eps, M, D, y_bf16, y_f32, mean, rstd, add_bf16, sum_out, st);
 }
 int simseg_layernorm_bwd(simseg_ctx* ctx, const void* dy, int dy_dtype, const float* dy2, const void* x, int x_dtype,
                          const float* gamma, const float* mean, const float* rstd, int64_t M, int D, float* dx,

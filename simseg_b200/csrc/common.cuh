@@ -61,14 +61,34 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-// exact-erf GELU, fp32 (erff is accurate to ~1 ulp; the reference uses nn.GELU() default = erf)
+// erf-GELU (the reference's nn.GELU() default) and its derivative, fp32.  erf uses Abramowitz-Stegun 7.1.26
+// (|abs err| <= 1.5e-7, far below the bf16 resolution of every consumer) so one MUFU.RCP + one MUFU.EX2 serve both
+// gelu(x) = x*Phi(x) and gelu'(x) = Phi(x) + x*phi(x):  exp(-x^2/2) is shared between erf(x/sqrt2) and phi(x).
+__device__ __forceinline__ void gelu_erf_both(float x, float& gelu, float& dgelu) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float e;                                             // exp(-z^2) = exp(-x^2/2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.44269504088896341f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float erfc_half = 0.5f * poly * e;             // 0.5 * erfc(|x|/sqrt2)
+  const float cdf = x >= 0.f ? 1.0f - erfc_half : erfc_half;
+  gelu = x * cdf;
+  dgelu = fmaf(x * 0.3989422804014327f, e, cdf);
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  float g, d;
+  gelu_erf_both(x, g, d);
+  return g;
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float g, d;
+  gelu_erf_both(x, g, d);
+  return d;
 }
 
 // 128-bit streaming loads/stores

@@ -14,15 +14,20 @@
 #include "common.cuh"
 #include "sm100.cuh"
 
+#include <cstring>
 #include <mutex>
 
 namespace simseg {
 
 using namespace sm100;
 
+#ifndef SIMSEG_STAGES256
+#define SIMSEG_STAGES256 4
+#endif
 constexpr int kBM = 128;           // tile rows = TMEM lanes
 constexpr int kSwizzleBytes = 128;  // one swizzle atom row = one K block (K-major) / 64 MN elements (bf16)
 constexpr int kNumEpiWarps = 8;
+constexpr int kStgTileBytes = kBM * 128;   // epilogue staging tile: 128 rows x 64 bf16, SWIZZLE_128B (TMA store/load box)
 constexpr int kGemmThreads = 32 * (2 + kNumEpiWarps);
 
 struct GemmParams {
@@ -43,6 +48,8 @@ struct GemmParams {
   const float* row_scale;
   float* col_sum;
   int32_t vec_ok;          // 16-byte aligned rows for d / residual / aux
+  int32_t tma_epi;         // bf16 output through swizzled smem staging + TMA store (coalesced), else direct stores
+  void* aux2;              // DGELU only: gelu(aux) written next to the gradient (bf16 [M,N])
   int32_t a_3d, b_3d;      // MN-major operand loaded with one 3-D TMA box per k-block
   int32_t dbg;             // bench-only: 1 = no TMA after the ring is primed, 2 = no MMA (results are garbage)
 };
@@ -52,26 +59,208 @@ struct GemmCfg {
   static constexpr int kABytes = kBM * kSwizzleBytes;          // 16 KB
   static constexpr int kBBytes = BN * kSwizzleBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN <= 128) ? 6 : (BN <= 192 ? 5 : 4);
+  // ring depth: measured on B200 the BN=256 mainloop is as fast with 3 stages as with 4 (it is L2-fabric bound, not
+  // latency bound), which leaves 64 KB for the epilogue staging tiles
+  static constexpr int kStages = (BN <= 128) ? 5 : (BN <= 192 ? 4 : 3);
   static constexpr int kAccStride = (BN <= 128) ? 128 : 256;    // TMEM columns between the two accumulators
   static constexpr int kTmemCols = 2 * kAccStride;              // 256 or 512 (power of two)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 4 * kStgTileBytes;       // four [128 rows][128 B] swizzled epilogue tiles
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4;
 };
+
+
+// ------------------------------------------------------------------------------------------------
+// Coalesced epilogue for bf16 outputs: TMEM -> registers -> fused math -> 128B-swizzled smem tile [128 rows][64 cols]
+// -> TMA store.  All 8 epilogue warps work on one 64-column chunk at a time (warp = TMEM lane quarter x 32-column
+// half); thread = one output row, so every smem access is a conflict-free 16-byte chunk of the thread's own row.
+//   EPI_NONE      out = acc (+bias)                                   staging tiles rotate over 4 slots
+//   EPI_BIAS_GELU aux = bf16(acc+bias) ; out = gelu(aux)              two stores per chunk, 2 x 2 slots
+//   EPI_DGELU     out = acc * gelu'(aux) ; aux2 = gelu(aux) ; column sums of out
+//                 aux tiles are TMA-LOADED two chunks ahead into a 3-slot ring; gelu(aux) overwrites the tile in place
+//                 and is TMA-stored from there (the backward pass never runs a separate GELU recompute kernel)
+__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tma(const GemmParams& p, const CUtensorMap& tmap_d, const CUtensorMap& tmap_x,
+                                             const CUtensorMap& tmap_x2, uint8_t* stg, uint64_t* acc_full, uint64_t* acc_empty,
+                                             uint64_t* aux_full, float* s_cs, uint32_t tmem_base, int total_tiles, int tiles_mn,
+                                             int warp, int lane) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kCh = BN / 64;
+  const int ew = warp - 2;
+  const int quarter = warp & 3;
+  const int half = ew >> 2;
+  const int r = quarter * 32 + lane;
+  const int sw = r & 7;
+  const bool elected = (ew == 0 && lane == 0);
+  const uint32_t row_off = static_cast<uint32_t>(r) * 128;
+  const int tid = ew * 32 + lane;                                   // 0..255 among the epilogue threads
+  uint32_t cc = 0;                                                  // flat chunk counter over (tile, chunk)
+
+  auto chunk_coords = [&](uint32_t f, int& m0, int& ncol) -> bool {
+    const int tile = static_cast<int>(blockIdx.x) + static_cast<int>(f / kCh) * static_cast<int>(gridDim.x);
+    if (tile >= total_tiles) return false;
+    const int mn = tile % tiles_mn;
+    m0 = (mn / p.n_tiles) * kBM;
+    ncol = (mn % p.n_tiles) * BN + static_cast<int>(f % kCh) * 64;
+    return true;
+  };
+  if (EPI == SIMSEG_EPI_DGELU && elected) {
+    for (uint32_t f = 0; f < 2; ++f) {
+      int m0, nc;
+      if (chunk_coords(f, m0, nc)) {
+        mbar_arrive_expect_tx(&aux_full[f % 3], kStgTileBytes);
+        tma_load_2d(stg + (1 + f % 3) * kStgTileBytes, &tmap_x, &aux_full[f % 3], nc, m0);
+      }
+    }
+  }
+
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int mn = tile % tiles_mn;
+    const int m0 = (mn / p.n_tiles) * kBM;
+    const int n0 = (mn % p.n_tiles) * BN;
+    mbar_wait(&acc_full[acc], acc_phase);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < kCh; ++c, ++cc) {
+      const int col_in_tile = c * 64 + half * 32;
+      const int col0 = n0 + col_in_tile;
+      uint32_t rr[32];
+      tmem_ld_32x32(t_row + col_in_tile, rr);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+      if (p.bias != nullptr) {
+        if (col0 + 32 <= p.N) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+        }
+      }
+      int out_slot, x_slot;
+      if (EPI == SIMSEG_EPI_BIAS_GELU) { x_slot = 2 * (cc & 1); out_slot = x_slot + 1; }
+      else if (EPI == SIMSEG_EPI_DGELU) { out_slot = 0; x_slot = 1 + static_cast<int>(cc % 3); }
+      else { out_slot = static_cast<int>(cc & 3); x_slot = 0; }
+      uint8_t* so = stg + out_slot * kStgTileBytes + row_off;
+      uint8_t* sx = stg + x_slot * kStgTileBytes + row_off;
+      uint32_t xo[16];                                              // second bf16 output of this row chunk (aux / aux2)
+      if (EPI == SIMSEG_EPI_BIAS_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          xo[j >> 1] = pack_bf16(v[j], v[j + 1]);                   // pre-activation, bf16 — exactly what backward reads
+          v[j] = gelu_erf(bf16_lo(xo[j >> 1]));
+          v[j + 1] = gelu_erf(bf16_hi(xo[j >> 1]));
+        }
+      } else if (EPI == SIMSEG_EPI_DGELU) {
+        mbar_wait(&aux_full[cc % 3], (cc / 3) & 1);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const uint4 u = *reinterpret_cast<const uint4*>(sx + (((half * 4 + q4) ^ sw) << 4));
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float g0, a0, g1, a1;
+            gelu_erf_both(bf16_lo(w[e]), a0, g0);
+            gelu_erf_both(bf16_hi(w[e]), a1, g1);
+            v[8 * q4 + 2 * e] *= g0;
+            v[8 * q4 + 2 * e + 1] *= g1;
+            xo[4 * q4 + e] = pack_bf16(a0, a1);
+          }
+        }
+      }
+      uint32_t o[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) o[j >> 1] = pack_bf16(v[j], v[j + 1]);
+      if (EPI == SIMSEG_EPI_DGELU && p.col_sum != nullptr) {
+        // column sums over this warp's 32 rows (butterfly transpose-reduce), then one shared-memory add per column
+#pragma unroll
+        for (int o2 = 16; o2 >= 1; o2 >>= 1) {
+          const bool upper = (lane & o2) != 0;
+#pragma unroll
+          for (int j = 0; j < o2; ++j) {
+            const float mine = upper ? v[j + o2] : v[j];
+            const float send = upper ? v[j] : v[j + o2];
+            v[j] = mine + __shfl_xor_sync(0xffffffffu, send, o2);
+          }
+        }
+        atomicAdd(&s_cs[col_in_tile + lane], v[0]);
+      }
+      // ---- staging slot must have been read by the TMA store that last used it
+      if (elected) {
+        if (EPI == SIMSEG_EPI_BIAS_GELU) tma_store_wait_read<1>();
+        else if (EPI == SIMSEG_EPI_DGELU) tma_store_wait_read<0>();
+        else tma_store_wait_read<3>();
+        if (EPI == SIMSEG_EPI_DGELU) {
+          int m2, nc2;
+          if (chunk_coords(cc + 2, m2, nc2)) {                       // slot (cc+2)%3 == (cc-1)%3: just released
+            mbar_arrive_expect_tx(&aux_full[(cc + 2) % 3], kStgTileBytes);
+            tma_load_2d(stg + (1 + (cc + 2) % 3) * kStgTileBytes, &tmap_x, &aux_full[(cc + 2) % 3], nc2, m2);
+          }
+        }
+      }
+      epi_bar(1);
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const uint32_t off = ((half * 4 + q4) ^ sw) << 4;
+        *reinterpret_cast<uint4*>(so + off) = make_uint4(o[4 * q4], o[4 * q4 + 1], o[4 * q4 + 2], o[4 * q4 + 3]);
+        if ((EPI == SIMSEG_EPI_BIAS_GELU && p.aux != nullptr) || (EPI == SIMSEG_EPI_DGELU && p.aux2 != nullptr))
+          *reinterpret_cast<uint4*>(sx + off) = make_uint4(xo[4 * q4], xo[4 * q4 + 1], xo[4 * q4 + 2], xo[4 * q4 + 3]);
+      }
+      fence_proxy_async_smem();
+      epi_bar(2);
+      if (elected) {
+        tma_store_2d(&tmap_d, stg + out_slot * kStgTileBytes, n0 + c * 64, m0);
+        if (EPI == SIMSEG_EPI_BIAS_GELU && p.aux != nullptr) tma_store_2d(&tmap_x, stg + x_slot * kStgTileBytes, n0 + c * 64, m0);
+        if (EPI == SIMSEG_EPI_DGELU && p.aux2 != nullptr) tma_store_2d(&tmap_x2, stg + x_slot * kStgTileBytes, n0 + c * 64, m0);
+        tma_store_commit();
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&acc_empty[acc]);
+    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    if (EPI == SIMSEG_EPI_DGELU && p.col_sum != nullptr) {
+      // every warp's shared-memory adds of this tile happened before the last epi_bar(1): flush and clear
+      if (tid < BN) {
+        const float x = s_cs[tid];
+        s_cs[tid] = 0.f;
+        if (n0 + tid < p.N) atomicAdd(p.col_sum + n0 + tid, x);
+      }
+      epi_bar(1);
+    }
+  }
+  if (elected) tma_store_wait<0>();
+}
 
 // ------------------------------------------------------------------------------------------------
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_x,
+            const __grid_constant__ CUtensorMap tmap_x2, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B (descriptor base_offset = 0)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* stg = smem + Cfg::kStages * Cfg::kStageBytes;      // 4 staging tiles (1024-byte aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;                       // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]  MMA -> TMA
   uint64_t* acc_full = bars + 2 * Cfg::kStages;    // [2]        MMA -> epilogue
   uint64_t* acc_empty = acc_full + 2;              // [2]        epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* aux_full = acc_empty + 2;              // [3]        TMA (aux-in tiles of the DGELU epilogue) -> epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 3);
+  float* s_cs = reinterpret_cast<float*>(bars + 32);           // [BN] per-tile column sums
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -87,12 +276,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], kNumEpiWarps);
     }
+    for (int s = 0; s < 3; ++s) mbar_init(&aux_full[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  if (threadIdx.x >= 64 && threadIdx.x - 64 < BN) s_cs[threadIdx.x - 64] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -202,6 +393,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   } else {
     // =============================== epilogue ===============================
+    if (p.tma_epi) {
+      epilogue_tma<BN, EPI>(p, tmap_d, tmap_x, tmap_x2, stg, acc_full, acc_empty, aux_full, s_cs, tmem_base, total_tiles, tiles_mn, warp, lane);
+    } else {
     const int ew = warp - 2;                 // 0..7
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int half = ew >> 2;                // column half handled by this warp
@@ -384,6 +578,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    }
   }
 
   tc_fence_before();
@@ -454,7 +649,7 @@ int make_tmap_mn3d(CUtensorMap* m, const void* ptr, int elem_bytes, int64_t k_ro
 }
 
 template <int BN, int EPI>
-static int launch_gemm(Ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+static int launch_gemm(Ctx* ctx, const CUtensorMap* tm, const GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   auto kfn = gemm_kernel<BN, EPI>;
@@ -464,20 +659,20 @@ static int launch_gemm(Ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, c
   }
   const int total = p.m_tiles * p.n_tiles * p.splits;
   const int grid = total < ctx->num_sms ? total : ctx->num_sms;
-  kfn<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, p);
+  kfn<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
   ctx->launches++;
   SIMSEG_LAUNCH_CHECK();
   return SIMSEG_OK;
 }
 
 template <int BN>
-static int dispatch_epi(Ctx* ctx, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+static int dispatch_epi(Ctx* ctx, int epi, const CUtensorMap* tm, const GemmParams& p, cudaStream_t st) {
   switch (epi) {
-    case SIMSEG_EPI_NONE: return launch_gemm<BN, SIMSEG_EPI_NONE>(ctx, ta, tb, p, st);
-    case SIMSEG_EPI_BIAS_GELU: return launch_gemm<BN, SIMSEG_EPI_BIAS_GELU>(ctx, ta, tb, p, st);
-    case SIMSEG_EPI_BIAS_RESIDUAL: return launch_gemm<BN, SIMSEG_EPI_BIAS_RESIDUAL>(ctx, ta, tb, p, st);
-    case SIMSEG_EPI_DGELU: return launch_gemm<BN, SIMSEG_EPI_DGELU>(ctx, ta, tb, p, st);
-    case SIMSEG_EPI_ROWSCALE: return launch_gemm<BN, SIMSEG_EPI_ROWSCALE>(ctx, ta, tb, p, st);
+    case SIMSEG_EPI_NONE: return launch_gemm<BN, SIMSEG_EPI_NONE>(ctx, tm, p, st);
+    case SIMSEG_EPI_BIAS_GELU: return launch_gemm<BN, SIMSEG_EPI_BIAS_GELU>(ctx, tm, p, st);
+    case SIMSEG_EPI_BIAS_RESIDUAL: return launch_gemm<BN, SIMSEG_EPI_BIAS_RESIDUAL>(ctx, tm, p, st);
+    case SIMSEG_EPI_DGELU: return launch_gemm<BN, SIMSEG_EPI_DGELU>(ctx, tm, p, st);
+    case SIMSEG_EPI_ROWSCALE: return launch_gemm<BN, SIMSEG_EPI_ROWSCALE>(ctx, tm, p, st);
   }
   set_error("unknown epilogue %d", epi);
   return SIMSEG_ERR_INVALID;
@@ -560,9 +755,28 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
     SIMSEG_CUDA(cudaMemset2DAsync(a->d, a->ldd * 4, 0, a->N * 4, a->M, st));
   }
 
-  CUtensorMap ta, tb;
+  CUtensorMap tm[5];
+  memset(tm, 0, sizeof(tm));
+  CUtensorMap& ta = tm[0];
+  CUtensorMap& tb = tm[1];
   const int mn_atom = kSwizzleBytes / eb;
   int rc;
+  // coalesced TMA-store epilogue: bf16 output, no split-K / accumulation, 16-byte aligned rows
+  const bool epi_ok = a->epilogue == SIMSEG_EPI_NONE || a->epilogue == SIMSEG_EPI_BIAS_GELU || a->epilogue == SIMSEG_EPI_DGELU;
+  auto row_ok16 = [](const void* ptr, int64_t ld) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0; };
+  bool tma_epi = epi_ok && p.out_bf16 && !p.atomic_out && row_ok16(a->d, a->ldd) && (a->reserved & 8) == 0;
+  if (a->aux) tma_epi = tma_epi && row_ok16(a->aux, a->ld_aux);
+  if (a->aux2) tma_epi = tma_epi && row_ok16(a->aux2, a->ld_aux2) && a->epilogue == SIMSEG_EPI_DGELU;
+  if (a->bias) tma_epi = tma_epi && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0;
+  if (a->epilogue != SIMSEG_EPI_DGELU && a->col_sum) tma_epi = false;
+  SIMSEG_CHECK_ARG(!(a->aux2 && !tma_epi), "gemm: aux2 needs the bf16 TMA epilogue (DGELU, bf16 out, 16-byte aligned rows)");
+  p.tma_epi = tma_epi ? 1 : 0;
+  p.aux2 = a->aux2;
+  if (tma_epi) {
+    if ((rc = make_tmap(&tm[2], a->d, 2, a->M, a->N, a->ldd, 64, kBM))) return rc;
+    if (a->aux && (rc = make_tmap(&tm[3], a->aux, 2, a->M, a->N, a->ld_aux, 64, kBM))) return rc;
+    if (a->aux2 && (rc = make_tmap(&tm[4], a->aux2, 2, a->M, a->N, a->ld_aux2, 64, kBM))) return rc;
+  }
   // MN-major operands whose MN extent is a whole number of 128-byte atoms take ONE 3-D box per k-block
   // (atoms past the matrix edge are zero-filled by TMA); ragged extents keep one 2-D box per atom.
   const bool no3d = (a->reserved & 4) != 0;
@@ -578,9 +792,9 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
   if (rc) return rc;
 
   switch (bn) {
-    case 128: return dispatch_epi<128>(ctx, a->epilogue, ta, tb, p, st);
-    case 192: return dispatch_epi<192>(ctx, a->epilogue, ta, tb, p, st);
-    default: return dispatch_epi<256>(ctx, a->epilogue, ta, tb, p, st);
+    case 128: return dispatch_epi<128>(ctx, a->epilogue, tm, p, st);
+    case 192: return dispatch_epi<192>(ctx, a->epilogue, tm, p, st);
+    default: return dispatch_epi<256>(ctx, a->epilogue, tm, p, st);
   }
 }
 

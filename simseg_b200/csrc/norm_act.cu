@@ -153,7 +153,8 @@ template <int V, bool XBF16>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps, int64_t M,
                                                             __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32,
-                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                            const __nv_bfloat16* __restrict__ add, float* __restrict__ sum_out) {
   constexpr int D = V * 128;
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -169,6 +170,16 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const void* __restri
   for (int64_t row = warp_global; row < M; row += nwarps) {
     float v[V][4];
     load_row<V, XBF16>(x, row, D, lane, v);
+    if (add != nullptr) {
+      // fused residual add: s = x + add (the bf16 output of the preceding Linear); s is the new residual stream
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        const uint2 u = *reinterpret_cast<const uint2*>(add + row * D + c);
+        v[i][0] += bf16_lo(u.x); v[i][1] += bf16_hi(u.x); v[i][2] += bf16_lo(u.y); v[i][3] += bf16_hi(u.y);
+        if (sum_out) *reinterpret_cast<float4*>(sum_out + row * D + c) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+      }
+    }
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < V; ++i) s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
@@ -292,14 +303,16 @@ static int ln_grid(Ctx* ctx, int64_t M) {
 }
 
 int layernorm_fwd_impl(Ctx* ctx, const void* x, int x_dtype, const float* gamma, const float* beta, float eps, int64_t M,
-                       int D, void* y_bf16, float* y_f32, float* mean, float* rstd, cudaStream_t st) {
+                       int D, void* y_bf16, float* y_f32, float* mean, float* rstd, const void* add_v, float* sum_out,
+                       cudaStream_t st) {
+  const __nv_bfloat16* add = reinterpret_cast<const __nv_bfloat16*>(add_v);
   SIMSEG_CHECK_ARG(M > 0, "layernorm_fwd: empty");
   SIMSEG_CHECK_ARG(D == 384 || D == 768 || D == 512 || D == 128 || D == 256, "layernorm: D=%d unsupported (128/256/384/512/768)", D);
   const int grid = ln_grid(ctx, M);
   auto* yb = reinterpret_cast<__nv_bfloat16*>(y_bf16);
 #define LN_FWD(V)                                                                                             \
-  if (x_dtype == SIMSEG_BF16) layernorm_fwd_kernel<V, true><<<grid, 256, 0, st>>>(x, gamma, beta, eps, M, yb, y_f32, mean, rstd); \
-  else layernorm_fwd_kernel<V, false><<<grid, 256, 0, st>>>(x, gamma, beta, eps, M, yb, y_f32, mean, rstd)
+  if (x_dtype == SIMSEG_BF16) layernorm_fwd_kernel<V, true><<<grid, 256, 0, st>>>(x, gamma, beta, eps, M, yb, y_f32, mean, rstd, add, sum_out); \
+  else layernorm_fwd_kernel<V, false><<<grid, 256, 0, st>>>(x, gamma, beta, eps, M, yb, y_f32, mean, rstd, add, sum_out)
   switch (D / 128) {
     case 1: LN_FWD(1); break;
     case 2: LN_FWD(2); break;

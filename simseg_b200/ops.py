@@ -63,7 +63,7 @@ def gemm(a: Tensor, b: Tensor, *, M: int, N: int, K: int, a_major: int = 0, b_ma
          out: Optional[Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, epilogue: int = EPI_NONE,
          bias: Optional[Tensor] = None, residual: Optional[Tensor] = None, aux: Optional[Tensor] = None,
          row_scale: Optional[Tensor] = None, col_sum: Optional[Tensor] = None, accumulate: bool = False,
-         tile_n: int = 0, _dbg: int = 0) -> Tensor:
+         aux2: Optional[Tensor] = None, tile_n: int = 0, _dbg: int = 0) -> Tensor:
     """D[M,N] = epilogue(sum_k A(m,k) B(n,k)).  a_major/b_major: 0 = operand stored [MN,K], 1 = stored [K,MN]."""
     lda, ldb = _rowmajor2d(a), _rowmajor2d(b)
     assert a.dtype == b.dtype
@@ -84,6 +84,9 @@ def gemm(a: Tensor, b: Tensor, *, M: int, N: int, K: int, a_major: int = 0, b_ma
     if aux is not None:
         assert aux.dtype == torch.bfloat16
         g.aux, g.ld_aux = aux.data_ptr(), _rowmajor2d(aux)
+    if aux2 is not None:
+        assert aux2.dtype == torch.bfloat16
+        g.aux2, g.ld_aux2 = aux2.data_ptr(), _rowmajor2d(aux2)
     if row_scale is not None:
         g.row_scale = row_scale.data_ptr()
     if col_sum is not None:
@@ -150,6 +153,21 @@ def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, *, want_bf
     check(_lib.load().simseg_layernorm_fwd(ctx(), _p(x), _dt(x), _p(gamma), _p(beta), eps, M, D, _p(yb), _p(yf),
                                            _p(mean), _p(rstd), _stream()), "layernorm_fwd")
     return yb, yf, mean, rstd
+
+
+def add_layernorm_fwd(x: Tensor, add: Tensor, gamma: Tensor, beta: Tensor, eps: float, *, want_sum=True, want_bf16=True,
+                      want_f32=False, want_stats=True):
+    """s = x (f32) + add (bf16); returns (s, LN(s) bf16, LN(s) f32, mean, rstd) — residual add fused into the LayerNorm."""
+    M, D = x.shape
+    assert x.is_contiguous() and add.is_contiguous() and x.dtype == torch.float32 and add.dtype == torch.bfloat16
+    sm = torch.empty((M, D), device=x.device, dtype=torch.float32) if want_sum else None
+    yb = torch.empty((M, D), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    yf = torch.empty((M, D), device=x.device, dtype=torch.float32) if want_f32 else None
+    mean = torch.empty(M, device=x.device, dtype=torch.float32) if want_stats else None
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32) if want_stats else None
+    check(_lib.load().simseg_add_layernorm_fwd(ctx(), _p(x), _p(add), _p(gamma), _p(beta), eps, M, D, _p(sm), _p(yb), _p(yf),
+                                               _p(mean), _p(rstd), _stream()), "add_layernorm_fwd")
+    return sm, yb, yf, mean, rstd
 
 
 def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, *, dy2: Optional[Tensor] = None,

@@ -15,7 +15,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import ops
-from ._lib import EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU, EPI_NONE
+from ._lib import EPI_BIAS_GELU, EPI_DGELU, EPI_NONE
 
 Tensor = torch.Tensor
 
@@ -90,23 +90,33 @@ def vit_forward(m, image: Tensor, wc: Bf16Weights, save: bool):
     if save:
         sv.patches = patches
     strides = (S * 3 * D, 3 * D, 64)
+    # Residual adds are fused into the LayerNorm that follows them (ops.add_layernorm_fwd): every Linear writes its
+    # bf16 output (+bias) through the coalesced TMA-store epilogue, exactly the tensor the reference's autocast produces,
+    # and the fp32 residual stream is updated where it is read anyway.
+    f = None                                      # bf16 output of the previous block's fc2, not yet added to x
     for blk in m.blocks:
-        y, _, mean1, rstd1 = ops.layernorm_fwd(x, blk.norm1.weight, blk.norm1.bias, 1e-6)
+        if f is None:
+            y, _, mean1, rstd1 = ops.layernorm_fwd(x, blk.norm1.weight, blk.norm1.bias, 1e-6)
+        else:
+            x, y, _, mean1, rstd1 = ops.add_layernorm_fwd(x, f, blk.norm1.weight, blk.norm1.bias, 1e-6)
         qkv = ops.linear_fwd(y, wc.get(blk.attn.qkv.weight), blk.attn.qkv.bias)
         q5 = qkv.view(B, S, 3, H, 64)
         o, lse = ops.attention_fwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], B, H, S, strides, None, 0.125)
         o = o.view(M, D)
-        x1 = ops.linear_fwd(o, wc.get(blk.attn.proj.weight), blk.attn.proj.bias, epilogue=EPI_BIAS_RESIDUAL,
-                            residual=x, out_dtype=torch.float32)
-        y2, _, mean2, rstd2 = ops.layernorm_fwd(x1, blk.norm2.weight, blk.norm2.bias, 1e-6)
+        pr = ops.linear_fwd(o, wc.get(blk.attn.proj.weight), blk.attn.proj.bias)
+        x1, y2, _, mean2, rstd2 = ops.add_layernorm_fwd(x, pr, blk.norm2.weight, blk.norm2.bias, 1e-6)
+        del pr
         h = torch.empty((M, 4 * D), device=x.device, dtype=torch.bfloat16) if save else None
         a = ops.linear_fwd(y2, wc.get(blk.mlp.fc1.weight), blk.mlp.fc1.bias, epilogue=EPI_BIAS_GELU, aux=h)
-        x2 = ops.linear_fwd(a, wc.get(blk.mlp.fc2.weight), blk.mlp.fc2.bias, epilogue=EPI_BIAS_RESIDUAL,
-                            residual=x1, out_dtype=torch.float32)
+        f = ops.linear_fwd(a, wc.get(blk.mlp.fc2.weight), blk.mlp.fc2.bias)
+        del a
         if save:
             sv.blocks.append(_Blk(x, mean1, rstd1, qkv, o, lse, x1, mean2, rstd2, h))
-        x = x2
-    tok_bf16, tok_f32, mean_n, rstd_n = ops.layernorm_fwd(x, m.norm.weight, m.norm.bias, 1e-6, want_f32=True)
+        x = x1
+    if f is None:
+        tok_bf16, tok_f32, mean_n, rstd_n = ops.layernorm_fwd(x, m.norm.weight, m.norm.bias, 1e-6, want_f32=True)
+    else:
+        x, tok_bf16, tok_f32, mean_n, rstd_n = ops.add_layernorm_fwd(x, f, m.norm.weight, m.norm.bias, 1e-6, want_f32=True)
     if save:
         sv.x_last, sv.mean_n, sv.rstd_n = x, mean_n, rstd_n
     return tok_f32.view(B, S, D), tok_bf16.view(B, S, D), sv
@@ -130,12 +140,13 @@ def vit_backward(m, sv: VitSaved, dtok: Tensor, wc: Bf16Weights, dtok2: Optional
     for i in range(nb - 1, -1, -1):
         blk, s = m.blocks[i], sv.blocks[i]
         # ---- MLP branch: x2 = x1 + fc2(gelu(fc1(LN2(x1))))
-        a = ops.gelu_fwd(s.h)
-        ops.linear_wgrad(g, a, _grad_of(blk.mlp.fc2.weight), accumulate=True)
-        del a
-        dh = ops.linear_dgrad(g, wc.get(blk.mlp.fc2.weight), epilogue=EPI_DGELU, aux=s.h,
+        # dgrad first: its epilogue multiplies by gelu'(h) AND emits a = gelu(h), which the fc2 wgrad then consumes
+        a = torch.empty_like(s.h)
+        dh = ops.linear_dgrad(g, wc.get(blk.mlp.fc2.weight), epilogue=EPI_DGELU, aux=s.h, aux2=a,
                               col_sum=_grad_of(blk.mlp.fc1.bias))
         s.h = None
+        ops.linear_wgrad(g, a, _grad_of(blk.mlp.fc2.weight), accumulate=True)
+        del a
         y2, _, _, _ = ops.layernorm_fwd(s.x1, blk.norm2.weight, blk.norm2.bias, 1e-6, want_stats=False)
         ops.linear_wgrad(dh, y2, _grad_of(blk.mlp.fc1.weight), accumulate=True)
         del y2
@@ -232,17 +243,18 @@ def bert_forward(m, input_ids: Tensor, attention_mask: Tensor, wc: Bf16Weights, 
         c, lse = ops.attention_fwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], B, H, T, strides, key_len, 0.125)
         c = c.view(M, D)
         ao = layer.attention.output
-        s1 = ops.linear_fwd(c, wc.get(ao.dense.weight), ao.dense.bias, epilogue=EPI_BIAS_RESIDUAL, residual=hf,
-                            out_dtype=torch.float32)
-        h1b, h1f, mean1, rstd1 = ops.layernorm_fwd(s1, ao.LayerNorm.weight, ao.LayerNorm.bias, 1e-12, want_f32=True)
+        d1 = ops.linear_fwd(c, wc.get(ao.dense.weight), ao.dense.bias)
+        s1, h1b, h1f, mean1, rstd1 = ops.add_layernorm_fwd(hf, d1, ao.LayerNorm.weight, ao.LayerNorm.bias, 1e-12, want_f32=True)
+        del d1
         F = layer.intermediate.dense.weight.shape[0]
         pre = torch.empty((M, F), device=e.device, dtype=torch.bfloat16) if save else None
         f = ops.linear_fwd(h1b, wc.get(layer.intermediate.dense.weight), layer.intermediate.dense.bias,
                            epilogue=EPI_BIAS_GELU, aux=pre)
-        s2 = ops.linear_fwd(f, wc.get(layer.output.dense.weight), layer.output.dense.bias, epilogue=EPI_BIAS_RESIDUAL,
-                            residual=h1f, out_dtype=torch.float32)
-        h2b, h2f, mean2, rstd2 = ops.layernorm_fwd(s2, layer.output.LayerNorm.weight, layer.output.LayerNorm.bias,
-                                                   1e-12, want_f32=True)
+        d2 = ops.linear_fwd(f, wc.get(layer.output.dense.weight), layer.output.dense.bias)
+        del f
+        s2, h2b, h2f, mean2, rstd2 = ops.add_layernorm_fwd(h1f, d2, layer.output.LayerNorm.weight, layer.output.LayerNorm.bias,
+                                                           1e-12, want_f32=True)
+        del d2
         if save:
             sv.layers.append(_Lyr(hb, qkv, c, lse, s1, mean1, rstd1, pre, s2, mean2, rstd2))
         hb, hf = h2b, h2f
@@ -269,11 +281,11 @@ def bert_backward(m, sv: BertSaved, dh: Tensor, wc: Bf16Weights, dh2: Optional[T
         ops.layernorm_bwd(dy, s.s2, layer.output.LayerNorm.weight, s.mean2, s.rstd2, dy2=dres, dx=ds2, dx_bf16=g2,
                           dgamma=_grad_of(layer.output.LayerNorm.weight), dbeta=_grad_of(layer.output.LayerNorm.bias),
                           dx_colsum=_grad_of(layer.output.dense.bias))
-        f = ops.gelu_fwd(s.pre)
+        f = torch.empty_like(s.pre)
+        dpre = ops.linear_dgrad(g2, wc.get(layer.output.dense.weight), epilogue=EPI_DGELU, aux=s.pre, aux2=f,
+                                col_sum=_grad_of(layer.intermediate.dense.bias))
         ops.linear_wgrad(g2, f, _grad_of(layer.output.dense.weight), accumulate=True)
         del f
-        dpre = ops.linear_dgrad(g2, wc.get(layer.output.dense.weight), epilogue=EPI_DGELU, aux=s.pre,
-                                col_sum=_grad_of(layer.intermediate.dense.bias))
         h1b, _, _, _ = ops.layernorm_fwd(s.s1, ao.LayerNorm.weight, ao.LayerNorm.bias, 1e-12, want_stats=False)
         ops.linear_wgrad(dpre, h1b, _grad_of(layer.intermediate.dense.weight), accumulate=True)
         dh1 = ops.linear_dgrad(dpre, wc.get(layer.intermediate.dense.weight))

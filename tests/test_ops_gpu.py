@@ -110,6 +110,58 @@ def test_gemm_epilogues(cuda):
     assert _rel(o, (pre - bias) * rs[:, None]) < 2e-5
 
 
+@pytest.mark.parametrize("M,N,K,tile_n", [(1000, 1536, 384, 0), (130, 200, 64, 128), (4500, 3072, 768, 256), (257, 1544, 128, 192)])
+def test_gemm_tma_epilogue_bf16(cuda, M, N, K, tile_n):
+    """The coalesced (swizzled smem + TMA store) epilogue for bf16 outputs: plain+bias, GELU with saved pre-activation,
+    and the backward dGELU that TMA-loads the pre-activation, emits gelu(pre) next to the gradient and column sums —
+    ragged M / N (TMA clips), more tiles than SMs (staging-slot recycling across tiles), against the direct-store path."""
+    ops = _ops()
+    from simseg_b200._lib import EPI_BIAS_GELU, EPI_DGELU
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    a = (torch.randn(M, K, device=cuda, generator=g) * 0.5).bfloat16()
+    b = (torch.randn(N, K, device=cuda, generator=g) * 0.1).bfloat16()
+    bias = torch.randn(N, device=cuda, generator=g) * 0.1
+    pre = a.float() @ b.float().T + bias
+    out = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, tile_n=tile_n)
+    assert _rel(out, pre) < 6e-3
+    legacy = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, tile_n=tile_n, _dbg=8)          # direct-store epilogue
+    assert torch.equal(out, legacy)
+    aux = torch.full((M, N), float("nan"), device=cuda, dtype=torch.bfloat16)
+    act = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, epilogue=EPI_BIAS_GELU, aux=aux, tile_n=tile_n)
+    assert torch.equal(aux, out)                                                  # same rounding of the pre-activation
+    assert (act.float() - gelu(aux.float())).abs().max().item() < 2e-2
+    act_noaux = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, epilogue=EPI_BIAS_GELU, tile_n=tile_n)
+    assert torch.equal(act_noaux, act)
+    # backward: d = (a @ b^T) * gelu'(aux), aux2 = gelu(aux), col_sum += sum_m d
+    cs = torch.zeros(N, device=cuda)
+    a2 = torch.full((M, N), float("nan"), device=cuda, dtype=torch.bfloat16)
+    dh = ops.gemm(a, b, M=M, N=N, K=K, epilogue=EPI_DGELU, aux=aux, aux2=a2, col_sum=cs, tile_n=tile_n)
+    h = aux.float().requires_grad_(True)
+    gelu(h).backward(pre - bias)
+    assert _rel(dh, h.grad) < 6e-3
+    assert _rel(cs, h.grad.sum(0)) < 2e-3
+    assert (a2.float() - gelu(aux.float())).abs().max().item() < 2e-2 and torch.isfinite(a2.float()).all()
+    assert (a2.float() - act.float()).abs().max().item() < 1e-6 + 8e-3 * act.float().abs().max().item()
+
+
+@pytest.mark.parametrize("D", [384, 768])
+def test_add_layernorm(cuda, D):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(D)
+    M = 777
+    x = torch.randn(M, D, device=cuda, generator=g)
+    add = torch.randn(M, D, device=cuda, generator=g).bfloat16()
+    gamma = 1 + 0.1 * torch.randn(D, device=cuda, generator=g)
+    beta = 0.1 * torch.randn(D, device=cuda, generator=g)
+    s, yb, yf, mean, rstd = ops.add_layernorm_fwd(x, add, gamma, beta, 1e-6, want_f32=True)
+    ref_s = x + add.float()
+    ref = torch.nn.functional.layer_norm(ref_s, (D,), gamma, beta, 1e-6)
+    assert torch.equal(s, ref_s)
+    assert (yf - ref).abs().max().item() < 1e-4 and _rel(yb, ref) < 6e-3
+    assert (mean - ref_s.mean(-1)).abs().max().item() < 1e-5
+    assert _rel(rstd, (ref_s.var(-1, unbiased=False) + 1e-6).rsqrt()) < 1e-5
+
+
 def test_gemm_tf32(cuda):
     ops = _ops()
     g = torch.Generator(device="cuda").manual_seed(5)

@@ -38,6 +38,9 @@ def run(B, H, S, masked, reps=5):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        run(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), False, reps=1)
+        sys.exit(0)
     run(4096, 6, 197, False)
     run(1024, 12, 197, False)
     run(4096, 12, 25, True)
