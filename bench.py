@@ -152,7 +152,9 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a collective mismatch must abort within minutes instead of hanging the box
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     assert a.global_batch % world == 0
     b = a.global_batch // world
     m = MODELS[a.model]
@@ -244,11 +246,13 @@ def run_ours(a):
             "gpu_launches": int(launches),
             "loss": float(last.get("loss", float("nan")))}
 
-    if rank == 0 and not a.no_extras:
+    if not a.no_extras:
         hbm, tf_sus, tf_burst, how = peaks()
-        line["roofline"] = gemm_roofline(trainer, dev_bufs[0], tf_sus, how)
-        line["train_flops"] = train_flops(a, m, ms_step, tf_sus)
-        line["patch_sim"] = patch_sim_bench(hbm, how)
+        roof = gemm_roofline(trainer, dev_bufs[0], tf_sus, how)      # a training step: EVERY rank takes part in its collectives
+        if rank == 0:
+            line["roofline"] = roof
+            line["train_flops"] = train_flops(a, m, ms_step, tf_sus)
+            line["patch_sim"] = patch_sim_bench(hbm, how)
     if world > 1:
         dist.barrier()
     if rank == 0:
