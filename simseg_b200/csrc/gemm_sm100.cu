@@ -3,13 +3,17 @@
 //   D[M,N] = epilogue( sum_k A[m,k] * B[n,k] )     bf16 (kind::f16) or fp32-as-tf32 (kind::tf32) operands,
 //                                                  fp32 accumulators in TMEM.
 //
-// One persistent CTA per SM, warp-specialised:
+// Persistent, warp-specialised, one CTA per SM; optionally two CTAs (the two SMs of a TPC) form a PAIR that works on
+// one 256 x BN tile with tcgen05 cta_group::2: each CTA stages its own 128 rows of A and HALF of the B columns, the
+// leader issues 256 x BN x 16 MMAs that read both CTAs' shared memory and write 128 accumulator lanes into each
+// CTA's TMEM.  Per flop that is 1/3 less L2->SM operand traffic than a single-CTA 128 x BN tile — the limit this
+// engine was running into.
 //   warp 0      TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
-//   warp 1      MMA issuer    (one elected thread, tcgen05.mma cta_group::1, 128 x BN x 16|8 per instruction)
-//   warps 2..9  epilogue      (tcgen05.ld 32x32b, fused bias / GELU / residual / dGELU / row-scale / column sums)
+//   warp 1      MMA issuer    (one elected thread of the leader CTA, tcgen05.mma, 128|256 x BN x 16|8 per instruction)
+//   warps 2..9  epilogue      (tcgen05.ld 32x32b, fused bias / GELU / dGELU / column sums; per-WARP staging + TMA stores)
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
-// Operands may be K-major (x @ W^T forward) or MN-major (dgrad reads W as [K,N]; wgrad reads dy and x as
-// [K=tokens, M|N]); only the TMA box pattern and the smem-descriptor strides differ.
+// Operands may be K-major (x @ W^T forward) or MN-major (wgrad reads dy and x as [K=tokens, M|N]); only the TMA box
+// pattern and the smem-descriptor strides differ.
 // Split-K (wgrad: K = all tokens) accumulates with vector fp32 reductions (red.global.add.v4.f32).
 #include "common.cuh"
 #include "sm100.cuh"
@@ -21,14 +25,12 @@ namespace simseg {
 
 using namespace sm100;
 
-#ifndef SIMSEG_STAGES256
-#define SIMSEG_STAGES256 4
-#endif
-constexpr int kBM = 128;           // tile rows = TMEM lanes
+constexpr int kBM = 128;            // tile rows per CTA = TMEM lanes
 constexpr int kSwizzleBytes = 128;  // one swizzle atom row = one K block (K-major) / 64 MN elements (bf16)
 constexpr int kNumEpiWarps = 8;
-constexpr int kStgTileBytes = kBM * 128;   // epilogue staging tile: 128 rows x 64 bf16, SWIZZLE_128B (TMA store/load box)
+constexpr int kEpiBoxBytes = 32 * 64;   // epilogue staging box: 32 rows x 32 bf16 columns, SWIZZLE_64B (TMA store/load box)
 constexpr int kGemmThreads = 32 * (2 + kNumEpiWarps);
+constexpr int kMaxSmem = 232448;
 
 struct GemmParams {
   int64_t M, N, K;
@@ -48,124 +50,150 @@ struct GemmParams {
   const float* row_scale;
   float* col_sum;
   int32_t vec_ok;          // 16-byte aligned rows for d / residual / aux
-  int32_t tma_epi;         // bf16 output through swizzled smem staging + TMA store (coalesced), else direct stores
+  int32_t tma_epi;         // bf16 output through per-warp swizzled smem staging + TMA store (coalesced), else direct stores
   void* aux2;              // DGELU only: gelu(aux) written next to the gradient (bf16 [M,N])
   int32_t a_3d, b_3d;      // MN-major operand loaded with one 3-D TMA box per k-block
   int32_t dbg;             // bench-only: 1 = no TMA after the ring is primed, 2 = no MMA (results are garbage)
 };
 
-template <int BN>
+template <int BN, int EPI, int CTAS>
 struct GemmCfg {
-  static constexpr int kABytes = kBM * kSwizzleBytes;          // 16 KB
-  static constexpr int kBBytes = BN * kSwizzleBytes;
+  static constexpr int kABytes = kBM * kSwizzleBytes;          // 16 KB: this CTA's 128 rows of A, one k-block
+  static constexpr int kBRows = BN / CTAS;                     // B columns staged by this CTA
+  static constexpr int kBBytes = kBRows * kSwizzleBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  // ring depth: measured on B200 the BN=256 mainloop is as fast with 3 stages as with 4 (it is L2-fabric bound, not
-  // latency bound), which leaves 64 KB for the epilogue staging tiles
-  static constexpr int kStages = (BN <= 128) ? 5 : (BN <= 192 ? 4 : 3);
+  // per-warp epilogue staging: EPI_NONE rotates 2 boxes; BIAS_GELU 2 x (out, aux); DGELU 3 aux-in boxes + 1 out box
+  static constexpr int kStgPerWarp = ((EPI == SIMSEG_EPI_BIAS_GELU || EPI == SIMSEG_EPI_DGELU) ? 4 : 2) * kEpiBoxBytes;
+  static constexpr int kStagingBytes = kNumEpiWarps * kStgPerWarp;
+  static constexpr int kBarBytes = 512;
+  static constexpr int kStagesFit = (kMaxSmem - 1024 - kStagingBytes - kBarBytes) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kAccStride = (BN <= 128) ? 128 : 256;    // TMEM columns between the two accumulators
   static constexpr int kTmemCols = 2 * kAccStride;              // 256 or 512 (power of two)
-  static constexpr int kStagingBytes = 4 * kStgTileBytes;       // four [128 rows][128 B] swizzled epilogue tiles
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + kBarBytes;
+  static_assert(kStages >= 3, "ring too shallow");
 };
 
-
 // ------------------------------------------------------------------------------------------------
-// Coalesced epilogue for bf16 outputs: TMEM -> registers -> fused math -> 128B-swizzled smem tile [128 rows][64 cols]
-// -> TMA store.  All 8 epilogue warps work on one 64-column chunk at a time (warp = TMEM lane quarter x 32-column
-// half); thread = one output row, so every smem access is a conflict-free 16-byte chunk of the thread's own row.
-//   EPI_NONE      out = acc (+bias)                                   staging tiles rotate over 4 slots
-//   EPI_BIAS_GELU aux = bf16(acc+bias) ; out = gelu(aux)              two stores per chunk, 2 x 2 slots
+// Coalesced epilogue for bf16 outputs.  Each epilogue warp owns one TMEM lane quarter (32 rows) and every second
+// 32-column chunk of the tile; per chunk it goes TMEM -> registers -> fused math -> its OWN SWIZZLE_64B staging box
+// [32 rows][32 bf16] -> TMA store.  Nothing is shared between warps, so the only synchronisation is __syncwarp and the
+// warp's own bulk-async groups / mbarriers (no CTA-wide barrier per chunk).  The next chunk's tcgen05.ld is in flight
+// while the current one is processed, and the accumulator stage is released as soon as the last load has landed.
+//   EPI_NONE      out = acc (+bias)                                   2 staging boxes
+//   EPI_BIAS_GELU aux = bf16(acc+bias) ; out = gelu(aux)              2 x (aux, out) boxes
 //   EPI_DGELU     out = acc * gelu'(aux) ; aux2 = gelu(aux) ; column sums of out
-//                 aux tiles are TMA-LOADED two chunks ahead into a 3-slot ring; gelu(aux) overwrites the tile in place
-//                 and is TMA-stored from there (the backward pass never runs a separate GELU recompute kernel)
-__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
-
-template <int BN, int EPI>
+//                 aux boxes are TMA-LOADED two chunks ahead into a 3-slot ring; gelu(aux) overwrites the box in place
+//                 and is TMA-stored from there (the backward pass never runs a separate GELU recompute kernel);
+//                 column sums stay in registers while the CTA keeps working on the same n-tile.
+template <int BN, int EPI, int CTAS>
 __device__ __forceinline__ void epilogue_tma(const GemmParams& p, const CUtensorMap& tmap_d, const CUtensorMap& tmap_x,
-                                             const CUtensorMap& tmap_x2, uint8_t* stg, uint64_t* acc_full, uint64_t* acc_empty,
-                                             uint64_t* aux_full, float* s_cs, uint32_t tmem_base, int total_tiles, int tiles_mn,
-                                             int warp, int lane) {
-  using Cfg = GemmCfg<BN>;
-  constexpr int kCh = BN / 64;
-  const int ew = warp - 2;
-  const int quarter = warp & 3;
-  const int half = ew >> 2;
-  const int r = quarter * 32 + lane;
-  const int sw = r & 7;
-  const bool elected = (ew == 0 && lane == 0);
-  const uint32_t row_off = static_cast<uint32_t>(r) * 128;
-  const int tid = ew * 32 + lane;                                   // 0..255 among the epilogue threads
-  uint32_t cc = 0;                                                  // flat chunk counter over (tile, chunk)
+                                             const CUtensorMap& tmap_x2, uint8_t* stg, uint64_t* acc_full,
+                                             uint32_t acc_empty_addr, uint64_t* aux_full, uint32_t tmem_base, int first_tile,
+                                             int tile_stride, int total_tiles, int tiles_mn, int row_base, int warp, int lane) {
+  using Cfg = GemmCfg<BN, EPI, CTAS>;
+  constexpr int kCw = BN / 64;                                      // 32-column chunks per warp and tile
+  const int quarter = warp & 3;                                     // TMEM lane quarter this warp may access
+  const int half = (warp - 2) >> 2;                                 // chunk parity handled by this warp
+  const int sw = (lane >> 1) & 3;                                   // SWIZZLE_64B: 16-byte chunk ^= (row >> 1) & 3
+  const uint32_t row_off = static_cast<uint32_t>(lane) * 64;
+  const bool has_bias = p.bias != nullptr;
+  const bool want_cs = (EPI == SIMSEG_EPI_DGELU) && p.col_sum != nullptr;
+  uint32_t f = 0;                                                   // flat chunk counter over (tile, chunk)
+  float cs[kCw];
+  int cs_n0 = -1;
+#pragma unroll
+  for (int j = 0; j < kCw; ++j) cs[j] = 0.f;
 
-  auto chunk_coords = [&](uint32_t f, int& m0, int& ncol) -> bool {
-    const int tile = static_cast<int>(blockIdx.x) + static_cast<int>(f / kCh) * static_cast<int>(gridDim.x);
+  auto coords = [&](uint32_t ff, int& row0, int& col0) -> bool {
+    const int tile = first_tile + static_cast<int>(ff / kCw) * tile_stride;
     if (tile >= total_tiles) return false;
     const int mn = tile % tiles_mn;
-    m0 = (mn / p.n_tiles) * kBM;
-    ncol = (mn % p.n_tiles) * BN + static_cast<int>(f % kCh) * 64;
+    row0 = (mn / p.n_tiles) * (kBM * CTAS) + row_base + quarter * 32;
+    col0 = (mn % p.n_tiles) * BN + (half + 2 * static_cast<int>(ff % kCw)) * 32;
     return true;
   };
-  if (EPI == SIMSEG_EPI_DGELU && elected) {
-    for (uint32_t f = 0; f < 2; ++f) {
-      int m0, nc;
-      if (chunk_coords(f, m0, nc)) {
-        mbar_arrive_expect_tx(&aux_full[f % 3], kStgTileBytes);
-        tma_load_2d(stg + (1 + f % 3) * kStgTileBytes, &tmap_x, &aux_full[f % 3], nc, m0);
+  auto flush_cs = [&]() {
+    if (cs_n0 < 0) return;
+#pragma unroll
+    for (int j = 0; j < kCw; ++j) {
+      const int c = cs_n0 + (half + 2 * j) * 32 + lane;
+      if (c < p.N) atomicAdd(p.col_sum + c, cs[j]);
+      cs[j] = 0.f;
+    }
+  };
+  if (EPI == SIMSEG_EPI_DGELU && lane == 0) {
+    for (uint32_t ff = 0; ff < 2; ++ff) {
+      int r0, c0;
+      if (coords(ff, r0, c0)) {
+        mbar_arrive_expect_tx(&aux_full[ff % 3], kEpiBoxBytes);
+        tma_load_2d(stg + (ff % 3) * kEpiBoxBytes, &tmap_x, &aux_full[ff % 3], c0, r0);
       }
     }
   }
 
   int acc = 0;
   uint32_t acc_phase = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+  for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
     const int mn = tile % tiles_mn;
-    const int m0 = (mn / p.n_tiles) * kBM;
     const int n0 = (mn % p.n_tiles) * BN;
+    const int row0 = (mn / p.n_tiles) * (kBM * CTAS) + row_base + quarter * 32;
+    float bias_r[kCw];                                              // lane l holds bias[column l of chunk j]
+#pragma unroll
+    for (int j = 0; j < kCw; ++j) {
+      const int c = n0 + (half + 2 * j) * 32 + lane;
+      bias_r[j] = (has_bias && c < p.N) ? __ldg(p.bias + c) : 0.f;
+    }
+    if (want_cs && n0 != cs_n0) {
+      flush_cs();
+      cs_n0 = n0;
+    }
     mbar_wait(&acc_full[acc], acc_phase);
     tc_fence_after();
     const uint32_t t_row = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll 1
-    for (int c = 0; c < kCh; ++c, ++cc) {
-      const int col_in_tile = c * 64 + half * 32;
-      const int col0 = n0 + col_in_tile;
-      uint32_t rr[32];
-      tmem_ld_32x32(t_row + col_in_tile, rr);
+    uint32_t ra[32], rb[32];
+    tmem_ld_32x32(t_row + half * 32, ra);
+#pragma unroll
+    for (int j = 0; j < kCw; ++j, ++f) {
+      uint32_t(&cur)[32] = (j & 1) ? rb : ra;
+      uint32_t(&nxt)[32] = (j & 1) ? ra : rb;
       tmem_ld_wait();
+      if (j + 1 < kCw) {
+        tmem_ld_32x32(t_row + (half + 2 * (j + 1)) * 32, nxt);
+      } else {
+        // every TMEM read of this warp has landed in registers: hand the accumulator stage back to the MMA issuer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc_empty_addr + acc * 8);
+      }
+      const int col = n0 + (half + 2 * j) * 32;
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
-      if (p.bias != nullptr) {
-        if (col0 + 32 <= p.N) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+      for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(cur[k]);
+      if (has_bias) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(b4 + j);
-            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
-        }
+        for (int k = 0; k < 32; ++k) v[k] += __shfl_sync(0xffffffffu, bias_r[j], k);
       }
-      int out_slot, x_slot;
-      if (EPI == SIMSEG_EPI_BIAS_GELU) { x_slot = 2 * (cc & 1); out_slot = x_slot + 1; }
-      else if (EPI == SIMSEG_EPI_DGELU) { out_slot = 0; x_slot = 1 + static_cast<int>(cc % 3); }
-      else { out_slot = static_cast<int>(cc & 3); x_slot = 0; }
-      uint8_t* so = stg + out_slot * kStgTileBytes + row_off;
-      uint8_t* sx = stg + x_slot * kStgTileBytes + row_off;
+      uint8_t* so;                                                  // staging box of `out`
+      uint8_t* sx;                                                  // staging box of aux (GELU: out; DGELU: in, then aux2 out)
+      if (EPI == SIMSEG_EPI_BIAS_GELU) { sx = stg + (f & 1) * (2 * kEpiBoxBytes); so = sx + kEpiBoxBytes; }
+      else if (EPI == SIMSEG_EPI_DGELU) { sx = stg + (f % 3) * kEpiBoxBytes; so = stg + 3 * kEpiBoxBytes; }
+      else { so = stg + (f & 1) * kEpiBoxBytes; sx = so; }
+      so += row_off;
+      sx += row_off;
       uint32_t xo[16];                                              // second bf16 output of this row chunk (aux / aux2)
       if (EPI == SIMSEG_EPI_BIAS_GELU) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          xo[j >> 1] = pack_bf16(v[j], v[j + 1]);                   // pre-activation, bf16 — exactly what backward reads
-          v[j] = gelu_erf(bf16_lo(xo[j >> 1]));
-          v[j + 1] = gelu_erf(bf16_hi(xo[j >> 1]));
+        for (int k = 0; k < 32; k += 2) {
+          xo[k >> 1] = pack_bf16(v[k], v[k + 1]);                   // pre-activation, bf16 — exactly what backward reads
+          v[k] = gelu_erf(bf16_lo(xo[k >> 1]));
+          v[k + 1] = gelu_erf(bf16_hi(xo[k >> 1]));
         }
       } else if (EPI == SIMSEG_EPI_DGELU) {
-        mbar_wait(&aux_full[cc % 3], (cc / 3) & 1);
+        mbar_wait(&aux_full[f % 3], (f / 3) & 1);
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
-          const uint4 u = *reinterpret_cast<const uint4*>(sx + (((half * 4 + q4) ^ sw) << 4));
+          const uint4 u = *reinterpret_cast<const uint4*>(sx + ((q4 ^ sw) << 4));
           const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -180,90 +208,81 @@ __device__ __forceinline__ void epilogue_tma(const GemmParams& p, const CUtensor
       }
       uint32_t o[16];
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) o[j >> 1] = pack_bf16(v[j], v[j + 1]);
-      if (EPI == SIMSEG_EPI_DGELU && p.col_sum != nullptr) {
-        // column sums over this warp's 32 rows (butterfly transpose-reduce), then one shared-memory add per column
+      for (int k = 0; k < 32; k += 2) o[k >> 1] = pack_bf16(v[k], v[k + 1]);
+      if (want_cs) {
+        // column sums over this warp's 32 rows (butterfly transpose-reduce): lane l ends up with column l
 #pragma unroll
         for (int o2 = 16; o2 >= 1; o2 >>= 1) {
           const bool upper = (lane & o2) != 0;
 #pragma unroll
-          for (int j = 0; j < o2; ++j) {
-            const float mine = upper ? v[j + o2] : v[j];
-            const float send = upper ? v[j] : v[j + o2];
-            v[j] = mine + __shfl_xor_sync(0xffffffffu, send, o2);
+          for (int k = 0; k < o2; ++k) {
+            const float mine = upper ? v[k + o2] : v[k];
+            const float send = upper ? v[k] : v[k + o2];
+            v[k] = mine + __shfl_xor_sync(0xffffffffu, send, o2);
           }
         }
-        atomicAdd(&s_cs[col_in_tile + lane], v[0]);
+        cs[j] += v[0];
       }
-      // ---- staging slot must have been read by the TMA store that last used it
-      if (elected) {
-        if (EPI == SIMSEG_EPI_BIAS_GELU) tma_store_wait_read<1>();
-        else if (EPI == SIMSEG_EPI_DGELU) tma_store_wait_read<0>();
-        else tma_store_wait_read<3>();
+      // ---- the staging boxes must have been read by the TMA stores that last used them
+      if (lane == 0) {
         if (EPI == SIMSEG_EPI_DGELU) {
-          int m2, nc2;
-          if (chunk_coords(cc + 2, m2, nc2)) {                       // slot (cc+2)%3 == (cc-1)%3: just released
-            mbar_arrive_expect_tx(&aux_full[(cc + 2) % 3], kStgTileBytes);
-            tma_load_2d(stg + (1 + (cc + 2) % 3) * kStgTileBytes, &tmap_x, &aux_full[(cc + 2) % 3], nc2, m2);
+          tma_store_wait_read<0>();
+          int r2, c2;
+          if (coords(f + 2, r2, c2)) {                               // slot (f+2)%3 == (f-1)%3: just released
+            mbar_arrive_expect_tx(&aux_full[(f + 2) % 3], kEpiBoxBytes);
+            tma_load_2d(stg + ((f + 2) % 3) * kEpiBoxBytes, &tmap_x, &aux_full[(f + 2) % 3], c2, r2);
           }
+        } else {
+          tma_store_wait_read<1>();
         }
       }
-      epi_bar(1);
+      __syncwarp();
+      const bool two = (EPI == SIMSEG_EPI_BIAS_GELU && p.aux != nullptr) || (EPI == SIMSEG_EPI_DGELU && p.aux2 != nullptr);
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
-        const uint32_t off = ((half * 4 + q4) ^ sw) << 4;
+        const uint32_t off = (q4 ^ sw) << 4;
         *reinterpret_cast<uint4*>(so + off) = make_uint4(o[4 * q4], o[4 * q4 + 1], o[4 * q4 + 2], o[4 * q4 + 3]);
-        if ((EPI == SIMSEG_EPI_BIAS_GELU && p.aux != nullptr) || (EPI == SIMSEG_EPI_DGELU && p.aux2 != nullptr))
-          *reinterpret_cast<uint4*>(sx + off) = make_uint4(xo[4 * q4], xo[4 * q4 + 1], xo[4 * q4 + 2], xo[4 * q4 + 3]);
+        if (two) *reinterpret_cast<uint4*>(sx + off) = make_uint4(xo[4 * q4], xo[4 * q4 + 1], xo[4 * q4 + 2], xo[4 * q4 + 3]);
       }
       fence_proxy_async_smem();
-      epi_bar(2);
-      if (elected) {
-        tma_store_2d(&tmap_d, stg + out_slot * kStgTileBytes, n0 + c * 64, m0);
-        if (EPI == SIMSEG_EPI_BIAS_GELU && p.aux != nullptr) tma_store_2d(&tmap_x, stg + x_slot * kStgTileBytes, n0 + c * 64, m0);
-        if (EPI == SIMSEG_EPI_DGELU && p.aux2 != nullptr) tma_store_2d(&tmap_x2, stg + x_slot * kStgTileBytes, n0 + c * 64, m0);
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tmap_d, so - row_off, col, row0);
+        if (EPI == SIMSEG_EPI_BIAS_GELU && p.aux != nullptr) tma_store_2d(&tmap_x, sx - row_off, col, row0);
+        if (EPI == SIMSEG_EPI_DGELU && p.aux2 != nullptr) tma_store_2d(&tmap_x2, sx - row_off, col, row0);
         tma_store_commit();
       }
     }
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&acc_empty[acc]);
     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    if (EPI == SIMSEG_EPI_DGELU && p.col_sum != nullptr) {
-      // every warp's shared-memory adds of this tile happened before the last epi_bar(1): flush and clear
-      if (tid < BN) {
-        const float x = s_cs[tid];
-        s_cs[tid] = 0.f;
-        if (n0 + tid < p.N) atomicAdd(p.col_sum + n0 + tid, x);
-      }
-      epi_bar(1);
-    }
   }
-  if (elected) tma_store_wait<0>();
+  if (want_cs) flush_cs();
+  if (lane == 0) tma_store_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int BN, int EPI>
+template <int BN, int EPI, int CTAS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_x,
             const __grid_constant__ CUtensorMap tmap_x2, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EPI, CTAS>;
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment is required by SWIZZLE_128B (descriptor base_offset = 0)
+  // 1024-byte alignment is required by SWIZZLE_128B (descriptor base_offset = 0); the dynamic-smem base offset is the
+  // same in both CTAs of a pair, so every carved address below is at the same offset in the peer.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stg = smem + Cfg::kStages * Cfg::kStageBytes;      // 4 staging tiles (1024-byte aligned)
+  uint8_t* stg = smem + Cfg::kStages * Cfg::kStageBytes;      // per-warp epilogue staging boxes
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg + Cfg::kStagingBytes);
-  uint64_t* full_bar = bars;                       // [kStages]  TMA -> MMA
-  uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]  MMA -> TMA
-  uint64_t* acc_full = bars + 2 * Cfg::kStages;    // [2]        MMA -> epilogue
-  uint64_t* acc_empty = acc_full + 2;              // [2]        epilogue -> MMA
-  uint64_t* aux_full = acc_empty + 2;              // [3]        TMA (aux-in tiles of the DGELU epilogue) -> epilogue
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 3);
-  float* s_cs = reinterpret_cast<float*>(bars + 32);           // [BN] per-tile column sums
+  uint64_t* full_bar = bars;                       // [8]   TMA -> MMA            (leader's are used by a pair)
+  uint64_t* empty_bar = bars + 8;                  // [8]   MMA -> TMA            (multicast to both CTAs of a pair)
+  uint64_t* acc_full = bars + 16;                  // [2]   MMA -> epilogue       (multicast)
+  uint64_t* acc_empty = bars + 18;                 // [2]   epilogue -> MMA       (leader's; both CTAs' warps arrive)
+  uint64_t* aux_full = bars + 20;                  // [8 warps][3]  TMA (aux-in boxes of the DGELU epilogue) -> warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 44);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -274,92 +293,117 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], kNumEpiWarps);
+      mbar_init(&acc_empty[s], kNumEpiWarps * CTAS);
     }
-    for (int s = 0; s < 3; ++s) mbar_init(&aux_full[s], 1);
+    for (int s = 0; s < 3 * kNumEpiWarps; ++s) mbar_init(&aux_full[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (CTAS == 2) { tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
   }
-  if (threadIdx.x >= 64 && threadIdx.x - 64 < BN) s_cs[threadIdx.x - 64] = 0.f;
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();               // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
   const int tiles_mn = p.m_tiles * p.n_tiles;
   const int k_elems = kSwizzleBytes / p.elem_bytes;      // K elements per k-block: 64 (bf16) or 32 (tf32)
+  const int first_tile = static_cast<int>(blockIdx.x) / CTAS;
+  const int tile_stride = static_cast<int>(gridDim.x) / CTAS;
+  const int row_base = static_cast<int>(rank) * kBM;     // this CTA's rows inside the (pair's) tile
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    // The whole warp runs the loop (so every value stays in uniform registers, which is what UTMALDG wants); one
+    // elected lane issues.
+    {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const uint32_t full0 = (CTAS == 2) ? mapa_shared(smem_u32(&full_bar[0]), 0) : 0u;   // leader's full barriers
+      const int mn_atom = kSwizzleBytes / p.elem_bytes;              // 64 bf16 / 32 tf32 elements
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
         const int split = tile / tiles_mn;
         const int mn = tile - split * tiles_mn;
-        const int m0 = (mn / p.n_tiles) * kBM;
-        const int n0 = (mn % p.n_tiles) * BN;
+        const int m0 = (mn / p.n_tiles) * (kBM * CTAS) + row_base;
+        const int n0 = (mn % p.n_tiles) * BN + static_cast<int>(rank) * Cfg::kBRows;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kABytes;
-          if (p.dbg == 1 && (phase != 0 || tile != static_cast<int>(blockIdx.x))) {
-            mbar_arrive(&full_bar[stage]);
-            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
-            continue;
+          if (elect_one()) {
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            uint8_t* sb = sa + Cfg::kABytes;
+            if (p.dbg == 1 && (phase != 0 || tile != first_tile)) {
+              if (leader) mbar_arrive(&full_bar[stage]);
+            } else {
+              if (leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * CTAS);
+              const uint32_t fb = full0 + stage * 8;
+              const int k0 = kb * k_elems;
+              if (!p.a_mn) {
+                if (CTAS == 2) tma_load_2d_2sm(sa, &tmap_a, fb, k0, m0);
+                else tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
+              } else {
+                // MN-major: boxes of (swizzle-row of MN elements) x k rows; one 3-D box when the extent allows
+                const int nbox = kBM / mn_atom;
+                const int box_bytes = Cfg::kABytes / nbox;
+                if (p.a_3d) {
+                  if (CTAS == 2) tma_load_3d_2sm(sa, &tmap_a, fb, 0, k0, m0 / mn_atom);
+                  else tma_load_3d(sa, &tmap_a, &full_bar[stage], 0, k0, m0 / mn_atom);
+                } else {
+                  for (int j = 0; j < nbox; ++j) {
+                    if (CTAS == 2) tma_load_2d_2sm(sa + j * box_bytes, &tmap_a, fb, m0 + j * mn_atom, k0);
+                    else tma_load_2d(sa + j * box_bytes, &tmap_a, &full_bar[stage], m0 + j * mn_atom, k0);
+                  }
+                }
+              }
+              if (!p.b_mn) {
+                if (CTAS == 2) tma_load_2d_2sm(sb, &tmap_b, fb, k0, n0);
+                else tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
+              } else {
+                const int nbox = Cfg::kBRows / mn_atom;
+                const int box_bytes = Cfg::kBBytes / nbox;
+                if (p.b_3d) {
+                  if (CTAS == 2) tma_load_3d_2sm(sb, &tmap_b, fb, 0, k0, n0 / mn_atom);
+                  else tma_load_3d(sb, &tmap_b, &full_bar[stage], 0, k0, n0 / mn_atom);
+                } else {
+                  for (int j = 0; j < nbox; ++j) {
+                    if (CTAS == 2) tma_load_2d_2sm(sb + j * box_bytes, &tmap_b, fb, n0 + j * mn_atom, k0);
+                    else tma_load_2d(sb + j * box_bytes, &tmap_b, &full_bar[stage], n0 + j * mn_atom, k0);
+                  }
+                }
+              }
+            }
           }
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          const int k0 = kb * k_elems;
-          if (!p.a_mn) {
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
-          } else {
-            // MN-major: boxes of (swizzle-row of MN elements) x (k_elems rows... see host: box = {mn_atom, k_rows})
-            const int mn_atom = kSwizzleBytes / p.elem_bytes;          // 64 bf16 / 32 tf32 elements
-            const int nbox = kBM / mn_atom;
-            const int box_bytes = Cfg::kABytes / nbox;
-            if (p.a_3d) tma_load_3d(sa, &tmap_a, &full_bar[stage], 0, k0, m0 / mn_atom);
-            else
-              for (int j = 0; j < nbox; ++j) tma_load_2d(sa + j * box_bytes, &tmap_a, &full_bar[stage], m0 + j * mn_atom, k0);
-          }
-          if (!p.b_mn) {
-            tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
-          } else {
-            const int mn_atom = kSwizzleBytes / p.elem_bytes;
-            const int nbox = BN / mn_atom;
-            const int box_bytes = Cfg::kBBytes / nbox;
-            if (p.b_3d) tma_load_3d(sb, &tmap_b, &full_bar[stage], 0, k0, n0 / mn_atom);
-            else
-              for (int j = 0; j < nbox; ++j) tma_load_2d(sb + j * box_bytes, &tmap_b, &full_bar[stage], n0 + j * mn_atom, k0);
-          }
+          __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(p.elem_bytes == 2 ? 1u : 2u, p.a_mn, p.b_mn, kBM, BN);
+    // =============================== MMA issuer (leader CTA only) ===============================
+    // Warp-uniform loop, one elected lane issues: descriptors are one 64-bit add away from per-kernel constants, so a
+    // k-block costs a few dozen instructions (the issuing thread, not the tensor pipe, used to be the limit).
+    if (leader) {
+      const uint32_t idesc = make_idesc(p.elem_bytes == 2 ? 1u : 2u, p.a_mn, p.b_mn, kBM * CTAS, BN);
       // K-major: consecutive UMMA_K slices are 32 B apart inside the 128 B swizzle row; 8-row groups 1024 B apart.
-      // MN-major: a UMMA_K slice (16 bf16 / 8 tf32 k-rows... = 32 B of K per row-group) spans k-rows of 128 B each,
+      // MN-major: a UMMA_K slice (16 bf16 / 8 tf32 k-rows) spans k-rows of 128 B each,
       //           8-row groups 1024 B apart (SBO), 64-element MN atoms one TMA box apart (LBO).
-      const int kk_steps = 4;                                   // 128 B / 32 B
+      const bool is_bf16 = p.elem_bytes == 2;
       const uint32_t umma_k = 32 / p.elem_bytes;                // 16 (bf16) / 8 (tf32)
       const uint32_t a_step = p.a_mn ? umma_k * kSwizzleBytes : 32;
       const uint32_t b_step = p.b_mn ? umma_k * kSwizzleBytes : 32;
       const uint32_t k_rows_bytes = (kSwizzleBytes / p.elem_bytes) * kSwizzleBytes;   // one MN-major box: k_elems rows x 128 B
-      const uint32_t a_lbo = p.a_mn ? k_rows_bytes : 16;
-      const uint32_t b_lbo = p.b_mn ? k_rows_bytes : 16;
+      const uint64_t adesc0 = make_smem_desc_sw128(smem_u32(smem), p.a_mn ? k_rows_bytes : 16, 1024);
+      const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smem) + Cfg::kABytes, p.b_mn ? k_rows_bytes : 16, 1024);
+      const uint64_t a_inc = a_step >> 4, b_inc = b_step >> 4;   // descriptor start-address field is in 16-byte units
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
         const int split = tile / tiles_mn;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
@@ -369,32 +413,56 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
-          if (p.dbg == 2 && kb > kb0) {
-            mbar_arrive(&empty_bar[stage]);
-            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
-            continue;
+          if (elect_one()) {
+            const uint64_t ad = adesc0 + static_cast<uint64_t>(stage * (Cfg::kStageBytes >> 4));
+            const uint64_t bd = bdesc0 + static_cast<uint64_t>(stage * (Cfg::kStageBytes >> 4));
+            const uint32_t first = (kb > kb0) ? 1u : 0u;
+            if (!(p.dbg == 2 && kb > kb0)) {
+              if (is_bf16) {
+                if (CTAS == 2) {
+                  umma_f16_2sm(d_tmem, ad, bd, idesc, first);
+                  umma_f16_2sm(d_tmem, ad + a_inc, bd + b_inc, idesc, 1u);
+                  umma_f16_2sm(d_tmem, ad + 2 * a_inc, bd + 2 * b_inc, idesc, 1u);
+                  umma_f16_2sm(d_tmem, ad + 3 * a_inc, bd + 3 * b_inc, idesc, 1u);
+                } else {
+                  umma_f16(d_tmem, ad, bd, idesc, first);
+                  umma_f16(d_tmem, ad + a_inc, bd + b_inc, idesc, 1u);
+                  umma_f16(d_tmem, ad + 2 * a_inc, bd + 2 * b_inc, idesc, 1u);
+                  umma_f16(d_tmem, ad + 3 * a_inc, bd + 3 * b_inc, idesc, 1u);
+                }
+              } else {
+                if (CTAS == 2) {
+                  umma_tf32_2sm(d_tmem, ad, bd, idesc, first);
+                  umma_tf32_2sm(d_tmem, ad + a_inc, bd + b_inc, idesc, 1u);
+                  umma_tf32_2sm(d_tmem, ad + 2 * a_inc, bd + 2 * b_inc, idesc, 1u);
+                  umma_tf32_2sm(d_tmem, ad + 3 * a_inc, bd + 3 * b_inc, idesc, 1u);
+                } else {
+                  umma_tf32(d_tmem, ad, bd, idesc, first);
+                  umma_tf32(d_tmem, ad + a_inc, bd + b_inc, idesc, 1u);
+                  umma_tf32(d_tmem, ad + 2 * a_inc, bd + 2 * b_inc, idesc, 1u);
+                  umma_tf32(d_tmem, ad + 3 * a_inc, bd + 3 * b_inc, idesc, 1u);
+                }
+              }
+            }
+            // frees this smem slot (in both CTAs of a pair) once the MMAs have read it
+            if (CTAS == 2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+            // accumulator complete -> epilogue warps (of both CTAs)
+            if (kb == kb1 - 1) { if (CTAS == 2) umma_commit_2sm(&acc_full[acc]); else umma_commit(&acc_full[acc]); }
           }
-#pragma unroll
-          for (int kk = 0; kk < kk_steps; ++kk) {
-            const uint64_t adesc = make_smem_desc_sw128(sa + kk * a_step, a_lbo, 1024);
-            const uint64_t bdesc = make_smem_desc_sw128(sb + kk * b_step, b_lbo, 1024);
-            const uint32_t accum = (kb > kb0 || kk > 0) ? 1u : 0u;
-            if (p.elem_bytes == 2) umma_f16(d_tmem, adesc, bdesc, idesc, accum);
-            else umma_tf32(d_tmem, adesc, bdesc, idesc, accum);
-          }
-          umma_commit(&empty_bar[stage]);            // frees this smem slot once the MMAs have read it
+          __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&acc_full[acc]);                 // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
     // =============================== epilogue ===============================
+    // the leader's acc_empty barriers (a shared::cta address is a valid shared::cluster address of the own CTA)
+    const uint32_t acc_empty_addr = (CTAS == 2) ? mapa_shared(smem_u32(&acc_empty[0]), 0) : smem_u32(&acc_empty[0]);
     if (p.tma_epi) {
-      epilogue_tma<BN, EPI>(p, tmap_d, tmap_x, tmap_x2, stg, acc_full, acc_empty, aux_full, s_cs, tmem_base, total_tiles, tiles_mn, warp, lane);
+      epilogue_tma<BN, EPI, CTAS>(p, tmap_d, tmap_x, tmap_x2, stg + (warp - 2) * Cfg::kStgPerWarp, acc_full, acc_empty_addr,
+                                  aux_full + 3 * (warp - 2), tmem_base, first_tile, tile_stride, total_tiles, tiles_mn, row_base,
+                                  warp, lane);
     } else {
     const int ew = warp - 2;                 // 0..7
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
@@ -405,10 +473,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int row_in_tile = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
       const int split = tile / tiles_mn;
       const int mn = tile - split * tiles_mn;
-      const int m0 = (mn / p.n_tiles) * kBM;
+      const int m0 = (mn / p.n_tiles) * (kBM * CTAS) + row_base;
       const int n0 = (mn % p.n_tiles) * BN;
       const int64_t row = m0 + row_in_tile;
       const bool row_ok = row < p.M;
@@ -575,7 +643,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (lane == 0) mbar_arrive_cluster(acc_empty_addr + acc * 8);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     }
@@ -583,9 +651,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();               // the peer may still read our smem / signal our barriers until here
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CTAS == 2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -609,8 +678,14 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D row-major tensor [rows, cols] (cols contiguous, leading dim ld elements); box = {box_cols, box_rows}
+static int make_tmap_sw(CUtensorMap* m, const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld,
+                        int box_cols, int box_rows, CUtensorMapSwizzle swz);
 int make_tmap(CUtensorMap* m, const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld,
               int box_cols, int box_rows) {
+  return make_tmap_sw(m, ptr, elem_bytes, rows, cols, ld, box_cols, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+static int make_tmap_sw(CUtensorMap* m, const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld,
+                        int box_cols, int box_rows, CUtensorMapSwizzle swz) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled not available (driver entry point lookup failed)"); return SIMSEG_ERR_CUDA; }
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
@@ -619,7 +694,7 @@ int make_tmap(CUtensorMap* m, const void* ptr, int elem_bytes, int64_t rows, int
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p rows=%lld cols=%lld ld=%lld box=%dx%d", static_cast<int>(r), ptr,
               static_cast<long long>(rows), static_cast<long long>(cols), static_cast<long long>(ld), box_cols, box_rows);
@@ -648,36 +723,50 @@ int make_tmap_mn3d(CUtensorMap* m, const void* ptr, int elem_bytes, int64_t k_ro
   return SIMSEG_OK;
 }
 
-template <int BN, int EPI>
-static int launch_gemm(Ctx* ctx, const CUtensorMap* tm, const GemmParams& p, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+template <int BN, int EPI, int CTAS>
+static int launch_gemm(Ctx* ctx, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
+  using Cfg = GemmCfg<BN, EPI, CTAS>;
   static bool attr_set = false;
-  auto kfn = gemm_kernel<BN, EPI>;
+  auto kfn = gemm_kernel<BN, EPI, CTAS>;
   if (!attr_set) {
     SIMSEG_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int total = p.m_tiles * p.n_tiles * p.splits;
-  const int grid = total < ctx->num_sms ? total : ctx->num_sms;
-  kfn<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
+  if (CTAS == 1) {
+    kfn<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    SIMSEG_CUDA(cudaLaunchKernelEx(&cfg, kfn, tm[0], tm[1], tm[2], tm[3], tm[4], p));
+  }
   ctx->launches++;
   SIMSEG_LAUNCH_CHECK();
   return SIMSEG_OK;
 }
 
-template <int BN>
-static int dispatch_epi(Ctx* ctx, int epi, const CUtensorMap* tm, const GemmParams& p, cudaStream_t st) {
+template <int BN, int CTAS>
+static int dispatch_epi(Ctx* ctx, int epi, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
   switch (epi) {
-    case SIMSEG_EPI_NONE: return launch_gemm<BN, SIMSEG_EPI_NONE>(ctx, tm, p, st);
-    case SIMSEG_EPI_BIAS_GELU: return launch_gemm<BN, SIMSEG_EPI_BIAS_GELU>(ctx, tm, p, st);
-    case SIMSEG_EPI_BIAS_RESIDUAL: return launch_gemm<BN, SIMSEG_EPI_BIAS_RESIDUAL>(ctx, tm, p, st);
-    case SIMSEG_EPI_DGELU: return launch_gemm<BN, SIMSEG_EPI_DGELU>(ctx, tm, p, st);
-    case SIMSEG_EPI_ROWSCALE: return launch_gemm<BN, SIMSEG_EPI_ROWSCALE>(ctx, tm, p, st);
+    case SIMSEG_EPI_NONE: return launch_gemm<BN, SIMSEG_EPI_NONE, CTAS>(ctx, tm, p, grid, st);
+    case SIMSEG_EPI_BIAS_GELU: return launch_gemm<BN, SIMSEG_EPI_BIAS_GELU, CTAS>(ctx, tm, p, grid, st);
+    case SIMSEG_EPI_BIAS_RESIDUAL: return launch_gemm<BN, SIMSEG_EPI_BIAS_RESIDUAL, CTAS>(ctx, tm, p, grid, st);
+    case SIMSEG_EPI_DGELU: return launch_gemm<BN, SIMSEG_EPI_DGELU, CTAS>(ctx, tm, p, grid, st);
+    case SIMSEG_EPI_ROWSCALE: return launch_gemm<BN, SIMSEG_EPI_ROWSCALE, CTAS>(ctx, tm, p, grid, st);
   }
   set_error("unknown epilogue %d", epi);
   return SIMSEG_ERR_INVALID;
 }
 
+// `reserved` bits (bench / debug only): 1 = no TMA, 2 = no MMA, 4 = 2-D boxes for MN-major operands, 8 = direct-store
+// epilogue, 16 = force single-CTA tiles, 32 = force CTA pairs.
 int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
   SIMSEG_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "gemm: empty problem M=%lld N=%lld K=%lld", (long long)a->M,
                    (long long)a->N, (long long)a->K);
@@ -696,32 +785,61 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
   if (a->epilogue == SIMSEG_EPI_DGELU) SIMSEG_CHECK_ARG(a->aux != nullptr, "gemm: aux (pre-activation) missing");
   if (a->epilogue == SIMSEG_EPI_ROWSCALE) SIMSEG_CHECK_ARG(a->row_scale != nullptr, "gemm: row_scale missing");
 
+  const int mn_atom = kSwizzleBytes / eb;
+  const int k_elems = kSwizzleBytes / eb;
+  const int kb_total = static_cast<int>(cdiv(a->K, k_elems));
+  const bool can_split = a->epilogue == SIMSEG_EPI_NONE && a->out_dtype == SIMSEG_F32 && a->col_sum == nullptr;
+
+  // ---- tile shape: BN in {128,192,256}, single CTA (128 rows) or CTA pair (256 rows)
   int bn = a->tile_n;
-  if (bn == 0) {
-    // smallest padding waste first, widest tile on ties (fewer A re-reads, better MMA efficiency)
-    const int cand[3] = {256, 192, 128};
-    int64_t best = -1;
-    for (int c : cand) {
-      const int64_t padded = cdiv(a->N, c) * c;
-      if (best < 0 || padded < best) { best = padded; bn = c; }
+  SIMSEG_CHECK_ARG(bn == 0 || bn == 128 || bn == 192 || bn == 256, "gemm: tile_n must be 0/128/192/256 (got %d)", bn);
+  int ctas = (a->reserved & 16) ? 1 : ((a->reserved & 32) ? 2 : 0);
+  if (eb != 2) ctas = 1;                                       // pairs are only instantiated for the bf16 path
+  auto pair_ok = [&](int n) { return !(a->b_major && (n / 2) % mn_atom != 0); };
+  if (ctas == 2 && bn != 0) SIMSEG_CHECK_ARG(pair_ok(bn), "gemm: CTA pairs need tile_n/2 to be a whole number of MN atoms");
+  if (bn == 0 || ctas == 0) {
+    // estimated time of every admissible (pair?, BN): waves of persistent units x per-tile cost.  Per-tile cost is
+    // BN x k-blocks of MMA issue (a pair's MMA covers twice the rows in the same time) plus a fixed prologue/epilogue
+    // term; pairs also cut the L2->SM operand traffic per flop by a third, which is what the single-CTA engine is
+    // bound by on large tiles (measured), hence the 0.8 factor.
+    double best = 1e300;
+    int best_bn = 256, best_c = 1;
+    for (int c = 1; c <= 2; ++c) {
+      if (ctas != 0 && c != ctas) continue;
+      if (c == 2 && eb != 2) continue;
+      for (int n : {256, 192, 128}) {
+        if (bn != 0 && n != bn) continue;
+        if (c == 2 && !pair_ok(n)) continue;
+        const int64_t mt = cdiv(a->M, kBM * c), nt = cdiv(a->N, n);
+        const int units = ctx->num_sms / c;
+        int64_t items = mt * nt;
+        int kbs = kb_total;
+        if (can_split && kb_total >= 32 && items < units) {    // split-K fills the machine
+          const int s = static_cast<int>(imin64(units / items, kb_total / 8));
+          if (s > 1) { kbs = static_cast<int>(cdiv(kb_total, s)); items *= cdiv(kb_total, kbs); }
+        }
+        const double waves = static_cast<double>(cdiv(items, units));
+        const double t = waves * (kbs + 3.0) * n * (c == 2 ? 0.8 : 1.0);
+        if (t < best * 0.999) { best = t; best_bn = n; best_c = c; }
+      }
     }
+    bn = best_bn;
+    ctas = best_c;
   }
-  SIMSEG_CHECK_ARG(bn == 128 || bn == 192 || bn == 256, "gemm: tile_n must be 128/192/256 (got %d)", bn);
 
   GemmParams p{};
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.a_mn = a->a_major ? 1 : 0; p.b_mn = a->b_major ? 1 : 0;
   p.elem_bytes = eb;
-  p.m_tiles = static_cast<int>(cdiv(a->M, kBM));
+  p.m_tiles = static_cast<int>(cdiv(a->M, kBM * ctas));
   p.n_tiles = static_cast<int>(cdiv(a->N, bn));
-  const int k_elems = kSwizzleBytes / eb;
-  p.kb_total = static_cast<int>(cdiv(a->K, k_elems));
+  p.kb_total = kb_total;
+  const int units_max = ctx->num_sms / ctas;
   // split-K only for plain fp32 accumulation outputs with few output tiles (wgrad: K = all tokens).
   // The split count is chosen for wave efficiency: work items (tiles x splits) should fill whole waves of
-  // num_sms persistent CTAs; among equally efficient choices the smallest split count wins (fewer atomics).
+  // persistent units; among equally efficient choices the smallest split count wins (fewer atomics).
   int splits = 1;
   const int tiles_mn = p.m_tiles * p.n_tiles;
-  const bool can_split = a->epilogue == SIMSEG_EPI_NONE && a->out_dtype == SIMSEG_F32 && a->col_sum == nullptr;
   if (can_split && p.kb_total >= 32) {
     const int max_splits = p.kb_total / 8 < 64 ? p.kb_total / 8 : 64;
     double best_eff = 0.0;
@@ -729,9 +847,9 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
       const int kbs = static_cast<int>(cdiv(p.kb_total, s));
       const int s_eff = static_cast<int>(cdiv(p.kb_total, kbs));
       const int64_t items = static_cast<int64_t>(tiles_mn) * s_eff;
-      const int64_t waves = cdiv(items, ctx->num_sms);
+      const int64_t waves = cdiv(items, units_max);
       // time ~ waves * (k-blocks per item + fixed per-item cost of ~6 k-blocks for prologue/epilogue)
-      const double eff = static_cast<double>(tiles_mn) * p.kb_total / (static_cast<double>(waves) * ctx->num_sms * (kbs + 6.0));
+      const double eff = static_cast<double>(tiles_mn) * p.kb_total / (static_cast<double>(waves) * units_max * (kbs + 6.0));
       if (eff > best_eff * 1.02) { best_eff = eff; splits = s_eff; }
     }
   }
@@ -759,7 +877,6 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
   memset(tm, 0, sizeof(tm));
   CUtensorMap& ta = tm[0];
   CUtensorMap& tb = tm[1];
-  const int mn_atom = kSwizzleBytes / eb;
   int rc;
   // coalesced TMA-store epilogue: bf16 output, no split-K / accumulation, 16-byte aligned rows
   const bool epi_ok = a->epilogue == SIMSEG_EPI_NONE || a->epilogue == SIMSEG_EPI_BIAS_GELU || a->epilogue == SIMSEG_EPI_DGELU;
@@ -767,34 +884,49 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
   bool tma_epi = epi_ok && p.out_bf16 && !p.atomic_out && row_ok16(a->d, a->ldd) && (a->reserved & 8) == 0;
   if (a->aux) tma_epi = tma_epi && row_ok16(a->aux, a->ld_aux);
   if (a->aux2) tma_epi = tma_epi && row_ok16(a->aux2, a->ld_aux2) && a->epilogue == SIMSEG_EPI_DGELU;
-  if (a->bias) tma_epi = tma_epi && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0;
   if (a->epilogue != SIMSEG_EPI_DGELU && a->col_sum) tma_epi = false;
   SIMSEG_CHECK_ARG(!(a->aux2 && !tma_epi), "gemm: aux2 needs the bf16 TMA epilogue (DGELU, bf16 out, 16-byte aligned rows)");
   p.tma_epi = tma_epi ? 1 : 0;
   p.aux2 = a->aux2;
   if (tma_epi) {
-    if ((rc = make_tmap(&tm[2], a->d, 2, a->M, a->N, a->ldd, 64, kBM))) return rc;
-    if (a->aux && (rc = make_tmap(&tm[3], a->aux, 2, a->M, a->N, a->ld_aux, 64, kBM))) return rc;
-    if (a->aux2 && (rc = make_tmap(&tm[4], a->aux2, 2, a->M, a->N, a->ld_aux2, 64, kBM))) return rc;
+    const CUtensorMapSwizzle s64 = CU_TENSOR_MAP_SWIZZLE_64B;
+    if ((rc = make_tmap_sw(&tm[2], a->d, 2, a->M, a->N, a->ldd, 32, 32, s64))) return rc;
+    if (a->aux && (rc = make_tmap_sw(&tm[3], a->aux, 2, a->M, a->N, a->ld_aux, 32, 32, s64))) return rc;
+    if (a->aux2 && (rc = make_tmap_sw(&tm[4], a->aux2, 2, a->M, a->N, a->ld_aux2, 32, 32, s64))) return rc;
   }
   // MN-major operands whose MN extent is a whole number of 128-byte atoms take ONE 3-D box per k-block
   // (atoms past the matrix edge are zero-filled by TMA); ragged extents keep one 2-D box per atom.
   const bool no3d = (a->reserved & 4) != 0;
+  const int b_rows = bn / ctas;                                // B columns staged per CTA
   p.a_3d = (p.a_mn && a->M % mn_atom == 0 && !no3d) ? 1 : 0;
   p.b_3d = (p.b_mn && a->N % mn_atom == 0 && !no3d) ? 1 : 0;
   if (!p.a_mn) rc = make_tmap(&ta, a->a, eb, a->M, a->K, a->lda, k_elems, kBM);
   else if (p.a_3d) rc = make_tmap_mn3d(&ta, a->a, eb, a->K, a->M, a->lda, k_elems, kBM / mn_atom);
   else rc = make_tmap(&ta, a->a, eb, a->K, a->M, a->lda, mn_atom, k_elems);
   if (rc) return rc;
-  if (!p.b_mn) rc = make_tmap(&tb, a->b, eb, a->N, a->K, a->ldb, k_elems, bn);
-  else if (p.b_3d) rc = make_tmap_mn3d(&tb, a->b, eb, a->K, a->N, a->ldb, k_elems, bn / mn_atom);
+  if (!p.b_mn) rc = make_tmap(&tb, a->b, eb, a->N, a->K, a->ldb, k_elems, b_rows);
+  else if (p.b_3d) rc = make_tmap_mn3d(&tb, a->b, eb, a->K, a->N, a->ldb, k_elems, b_rows / mn_atom);
   else rc = make_tmap(&tb, a->b, eb, a->K, a->N, a->ldb, mn_atom, k_elems);
   if (rc) return rc;
 
+  // persistent grid: one unit (CTA or CTA pair) per SM (pair); with fused column sums keep every unit on ONE n-tile
+  // (unit count a multiple of n_tiles) so the sums stay in registers until the unit is done
+  const int total = p.m_tiles * p.n_tiles * p.splits;
+  int units = total < units_max ? total : units_max;
+  if (tma_epi && a->col_sum && p.n_tiles <= units) units = (units / p.n_tiles) * p.n_tiles;
+  const int grid = units * ctas;
+
+  if (ctas == 2) {
+    switch (bn) {
+      case 128: return dispatch_epi<128, 2>(ctx, a->epilogue, tm, p, grid, st);
+      case 192: return dispatch_epi<192, 2>(ctx, a->epilogue, tm, p, grid, st);
+      default: return dispatch_epi<256, 2>(ctx, a->epilogue, tm, p, grid, st);
+    }
+  }
   switch (bn) {
-    case 128: return dispatch_epi<128>(ctx, a->epilogue, tm, p, st);
-    case 192: return dispatch_epi<192>(ctx, a->epilogue, tm, p, st);
-    default: return dispatch_epi<256>(ctx, a->epilogue, tm, p, st);
+    case 128: return dispatch_epi<128, 1>(ctx, a->epilogue, tm, p, grid, st);
+    case 192: return dispatch_epi<192, 1>(ctx, a->epilogue, tm, p, grid, st);
+    default: return dispatch_epi<256, 1>(ctx, a->epilogue, tm, p, grid, st);
   }
 }
 

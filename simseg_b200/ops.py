@@ -103,9 +103,10 @@ def linear_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, **kw) -> Ten
     return gemm(x, w, M=x.shape[0], N=w.shape[0], K=x.shape[1], bias=bias, **kw)
 
 
-def linear_dgrad(dy: Tensor, w: Tensor, **kw) -> Tensor:
-    """dx = dy @ w: dy [M,N] bf16, w [N,K] bf16 (read as a [K=N_out, N=K_in] MN-major B operand)."""
-    return gemm(dy, w, M=dy.shape[0], N=w.shape[1], K=dy.shape[1], a_major=0, b_major=1, **kw)
+def linear_dgrad(dy: Tensor, w_t: Tensor, **kw) -> Tensor:
+    """dx = dy @ w: dy [M,N_out] bf16, w_t = w^T [K_in,N_out] bf16 (the per-step transposed bf16 weight copy, so dgrad
+    runs the same K-major TMA path as forward)."""
+    return gemm(dy, w_t, M=dy.shape[0], N=w_t.shape[0], K=dy.shape[1], a_major=0, b_major=0, **kw)
 
 
 def linear_wgrad(dy: Tensor, x: Tensor, out: Tensor, accumulate: bool = False) -> Tensor:

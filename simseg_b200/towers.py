@@ -40,11 +40,26 @@ class Bf16Weights:
             self._c[k] = ops.cast_bf16(w.reshape(w.shape[0], -1))
         return self._c[k]
 
+    def get_t(self, p: Tensor) -> Tensor:
+        """bf16 W^T [K_in, N_out]: the K-major B operand of dgrad (dx = dy @ W), written by the same cast kernel."""
+        k = ("t", id(p))
+        if k not in self._c:
+            w = p.detach()
+            self._c[id(p)], self._c[k] = ops.cast_bf16(w.reshape(w.shape[0], -1), transpose_too=True)
+        return self._c[k]
+
     def packed(self, key: str, ps: List[Tensor]) -> Tensor:
         """Row-concatenation of several [n_i, K] weights as one bf16 matrix (BERT q/k/v -> one GEMM)."""
         if key not in self._c:
             self._c[key] = torch.cat([self.get(p) for p in ps], 0)
         return self._c[key]
+
+    def packed_t(self, key: str, ps: List[Tensor]) -> Tensor:
+        """Transpose of ``packed``: [K, sum n_i]."""
+        k = ("t", key)
+        if k not in self._c:
+            self._c[k] = torch.cat([self.get_t(p) for p in ps], 1).contiguous()
+        return self._c[k]
 
     def clear(self):
         self._c.clear()
@@ -142,7 +157,7 @@ def vit_backward(m, sv: VitSaved, dtok: Tensor, wc: Bf16Weights, dtok2: Optional
         # ---- MLP branch: x2 = x1 + fc2(gelu(fc1(LN2(x1))))
         # dgrad first: its epilogue multiplies by gelu'(h) AND emits a = gelu(h), which the fc2 wgrad then consumes
         a = torch.empty_like(s.h)
-        dh = ops.linear_dgrad(g, wc.get(blk.mlp.fc2.weight), epilogue=EPI_DGELU, aux=s.h, aux2=a,
+        dh = ops.linear_dgrad(g, wc.get_t(blk.mlp.fc2.weight), epilogue=EPI_DGELU, aux=s.h, aux2=a,
                               col_sum=_grad_of(blk.mlp.fc1.bias))
         s.h = None
         ops.linear_wgrad(g, a, _grad_of(blk.mlp.fc2.weight), accumulate=True)
@@ -150,7 +165,7 @@ def vit_backward(m, sv: VitSaved, dtok: Tensor, wc: Bf16Weights, dtok2: Optional
         y2, _, _, _ = ops.layernorm_fwd(s.x1, blk.norm2.weight, blk.norm2.bias, 1e-6, want_stats=False)
         ops.linear_wgrad(dh, y2, _grad_of(blk.mlp.fc1.weight), accumulate=True)
         del y2
-        dy2 = ops.linear_dgrad(dh, wc.get(blk.mlp.fc1.weight))
+        dy2 = ops.linear_dgrad(dh, wc.get_t(blk.mlp.fc1.weight))
         del dh
         ops.layernorm_bwd(dy2, s.x1, blk.norm2.weight, s.mean2, s.rstd2, dx=dx, dx_accumulate=True, dx_bf16=g,
                           dgamma=_grad_of(blk.norm2.weight), dbeta=_grad_of(blk.norm2.bias),
@@ -159,7 +174,7 @@ def vit_backward(m, sv: VitSaved, dtok: Tensor, wc: Bf16Weights, dtok2: Optional
         s.x1 = None
         # ---- attention branch: x1 = x + proj(attn(qkv(LN1(x))))
         ops.linear_wgrad(g, s.o, _grad_of(blk.attn.proj.weight), accumulate=True)
-        do = ops.linear_dgrad(g, wc.get(blk.attn.proj.weight))
+        do = ops.linear_dgrad(g, wc.get_t(blk.attn.proj.weight))
         dqkv = torch.empty_like(s.qkv)
         q5, d5 = s.qkv.view(B, S, 3, H, 64), dqkv.view(B, S, 3, H, 64)
         ops.attention_bwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], s.o, do, s.lse, B, H, S, strides, None, 0.125,
@@ -170,7 +185,7 @@ def vit_backward(m, sv: VitSaved, dtok: Tensor, wc: Bf16Weights, dtok2: Optional
         y, _, _, _ = ops.layernorm_fwd(s.x, blk.norm1.weight, blk.norm1.bias, 1e-6, want_stats=False)
         ops.linear_wgrad(dqkv, y, _grad_of(blk.attn.qkv.weight), accumulate=True)
         del y
-        dy = ops.linear_dgrad(dqkv, wc.get(blk.attn.qkv.weight))
+        dy = ops.linear_dgrad(dqkv, wc.get_t(blk.attn.qkv.weight))
         del dqkv
         prev_bias = _grad_of(m.blocks[i - 1].mlp.fc2.bias) if i > 0 else None
         ops.layernorm_bwd(dy, s.x, blk.norm1.weight, s.mean1, s.rstd1, dx=dx, dx_accumulate=True, dx_bf16=g,
@@ -282,13 +297,13 @@ def bert_backward(m, sv: BertSaved, dh: Tensor, wc: Bf16Weights, dh2: Optional[T
                           dgamma=_grad_of(layer.output.LayerNorm.weight), dbeta=_grad_of(layer.output.LayerNorm.bias),
                           dx_colsum=_grad_of(layer.output.dense.bias))
         f = torch.empty_like(s.pre)
-        dpre = ops.linear_dgrad(g2, wc.get(layer.output.dense.weight), epilogue=EPI_DGELU, aux=s.pre, aux2=f,
+        dpre = ops.linear_dgrad(g2, wc.get_t(layer.output.dense.weight), epilogue=EPI_DGELU, aux=s.pre, aux2=f,
                                 col_sum=_grad_of(layer.intermediate.dense.bias))
         ops.linear_wgrad(g2, f, _grad_of(layer.output.dense.weight), accumulate=True)
         del f
         h1b, _, _, _ = ops.layernorm_fwd(s.s1, ao.LayerNorm.weight, ao.LayerNorm.bias, 1e-12, want_stats=False)
         ops.linear_wgrad(dpre, h1b, _grad_of(layer.intermediate.dense.weight), accumulate=True)
-        dh1 = ops.linear_dgrad(dpre, wc.get(layer.intermediate.dense.weight))
+        dh1 = ops.linear_dgrad(dpre, wc.get_t(layer.intermediate.dense.weight))
         del dpre, h1b
         # h1 = LN(s1), s1 = attn.out.dense(c) + h_in ; dh1_total = dh1 + ds2
         ds1 = torch.empty((M, D), device=dev, dtype=torch.float32)
@@ -298,7 +313,7 @@ def bert_backward(m, sv: BertSaved, dh: Tensor, wc: Bf16Weights, dh2: Optional[T
                           dx_colsum=_grad_of(ao.dense.bias))
         del dh1, ds2
         ops.linear_wgrad(g1, s.c, _grad_of(ao.dense.weight), accumulate=True)
-        dc = ops.linear_dgrad(g1, wc.get(ao.dense.weight))
+        dc = ops.linear_dgrad(g1, wc.get_t(ao.dense.weight))
         dqkv = torch.empty_like(s.qkv)
         q5, d5 = s.qkv.view(B, T, 3, H, 64), dqkv.view(B, T, 3, H, 64)
         ops.attention_bwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], s.c, dc, s.lse, B, H, T, strides, sv.key_len, 0.125,
@@ -309,7 +324,7 @@ def bert_backward(m, sv: BertSaved, dh: Tensor, wc: Bf16Weights, dh2: Optional[T
         for j, p in enumerate(qp):
             _grad_of(p.bias).add_(bsum[j * D:(j + 1) * D])
             ops.linear_wgrad(dqkv[:, j * D:(j + 1) * D], s.h_in, _grad_of(p.weight), accumulate=True)
-        dy = ops.linear_dgrad(dqkv, wc.packed(f"bert.qkv.{li}", [p.weight for p in qp]))
+        dy = ops.linear_dgrad(dqkv, wc.packed_t(f"bert.qkv.{li}", [p.weight for p in qp]))
         dres = ds1
         sv.layers[li] = None
     de = torch.empty((M, D), device=dev, dtype=torch.float32)

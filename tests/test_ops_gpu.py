@@ -27,24 +27,27 @@ def gelu(x):
 
 @pytest.mark.parametrize("M,N,K,tile_n", [(256, 128, 64, 128), (128, 256, 128, 256), (300, 384, 384, 0),
                                           (1000, 1152, 384, 192), (777, 512, 768, 0), (4096, 1536, 384, 0),
-                                          (130, 171, 512, 192), (64, 20, 512, 0)])
-def test_gemm_kk_plain(cuda, M, N, K, tile_n):
+                                          (130, 171, 512, 192), (64, 20, 512, 0), (20000, 768, 200, 256)])
+@pytest.mark.parametrize("mode", [16, 32], ids=["cta1", "pair"])
+def test_gemm_kk_plain(cuda, M, N, K, tile_n, mode):
+    """mode: 16 = single-CTA 128-row tiles, 32 = CTA pairs (tcgen05 cta_group::2, 256-row tiles)."""
     ops = _ops()
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     a = torch.randn(M, K, device=cuda, generator=g).bfloat16()
     b = torch.randn(N, K, device=cuda, generator=g).bfloat16()
     bias = torch.randn(N, device=cuda, generator=g)
     ref = a.float() @ b.float().T + bias
-    out = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, out_dtype=torch.float32, tile_n=tile_n)
+    out = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, out_dtype=torch.float32, tile_n=tile_n, _dbg=mode)
     torch.cuda.synchronize()
     assert _rel(out, ref) < 2e-5
-    out16 = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, out_dtype=torch.bfloat16, tile_n=tile_n)
+    out16 = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, out_dtype=torch.bfloat16, tile_n=tile_n, _dbg=mode)
     assert _rel(out16, ref) < 6e-3
 
 
 @pytest.mark.parametrize("a_major,b_major", [(0, 1), (1, 1), (1, 0)])
 @pytest.mark.parametrize("M,N,K", [(256, 128, 128), (333, 384, 200), (384, 1536, 3000), (512, 768, 64)])
-def test_gemm_majors(cuda, a_major, b_major, M, N, K):
+@pytest.mark.parametrize("mode", [16, 32], ids=["cta1", "pair"])
+def test_gemm_majors(cuda, a_major, b_major, M, N, K, mode):
     ops = _ops()
     K8 = (K + 7) // 8 * 8
     g = torch.Generator(device="cuda").manual_seed(7 * M + N + K)
@@ -60,7 +63,7 @@ def test_gemm_majors(cuda, a_major, b_major, M, N, K):
         b_st = torch.zeros(K8, N8, device=cuda, dtype=torch.bfloat16); b_st[:, :N] = Bm.T
     else:
         b_st = Bm
-    out = ops.gemm(a_st, b_st, M=M, N=N, K=K8, a_major=a_major, b_major=b_major, out_dtype=torch.float32)
+    out = ops.gemm(a_st, b_st, M=M, N=N, K=K8, a_major=a_major, b_major=b_major, out_dtype=torch.float32, _dbg=mode)
     assert _rel(out, ref) < 2e-5
 
 
@@ -110,8 +113,10 @@ def test_gemm_epilogues(cuda):
     assert _rel(o, (pre - bias) * rs[:, None]) < 2e-5
 
 
-@pytest.mark.parametrize("M,N,K,tile_n", [(1000, 1536, 384, 0), (130, 200, 64, 128), (4500, 3072, 768, 256), (257, 1544, 128, 192)])
-def test_gemm_tma_epilogue_bf16(cuda, M, N, K, tile_n):
+@pytest.mark.parametrize("M,N,K,tile_n", [(1000, 1536, 384, 0), (130, 200, 64, 128), (4500, 3072, 768, 256), (257, 1544, 128, 192),
+                                          (40000, 1536, 384, 256)])
+@pytest.mark.parametrize("mode", [16, 32], ids=["cta1", "pair"])
+def test_gemm_tma_epilogue_bf16(cuda, M, N, K, tile_n, mode):
     """The coalesced (swizzled smem + TMA store) epilogue for bf16 outputs: plain+bias, GELU with saved pre-activation,
     and the backward dGELU that TMA-loads the pre-activation, emits gelu(pre) next to the gradient and column sums —
     ragged M / N (TMA clips), more tiles than SMs (staging-slot recycling across tiles), against the direct-store path."""
@@ -122,20 +127,20 @@ def test_gemm_tma_epilogue_bf16(cuda, M, N, K, tile_n):
     b = (torch.randn(N, K, device=cuda, generator=g) * 0.1).bfloat16()
     bias = torch.randn(N, device=cuda, generator=g) * 0.1
     pre = a.float() @ b.float().T + bias
-    out = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, tile_n=tile_n)
+    out = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, tile_n=tile_n, _dbg=mode)
     assert _rel(out, pre) < 6e-3
-    legacy = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, tile_n=tile_n, _dbg=8)          # direct-store epilogue
+    legacy = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, tile_n=tile_n, _dbg=mode | 8)          # direct-store epilogue
     assert torch.equal(out, legacy)
     aux = torch.full((M, N), float("nan"), device=cuda, dtype=torch.bfloat16)
-    act = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, epilogue=EPI_BIAS_GELU, aux=aux, tile_n=tile_n)
+    act = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, epilogue=EPI_BIAS_GELU, aux=aux, tile_n=tile_n, _dbg=mode)
     assert torch.equal(aux, out)                                                  # same rounding of the pre-activation
     assert (act.float() - gelu(aux.float())).abs().max().item() < 2e-2
-    act_noaux = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, epilogue=EPI_BIAS_GELU, tile_n=tile_n)
+    act_noaux = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, epilogue=EPI_BIAS_GELU, tile_n=tile_n, _dbg=mode)
     assert torch.equal(act_noaux, act)
     # backward: d = (a @ b^T) * gelu'(aux), aux2 = gelu(aux), col_sum += sum_m d
     cs = torch.zeros(N, device=cuda)
     a2 = torch.full((M, N), float("nan"), device=cuda, dtype=torch.bfloat16)
-    dh = ops.gemm(a, b, M=M, N=N, K=K, epilogue=EPI_DGELU, aux=aux, aux2=a2, col_sum=cs, tile_n=tile_n)
+    dh = ops.gemm(a, b, M=M, N=N, K=K, epilogue=EPI_DGELU, aux=aux, aux2=a2, col_sum=cs, tile_n=tile_n, _dbg=mode)
     h = aux.float().requires_grad_(True)
     gelu(h).backward(pre - bias)
     assert _rel(dh, h.grad) < 6e-3

@@ -10,7 +10,7 @@ dev = "cuda"
 
 
 def t_ms(fn, reps):
-    for _ in range(3):
+    for _ in range(3 if reps > 1 else 0):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -38,33 +38,39 @@ def bench(tag, M, N, K, a_major=0, b_major=0, epi=EPI_NONE, out_dtype=torch.bflo
     if epi == EPI_DGELU:
         kw["aux"] = torch.randn(M, N, device=dev, dtype=bf)
         kw["col_sum"] = torch.zeros(N, device=dev)
+        if out_dtype == bf:
+            kw["aux2"] = torch.empty(M, N, device=dev, dtype=bf)
     if accumulate:
         kw["accumulate"] = True
-    if dbg:
-        kw["_dbg"] = dbg
     res = []
     for tn in tile_ns:
-        ms = t_ms(lambda: ops.gemm(A, B, tile_n=tn, **kw), reps)
-        res.append(f"bn={tn}: {ms:7.3f} ms {2.0 * M * N * K / ms / 1e9:7.1f} TF/s")
+        # tn: tile_n, or (tile_n, mode) with mode 16 = single CTA, 32 = CTA pair; 0 = engine's own choice
+        tile, mode = tn if isinstance(tn, tuple) else (tn, 0)
+        kw["_dbg"] = dbg | mode
+        try:
+            ms = t_ms(lambda: ops.gemm(A, B, tile_n=tile, **kw), reps)
+            res.append(f"{'auto' if not mode else ('c1' if mode == 16 else 'c2')}/{tile}: {ms:6.3f} ms {2.0 * M * N * K / ms / 1e9:6.0f}")
+        except Exception as e:
+            res.append(f"{mode}/{tile}: n/a")
     # cuBLAS reference point for the same math (library call, only as a yardstick)
     if not dbg:
         Ao, Bo = (A.t() if a_major else A), (B if b_major else B.t())
         ms = t_ms(lambda: torch.matmul(Ao, Bo), reps)
-        res.append(f"cublas {ms:7.3f} ms {2.0 * M * N * K / ms / 1e9:7.1f} TF/s")
+        res.append(f"cublas {ms:6.3f} ms {2.0 * M * N * K / ms / 1e9:6.0f}")
     print(f"{tag:34s} M={M:7d} N={N:5d} K={K:7d} | " + " | ".join(res), flush=True)
 
 
 def tower(name, M, D, F, reps):
     f32 = torch.float32
-    tn = (0, 128, 192, 256)
+    tn = (0, (128, 16), (192, 16), (256, 16), (128, 32), (192, 32), (256, 32))
     bench(f"{name} qkv fwd", M, 3 * D, D, reps=reps, tile_ns=tn)
-    bench(f"{name} proj fwd +res(f32)", M, D, D, epi=EPI_BIAS_RESIDUAL, out_dtype=f32, reps=reps, tile_ns=tn)
+    bench(f"{name} proj fwd", M, D, D, reps=reps, tile_ns=tn)
     bench(f"{name} fc1 fwd gelu+aux", M, F, D, epi=EPI_BIAS_GELU, reps=reps, tile_ns=tn)
-    bench(f"{name} fc2 fwd +res(f32)", M, D, F, epi=EPI_BIAS_RESIDUAL, out_dtype=f32, reps=reps, tile_ns=tn)
-    bench(f"{name} fc2 dgrad dgelu+colsum", M, F, D, b_major=1, epi=EPI_DGELU, reps=reps, tile_ns=tn)
-    bench(f"{name} fc1 dgrad", M, D, F, b_major=1, reps=reps, tile_ns=tn)
-    bench(f"{name} qkv dgrad", M, D, 3 * D, b_major=1, reps=reps, tile_ns=tn)
-    bench(f"{name} proj dgrad", M, D, D, b_major=1, reps=reps, tile_ns=tn)
+    bench(f"{name} fc2 fwd", M, D, F, reps=reps, tile_ns=tn)
+    bench(f"{name} fc2 dgrad dgelu+colsum", M, F, D, epi=EPI_DGELU, reps=reps, tile_ns=tn)
+    bench(f"{name} fc1 dgrad", M, D, F, reps=reps, tile_ns=tn)
+    bench(f"{name} qkv dgrad", M, D, 3 * D, reps=reps, tile_ns=tn)
+    bench(f"{name} proj dgrad", M, D, D, reps=reps, tile_ns=tn)
     bench(f"{name} fc2 wgrad", D, F, M, a_major=1, b_major=1, out_dtype=f32, reps=reps, tile_ns=tn, accumulate=True)
     bench(f"{name} fc1 wgrad", F, D, M, a_major=1, b_major=1, out_dtype=f32, reps=reps, tile_ns=tn, accumulate=True)
     bench(f"{name} qkv wgrad", 3 * D, D, M, a_major=1, b_major=1, out_dtype=f32, reps=reps, tile_ns=tn, accumulate=True)
@@ -78,6 +84,14 @@ if __name__ == "__main__":
         od = torch.float32 if sys.argv[8] == "f32" else torch.bfloat16
         bench("one", M, N, K, a_major=am, b_major=bm, epi=epi, out_dtype=od, reps=2, tile_ns=(int(sys.argv[9]),),
               accumulate=len(sys.argv) > 10)
+        sys.exit(0)
+    if which == "prof":     # one launch per configuration, for `ncu --set full -k regex:gemm_kernel`
+        f32 = torch.float32
+        bench("vit-b fc1 dgrad c1/256", 201728, 768, 3072, reps=1, tile_ns=((256, 16),), dbg=64)
+        bench("vit-b fc1 dgrad c2/256", 201728, 768, 3072, reps=1, tile_ns=((256, 32),), dbg=64)
+        bench("vit-s fc2 dgrad dgelu c1/256", 806912, 1536, 384, epi=EPI_DGELU, reps=1, tile_ns=((256, 16),), dbg=64)
+        bench("vit-s qkv fwd c1/256", 806912, 1152, 384, reps=1, tile_ns=((256, 16),), dbg=64)
+        bench("vit-s fc2 wgrad c1/256", 384, 1536, 806912, a_major=1, b_major=1, out_dtype=f32, reps=1, tile_ns=((256, 16),), accumulate=True, dbg=64)
         sys.exit(0)
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
     if which == "layouts":
