@@ -798,33 +798,25 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
   auto pair_ok = [&](int n) { return !(a->b_major && (n / 2) % mn_atom != 0); };
   if (ctas == 2 && bn != 0) SIMSEG_CHECK_ARG(pair_ok(bn), "gemm: CTA pairs need tile_n/2 to be a whole number of MN atoms");
   if (bn == 0 || ctas == 0) {
-    // estimated time of every admissible (pair?, BN): waves of persistent units x per-tile cost.  Per-tile cost is
-    // BN x k-blocks of MMA issue (a pair's MMA covers twice the rows in the same time) plus a fixed prologue/epilogue
-    // term; pairs also cut the L2->SM operand traffic per flop by a third, which is what the single-CTA engine is
-    // bound by on large tiles (measured), hence the 0.8 factor.
-    double best = 1e300;
-    int best_bn = 256, best_c = 1;
-    for (int c = 1; c <= 2; ++c) {
-      if (ctas != 0 && c != ctas) continue;
-      if (c == 2 && eb != 2) continue;
-      for (int n : {256, 192, 128}) {
-        if (bn != 0 && n != bn) continue;
-        if (c == 2 && !pair_ok(n)) continue;
-        const int64_t mt = cdiv(a->M, kBM * c), nt = cdiv(a->N, n);
-        const int units = ctx->num_sms / c;
-        int64_t items = mt * nt;
-        int kbs = kb_total;
-        if (can_split && kb_total >= 32 && items < units) {    // split-K fills the machine
-          const int s = static_cast<int>(imin64(units / items, kb_total / 8));
-          if (s > 1) { kbs = static_cast<int>(cdiv(kb_total, s)); items *= cdiv(kb_total, kbs); }
-        }
-        const double waves = static_cast<double>(cdiv(items, units));
-        const double t = waves * (kbs + 3.0) * n * (c == 2 ? 0.8 : 1.0);
-        if (t < best * 0.999) { best = t; best_bn = n; best_c = c; }
+    // Measured on B200 (profiles/r01_gemm_microbench_v2.txt):
+    //  * K-major operands: CTA pairs win whenever there are enough 256-row tiles to occupy every SM pair; the tile
+    //    width is the one that pads N least (256 on ties: fewer A re-reads).
+    //  * MN-major operands (wgrad, split-K): single-CTA 128 x 256 tiles are fastest even when N is padded.
+    //  * few tiles: single CTAs (twice as many work items); shrink BN until the SMs are covered.
+    const bool mn_major = a->a_major || a->b_major;
+    auto padded = [&](int n) { return cdiv(a->N, n) * n; };
+    int auto_bn = 256;
+    if (!mn_major || a->N <= 192) {
+      for (int n : {192, 128}) if (padded(n) < padded(auto_bn)) auto_bn = n;
+    }
+    if (bn == 0) bn = auto_bn;
+    if (ctas == 0) {
+      const int64_t pair_tiles = cdiv(a->M, 2 * kBM) * cdiv(a->N, bn);
+      ctas = (eb == 2 && !mn_major && pair_ok(bn) && pair_tiles >= ctx->num_sms / 2) ? 2 : 1;
+      if (ctas == 1 && a->tile_n == 0 && !can_split) {
+        while (bn > 128 && cdiv(a->M, kBM) * cdiv(a->N, bn) < ctx->num_sms) bn -= 64;
       }
     }
-    bn = best_bn;
-    ctas = best_c;
   }
 
   GemmParams p{};

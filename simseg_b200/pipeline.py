@@ -236,7 +236,7 @@ def _project_backward(ctx, gf_bf16: Tensor, xb: Tensor):
     w = ctx.weight
     if w.requires_grad:
         ops.linear_wgrad(gf_bf16.view(B * S, E), xb.view(B * S, D), towers._grad_of(w), accumulate=True)
-    dfull = ops.linear_dgrad(gf_bf16.view(B * S, E), ctx.shared.wc.get(w), out_dtype=torch.float32).view(B, S, D)
+    dfull = ops.linear_dgrad(gf_bf16.view(B * S, E), ctx.shared.wc.get_t(w), out_dtype=torch.float32).view(B, S, D)
     dx = dfull[:, ctx.t0:ctx.t0 + ctx.nt]
     dx._simseg_full = dfull
     return dx, None, None
