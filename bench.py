@@ -153,6 +153,8 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: one JSON line only
         # a collective mismatch must abort within minutes instead of hanging the box
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     assert a.global_batch % world == 0

@@ -9,11 +9,14 @@
 // normalisation costs no extra HBM traffic.  The epilogue scales by 1/||patch||, takes the row argmax, transposes
 // 32x32 blocks through padded smem and stores 128-byte row segments (rows of sim are contiguous in HBM).
 //
-// Persistent CTAs (one per SM, 10 warps):  warp 0 TMA producer | warp 1 MMA issuer | warps 2-5 row norms |
-// warps 6-9 epilogue (one TMEM lane quarter each).
+// Persistent CTAs (one per SM, 14 warps):  warp 0 TMA producer | warp 1 MMA issuer | warps 2-5 row norms |
+// warps 6-13 epilogue (two per TMEM lane quarter, taking alternate 32-column chunks; the row argmax of the pair is
+// combined through shared memory).
 // Algorithmic HBM bytes per row: E*2 + C*4 + 4  (DESIGN.md).
 #include "common.cuh"
 #include "sm100.cuh"
+
+#include <cstdlib>
 
 namespace simseg {
 
@@ -21,8 +24,8 @@ using namespace sm100;
 
 constexpr int kPsBM = 128;
 constexpr int kPsStageBytes = kPsBM * 128;          // 128 rows x 64 bf16
-constexpr int kPsThreads = 320;
-constexpr int kPsStagingBytes = 4 * 32 * 33 * 4;
+constexpr int kPsThreads = 448;            // 14 warps: TMA, MMA, 4 row-norm, 8 epilogue
+constexpr int kPsStagingBytes = 8 * 32 * 33 * 4;   // one padded 32x32 fp32 transpose tile per epilogue warp
 constexpr int kPsMaxStages = 8;
 
 struct PatchSimParams {
@@ -33,26 +36,65 @@ struct PatchSimParams {
   int32_t* argmax;
 };
 
+// cluster-scope mbarrier ops for the CTA-pair variant (the peer's "data landed" signal is relayed to the leader)
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("simseg: cluster mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+// CTAS == 2: a CTA pair works on 256 patch rows; each CTA stages its own 128 rows and HALF of the class-text matrix
+// (so C = 171 leaves room for a 7-stage ring instead of 2), the leader issues 256 x Cpad x 16 MMAs (cta_group::2).
+// Each CTA's TMA loads signal its OWN barriers (its norm warps read the stages locally); the peer's otherwise idle
+// warp 1 relays "stage landed" to the leader, whose MMA thread waits for both halves.
+template <int CTAS>
 __global__ void __launch_bounds__(kPsThreads, 1)
 patch_sim_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant__ CUtensorMap tmap_t, const PatchSimParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int text_kb_bytes = p.npad * 128;
+  const int text_rows = p.npad / CTAS;                                // class rows staged by this CTA
+  const int text_kb_bytes = text_rows * 128;
   uint8_t* s_text = smem;
   uint8_t* s_ring = s_text + p.kblocks * text_kb_bytes;
   float* s_stage = reinterpret_cast<float*>(s_ring + p.stages * kPsStageBytes);
   float* s_inv = s_stage + kPsStagingBytes / 4;                       // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_inv + 2 * kPsBM);
-  uint64_t* full_bar = bars;                                         // [stages]  TMA -> MMA + norm
+  float* s_arg = s_inv + 2 * kPsBM;                                  // [4 quarters][32 rows][2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_arg + 4 * 64);
+  uint64_t* full_bar = bars;                                         // [stages]  TMA -> MMA + norm (local data)
   uint64_t* empty_bar = full_bar + kPsMaxStages;                     // [stages]  MMA commit + 4 norm warps -> TMA
   uint64_t* acc_full = empty_bar + kPsMaxStages;                     // [2] MMA -> epilogue
-  uint64_t* acc_empty = acc_full + 2;                                // [2] epilogue -> MMA, norm
+  uint64_t* acc_empty = acc_full + 2;                                // [2] epilogue -> norm (and MMA when CTAS == 1)
   uint64_t* norm_full = acc_empty + 2;                               // [2] norm -> epilogue
   uint64_t* text_bar = norm_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(text_bar + 1);
+  uint64_t* peer_full = text_bar + 1;                                // [stages] leader only: the peer's stage landed
+  uint64_t* peer_text = peer_full + kPsMaxStages;                    //          leader only: the peer's text landed
+  uint64_t* pair_empty = peer_text + 1;                              // [2] leader only: both CTAs' epilogues done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pair_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int first_tile = static_cast<int>(blockIdx.x) / CTAS;
+  const int tile_stride = static_cast<int>(gridDim.x) / CTAS;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_p);
@@ -60,72 +102,110 @@ patch_sim_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_consta
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 5);
+      mbar_init(&peer_full[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);
+      mbar_init(&acc_empty[s], 8);
       mbar_init(&norm_full[s], 4);
+      mbar_init(&pair_empty[s], 16);
     }
     mbar_init(text_bar, 1);
+    mbar_init(peer_text, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, p.tmem_cols);
-    tmem_relinquish();
+    if (CTAS == 2) { tmem_alloc_2sm(tmem_slot, p.tmem_cols); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // =============================== TMA producer ===============================
-    if (lane == 0) {
+    // =============================== TMA producer (warp-uniform loop, elected lane issues) ===============================
+    if (elect_one()) {
       mbar_arrive_expect_tx(text_bar, static_cast<uint32_t>(p.kblocks * text_kb_bytes));
       for (int kb = 0; kb < p.kblocks; ++kb)
-        tma_load_2d_hint(s_text + kb * text_kb_bytes, &tmap_t, text_bar, kb * 64, 0, kEvictLast);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-        const int m0 = tile * kPsBM;
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+        tma_load_2d_hint(s_text + kb * text_kb_bytes, &tmap_t, text_bar, kb * 64, static_cast<int>(rank) * text_rows, kEvictLast);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = first_tile; tile < p.tiles; tile += tile_stride) {
+      const int m0 = tile * (kPsBM * CTAS) + static_cast<int>(rank) * kPsBM;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[stage], kPsStageBytes);
           tma_load_2d_hint(s_ring + stage * kPsStageBytes, &tmap_p, &full_bar[stage], kb * 64, m0, kEvictFirst);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(1u, 0u, 0u, kPsBM, static_cast<uint32_t>(p.npad));
+    if (leader) {
+      // =============================== MMA issuer ===============================
+      const uint32_t idesc = make_idesc(1u, 0u, 0u, kPsBM * CTAS, static_cast<uint32_t>(p.npad));
       mbar_wait(text_bar, 0);
+      if (CTAS == 2) mbar_wait(peer_text, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const uint32_t s_text_u32 = smem_u32(s_text);
-      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      const uint64_t adesc0 = make_smem_desc_sw128(smem_u32(s_ring), 16, 1024);
+      const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(s_text), 16, 1024);
+      for (int tile = first_tile; tile < p.tiles; tile += tile_stride) {
+        if (CTAS == 2) mbar_wait(&pair_empty[acc], acc_phase ^ 1); else mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          if (CTAS == 2) mbar_wait(&peer_full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(s_ring + stage * kPsStageBytes);
-          const uint32_t sb = s_text_u32 + kb * text_kb_bytes;
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t adesc = make_smem_desc_sw128(sa + kk * 32, 16, 1024);
-            const uint64_t bdesc = make_smem_desc_sw128(sb + kk * 32, 16, 1024);
-            umma_f16(d_tmem, adesc, bdesc, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+          if (elect_one()) {
+            const uint64_t ad = adesc0 + static_cast<uint64_t>(stage * (kPsStageBytes >> 4));
+            const uint64_t bd = bdesc0 + static_cast<uint64_t>(kb * (text_kb_bytes >> 4));
+            const uint32_t first = kb > 0 ? 1u : 0u;
+            if (CTAS == 2) {
+              umma_f16_2sm(d_tmem, ad, bd, idesc, first);
+              umma_f16_2sm(d_tmem, ad + 2, bd + 2, idesc, 1u);
+              umma_f16_2sm(d_tmem, ad + 4, bd + 4, idesc, 1u);
+              umma_f16_2sm(d_tmem, ad + 6, bd + 6, idesc, 1u);
+              umma_commit_2sm(&empty_bar[stage]);
+              if (kb == p.kblocks - 1) umma_commit_2sm(&acc_full[acc]);
+            } else {
+              umma_f16(d_tmem, ad, bd, idesc, first);
+              umma_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+              umma_f16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+              umma_f16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+              umma_commit(&empty_bar[stage]);
+              if (kb == p.kblocks - 1) umma_commit(&acc_full[acc]);
+            }
           }
-          umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&acc_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    } else {
+      // =============================== peer: relay "landed" to the leader's MMA thread ===============================
+      const uint32_t r_text = mapa_shared(smem_u32(peer_text), 0);
+      const uint32_t r_full = mapa_shared(smem_u32(&peer_full[0]), 0);
+      mbar_wait(text_bar, 0);
+      if (lane == 0) mbar_arrive_cluster(r_text);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = first_tile; tile < p.tiles; tile += tile_stride) {
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          if (lane == 0) mbar_arrive_cluster(r_full + stage * 8);
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp < 6) {
@@ -137,7 +217,7 @@ patch_sim_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_consta
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < p.tiles; tile += tile_stride) {
       float ss0 = 0.f, ss1 = 0.f;
       for (int kb = 0; kb < p.kblocks; ++kb) {
         mbar_wait(&full_bar[stage], phase);
@@ -163,14 +243,17 @@ patch_sim_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_consta
     }
   } else {
     // =============================== epilogue ===============================
-    const int quarter = warp & 3;
+    const int quarter = warp & 3;                             // TMEM lane quarter (rows quarter*32 .. +32 of the tile)
+    const int half = (warp - 6) >> 2;                         // 0: even 32-column chunks, 1: odd chunks
     float* stg = s_stage + (warp - 6) * (32 * 33);
+    float* s_best = s_arg + quarter * 64;                     // [32 rows][value, index bits] handed from half 1 to half 0
     const int row_in_tile = quarter * 32 + lane;
     const int nchunks = (p.npad + 31) >> 5;
+    const uint32_t r_pair_empty = (CTAS == 2) ? mapa_shared(smem_u32(&pair_empty[0]), 0) : 0u;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-      const int64_t m0 = static_cast<int64_t>(tile) * kPsBM;
+    for (int tile = first_tile; tile < p.tiles; tile += tile_stride) {
+      const int64_t m0 = static_cast<int64_t>(tile) * (kPsBM * CTAS) + static_cast<int64_t>(rank) * kPsBM;
       const int64_t wrow0 = m0 + quarter * 32;                // first global row of this warp
       mbar_wait(&norm_full[acc], acc_phase);
       const float inv = s_inv[acc * kPsBM + row_in_tile];
@@ -181,11 +264,22 @@ patch_sim_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_consta
       int besti = 0;
       const int64_t rows_left = p.rows - wrow0;
       const int rows_here = rows_left < 32 ? static_cast<int>(rows_left) : 32;      // may be <= 0 for the ragged last tile
-      for (int c = 0; c < nchunks; ++c) {
+      bool released = false;
+      for (int c = half; c < nchunks; c += 2) {
         const int c0 = c * 32;
         uint32_t r[32];
         tmem_ld_32x32(t_row + c0, r);
         tmem_ld_wait();
+        if (c + 2 >= nchunks) {
+          // all TMEM reads of this warp are in registers: release the accumulator before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&acc_empty[acc]);
+            if (CTAS == 2) mbar_arrive_cluster(r_pair_empty + acc * 8);
+          }
+          released = true;
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float v = __uint_as_float(r[j]) * inv;
@@ -195,25 +289,47 @@ patch_sim_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_consta
         __syncwarp();
         if (c0 + lane < p.C) {
           float* out = p.sim + wrow0 * p.C + c0 + lane;
-#pragma unroll 8
-          for (int rr = 0; rr < 32; ++rr)
-            if (rr < rows_here) __stcs(out + static_cast<int64_t>(rr) * p.C, stg[rr * 33 + lane]);
+          const float* src = stg + lane;
+          if (rows_here == 32) {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) __stcs(out + rr * p.C, src[rr * 33]);
+          } else {
+            for (int rr = 0; rr < rows_here; ++rr) __stcs(out + rr * p.C, src[rr * 33]);
+          }
         }
         __syncwarp();
       }
-      if (p.argmax != nullptr && lane < rows_here) p.argmax[wrow0 + lane] = besti;
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (!released) {                                        // this warp had no chunk (C <= 32 and half == 1)
+        if (lane == 0) {
+          mbar_arrive(&acc_empty[acc]);
+          if (CTAS == 2) mbar_arrive_cluster(r_pair_empty + acc * 8);
+        }
+      }
+      // first-max argmax over both halves of the row: half 1 hands (value, index) to half 0 of the same lane quarter
+      if (p.argmax != nullptr) {
+        if (half == 1) {
+          s_best[2 * lane] = best;
+          s_best[2 * lane + 1] = __int_as_float(besti);
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        if (half == 0) {
+          const float ob = s_best[2 * lane];
+          const int oi = __float_as_int(s_best[2 * lane + 1]);
+          if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+          if (lane < rows_here) p.argmax[wrow0 + lane] = besti;
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");     // s_best may be rewritten only after it was read
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (CTAS == 2) tmem_dealloc_2sm(tmem_base, p.tmem_cols); else tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -227,31 +343,58 @@ int patch_sim_fused_impl(Ctx* ctx, const void* patches, int64_t rows, int E, con
   p.rows = rows; p.C = C; p.E = E; p.normalize = normalize;
   p.npad = ((C + 15) / 16) * 16;
   p.kblocks = E / 64;
-  p.tiles = static_cast<int>(cdiv(rows, kPsBM));
   p.acc_stride = static_cast<uint32_t>(((p.npad + 31) / 32) * 32);
   uint32_t cols = 32;
   while (cols < 2 * p.acc_stride) cols <<= 1;
   p.tmem_cols = cols;
   p.sim = sim; p.argmax = argmax;
   const int kMaxSmem = 232448;
-  const int fixed = 1024 + p.kblocks * p.npad * 128 + kPsStagingBytes + 2 * kPsBM * 4 + 256;
-  int stages = (kMaxSmem - fixed) / kPsStageBytes;
-  if (stages > kPsMaxStages) stages = kPsMaxStages;
+  auto stages_for = [&](int ctas) {
+    const int fixed = 1024 + p.kblocks * (p.npad / ctas) * 128 + kPsStagingBytes + 2 * kPsBM * 4 + 1024 + 512;
+    int stages = (kMaxSmem - fixed) / kPsStageBytes;
+    return stages > kPsMaxStages ? kPsMaxStages : stages;
+  };
+  // a CTA pair splits the text matrix: used when a single CTA could not keep >= 5 patch stages (80 KB) in flight
+  const char* force = getenv("SIMSEG_PATCH_SIM_CTAS");
+  int ctas = (stages_for(1) >= 5 || rows <= kPsBM) ? 1 : 2;
+  if (force) ctas = atoi(force) == 2 ? 2 : 1;
+  const int stages = stages_for(ctas);
   if (stages < 2) return SIMSEG_ERR_UNSUPPORTED;
   p.stages = stages;
-  const int smem_bytes = fixed + stages * kPsStageBytes;
-  static int max_set = 0;
-  if (smem_bytes > max_set) {
-    SIMSEG_CUDA(cudaFuncSetAttribute(patch_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    max_set = smem_bytes;
-  }
+  p.tiles = static_cast<int>(cdiv(rows, kPsBM * ctas));
+  const int smem_bytes = 1024 + p.kblocks * (p.npad / ctas) * 128 + kPsStagingBytes + 2 * kPsBM * 4 + 1024 + 512 + stages * kPsStageBytes;
   CUtensorMap tp, tt;
   int rc = make_tmap(&tp, patches, 2, rows, E, E, 64, kPsBM);
   if (rc) return rc;
-  rc = make_tmap(&tt, text, 2, C, E, E, 64, p.npad);
+  rc = make_tmap(&tt, text, 2, C, E, E, 64, p.npad / ctas);
   if (rc) return rc;
-  const int grid = p.tiles < ctx->num_sms ? p.tiles : ctx->num_sms;
-  patch_sim_kernel<<<grid, kPsThreads, smem_bytes, st>>>(tp, tt, p);
+  const int units_max = ctx->num_sms / ctas;
+  const int units = p.tiles < units_max ? p.tiles : units_max;
+  if (ctas == 1) {
+    static int max_set = 0;
+    if (smem_bytes > max_set) {
+      SIMSEG_CUDA(cudaFuncSetAttribute(patch_sim_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      max_set = smem_bytes;
+    }
+    patch_sim_kernel<1><<<units, kPsThreads, smem_bytes, st>>>(tp, tt, p);
+  } else {
+    static int max_set2 = 0;
+    if (smem_bytes > max_set2) {
+      SIMSEG_CUDA(cudaFuncSetAttribute(patch_sim_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      max_set2 = smem_bytes;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(units * 2);
+    cfg.blockDim = dim3(kPsThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    SIMSEG_CUDA(cudaLaunchKernelEx(&cfg, patch_sim_kernel<2>, tp, tt, p));
+  }
   ctx->launches++;
   SIMSEG_LAUNCH_CHECK();
   return SIMSEG_OK;

@@ -212,3 +212,19 @@ def test_retrieval_rank_properties_large(cuda):
     match = rg[None, :] == lg[:, None]
     best = sim.masked_fill(~match, float("-inf")).max(1)[0]
     assert torch.equal(rank.long(), (sim > best[:, None]).sum(1))
+
+
+@pytest.mark.parametrize("rows,C", [(12544, 171), (300, 256), (4097, 130), (20000, 20)])
+def test_patch_text_sim_pair_equals_single(cuda, rows, C, monkeypatch):
+    """The CTA-pair variant (tcgen05 cta_group::2, text matrix split across the two CTAs) and the single-CTA variant of
+    the fused kernel compute the same map and the same argmax."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(rows + C)
+    p = torch.randn(rows, 512, device=cuda, generator=g).bfloat16()
+    t = torch.nn.functional.normalize(torch.randn(C, 512, device=cuda, generator=g), dim=-1).bfloat16()
+    monkeypatch.setenv("SIMSEG_PATCH_SIM_CTAS", "1")
+    s1, a1 = ops.patch_text_sim(p, t)
+    monkeypatch.setenv("SIMSEG_PATCH_SIM_CTAS", "2")
+    s2, a2 = ops.patch_text_sim(p, t)
+    assert float((s1 - s2).abs().max()) < 1e-6
+    assert torch.equal(a2.long(), s2.argmax(-1)) and torch.equal(a1.long(), s1.argmax(-1))
