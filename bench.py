@@ -246,6 +246,7 @@ def run_ours(a):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": 4 * world,
                     "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
+            "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
             "loss": float(last.get("loss", float("nan")))}
 
     if not a.no_extras:

@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "sm100.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -269,7 +270,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B (descriptor base_offset = 0); the dynamic-smem base offset is the
   // same in both CTAs of a pair, so every carved address below is at the same offset in the peer.
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* stg = smem + Cfg::kStages * Cfg::kStageBytes;      // per-warp epilogue staging boxes
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;                       // [8]   TMA -> MMA            (leader's are used by a pair)
@@ -712,9 +713,13 @@ int make_tmap_mn3d(CUtensorMap* m, const void* ptr, int elem_bytes, int64_t k_ro
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * elem_bytes, static_cast<cuuint64_t>(kSwizzleBytes)};
   cuuint32_t box[3] = {static_cast<cuuint32_t>(atom), static_cast<cuuint32_t>(box_k), static_cast<cuuint32_t>(box_atoms)};
   cuuint32_t estr[3] = {1, 1, 1};
+  static int promo = -1;
+  if (promo < 0) { const char* e = getenv("SIMSEG_TMA_PROMO"); promo = e ? atoi(e) : 3; }
+  const CUtensorMapL2promotion pr = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                    : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   CUresult r = enc(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_SWIZZLE_128B, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(3d) failed (%d): ptr=%p k_rows=%lld mn=%lld ld=%lld box_k=%d atoms=%d", static_cast<int>(r),
               ptr, static_cast<long long>(k_rows), static_cast<long long>(mn_cols), static_cast<long long>(ld), box_k, box_atoms);

@@ -69,7 +69,7 @@ template <int CTAS>
 __global__ void __launch_bounds__(kPsThreads, 1)
 patch_sim_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant__ CUtensorMap tmap_t, const PatchSimParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
   const int text_rows = p.npad / CTAS;                                // class rows staged by this CTA
   const int text_kb_bytes = text_rows * 128;
   uint8_t* s_text = smem;
