@@ -345,6 +345,305 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   }
 }
 
+// ================================================================================================
+// tcgen05 attention FORWARD for head_dim 64 and S <= 224 (ViT: 197 tokens; BERT: 77).
+//
+// Work unit = (batch, head, 128-row query tile).  All keys of a sequence fit one TMEM accumulator, so the softmax is
+// exact two-pass (row max, then exp / sum) with no online rescaling:
+//   warp 0      TMA: K, V of an item (all keys, double buffered across items), Q tile per unit (double buffered)
+//   warp 1      one elected thread issues  S_u = Q_u K^T  (128 x keys, TMEM cols [0|stride) by unit parity) and, one
+//               unit later, O_u = P_u V (128 x 64, TMEM cols 2*stride..) — so QK^T of the next unit runs on the tensor
+//               pipe while the softmax warps work on the current one
+//   warps 2-9   softmax: two warps per TMEM lane quarter take alternate 32-key chunks: tcgen05.ld S, max, exp2 (MUFU — the
+//               real bound of this kernel), row sum, P (bf16) into 128B-swizzled smem as the K-major A operand of P V; the
+//               same warps drain O of the previous unit, scale by 1/sum and store the output rows + the log-sum-exp.
+// Keys >= key_len[b] (BERT padding) and the zero-filled tail columns get P = 0.
+constexpr int kAfThreads = 320;
+
+struct AttnFwdParams {
+  int32_t B, H, S, nqt, nkt, nkc, stride, items, kv_stages;
+  float scale_log2e;
+  const int32_t* key_len;
+  float* lse;                 // [B,H,S]
+  __nv_bfloat16* out;         // [B,S,H*64]
+};
+
+__global__ void __launch_bounds__(kAfThreads, 1)
+attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                        const __grid_constant__ CUtensorMap tm_v, const AttnFwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;                    // every byte of the 227 KB is used: no alignment slack
+  if ((smem_u32(smem_raw) & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("simseg: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+  uint8_t* sQ = smem;                          // [2 units][16 KB]
+  uint8_t* sK = sQ + 2 * kTileBytes;           // [kv_stages items][nkt tiles x 16 KB]  rows = keys, contiguous over the tiles
+  uint8_t* sV = sK + 4 * kTileBytes;           // (2 stages of 2 tiles, or 4 stages of 1 tile when S <= 128)
+  uint8_t* sP = sV + 4 * kTileBytes;           // [4 key atoms][128 rows][128 B]
+  float* s_xchg = reinterpret_cast<float*>(sP + 4 * kTileBytes);     // [256 row sums | 256 row maxima] exchanged between the two warps of a row
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_xchg + 512);
+  uint64_t* q_full = bars;            // [2]
+  uint64_t* q_empty = bars + 2;       // [2]
+  uint64_t* kv_full = bars + 4;       // [4]
+  uint64_t* kv_empty = bars + 8;      // [4]
+  uint64_t* s_full = bars + 12;       // [2] MMA -> softmax group g
+  uint64_t* s_empty = bars + 14;      // [2] group g -> MMA (4 warps)
+  uint64_t* p_ready = bars + 16;      // softmax -> MMA (4 warps)
+  uint64_t* p_free = bars + 17;       // MMA -> softmax : P V has read P
+  uint64_t* o_full = bars + 18;       // MMA -> softmax group : O complete
+  uint64_t* o_free = bars + 19;       // group -> MMA (4 warps) : O drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_q); prefetch_tmap(&tm_k); prefetch_tmap(&tm_v);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
+    }
+    for (int i = 0; i < 4; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(p_ready, 8); mbar_init(p_free, 1); mbar_init(o_full, 1); mbar_init(o_free, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tO = tmem_base + 2 * p.stride;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    uint32_t u = 0, itc = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++itc) {
+      const int b = item / p.H, h = item - b * p.H;
+      const uint32_t kb = itc % p.kv_stages;
+      mbar_wait(&kv_empty[kb], ((itc / p.kv_stages) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&kv_full[kb], 2 * p.nkt * kTileBytes);
+        for (int t = 0; t < p.nkt; ++t) {
+          tma_load_4d(sK + (p.nkt * kb + t) * kTileBytes, &tm_k, &kv_full[kb], 0, h, t * kTile, b);
+          tma_load_4d(sV + (p.nkt * kb + t) * kTileBytes, &tm_v, &kv_full[kb], 0, h, t * kTile, b);
+        }
+      }
+      __syncwarp();
+      for (int qt = 0; qt < p.nqt; ++qt, ++u) {
+        mbar_wait(&q_empty[u & 1], ((u >> 1) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&q_full[u & 1], kTileBytes);
+          tma_load_4d(sQ + (u & 1) * kTileBytes, &tm_q, &q_full[u & 1], 0, h, qt * kTile, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    const uint32_t id_s = make_idesc(1u, 0u, 0u, kTile, static_cast<uint32_t>(p.nkc));   // A, B K-major, N = keys
+    const uint32_t id_o = make_idesc(1u, 0u, 1u, kTile, 64u);                            // A K-major (P), B MN-major (V)
+    const uint32_t aP = smem_u32(sP);
+    const int ksteps = p.nkc >> 4;
+    uint32_t u = 0, itc = 0;
+    uint32_t prev_kb = 0, prev_last = 0;
+    auto issue_pv = [&](uint32_t w, uint32_t kb, uint32_t last) {
+      mbar_wait(p_ready, w & 1);
+      mbar_wait(o_free, (w & 1) ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t aV = smem_u32(sV + p.nkt * kb * kTileBytes);
+        for (int ks = 0; ks < ksteps; ++ks)
+          umma_f16(tO, make_smem_desc_sw128(aP + (ks >> 2) * kTileBytes + (ks & 3) * 32, 16, 1024),
+                   make_smem_desc_sw128(aV + ks * 2048, 16384, 1024), id_o, ks > 0 ? 1u : 0u);
+        umma_commit(o_full);
+        umma_commit(p_free);
+        if (last) umma_commit(&kv_empty[kb]);
+      }
+      __syncwarp();
+    };
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++itc) {
+      const uint32_t kb = itc % p.kv_stages;
+      for (int qt = 0; qt < p.nqt; ++qt, ++u) {
+        if (qt == 0) mbar_wait(&kv_full[kb], (itc / p.kv_stages) & 1);
+        mbar_wait(&q_full[u & 1], (u >> 1) & 1);
+        mbar_wait(&s_empty[u & 1], ((u >> 1) & 1) ^ 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t aQ = smem_u32(sQ + (u & 1) * kTileBytes), aK = smem_u32(sK + p.nkt * kb * kTileBytes);
+          const uint32_t tS = tmem_base + (u & 1) * p.stride;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_f16(tS, make_smem_desc_sw128(aQ + kk * 32, 16, 1024), make_smem_desc_sw128(aK + kk * 32, 16, 1024), id_s,
+                     kk > 0 ? 1u : 0u);
+          umma_commit(&s_full[u & 1]);
+          umma_commit(&q_empty[u & 1]);            // Q is only read by these MMAs: reload its buffer as early as possible
+        }
+        __syncwarp();
+        if (u > 0) issue_pv(u - 1, prev_kb, prev_last);
+        prev_kb = kb;
+        prev_last = (qt == p.nqt - 1) ? 1u : 0u;
+      }
+    }
+    if (u > 0) issue_pv(u - 1, prev_kb, prev_last);
+  } else {
+    // =============================== softmax + output (8 warps on every unit) ===============================
+    // Two warps share a TMEM lane quarter (32 query rows) and take alternate 32-key chunks; the row max and the row
+    // sum are combined through shared memory (one 64-thread named barrier each).  Order per unit u:
+    //   pass 1 (max) of u | drain O of u-1 (its P V has long finished) | pass 2 (exp, P) of u
+    // so the only wait on the tensor pipe is the short P V of u-1 before P is overwritten.
+    const int half = (warp - 2) >> 2;          // chunk parity taken by this warp
+    const int quarter = warp & 3;              // TMEM lane quarter
+    const int r = quarter * 32 + lane;         // row inside the tile
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const int sw = r & 7;
+    const int me = (half * 4 + quarter) * 32 + lane, mate = ((half ^ 1) * 4 + quarter) * 32 + lane;
+    uint32_t u = 0;
+    // state of the previous unit, kept for its deferred output
+    bool pv_pending = false, p_q_ok = false, p_live = false;
+    float p_sum = 1.f, p_ms = 0.f;
+    int64_t p_row = 0, p_lse = 0;
+    auto drain = [&](uint32_t w) {
+      mbar_wait(o_full, w & 1);
+      tc_fence_after();
+      if (p_live) {
+        uint32_t o0[32];
+        tmem_ld_32x32(tO + lane_off + half * 32, o0);
+        tmem_ld_wait();
+        if (p_q_ok) {
+          const float inv = 1.0f / p_sum;
+          __nv_bfloat16* po = p.out + p_row + half * 32;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 a;
+            a.x = pack_bf16(__uint_as_float(o0[8 * j]) * inv, __uint_as_float(o0[8 * j + 1]) * inv);
+            a.y = pack_bf16(__uint_as_float(o0[8 * j + 2]) * inv, __uint_as_float(o0[8 * j + 3]) * inv);
+            a.z = pack_bf16(__uint_as_float(o0[8 * j + 4]) * inv, __uint_as_float(o0[8 * j + 5]) * inv);
+            a.w = pack_bf16(__uint_as_float(o0[8 * j + 6]) * inv, __uint_as_float(o0[8 * j + 7]) * inv);
+            reinterpret_cast<uint4*>(po)[j] = a;
+          }
+          if (half == 0 && p.lse) p.lse[p_lse] = (p_ms + log2f(p_sum)) * 0.69314718055994531f;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);
+    };
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int b = item / p.H, h = item - b * p.H;
+      const int klen = p.key_len ? min(max(p.key_len[b], 1), p.S) : p.S;
+      const int nch = (klen + 31) >> 5;                                    // 32-key chunks that hold a live key
+      for (int qt = 0; qt < p.nqt; ++qt, ++u) {
+        const int qrow = qt * kTile + r;
+        const bool q_ok = qrow < p.S;
+        const bool warp_live = qt * kTile + quarter * 32 < p.S;             // any live row in this warp
+        const uint32_t tS = tmem_base + (u & 1) * p.stride + lane_off;
+        mbar_wait(&s_full[u & 1], (u >> 1) & 1);
+        tc_fence_after();
+        // ---- pass 1: row max over this warp's chunks (chunk = half + 2k), exchanged with the mate warp
+        float m = -INFINITY;
+        if (warp_live) {
+          for (int c = half; c < nch; c += 2) {
+            uint32_t x[32];
+            tmem_ld_32x32(tS + c * 32, x);
+            tmem_ld_wait();
+            if (c * 32 + 32 <= klen) {                                     // whole chunk live: no per-key predicate
+              float m0 = fmaxf(__uint_as_float(x[0]), __uint_as_float(x[1]));
+              float m1 = fmaxf(__uint_as_float(x[2]), __uint_as_float(x[3]));
+#pragma unroll
+              for (int j = 4; j < 32; j += 2) {
+                m0 = fmaxf(m0, __uint_as_float(x[j]));
+                m1 = fmaxf(m1, __uint_as_float(x[j + 1]));
+              }
+              m = fmaxf(m, fmaxf(m0, m1));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) m = (c * 32 + j < klen) ? fmaxf(m, __uint_as_float(x[j])) : m;
+            }
+          }
+        }
+        s_xchg[256 + me] = m;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        m = fmaxf(m, s_xchg[256 + mate]);
+        const float ms = m * p.scale_log2e;
+        // ---- output of the previous unit (needs o_free before this unit's P V can start)
+        if (pv_pending) drain(u - 1);
+        // ---- pass 2: P = exp2(s*scale*log2e - max), row sums, bf16 P into the swizzled A-operand layout
+        mbar_wait(p_free, (u & 1) ^ 1);                                   // P V of the previous unit has read sP
+        float sum = 0.f;
+        if (warp_live) {
+          for (int c = half; c < nch; c += 2) {
+            uint32_t x[32];
+            tmem_ld_32x32(tS + c * 32, x);
+            tmem_ld_wait();
+            uint32_t pp[16];
+            if (c * 32 + 32 <= klen) {
+              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(x[j]), p.scale_log2e, -ms));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(x[j + 1]), p.scale_log2e, -ms));
+                const float p2 = ex2_approx(fmaf(__uint_as_float(x[j + 2]), p.scale_log2e, -ms));
+                const float p3 = ex2_approx(fmaf(__uint_as_float(x[j + 3]), p.scale_log2e, -ms));
+                s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+                pp[j >> 1] = pack_bf16(p0, p1);
+                pp[(j >> 1) + 1] = pack_bf16(p2, p3);
+              }
+              sum += (s0 + s1) + (s2 + s3);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                float p0 = ex2_approx(fmaf(__uint_as_float(x[j]), p.scale_log2e, -ms));
+                float p1 = ex2_approx(fmaf(__uint_as_float(x[j + 1]), p.scale_log2e, -ms));
+                p0 = (c * 32 + j < klen) ? p0 : 0.f;
+                p1 = (c * 32 + j + 1 < klen) ? p1 : 0.f;
+                sum += p0 + p1;
+                pp[j >> 1] = pack_bf16(p0, p1);
+              }
+            }
+            const uint32_t rowoff = (c >> 1) * kTileBytes + r * 128;
+            const int ch0 = (c & 1) * 4;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              *reinterpret_cast<uint4*>(sP + rowoff + (((ch0 + q4) ^ sw) << 4)) =
+                  make_uint4(pp[4 * q4], pp[4 * q4 + 1], pp[4 * q4 + 2], pp[4 * q4 + 3]);
+          }
+          // keys between the last live chunk and the MMA's K extent (nkc) must read as P = 0
+          for (int c = nch + ((nch & 1) != half ? 1 : 0); c * 32 < p.nkc; c += 2) {
+            const uint32_t rowoff = (c >> 1) * kTileBytes + r * 128;
+            const int ch0 = (c & 1) * 4;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              *reinterpret_cast<uint4*>(sP + rowoff + (((ch0 + q4) ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
+          }
+        }
+        // row sum of the pair through shared memory (second barrier: the slots are rewritten by the next unit)
+        s_xchg[me] = sum;
+        tc_fence_before();
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        sum += s_xchg[mate];
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        if (lane == 0) { mbar_arrive(p_ready); mbar_arrive(&s_empty[u & 1]); }
+        pv_pending = true; p_q_ok = q_ok; p_live = warp_live; p_sum = sum; p_ms = ms;
+        p_row = (static_cast<int64_t>(b) * p.S + qrow) * (p.H * 64) + h * 64;
+        p_lse = (static_cast<int64_t>(b) * p.H + h) * p.S + qrow;
+      }
+    }
+    if (pv_pending) drain(u - 1);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn4)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -411,6 +710,50 @@ int attention_bwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v,
   attention_bwd_tc_kernel<<<grid, kAbThreads, smem_bytes, st>>>(tq, tk, tv, tdo, p);
   ctx->launches++;
   SIMSEG_LAUNCH_CHECK();
+  return SIMSEG_OK;
+}
+
+// SIMSEG_ERR_UNSUPPORTED => caller uses the mma.sync kernel (S > 224, unaligned pointers ...)
+int attention_fwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v, int64_t sb, int64_t ss, int64_t sh, int B, int H,
+                          int S, const int32_t* key_len, float scale, void* out, float* lse, cudaStream_t st) {
+  if (S > 224 || S < 1) return SIMSEG_ERR_UNSUPPORTED;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+                       reinterpret_cast<uintptr_t>(out);
+  if ((al & 15) || sb % 8 || ss % 8 || sh % 8) return SIMSEG_ERR_UNSUPPORTED;
+  if ((H > 1 && sh * 2 >= (int64_t(1) << 40)) || ss * 2 >= (int64_t(1) << 40)) return SIMSEG_ERR_UNSUPPORTED;
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_tmap_bshd(&tq, q, B, H, S, sb, ss, sh))) return rc;
+  if ((rc = make_tmap_bshd(&tk, k, B, H, S, sb, ss, sh))) return rc;
+  if ((rc = make_tmap_bshd(&tv, v, B, H, S, sb, ss, sh))) return rc;
+  AttnFwdParams p{};
+  p.B = B; p.H = H; p.S = S;
+  p.nqt = (S + kTile - 1) / kTile; p.nkt = p.nqt;
+  p.nkc = (S + 15) & ~15;
+  p.stride = (p.nkc + 31) & ~31;
+  p.items = B * H;
+  p.kv_stages = p.nkt == 1 ? 4 : 2;
+  p.scale_log2e = scale * 1.44269504088896341f;
+  p.key_len = key_len; p.lse = lse; p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  const int smem_bytes = 14 * kTileBytes + 2048 + 256;   // the dynamic segment itself is 1024-byte aligned (checked in-kernel)
+  static bool attr_set = false;
+  if (!attr_set) {
+    SIMSEG_CUDA(cudaFuncSetAttribute(attention_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_set = true;
+  }
+  const int grid = p.items < ctx->num_sms ? p.items : ctx->num_sms;
+  attention_fwd_tc_kernel<<<grid, kAfThreads, smem_bytes, st>>>(tq, tk, tv, p);
+  ctx->launches++;
+  {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      cudaFuncAttributes fa;
+      cudaFuncGetAttributes(&fa, attention_fwd_tc_kernel);
+      set_error("attention_fwd_tc launch failed: %s (regs %d, max threads/block %d, static smem %zu, dynamic %d, local %zu)",
+                cudaGetErrorString(e), fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, smem_bytes, fa.localSizeBytes);
+      return SIMSEG_ERR_CUDA;
+    }
+  }
   return SIMSEG_OK;
 }
 

@@ -37,6 +37,7 @@ int row_inv_norm_impl(Ctx*, const void*, int, int64_t, int, float*, cudaStream_t
 int row_argmax_impl(Ctx*, const float*, int64_t, int, int32_t*, cudaStream_t);
 int retrieval_rank_impl(Ctx*, const float*, int, int, const int64_t*, const int64_t*, int32_t*, cudaStream_t);
 int attention_bwd_tc_impl(Ctx*, const void*, const void*, const void*, const void*, const void*, const float*, int64_t, int64_t, int64_t, int, int, int, const int32_t*, float, void*, void*, void*, cudaStream_t);
+int attention_fwd_tc_impl(Ctx*, const void*, const void*, const void*, int64_t, int64_t, int64_t, int, int, int, const int32_t*, float, void*, float*, cudaStream_t);
 int patch_sim_fused_impl(Ctx*, const void*, int64_t, int, const void*, int, int, float*, int32_t*, cudaStream_t);
 
 // fp32 product in the requested precision: C[M,N] (+)= A(m,k) B(n,k)
@@ -133,6 +134,14 @@ int simseg_attention_fwd(simseg_ctx* ctx, const void* q, const void* k, const vo
                          int64_t stride_h, int B, int H, int S, const int32_t* key_len, float scale, void* out, float* lse,
                          void* stream) {
   CTX_OR_FAIL();
+  // tcgen05 kernel for 64 <= S <= 224 (attention_sm100.cu); other shapes run the mma.sync kernel.
+  // SIMSEG_ATTN_FWD=mma|tc overrides the choice (tests exercise both).
+  const char* force = getenv("SIMSEG_ATTN_FWD");
+  const bool want_tc = force ? (force[0] == 't') : (S >= 64);
+  if (want_tc) {
+    const int rc = attention_fwd_tc_impl(c, q, k, v, stride_b, stride_s, stride_h, B, H, S, key_len, scale, out, lse, st);
+    if (rc != SIMSEG_ERR_UNSUPPORTED) return rc;
+  }
   return attention_fwd_impl(c, q, k, v, stride_b, stride_s, stride_h, B, H, S, key_len, scale, out, lse, st);
 }
 int simseg_attention_bwd(simseg_ctx* ctx, const void* q, const void* k, const void* v, const void* out, const void* dout,

@@ -328,3 +328,35 @@ def test_misc_elementwise(cuda):
     assert _rel(ops.colsum(x.bfloat16()), x.bfloat16().float().sum(0)) < 1e-5
     h = torch.randn(64, 1536, device=cuda, generator=g).bfloat16()
     assert (ops.gelu_fwd(h).float() - gelu(h.float())).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("impl", ["tc", "mma"])
+@pytest.mark.parametrize("B,H,S,masked", [(3, 6, 197, False), (2, 12, 224, True), (7, 12, 25, True), (4, 12, 77, True),
+                                          (2, 2, 129, True), (60, 6, 197, False), (3, 1, 128, False), (300, 2, 64, True)])
+def test_attention_fwd_both_kernels(cuda, impl, B, H, S, masked, monkeypatch):
+    """Forward through the tcgen05 kernel (S <= 224: exact two-pass softmax out of TMEM, two alternating softmax
+    groups) and through the mma.sync kernel, selected explicitly; more work items than SMs exercises the persistent
+    loop, the K/V / Q / S / P / O buffer recycling and every barrier phase."""
+    ops = _ops()
+    monkeypatch.setenv("SIMSEG_ATTN_FWD", impl)
+    g = torch.Generator(device="cuda").manual_seed(S + B)
+    D = H * 64
+    qkv = (torch.randn(B, S, 3, H, 64, device=cuda, generator=g)).bfloat16()
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    strides = (S * 3 * D, 3 * D, 64)
+    klen = None
+    if masked:
+        klen = torch.randint(1, S + 1, (B,), device=cuda, generator=g, dtype=torch.int32)
+        klen[0] = S
+    out = torch.full((B, S, D), float("nan"), device=cuda, dtype=torch.bfloat16)
+    lse = torch.full((B, H, S), float("nan"), device=cuda)
+    ops.attention_fwd(q, k, v, B, H, S, strides, klen, 0.125, out=out, lse=lse)
+    qf, kf, vf = [t.float().permute(0, 2, 1, 3) for t in (q, k, v)]
+    s = (qf @ kf.transpose(-1, -2)) * 0.125
+    if masked:
+        km = torch.arange(S, device=cuda)[None] >= klen[:, None]
+        s = s.masked_fill(km[:, None, None, :], float("-inf"))
+    ref_o = (torch.softmax(s, -1) @ vf).permute(0, 2, 1, 3).reshape(B, S, D)
+    assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
+    assert (out.float() - ref_o).abs().max().item() < 3e-2
+    assert (lse - torch.logsumexp(s, -1)).abs().max().item() < 2e-3
