@@ -172,8 +172,18 @@ __device__ __forceinline__ void epilogue_tma(const GemmParams& p, const CUtensor
 #pragma unroll
       for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(cur[k]);
       if (has_bias) {
+        if (col + 32 <= p.N) {
+          // every lane reads the same 128 bytes: eight broadcast loads served by L1 (cheaper than 32 shuffles)
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] += __shfl_sync(0xffffffffu, bias_r[j], k);
+          for (int k = 0; k < 8; ++k) {
+            const float4 bb = __ldg(b4 + k);
+            v[4 * k] += bb.x; v[4 * k + 1] += bb.y; v[4 * k + 2] += bb.z; v[4 * k + 3] += bb.w;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] += __shfl_sync(0xffffffffu, bias_r[j], k);
+        }
       }
       uint8_t* so;                                                  // staging box of `out`
       uint8_t* sx;                                                  // staging box of aux (GELU: out; DGELU: in, then aux2 out)
@@ -881,6 +891,7 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
   bool tma_epi = epi_ok && p.out_bf16 && !p.atomic_out && row_ok16(a->d, a->ldd) && (a->reserved & 8) == 0;
   if (a->aux) tma_epi = tma_epi && row_ok16(a->aux, a->ld_aux);
   if (a->aux2) tma_epi = tma_epi && row_ok16(a->aux2, a->ld_aux2) && a->epilogue == SIMSEG_EPI_DGELU;
+  if (a->bias) tma_epi = tma_epi && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0;
   if (a->epilogue != SIMSEG_EPI_DGELU && a->col_sum) tma_epi = false;
   SIMSEG_CHECK_ARG(!(a->aux2 && !tma_epi), "gemm: aux2 needs the bf16 TMA epilogue (DGELU, bf16 out, 16-byte aligned rows)");
   p.tma_epi = tma_epi ? 1 : 0;

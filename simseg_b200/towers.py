@@ -78,6 +78,8 @@ class _Blk:
     mean2: Tensor = None
     rstd2: Tensor = None
     h: Tensor = None          # bf16 [M,4D] fc1 pre-activation
+    y: Tensor = None          # bf16 [M,D]  LN1 output (wgrad operand; 0.6 GB/layer at b=4096 is cheaper than re-reading x)
+    y2: Tensor = None         # bf16 [M,D]  LN2 output
 
 
 @dataclass
@@ -126,7 +128,7 @@ def vit_forward(m, image: Tensor, wc: Bf16Weights, save: bool):
         f = ops.linear_fwd(a, wc.get(blk.mlp.fc2.weight), blk.mlp.fc2.bias)
         del a
         if save:
-            sv.blocks.append(_Blk(x, mean1, rstd1, qkv, o, lse, x1, mean2, rstd2, h))
+            sv.blocks.append(_Blk(x, mean1, rstd1, qkv, o, lse, x1, mean2, rstd2, h, y, y2))
         x = x1
     if f is None:
         tok_bf16, tok_f32, mean_n, rstd_n = ops.layernorm_fwd(x, m.norm.weight, m.norm.bias, 1e-6, want_f32=True)
@@ -162,9 +164,8 @@ def vit_backward(m, sv: VitSaved, dtok: Tensor, wc: Bf16Weights, dtok2: Optional
         s.h = None
         ops.linear_wgrad(g, a, _grad_of(blk.mlp.fc2.weight), accumulate=True)
         del a
-        y2, _, _, _ = ops.layernorm_fwd(s.x1, blk.norm2.weight, blk.norm2.bias, 1e-6, want_stats=False)
-        ops.linear_wgrad(dh, y2, _grad_of(blk.mlp.fc1.weight), accumulate=True)
-        del y2
+        ops.linear_wgrad(dh, s.y2, _grad_of(blk.mlp.fc1.weight), accumulate=True)
+        s.y2 = None
         dy2 = ops.linear_dgrad(dh, wc.get_t(blk.mlp.fc1.weight))
         del dh
         ops.layernorm_bwd(dy2, s.x1, blk.norm2.weight, s.mean2, s.rstd2, dx=dx, dx_accumulate=True, dx_bf16=g,
@@ -182,9 +183,8 @@ def vit_backward(m, sv: VitSaved, dtok: Tensor, wc: Bf16Weights, dtok2: Optional
         del do
         s.o = s.qkv = s.lse = None
         ops.colsum(dqkv, _grad_of(blk.attn.qkv.bias), accumulate=True)
-        y, _, _, _ = ops.layernorm_fwd(s.x, blk.norm1.weight, blk.norm1.bias, 1e-6, want_stats=False)
-        ops.linear_wgrad(dqkv, y, _grad_of(blk.attn.qkv.weight), accumulate=True)
-        del y
+        ops.linear_wgrad(dqkv, s.y, _grad_of(blk.attn.qkv.weight), accumulate=True)
+        s.y = None
         dy = ops.linear_dgrad(dqkv, wc.get_t(blk.attn.qkv.weight))
         del dqkv
         prev_bias = _grad_of(m.blocks[i - 1].mlp.fc2.bias) if i > 0 else None
@@ -209,6 +209,7 @@ class _Lyr:
     mean1: Tensor = None
     rstd1: Tensor = None
     pre: Tensor = None        # bf16 [M,F] intermediate pre-activation
+    h1b: Tensor = None        # bf16 [M,D] attention.output LayerNorm result (wgrad operand)
     s2: Tensor = None         # fp32 [M,D] output pre-LN sum
     mean2: Tensor = None
     rstd2: Tensor = None
@@ -271,7 +272,7 @@ def bert_forward(m, input_ids: Tensor, attention_mask: Tensor, wc: Bf16Weights, 
                                                            1e-12, want_f32=True)
         del d2
         if save:
-            sv.layers.append(_Lyr(hb, qkv, c, lse, s1, mean1, rstd1, pre, s2, mean2, rstd2))
+            sv.layers.append(_Lyr(hb, qkv, c, lse, s1, mean1, rstd1, pre, h1b, s2, mean2, rstd2))
         hb, hf = h2b, h2f
     return hf.view(B, T, D), hb.view(B, T, D), sv
 
@@ -301,10 +302,9 @@ def bert_backward(m, sv: BertSaved, dh: Tensor, wc: Bf16Weights, dh2: Optional[T
                                 col_sum=_grad_of(layer.intermediate.dense.bias))
         ops.linear_wgrad(g2, f, _grad_of(layer.output.dense.weight), accumulate=True)
         del f
-        h1b, _, _, _ = ops.layernorm_fwd(s.s1, ao.LayerNorm.weight, ao.LayerNorm.bias, 1e-12, want_stats=False)
-        ops.linear_wgrad(dpre, h1b, _grad_of(layer.intermediate.dense.weight), accumulate=True)
+        ops.linear_wgrad(dpre, s.h1b, _grad_of(layer.intermediate.dense.weight), accumulate=True)
         dh1 = ops.linear_dgrad(dpre, wc.get_t(layer.intermediate.dense.weight))
-        del dpre, h1b
+        del dpre
         # h1 = LN(s1), s1 = attn.out.dense(c) + h_in ; dh1_total = dh1 + ds2
         ds1 = torch.empty((M, D), device=dev, dtype=torch.float32)
         g1 = g2
