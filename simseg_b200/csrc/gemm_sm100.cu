@@ -55,6 +55,7 @@ struct GemmParams {
   void* aux2;              // DGELU only: gelu(aux) written next to the gradient (bf16 [M,N])
   int32_t a_3d, b_3d;      // MN-major operand loaded with one 3-D TMA box per k-block
   int32_t dbg;             // bench-only: 1 = no TMA after the ring is primed, 2 = no MMA (results are garbage)
+  int32_t d_trans;         // fp32 atomic output stored transposed: element (m, n) at d[n * ldd + m]  (wgrad computed as dW^T)
 };
 
 template <int BN, int EPI, int CTAS>
@@ -64,13 +65,20 @@ struct GemmCfg {
   static constexpr int kBBytes = kBRows * kSwizzleBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // per-warp epilogue staging: EPI_NONE rotates 2 boxes; BIAS_GELU 2 x (out, aux); DGELU 3 aux-in boxes + 1 out box
-  static constexpr int kStgPerWarp = ((EPI == SIMSEG_EPI_BIAS_GELU || EPI == SIMSEG_EPI_DGELU) ? 4 : 2) * kEpiBoxBytes;
+  static constexpr int kStgPerWarp = (BN > 256) ? 0 : ((EPI == SIMSEG_EPI_BIAS_GELU || EPI == SIMSEG_EPI_DGELU) ? 4 : 2) * kEpiBoxBytes;
   static constexpr int kStagingBytes = kNumEpiWarps * kStgPerWarp;
   static constexpr int kBarBytes = 512;
   static constexpr int kStagesFit = (kMaxSmem - 1024 - kStagingBytes - kBarBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
-  static constexpr int kAccStride = (BN <= 128) ? 128 : 256;    // TMEM columns between the two accumulators
-  static constexpr int kTmemCols = 2 * kAccStride;              // 256 or 512 (power of two)
+  // BN <= 256: two accumulator stages (epilogue of tile i overlaps the MMAs of tile i+1).  BN = 384 / 512 ("wide", CTA
+  // pairs, split-K wgrad): ONE accumulator over up to all 512 TMEM columns, two MMAs (N = 256 + BN-256) per k-step —
+  // each unit works on one long K slice, so there is nothing to overlap, and the operand bytes per flop drop to
+  // (32 KB + BN*128 B) per 256 x BN x 64 MACs.
+  static constexpr bool kWide = BN > 256;
+  static constexpr int kAccStages = kWide ? 1 : 2;
+  static constexpr int kAccStride = (BN <= 128) ? 128 : (kWide ? 512 : 256);    // TMEM columns between accumulators
+  static constexpr int kTmemCols = kWide ? 512 : 2 * kAccStride;                // 256 or 512 (power of two)
+  static_assert(!kWide || CTAS == 2, "wide tiles are a CTA-pair configuration");
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + kBarBytes;
   static_assert(kStages >= 3, "ring too shallow");
 };
@@ -264,7 +272,7 @@ __device__ __forceinline__ void epilogue_tma(const GemmParams& p, const CUtensor
         tma_store_commit();
       }
     }
-    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    if (++acc == Cfg::kAccStages) { acc = 0; acc_phase ^= 1; }
   }
   if (want_cs) flush_cs();
   if (lane == 0) tma_store_wait<0>();
@@ -373,6 +381,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               if (!p.b_mn) {
                 if (CTAS == 2) tma_load_2d_2sm(sb, &tmap_b, fb, k0, n0);
                 else tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
+              } else if (Cfg::kWide) {
+                // wide pair tile: per CTA two column groups (one per MMA), one 3-D box per 64-column atom
+                constexpr int kAtoms0 = 2, kAtoms1 = (BN - 256) / 128;      // atoms per CTA for MMA 0 (N=256) and MMA 1
+                const int nt0 = (mn % p.n_tiles) * BN;
+#pragma unroll
+                for (int a2 = 0; a2 < kAtoms0 + kAtoms1; ++a2) {
+                  const int col = a2 < kAtoms0 ? nt0 + static_cast<int>(rank) * 128 + a2 * 64
+                                               : nt0 + 256 + static_cast<int>(rank) * (kAtoms1 * 64) + (a2 - kAtoms0) * 64;
+                  tma_load_3d_2sm(sb + a2 * 8192, &tmap_b, fb, 0, k0, col / 64);
+                }
               } else {
                 const int nbox = Cfg::kBRows / mn_atom;
                 const int box_bytes = Cfg::kBBytes / nbox;
@@ -398,7 +416,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // Warp-uniform loop, one elected lane issues: descriptors are one 64-bit add away from per-kernel constants, so a
     // k-block costs a few dozen instructions (the issuing thread, not the tensor pipe, used to be the limit).
     if (leader) {
-      const uint32_t idesc = make_idesc(p.elem_bytes == 2 ? 1u : 2u, p.a_mn, p.b_mn, kBM * CTAS, BN);
+      const uint32_t idesc = make_idesc(p.elem_bytes == 2 ? 1u : 2u, p.a_mn, p.b_mn, kBM * CTAS, Cfg::kWide ? 256 : BN);
+      const uint32_t idesc1 = make_idesc(1u, p.a_mn, p.b_mn, kBM * CTAS, Cfg::kWide ? BN - 256 : 16);   // wide tiles: second MMA
       // K-major: consecutive UMMA_K slices are 32 B apart inside the 128 B swizzle row; 8-row groups 1024 B apart.
       // MN-major: a UMMA_K slice (16 bf16 / 8 tf32 k-rows) spans k-rows of 128 B each,
       //           8-row groups 1024 B apart (SBO), 64-element MN atoms one TMA box apart (LBO).
@@ -430,7 +449,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const uint32_t first = (kb > kb0) ? 1u : 0u;
             if (!(p.dbg == 2 && kb > kb0)) {
               if (is_bf16) {
-                if (CTAS == 2) {
+                if (Cfg::kWide) {
+                  // columns 0..255 and 256..BN-1 of the accumulator: two MMAs per k-step (bf16, MN-major operands)
+                  const uint64_t bd1 = bd + (16384 >> 4);                  // second column group: 2 atoms x 8 KB further
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk) {
+                    const uint32_t accf = (kk == 0) ? first : 1u;
+                    umma_f16_2sm(d_tmem, ad + kk * a_inc, bd + kk * b_inc, idesc, accf);
+                    umma_f16_2sm(d_tmem + 256, ad + kk * a_inc, bd1 + kk * b_inc, idesc1, accf);
+                  }
+                } else if (CTAS == 2) {
                   umma_f16_2sm(d_tmem, ad, bd, idesc, first);
                   umma_f16_2sm(d_tmem, ad + a_inc, bd + b_inc, idesc, 1u);
                   umma_f16_2sm(d_tmem, ad + 2 * a_inc, bd + 2 * b_inc, idesc, 1u);
@@ -463,7 +491,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == Cfg::kAccStages) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
@@ -594,7 +622,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         // ---- store
         if (row_ok) {
-          if (p.atomic_out) {
+          if (p.atomic_out && p.d_trans) {
+            // D^T: lanes hold consecutive m, so each reduction instruction covers 32 consecutive floats of one output row
+            float* dp = reinterpret_cast<float*>(p.d) + col0 * p.ldd + row;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dp + j * p.ldd), "f"(v[j]) : "memory");
+          } else if (p.atomic_out) {
             float* dp = reinterpret_cast<float*>(p.d) + row * p.ldd + col0;
             if (full_chunk && p.vec_ok) {
 #pragma unroll
@@ -655,7 +689,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(acc_empty_addr + acc * 8);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == Cfg::kAccStages) { acc = 0; acc_phase ^= 1; }
     }
     }
   }
@@ -781,7 +815,7 @@ static int dispatch_epi(Ctx* ctx, int epi, const CUtensorMap* tm, const GemmPara
 }
 
 // `reserved` bits (bench / debug only): 1 = no TMA, 2 = no MMA, 4 = 2-D boxes for MN-major operands, 8 = direct-store
-// epilogue, 16 = force single-CTA tiles, 32 = force CTA pairs.
+// epilogue, 16 = force single-CTA tiles, 32 = force CTA pairs, 128 = no wide (256 x 384|512) split-K tiles.
 int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
   SIMSEG_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "gemm: empty problem M=%lld N=%lld K=%lld", (long long)a->M,
                    (long long)a->N, (long long)a->K);
@@ -834,7 +868,45 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
     }
   }
 
+  // ---- split-K weight gradients (both operands MN-major, fp32 atomic output): CTA pairs on 256 x 384|512 tiles.
+  // Such a tile moves (32 KB + BN*128 B) of operands per 256 x BN x 64 MACs — 1.8x fewer L2->SM bytes per flop than
+  // 128 x 256 single-CTA tiles, which are pinned at the ~11 TB/s L2 fabric limit because no two units of a split-K
+  // GEMM ever read the same bytes.  dW or dW^T is computed, whichever wastes fewer padded rows/columns.
+  simseg_gemm_args sw;
+  int wide_bn = 0, d_trans = 0;
+  const bool wide_ok = eb == 2 && a->a_major && a->b_major && can_split && a->bias == nullptr && a->tile_n == 0 &&
+                       (a->reserved & (16 | 128)) == 0 && a->M % 64 == 0 && a->N % 64 == 0 && kb_total >= 64 &&
+                       (reinterpret_cast<uintptr_t>(a->d) & 15) == 0;
+  if (wide_ok) {
+    auto cost = [&](int64_t m, int64_t n, int& bn_out) {
+      double best = 1e300;
+      for (int cand : {384, 512}) {
+        const double c = static_cast<double>(cdiv(m, 256) * 256) * static_cast<double>(cdiv(n, cand) * cand);
+        if (c < best) { best = c; bn_out = cand; }
+      }
+      return best;
+    };
+    int bn_n = 0, bn_t = 0;
+    const double c_n = cost(a->M, a->N, bn_n), c_t = cost(a->N, a->M, bn_t);
+    // only worth it when the padded problem stays within ~35 % of the real one
+    const double real = static_cast<double>(a->M) * static_cast<double>(a->N);
+    if ((c_t < c_n ? c_t : c_n) <= 1.35 * real) {
+      if (c_t < c_n) {
+        sw = *a;
+        sw.a = a->b; sw.b = a->a; sw.M = a->N; sw.N = a->M; sw.lda = a->ldb; sw.ldb = a->lda;
+        a = &sw;
+        d_trans = 1;
+        wide_bn = bn_t;
+      } else {
+        wide_bn = bn_n;
+      }
+      bn = wide_bn;
+      ctas = 2;
+    }
+  }
+
   GemmParams p{};
+  p.d_trans = d_trans;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.a_mn = a->a_major ? 1 : 0; p.b_mn = a->b_major ? 1 : 0;
   p.elem_bytes = eb;
@@ -864,7 +936,7 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
   p.splits = static_cast<int>(cdiv(p.kb_total, p.kb_per_split));
   p.d = a->d; p.ldd = a->ldd;
   p.out_bf16 = a->out_dtype == SIMSEG_BF16;
-  p.atomic_out = (p.splits > 1 || a->accumulate) ? 1 : 0;
+  p.atomic_out = (p.splits > 1 || a->accumulate || wide_bn) ? 1 : 0;     // wide tiles only have the reduction store path
   p.bias = a->bias; p.residual = a->residual; p.ld_res = a->ld_res; p.res_bf16 = a->res_dtype == SIMSEG_BF16;
   p.aux = a->aux; p.ld_aux = a->ld_aux; p.row_scale = a->row_scale; p.col_sum = a->col_sum;
   const int ob = p.out_bf16 ? 2 : 4;
@@ -875,9 +947,10 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
   p.vec_ok = vec ? 1 : 0;
   p.dbg = a->reserved & 3;
 
-  if (p.splits > 1 && !a->accumulate) {
-    // split-K partial sums are reduced with atomics: start from zero
-    SIMSEG_CUDA(cudaMemset2DAsync(a->d, a->ldd * 4, 0, a->N * 4, a->M, st));
+  if ((p.splits > 1 || wide_bn) && !a->accumulate) {
+    // partial sums are reduced with atomics: start from zero (D is stored [N, M] when d_trans)
+    const int64_t rows = d_trans ? a->N : a->M, width = d_trans ? a->M : a->N;
+    SIMSEG_CUDA(cudaMemset2DAsync(a->d, a->ldd * 4, 0, width * 4, rows, st));
   }
 
   CUtensorMap tm[5];
@@ -913,6 +986,7 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
   else rc = make_tmap(&ta, a->a, eb, a->K, a->M, a->lda, mn_atom, k_elems);
   if (rc) return rc;
   if (!p.b_mn) rc = make_tmap(&tb, a->b, eb, a->N, a->K, a->ldb, k_elems, b_rows);
+  else if (wide_bn) rc = make_tmap_mn3d(&tb, a->b, eb, a->K, a->N, a->ldb, k_elems, 1);
   else if (p.b_3d) rc = make_tmap_mn3d(&tb, a->b, eb, a->K, a->N, a->ldb, k_elems, b_rows / mn_atom);
   else rc = make_tmap(&tb, a->b, eb, a->K, a->N, a->ldb, mn_atom, k_elems);
   if (rc) return rc;
@@ -924,6 +998,8 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
   if (tma_epi && a->col_sum && p.n_tiles <= units) units = (units / p.n_tiles) * p.n_tiles;
   const int grid = units * ctas;
 
+  if (wide_bn == 384) return launch_gemm<384, SIMSEG_EPI_NONE, 2>(ctx, tm, p, grid, st);
+  if (wide_bn == 512) return launch_gemm<512, SIMSEG_EPI_NONE, 2>(ctx, tm, p, grid, st);
   if (ctas == 2) {
     switch (bn) {
       case 128: return dispatch_epi<128, 2>(ctx, a->epilogue, tm, p, grid, st);

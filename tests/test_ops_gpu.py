@@ -360,3 +360,22 @@ def test_attention_fwd_both_kernels(cuda, impl, B, H, S, masked, monkeypatch):
     assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
     assert (out.float() - ref_o).abs().max().item() < 3e-2
     assert (lse - torch.logsumexp(s, -1)).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("T,Do,Di", [(30000, 384, 1536), (30000, 1536, 384), (20000, 1152, 384), (9000, 384, 384),
+                                     (16000, 768, 3072), (16000, 2304, 768), (5000, 448, 320), (4100, 512, 171 * 0 + 192)])
+def test_gemm_wgrad_wide_pair_tiles(cuda, T, Do, Di):
+    """Split-K weight gradients on CTA-pair 256 x 384|512 tiles (one TMEM accumulator, two MMAs per k-step, dW or dW^T
+    whichever pads less, reduction stores) against the single-CTA path (_dbg=128 disables the wide tiles) and fp32 torch."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(T + Do)
+    dy = torch.randn(T, Do, device=cuda, generator=g).bfloat16()
+    x = torch.randn(T, Di, device=cuda, generator=g).bfloat16()
+    ref = dy.float().T @ x.float()
+    out = torch.full((Do, Di), float("nan"), device=cuda)
+    ops.linear_wgrad(dy, x, out)
+    assert _rel(out, ref) < 1e-4
+    ops.linear_wgrad(dy, x, out, accumulate=True)
+    assert _rel(out, 2 * ref) < 1e-4
+    legacy = ops.gemm(dy, x, M=Do, N=Di, K=T, a_major=1, b_major=1, out_dtype=torch.float32, _dbg=128)
+    assert _rel(legacy, ref) < 1e-4
