@@ -305,34 +305,50 @@ def gemm_roofline(trainer, batch, tf_peak, how):
             "gemm_ms_per_step": ms}
 
 
-def patch_sim_bench(hbm_peak, how):
-    """BASELINE.json configs[3]: 64 images x 196 patches x 171 classes, bf16 patch embeddings in HBM -> fp32 map + argmax.
-    16 distinct input/output sets (>= 370 MB) are cycled so no launch finds its operands in L2."""
+def _patch_sim_time(ps, t, reps):
     import torch
     from simseg_b200 import ops
-    B, N, C, E = 64, 196, 171, 512
-    nset = 16
-    g = torch.Generator(device="cuda").manual_seed(3)
-    ps = [torch.randn(B, N, E, device="cuda", generator=g).bfloat16() for _ in range(nset)]
-    t = torch.nn.functional.normalize(torch.randn(C, E, device="cuda", generator=g), dim=-1).bfloat16()
-    for i in range(nset):
-        ops.patch_text_sim(ps[i], t)
+    for x in ps:
+        ops.patch_text_sim(x, t)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 10
     e0.record()
     for _ in range(reps):
-        for i in range(nset):
-            ops.patch_text_sim(ps[i], t)
+        for x in ps:
+            ops.patch_text_sim(x, t)
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / (reps * nset)
+    return e0.elapsed_time(e1) / (reps * len(ps))
+
+
+def patch_sim_bench(hbm_peak, how):
+    """Dense patch-text similarity map (bf16 patch embeddings in HBM -> fp32 map + argmax), 196 patches x 171 classes.
+    Two points: BASELINE.json configs[3] (batch 64: 21 MB per launch, latency-bound) and 4096 maps per launch (1.37 GB,
+    the kernel's HBM-bound regime — the roofline figure).  Inputs are cycled / larger than L2 so no launch is L2-served."""
+    import torch
+    N, C, E = 196, 171, 512
+    g = torch.Generator(device="cuda").manual_seed(3)
+    t = torch.nn.functional.normalize(torch.randn(C, E, device="cuda", generator=g), dim=-1).bfloat16()
     bytes_per_map = N * E * 2 + N * C * 4 + N * 4
-    ach = B * bytes_per_map / (ms / 1e3) / 1e9
-    return {"workload": "ViT-B seg inference map: 64 x 196 patches x 171 classes, bf16 in, fp32 map + argmax",
-            "value": B / (ms / 1e3), "unit": "maps/s", "ms_per_batch": ms,
+    # batch 64 (BASELINE config): 16 distinct input sets (>= 370 MB) are cycled
+    ps64 = [torch.randn(64, N, E, device="cuda", generator=g).bfloat16() for _ in range(16)]
+    ms64 = _patch_sim_time(ps64, t, 10)
+    del ps64
+    # batch 4096: one 0.8 GB input, 0.55 GB output per launch
+    big = [torch.randn(4096, N, E, device="cuda", generator=g).bfloat16()]
+    ms4k = _patch_sim_time(big, t, 5)
+    del big
+    torch.cuda.empty_cache()
+    ach = 4096 * bytes_per_map / (ms4k / 1e3) / 1e9
+    ach64 = 64 * bytes_per_map / (ms64 / 1e3) / 1e9
+    return {"workload": "ViT-B seg inference map: 196 patches x 171 classes per map, bf16 in, fp32 map + argmax",
+            "value": 4096 / (ms4k / 1e3), "unit": "maps/s", "batch": 4096, "ms_per_batch": ms4k,
+            "batch64": {"value": 64 / (ms64 / 1e3), "unit": "maps/s", "ms_per_batch": ms64, "achieved_gbs": ach64,
+                        "note": "BASELINE configs[3] batch: 21 MB per launch, launch/latency-bound"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                         "traffic": None, "peak_source": how, "algorithmic_bytes_per_map": bytes_per_map}}
+                         "traffic": 1328.5e6, "traffic_source": "ncu --set full, dram__bytes_read+write per launch at batch 4096 "
+                                                               "(profiles/r01_ncu_patch_sim.txt); algorithmic 1374.4e6",
+                         "peak_source": how, "algorithmic_bytes_per_map": bytes_per_map}}
 
 
 def main():

@@ -76,7 +76,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   uint64_t* dkv_free = bars + 12;     // EW -> MMA : dK/dV drained                               (8 warps)
   uint64_t* dq_full = bars + 13;
   uint64_t* dq_free = bars + 14;      //                                                          (8 warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -126,62 +126,66 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // Warp-uniform loops, one elected lane issues (values stay in uniform registers; a descriptor is a 64-bit add away
+    // from two constants).  Issued from inside `if (lane == 0)` this thread — ~45 instructions per MMA — was the
+    // slowest stage of the kernel.
+    {
       uint32_t kvc = 0, it = 0, g = 0, drains = 0;
       const uint32_t id_sdp_base = make_idesc(1u, 0u, 0u, kTile, 16u) & ~(0x3Fu << 17);     // N filled per key tile
       const uint32_t id_dkv = make_idesc(1u, 1u, 1u, kTile, 64u);                           // A, B MN-major
       const uint32_t id_dq = make_idesc(1u, 0u, 1u, kTile, 64u);                            // A K-major, B MN-major
+      const uint64_t kd = make_smem_desc_sw128(0, 16, 1024);                                // K-major operand template
+      const uint64_t md = make_smem_desc_sw128(0, 16384, 1024);                             // MN-major operand template
+      const uint32_t aP = smem_u32(sP) >> 4, adS = smem_u32(sdS) >> 4;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         for (int kt = 0; kt < p.nkt; ++kt, ++kvc) {
           const uint32_t buf = kvc & 1;
           const int nkc = min(kTile, ceil16(p.S - kt * kTile));               // key columns of this tile (multiple of 16)
           const uint32_t id_sdp = id_sdp_base | (static_cast<uint32_t>(nkc >> 3) << 17);
           mbar_wait(&kv_full[buf], (kvc >> 1) & 1);
-          const uint32_t aK = smem_u32(sK + buf * kTileBytes), aV = smem_u32(sV + buf * kTileBytes);
+          const uint32_t aK = smem_u32(sK + buf * kTileBytes) >> 4, aV = smem_u32(sV + buf * kTileBytes) >> 4;
           for (int qt = 0; qt < p.nqt; ++qt, ++g) {
             if (kt == 0) mbar_wait(&qdo_full[qt], it & 1);
             tc_fence_after();
-            const uint32_t aQ = smem_u32(sQ + qt * kTileBytes), adO = smem_u32(sdO + qt * kTileBytes);
+            const uint32_t aQ = smem_u32(sQ + qt * kTileBytes) >> 4, adO = smem_u32(sdO + qt * kTileBytes) >> 4;
             // ---- S = Q K^T, dP = dO V^T   (K = d = 64: four K-steps inside one 128-byte swizzle row)
+            if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_f16(tS, make_smem_desc_sw128(aQ + kk * 32, 16, 1024), make_smem_desc_sw128(aK + kk * 32, 16, 1024), id_sdp,
-                       kk > 0 ? 1u : 0u);
+              for (int kk = 0; kk < 4; ++kk) umma_f16(tS, kd + aQ + 2 * kk, kd + aK + 2 * kk, id_sdp, kk > 0 ? 1u : 0u);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_f16(tdP, make_smem_desc_sw128(adO + kk * 32, 16, 1024), make_smem_desc_sw128(aV + kk * 32, 16, 1024), id_sdp,
-                       kk > 0 ? 1u : 0u);
-            umma_commit(sdp_full);
+              for (int kk = 0; kk < 4; ++kk) umma_f16(tdP, kd + adO + 2 * kk, kd + aV + 2 * kk, id_sdp, kk > 0 ? 1u : 0u);
+              umma_commit(sdp_full);
+            }
+            __syncwarp();
             // ---- wait for P / dS
             mbar_wait(ew_done, g & 1);
-            tc_fence_after();
             if (qt == 0 && drains > 0) mbar_wait(dkv_free, (drains - 1) & 1);
             if (kt == 0 && qt == 0 && it > 0) mbar_wait(dq_free, (it - 1) & 1);
             tc_fence_after();
-            const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
             const int qsteps = min(kTile, ceil16(p.S - qt * kTile)) >> 4;      // K-steps over query rows
             const int ksteps = nkc >> 4;                                       // K-steps over keys
-            // dV += P^T dO ; dK += dS^T Q      (A MN-major: key atoms 16 KB apart; K-step = 16 q rows = 2048 B)
-            for (int ks = 0; ks < qsteps; ++ks)
-              umma_f16(tdV, make_smem_desc_sw128(aP + ks * 2048, 16384, 1024), make_smem_desc_sw128(adO + ks * 2048, 16384, 1024),
-                       id_dkv, (qt > 0 || ks > 0) ? 1u : 0u);
-            for (int ks = 0; ks < qsteps; ++ks)
-              umma_f16(tdK, make_smem_desc_sw128(adS + ks * 2048, 16384, 1024), make_smem_desc_sw128(aQ + ks * 2048, 16384, 1024),
-                       id_dkv, (qt > 0 || ks > 0) ? 1u : 0u);
-            // dQ += dS K                        (A K-major: 4 K-steps per 64-key atom; B MN-major: K-step = 16 key rows)
-            for (int ks = 0; ks < ksteps; ++ks)
-              umma_f16(tdQ + 64 * qt, make_smem_desc_sw128(adS + (ks >> 2) * kTileBytes + (ks & 3) * 32, 16, 1024),
-                       make_smem_desc_sw128(aK + ks * 2048, 16384, 1024), id_dq, (kt > 0 || ks > 0) ? 1u : 0u);
-            umma_commit(pds_free);
-            if (qt == p.nqt - 1) {
-              umma_commit(dkv_full);
-              umma_commit(&kv_empty[buf]);
-              ++drains;
+            if (elect_one()) {
+              // dV += P^T dO ; dK += dS^T Q      (A MN-major: key atoms 16 KB apart; K-step = 16 q rows = 2048 B)
+              for (int ks = 0; ks < qsteps; ++ks)
+                umma_f16(tdV, md + aP + 128 * ks, md + adO + 128 * ks, id_dkv, (qt > 0 || ks > 0) ? 1u : 0u);
+              for (int ks = 0; ks < qsteps; ++ks)
+                umma_f16(tdK, md + adS + 128 * ks, md + aQ + 128 * ks, id_dkv, (qt > 0 || ks > 0) ? 1u : 0u);
+              // dQ += dS K                        (A K-major: 4 K-steps per 64-key atom; B MN-major: K-step = 16 key rows)
+              for (int ks = 0; ks < ksteps; ++ks)
+                umma_f16(tdQ + 64 * qt, kd + adS + (ks >> 2) * (kTileBytes >> 4) + (ks & 3) * 2, md + aK + 128 * ks, id_dq,
+                         (kt > 0 || ks > 0) ? 1u : 0u);
+              umma_commit(pds_free);
+              if (qt == p.nqt - 1) {
+                umma_commit(dkv_full);
+                umma_commit(&kv_empty[buf]);
+              }
+              if (kt == p.nkt - 1) {
+                umma_commit(&qdo_empty[qt]);
+                if (qt == p.nqt - 1) umma_commit(dq_full);
+              }
             }
-            if (kt == p.nkt - 1) {
-              umma_commit(&qdo_empty[qt]);
-              if (qt == p.nqt - 1) umma_commit(dq_full);
-            }
+            __syncwarp();
+            if (qt == p.nqt - 1) ++drains;
           }
         }
       }
@@ -205,21 +209,24 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         for (int qt = 0; qt < p.nqt; ++qt, ++g) {
           const int qrow = qt * kTile + r;
           const bool q_ok = qrow < p.S;
+          // D = rowsum(dO * O) and lse (log2 units) — once per (item, query tile).  The O row and lse are requested from
+          // global here and first touched after the wait for S / dP below, which hides their latency.
+          uint4 o[8];
+          float l2raw = 0.f;
           if (kt == 0) {
-            // D = rowsum(dO * O), lse in log2 units — once per (item, query tile).  The O row and lse are fetched from
-            // global BEFORE waiting for the dO tile so their latency overlaps the TMA wait.
-            uint4 o[8];
-            float l2 = 0.f;
             if (q_ok) {
               const uint4* orow = reinterpret_cast<const uint4*>(p.out + (static_cast<int64_t>(b) * p.S + qrow) * (p.H * 64) + h * 64);
 #pragma unroll
               for (int j = 0; j < 8; ++j) o[j] = __ldg(orow + j);
-              l2 = __ldg(p.lse + (static_cast<int64_t>(b) * p.H + h) * p.S + qrow) * 1.44269504088896341f;
+              l2raw = __ldg(p.lse + (static_cast<int64_t>(b) * p.H + h) * p.S + qrow);
             } else {
 #pragma unroll
               for (int j = 0; j < 8; ++j) o[j] = make_uint4(0, 0, 0, 0);
             }
-            mbar_wait(&qdo_full[qt], it & 1);
+          }
+          mbar_wait(sdp_full, g & 1);                                  // implies the Q / dO tiles of this qt have landed
+          tc_fence_after();
+          if (kt == 0) {
             float d = 0.f;
             const uint8_t* dorow = sdO + qt * kTileBytes + r * 128;
 #pragma unroll
@@ -229,12 +236,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                    bf16_hi(a.y) * bf16_hi(o[j].y) + bf16_lo(a.z) * bf16_lo(o[j].z) + bf16_hi(a.z) * bf16_hi(o[j].z) +
                    bf16_lo(a.w) * bf16_lo(o[j].w) + bf16_hi(a.w) * bf16_hi(o[j].w);
             }
+            const float l2 = l2raw * 1.44269504088896341f;
             if (qt == 0) { Dv[0] = d; L2v[0] = l2; } else { Dv[1] = d; L2v[1] = l2; }
           }
           const float Dq = qt == 0 ? Dv[0] : Dv[1];
           const float Lq = qt == 0 ? L2v[0] : L2v[1];
-          mbar_wait(sdp_full, g & 1);
-          tc_fence_after();
           bool waited_free = (g == 0);
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
@@ -244,6 +250,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             tmem_ld_32x32(tS + lane_off + col0, sr);
             tmem_ld_32x32(tdP + lane_off + col0, dr);
             tmem_ld_wait();
+
             uint32_t pp[16], dd[16];
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
@@ -282,6 +289,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             tmem_ld_32x32(tdV + lane_off + half * 32, a);
             tmem_ld_32x32(tdK + lane_off + half * 32, c2);
             tmem_ld_wait();
+            // dK / dV are in registers: release the accumulators BEFORE the global stores (an mbarrier arrive has release
+            // semantics — placed after the stores it would wait for them to drain)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dkv_free);
             const int key = kt * kTile + r;
             if (key < p.S) {
               __nv_bfloat16* pv = p.dv + base + static_cast<int64_t>(key) * p.ss + half * 32;
@@ -301,35 +313,40 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                 reinterpret_cast<uint4*>(pk)[j] = w;
               }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(dkv_free);
             ++drains;
             if (kt == p.nkt - 1) {
               // ---- drain dQ of both query tiles
               mbar_wait(dq_full, it & 1);
               tc_fence_after();
-              for (int t = 0; t < p.nqt; ++t) {
+              // both query tiles are pulled out of TMEM (the first one packed to bf16 right away to save registers),
+              // then the accumulator is released BEFORE the global stores (see above)
+              uint32_t q0[16], q1[16];
+              {
                 uint32_t a2[32];
-                tmem_ld_32x32(tdQ + 64 * t + lane_off + half * 32, a2);
+                tmem_ld_32x32(tdQ + lane_off + half * 32, a2);
                 tmem_ld_wait();
-                const int qr = t * kTile + r;
-                if (qr < p.S) {
-                  __nv_bfloat16* pq = p.dq + base + static_cast<int64_t>(qr) * p.ss + half * 32;
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    uint4 u;
-                    u.x = pack_bf16(__uint_as_float(a2[8 * j]) * p.scale, __uint_as_float(a2[8 * j + 1]) * p.scale);
-                    u.y = pack_bf16(__uint_as_float(a2[8 * j + 2]) * p.scale, __uint_as_float(a2[8 * j + 3]) * p.scale);
-                    u.z = pack_bf16(__uint_as_float(a2[8 * j + 4]) * p.scale, __uint_as_float(a2[8 * j + 5]) * p.scale);
-                    u.w = pack_bf16(__uint_as_float(a2[8 * j + 6]) * p.scale, __uint_as_float(a2[8 * j + 7]) * p.scale);
-                    reinterpret_cast<uint4*>(pq)[j] = u;
-                  }
+                for (int j = 0; j < 16; ++j) q0[j] = pack_bf16(__uint_as_float(a2[2 * j]) * p.scale, __uint_as_float(a2[2 * j + 1]) * p.scale);
+                if (p.nqt > 1) {
+                  tmem_ld_32x32(tdQ + 64 + lane_off + half * 32, a2);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) q1[j] = pack_bf16(__uint_as_float(a2[2 * j]) * p.scale, __uint_as_float(a2[2 * j + 1]) * p.scale);
                 }
               }
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(dq_free);
+              if (r < p.S) {
+                uint4* pq = reinterpret_cast<uint4*>(p.dq + base + static_cast<int64_t>(r) * p.ss + half * 32);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pq[j] = make_uint4(q0[4 * j], q0[4 * j + 1], q0[4 * j + 2], q0[4 * j + 3]);
+              }
+              if (p.nqt > 1 && kTile + r < p.S) {
+                uint4* pq = reinterpret_cast<uint4*>(p.dq + base + static_cast<int64_t>(kTile + r) * p.ss + half * 32);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pq[j] = make_uint4(q1[4 * j], q1[4 * j + 1], q1[4 * j + 2], q1[4 * j + 3]);
+              }
             }
           }
         }
@@ -513,6 +530,9 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         uint32_t o0[32];
         tmem_ld_32x32(tO + lane_off + half * 32, o0);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_free);                            // O is in registers: release it before the stores
         if (p_q_ok) {
           const float inv = 1.0f / p_sum;
           __nv_bfloat16* po = p.out + p_row + half * 32;
@@ -528,9 +548,11 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           if (half == 0 && p.lse) p.lse[p_lse] = (p_ms + log2f(p_sum)) * 0.69314718055994531f;
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_free);
+      if (!p_live) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_free);
+      }
     };
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int b = item / p.H, h = item - b * p.H;

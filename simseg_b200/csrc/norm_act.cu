@@ -42,45 +42,64 @@ int cast_bf16_impl(Ctx* ctx, const float* src, void* dst, void* dst_t, int64_t r
 
 // ------------------------------------------------------------------------------------------------
 // column sums: out[n] += sum_m x[m,n].  Block = 32 column-lanes x 8 row-lanes, each lane owns 4 columns.
+// bf16: 8 columns (one 16-byte load) per thread, 4 rows in flight per thread; fp32: 4 columns per thread.
 template <bool BF16>
-__global__ void colsum_kernel(const void* __restrict__ x, int64_t M, int64_t N, int64_t ldx, float* __restrict__ out,
-                              int64_t rows_per_block) {
-  const int64_t c0 = (static_cast<int64_t>(blockIdx.x) * 32 + threadIdx.x) * 4;
+__global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x, int64_t M, int64_t N, int64_t ldx,
+                                                     float* __restrict__ out, int64_t rows_per_block) {
+  constexpr int CPT = BF16 ? 8 : 4;                       // columns per thread
+  const int64_t c0 = (static_cast<int64_t>(blockIdx.x) * 32 + threadIdx.x) * CPT;
   const int64_t r_begin = blockIdx.y * rows_per_block;
   const int64_t r_end = min(M, r_begin + rows_per_block);
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  float a[CPT];
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) a[j] = 0.f;
   if (c0 < N) {
-    const bool full = c0 + 4 <= N;
-    for (int64_t r = r_begin + threadIdx.y; r < r_end; r += 8) {
-      if (BF16) {
-        const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(x) + r * ldx + c0;
-        if (full) {
-          const uint2 u = *reinterpret_cast<const uint2*>(p);
-          a0 += bf16_lo(u.x); a1 += bf16_hi(u.x); a2 += bf16_lo(u.y); a3 += bf16_hi(u.y);
-        } else {
-          a0 += __bfloat162float(p[0]);
-          if (c0 + 1 < N) a1 += __bfloat162float(p[1]);
-          if (c0 + 2 < N) a2 += __bfloat162float(p[2]);
+    const bool full = c0 + CPT <= N;
+    if (full) {
+      int64_t r = r_begin + threadIdx.y;
+      for (; r + 24 < r_end; r += 32) {                   // four independent 16-byte loads in flight
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const char* pp = reinterpret_cast<const char*>(x) + ((r + 8 * k) * ldx + c0) * (BF16 ? 2 : 4);
+          u[k] = ldg_nc_v4(pp);
         }
-      } else {
-        const float* p = reinterpret_cast<const float*>(x) + r * ldx + c0;
-        if (full) {
-          const float4 f = *reinterpret_cast<const float4*>(p);
-          a0 += f.x; a1 += f.y; a2 += f.z; a3 += f.w;
-        } else {
-          a0 += p[0];
-          if (c0 + 1 < N) a1 += p[1];
-          if (c0 + 2 < N) a2 += p[2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (BF16) {
+            a[0] += bf16_lo(u[k].x); a[1] += bf16_hi(u[k].x); a[2] += bf16_lo(u[k].y); a[3] += bf16_hi(u[k].y);
+            a[4 % CPT] += BF16 ? bf16_lo(u[k].z) : 0.f; a[5 % CPT] += BF16 ? bf16_hi(u[k].z) : 0.f;
+            a[6 % CPT] += BF16 ? bf16_lo(u[k].w) : 0.f; a[7 % CPT] += BF16 ? bf16_hi(u[k].w) : 0.f;
+          } else {
+            a[0] += __uint_as_float(u[k].x); a[1] += __uint_as_float(u[k].y);
+            a[2] += __uint_as_float(u[k].z); a[3] += __uint_as_float(u[k].w);
+          }
         }
       }
+      for (; r < r_end; r += 8) {
+        const uint4 u = ldg_nc_v4(reinterpret_cast<const char*>(x) + (r * ldx + c0) * (BF16 ? 2 : 4));
+        if (BF16) {
+          a[0] += bf16_lo(u.x); a[1] += bf16_hi(u.x); a[2] += bf16_lo(u.y); a[3] += bf16_hi(u.y);
+          a[4 % CPT] += BF16 ? bf16_lo(u.z) : 0.f; a[5 % CPT] += BF16 ? bf16_hi(u.z) : 0.f;
+          a[6 % CPT] += BF16 ? bf16_lo(u.w) : 0.f; a[7 % CPT] += BF16 ? bf16_hi(u.w) : 0.f;
+        } else {
+          a[0] += __uint_as_float(u.x); a[1] += __uint_as_float(u.y); a[2] += __uint_as_float(u.z); a[3] += __uint_as_float(u.w);
+        }
+      }
+    } else {
+      for (int64_t r = r_begin + threadIdx.y; r < r_end; r += 8)
+        for (int j = 0; j < CPT; ++j)
+          if (c0 + j < N)
+            a[j] += BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[r * ldx + c0 + j])
+                         : reinterpret_cast<const float*>(x)[r * ldx + c0 + j];
     }
   }
-  __shared__ float red[8][32][4];
-  red[threadIdx.y][threadIdx.x][0] = a0; red[threadIdx.y][threadIdx.x][1] = a1;
-  red[threadIdx.y][threadIdx.x][2] = a2; red[threadIdx.y][threadIdx.x][3] = a3;
+  __shared__ float red[8][32][CPT + 1];
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) red[threadIdx.y][threadIdx.x][j] = a[j];
   __syncthreads();
   if (threadIdx.y == 0 && c0 < N) {
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < CPT; ++j) {
       float s = 0.f;
       for (int y = 0; y < 8; ++y) s += red[y][threadIdx.x][j];
       if (c0 + j < N) atomicAdd(out + c0 + j, s);
@@ -94,7 +113,7 @@ int colsum_impl(Ctx* ctx, const void* x, int dtype, int64_t M, int64_t N, int64_
   const int eb = dtype == SIMSEG_BF16 ? 2 : 4;
   SIMSEG_CHECK_ARG((ldx * eb) % 16 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "colsum: rows must be 16B aligned");
   if (!accumulate) SIMSEG_CUDA(cudaMemsetAsync(out, 0, N * sizeof(float), st));
-  const int64_t col_blocks = cdiv(N, 128);
+  const int64_t col_blocks = cdiv(N, dtype == SIMSEG_BF16 ? 256 : 128);
   int64_t row_blocks = cdiv(static_cast<int64_t>(ctx->num_sms) * 8, col_blocks);
   const int64_t max_rb = cdiv(M, 64);
   if (row_blocks > max_rb) row_blocks = max_rb;
@@ -232,6 +251,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
     float xv[V][4], dv[V][4];
     load_row<V, XBF16>(x, row, D, lane, xv);
     load_row<V, DYBF16>(dy, row, D, lane, dv);
+    // the running residual gradient is requested together with x and dy (one HBM round trip per row, not two)
+    float pv[V][4];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dx_accumulate) f = *reinterpret_cast<const float4*>(dx + row * D + (i * 32 + lane) * 4);
+      pv[i][0] = f.x; pv[i][1] = f.y; pv[i][2] = f.z; pv[i][3] = f.w;
+    }
     if (dy2) {
 #pragma unroll
       for (int i = 0; i < V; ++i) {
@@ -260,11 +287,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
       const int c = (i * 32 + lane) * 4;
       float o[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = rs * (dv[i][j] - c1 - xv[i][j] * c2);
-      if (dx_accumulate) {
-        const float4 f = *reinterpret_cast<const float4*>(dx + row * D + c);
-        o[0] += f.x; o[1] += f.y; o[2] += f.z; o[3] += f.w;
-      }
+      for (int j = 0; j < 4; ++j) o[j] = rs * (dv[i][j] - c1 - xv[i][j] * c2) + pv[i][j];
       if (dx) *reinterpret_cast<float4*>(dx + row * D + c) = make_float4(o[0], o[1], o[2], o[3]);
       if (dx_bf16) {
         uint2 u; u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]);
