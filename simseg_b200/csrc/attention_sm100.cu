@@ -18,6 +18,8 @@
 #include "common.cuh"
 #include "sm100.cuh"
 
+#include <cstdlib>
+
 namespace simseg {
 
 using namespace sm100;
@@ -29,6 +31,7 @@ constexpr int kPBytes = 2 * kTileBytes;    // P or dS: [2 key atoms][128 q rows]
 
 struct AttnBwdParams {
   int32_t B, H, S, nqt, nkt, items;
+  int32_t G, lg, HG, rows, tile_tx;   // packed mode (G > 1): G heads of one sequence per tile, row = token * G + head
   float scale, scale_log2e;
   const int32_t* key_len;
   const float* lse;                 // [B,H,S]
@@ -95,6 +98,12 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  if (p.G > 1) {
+    // packed boxes cover only S*G rows of a tile: the rows behind them must hold finite values (0 x NaN = NaN in the MMAs)
+    uint4* z = reinterpret_cast<uint4*>(sQ);
+    for (int i = threadIdx.x; i < 8 * kTileBytes / 16; i += kAbThreads) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -106,17 +115,17 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     if (lane == 0) {
       uint32_t kvc = 0, it = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-        const int b = item / p.H, h = item - b * p.H;
+        const int b = item / p.HG, h = (item - b * p.HG) * p.G;
         for (int kt = 0; kt < p.nkt; ++kt, ++kvc) {
           const uint32_t buf = kvc & 1, ph = (kvc >> 1) & 1;
           mbar_wait(&kv_empty[buf], ph ^ 1);
-          mbar_arrive_expect_tx(&kv_full[buf], 2 * kTileBytes);
+          mbar_arrive_expect_tx(&kv_full[buf], 2 * p.tile_tx);
           tma_load_4d(sK + buf * kTileBytes, &tm_k, &kv_full[buf], 0, h, kt * kTile, b);
           tma_load_4d(sV + buf * kTileBytes, &tm_v, &kv_full[buf], 0, h, kt * kTile, b);
           if (kt == 0) {
             for (int qt = 0; qt < p.nqt; ++qt) {
               mbar_wait(&qdo_empty[qt], (it & 1) ^ 1);
-              mbar_arrive_expect_tx(&qdo_full[qt], 2 * kTileBytes);
+              mbar_arrive_expect_tx(&qdo_full[qt], 2 * p.tile_tx);
               tma_load_4d(sQ + qt * kTileBytes, &tm_q, &qdo_full[qt], 0, h, qt * kTile, b);
               tma_load_4d(sdO + qt * kTileBytes, &tm_do, &qdo_full[qt], 0, h, qt * kTile, b);
             }
@@ -140,7 +149,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         for (int kt = 0; kt < p.nkt; ++kt, ++kvc) {
           const uint32_t buf = kvc & 1;
-          const int nkc = min(kTile, ceil16(p.S - kt * kTile));               // key columns of this tile (multiple of 16)
+          const int nkc = min(kTile, ceil16(p.rows - kt * kTile));            // key columns of this tile (multiple of 16)
           const uint32_t id_sdp = id_sdp_base | (static_cast<uint32_t>(nkc >> 3) << 17);
           mbar_wait(&kv_full[buf], (kvc >> 1) & 1);
           const uint32_t aK = smem_u32(sK + buf * kTileBytes) >> 4, aV = smem_u32(sV + buf * kTileBytes) >> 4;
@@ -162,7 +171,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             if (qt == 0 && drains > 0) mbar_wait(dkv_free, (drains - 1) & 1);
             if (kt == 0 && qt == 0 && it > 0) mbar_wait(dq_free, (it - 1) & 1);
             tc_fence_after();
-            const int qsteps = min(kTile, ceil16(p.S - qt * kTile)) >> 4;      // K-steps over query rows
+            const int qsteps = min(kTile, ceil16(p.rows - qt * kTile)) >> 4;   // K-steps over query rows
             const int ksteps = nkc >> 4;                                       // K-steps over keys
             if (elect_one()) {
               // dV += P^T dO ; dK += dS^T Q      (A MN-major: key atoms 16 KB apart; K-step = 16 q rows = 2048 B)
@@ -200,25 +209,32 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     const int sw = r & 7;
     uint32_t it = 0, g = 0, drains = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-      const int b = item / p.H, h = item - b * p.H;
-      const int klen = p.key_len ? min(max(p.key_len[b], 1), p.S) : p.S;
-      const int64_t base = static_cast<int64_t>(b) * p.sb + static_cast<int64_t>(h) * p.sh;
+      const int b = item / p.HG, h0 = (item - b * p.HG) * p.G;
+      // klen = live key COLUMNS (packed: key tokens * G, column = token * G + head); a column is live for a row iff it
+      // belongs to the row's head
+      const int klen = (p.key_len ? min(max(p.key_len[b], 1), p.S) : p.S) * p.G;
+      const int gm = p.G - 1, rg = r & gm;
+      const int64_t base_b = static_cast<int64_t>(b) * p.sb;
+      auto row_off = [&](int row) {                                   // (token, head) of a tile row -> q/k/v element offset
+        return base_b + static_cast<int64_t>(row >> p.lg) * p.ss + static_cast<int64_t>(h0 + (row & gm)) * p.sh;
+      };
       float Dv[2] = {0.f, 0.f}, L2v[2] = {0.f, 0.f};
       for (int kt = 0; kt < p.nkt; ++kt) {
-        const int nkc = min(kTile, ceil16(p.S - kt * kTile));
+        const int nkc = min(kTile, ceil16(p.rows - kt * kTile));
         for (int qt = 0; qt < p.nqt; ++qt, ++g) {
           const int qrow = qt * kTile + r;
-          const bool q_ok = qrow < p.S;
+          const bool q_ok = qrow < p.rows;
           // D = rowsum(dO * O) and lse (log2 units) — once per (item, query tile).  The O row and lse are requested from
           // global here and first touched after the wait for S / dP below, which hides their latency.
           uint4 o[8];
           float l2raw = 0.f;
           if (kt == 0) {
             if (q_ok) {
-              const uint4* orow = reinterpret_cast<const uint4*>(p.out + (static_cast<int64_t>(b) * p.S + qrow) * (p.H * 64) + h * 64);
+              const int tok = qrow >> p.lg, hh = h0 + (qrow & gm);
+              const uint4* orow = reinterpret_cast<const uint4*>(p.out + (static_cast<int64_t>(b) * p.S + tok) * (p.H * 64) + hh * 64);
 #pragma unroll
               for (int j = 0; j < 8; ++j) o[j] = __ldg(orow + j);
-              l2raw = __ldg(p.lse + (static_cast<int64_t>(b) * p.H + h) * p.S + qrow);
+              l2raw = __ldg(p.lse + (static_cast<int64_t>(b) * p.H + hh) * p.S + tok);
             } else {
 #pragma unroll
               for (int j = 0; j < 8; ++j) o[j] = make_uint4(0, 0, 0, 0);
@@ -257,8 +273,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
               const int key = kt * kTile + col0 + j;
               float p0 = ex2_approx(fmaf(__uint_as_float(sr[j]), p.scale_log2e, -Lq));
               float p1 = ex2_approx(fmaf(__uint_as_float(sr[j + 1]), p.scale_log2e, -Lq));
-              p0 = (q_ok && key < klen) ? p0 : 0.f;
-              p1 = (q_ok && key + 1 < klen) ? p1 : 0.f;
+              p0 = (q_ok && key < klen && (key & gm) == rg) ? p0 : 0.f;
+              p1 = (q_ok && key + 1 < klen && ((key + 1) & gm) == rg) ? p1 : 0.f;
               const float d0 = p0 * (__uint_as_float(dr[j]) - Dq);
               const float d1 = p1 * (__uint_as_float(dr[j + 1]) - Dq);
               pp[j >> 1] = pack_bf16(p0, p1);
@@ -295,9 +311,9 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive(dkv_free);
             const int key = kt * kTile + r;
-            if (key < p.S) {
-              __nv_bfloat16* pv = p.dv + base + static_cast<int64_t>(key) * p.ss + half * 32;
-              __nv_bfloat16* pk = p.dk + base + static_cast<int64_t>(key) * p.ss + half * 32;
+            if (key < p.rows) {
+              __nv_bfloat16* pv = p.dv + row_off(key) + half * 32;
+              __nv_bfloat16* pk = p.dk + row_off(key) + half * 32;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 uint4 u, w;
@@ -337,13 +353,13 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(dq_free);
-              if (r < p.S) {
-                uint4* pq = reinterpret_cast<uint4*>(p.dq + base + static_cast<int64_t>(r) * p.ss + half * 32);
+              if (r < p.rows) {
+                uint4* pq = reinterpret_cast<uint4*>(p.dq + row_off(r) + half * 32);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) pq[j] = make_uint4(q0[4 * j], q0[4 * j + 1], q0[4 * j + 2], q0[4 * j + 3]);
               }
-              if (p.nqt > 1 && kTile + r < p.S) {
-                uint4* pq = reinterpret_cast<uint4*>(p.dq + base + static_cast<int64_t>(kTile + r) * p.ss + half * 32);
+              if (p.nqt > 1 && kTile + r < p.rows) {
+                uint4* pq = reinterpret_cast<uint4*>(p.dq + row_off(kTile + r) + half * 32);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) pq[j] = make_uint4(q1[4 * j], q1[4 * j + 1], q1[4 * j + 2], q1[4 * j + 3]);
               }
@@ -375,10 +391,14 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 //               real bound of this kernel), row sum, P (bf16) into 128B-swizzled smem as the K-major A operand of P V; the
 //               same warps drain O of the previous unit, scale by 1/sum and store the output rows + the log-sum-exp.
 // Keys >= key_len[b] (BERT padding) and the zero-filled tail columns get P = 0.
+// Short sequences (S * G <= 128, e.g. BERT's 25 tokens): G heads of one sequence are PACKED into one tile by a single
+// TMA box {64 d, G heads, S tokens} (row = token * G + head); S = Q K^T is then block-sparse and entries whose row and
+// column belong to different heads are masked like padding — 4x fewer units, each with full-size MMAs.
 constexpr int kAfThreads = 320;
 
 struct AttnFwdParams {
   int32_t B, H, S, nqt, nkt, nkc, stride, items, kv_stages;
+  int32_t G, lg, HG, rows, tile_tx;   // packed mode (G > 1): G heads of one sequence share a 128-row tile, row = token * G + head
   float scale_log2e;
   const int32_t* key_len;
   float* lse;                 // [B,H,S]
@@ -429,6 +449,12 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  if (p.G > 1) {
+    // packed boxes cover only S*G rows of a tile: the rows behind them must hold finite values (P = 0 times NaN is NaN)
+    uint4* z = reinterpret_cast<uint4*>(sQ);
+    for (int i = threadIdx.x; i < 10 * kTileBytes / 16; i += kAfThreads) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -439,11 +465,11 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     // =============================== TMA producer ===============================
     uint32_t u = 0, itc = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++itc) {
-      const int b = item / p.H, h = item - b * p.H;
+      const int b = item / p.HG, h = (item - b * p.HG) * p.G;
       const uint32_t kb = itc % p.kv_stages;
       mbar_wait(&kv_empty[kb], ((itc / p.kv_stages) & 1) ^ 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(&kv_full[kb], 2 * p.nkt * kTileBytes);
+        mbar_arrive_expect_tx(&kv_full[kb], 2 * p.nkt * p.tile_tx);
         for (int t = 0; t < p.nkt; ++t) {
           tma_load_4d(sK + (p.nkt * kb + t) * kTileBytes, &tm_k, &kv_full[kb], 0, h, t * kTile, b);
           tma_load_4d(sV + (p.nkt * kb + t) * kTileBytes, &tm_v, &kv_full[kb], 0, h, t * kTile, b);
@@ -453,7 +479,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       for (int qt = 0; qt < p.nqt; ++qt, ++u) {
         mbar_wait(&q_empty[u & 1], ((u >> 1) & 1) ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&q_full[u & 1], kTileBytes);
+          mbar_arrive_expect_tx(&q_full[u & 1], p.tile_tx);
           tma_load_4d(sQ + (u & 1) * kTileBytes, &tm_q, &q_full[u & 1], 0, h, qt * kTile, b);
         }
         __syncwarp();
@@ -555,13 +581,16 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       }
     };
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-      const int b = item / p.H, h = item - b * p.H;
-      const int klen = p.key_len ? min(max(p.key_len[b], 1), p.S) : p.S;
-      const int nch = (klen + 31) >> 5;                                    // 32-key chunks that hold a live key
+      const int b = item / p.HG, h0 = (item - b * p.HG) * p.G;
+      // klen = live key COLUMNS of the tile (packed: key tokens * G, column = token * G + head)
+      const int klen = (p.key_len ? min(max(p.key_len[b], 1), p.S) : p.S) * p.G;
+      const int nch = (klen + 31) >> 5;                                    // 32-column chunks that hold a live key
+      const int gm = p.G - 1, rg = r & gm;                                 // a column is live iff it is this row's head
+      const bool dense = p.G == 1;
       for (int qt = 0; qt < p.nqt; ++qt, ++u) {
-        const int qrow = qt * kTile + r;
-        const bool q_ok = qrow < p.S;
-        const bool warp_live = qt * kTile + quarter * 32 < p.S;             // any live row in this warp
+        const int qrow = qt * kTile + r;                                    // packed: row = token * G + head
+        const bool q_ok = qrow < p.rows;
+        const bool warp_live = qt * kTile + quarter * 32 < p.rows;          // any live row in this warp
         const uint32_t tS = tmem_base + (u & 1) * p.stride + lane_off;
         mbar_wait(&s_full[u & 1], (u >> 1) & 1);
         tc_fence_after();
@@ -572,7 +601,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             uint32_t x[32];
             tmem_ld_32x32(tS + c * 32, x);
             tmem_ld_wait();
-            if (c * 32 + 32 <= klen) {                                     // whole chunk live: no per-key predicate
+            if (dense && c * 32 + 32 <= klen) {                            // whole chunk live: no per-key predicate
               float m0 = fmaxf(__uint_as_float(x[0]), __uint_as_float(x[1]));
               float m1 = fmaxf(__uint_as_float(x[2]), __uint_as_float(x[3]));
 #pragma unroll
@@ -583,7 +612,8 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
               m = fmaxf(m, fmaxf(m0, m1));
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) m = (c * 32 + j < klen) ? fmaxf(m, __uint_as_float(x[j])) : m;
+              for (int j = 0; j < 32; ++j)
+                m = (c * 32 + j < klen && ((c * 32 + j) & gm) == rg) ? fmaxf(m, __uint_as_float(x[j])) : m;
             }
           }
         }
@@ -602,7 +632,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             tmem_ld_32x32(tS + c * 32, x);
             tmem_ld_wait();
             uint32_t pp[16];
-            if (c * 32 + 32 <= klen) {
+            if (dense && c * 32 + 32 <= klen) {
               float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -620,8 +650,8 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
               for (int j = 0; j < 32; j += 2) {
                 float p0 = ex2_approx(fmaf(__uint_as_float(x[j]), p.scale_log2e, -ms));
                 float p1 = ex2_approx(fmaf(__uint_as_float(x[j + 1]), p.scale_log2e, -ms));
-                p0 = (c * 32 + j < klen) ? p0 : 0.f;
-                p1 = (c * 32 + j + 1 < klen) ? p1 : 0.f;
+                p0 = (c * 32 + j < klen && ((c * 32 + j) & gm) == rg) ? p0 : 0.f;
+                p1 = (c * 32 + j + 1 < klen && ((c * 32 + j + 1) & gm) == rg) ? p1 : 0.f;
                 sum += p0 + p1;
                 pp[j >> 1] = pack_bf16(p0, p1);
               }
@@ -651,8 +681,11 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
         if (lane == 0) { mbar_arrive(p_ready); mbar_arrive(&s_empty[u & 1]); }
         pv_pending = true; p_q_ok = q_ok; p_live = warp_live; p_sum = sum; p_ms = ms;
-        p_row = (static_cast<int64_t>(b) * p.S + qrow) * (p.H * 64) + h * 64;
-        p_lse = (static_cast<int64_t>(b) * p.H + h) * p.S + qrow;
+        {
+          const int tok = qrow >> p.lg, hh = h0 + (qrow & gm);
+          p_row = (static_cast<int64_t>(b) * p.S + tok) * (p.H * 64) + hh * 64;
+          p_lse = (static_cast<int64_t>(b) * p.H + hh) * p.S + tok;
+        }
       }
     }
     if (pv_pending) drain(u - 1);
@@ -672,7 +705,8 @@ typedef CUresult (*EncodeTiledFn4)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // {64 d, H heads, S tokens, B batch} bf16 view of a (batch, token, head)-strided tensor; box = 128 tokens of one head
-static int make_tmap_bshd(CUtensorMap* m, const void* ptr, int B, int H, int S, int64_t sb, int64_t ss, int64_t sh) {
+// G > 1: one box = {64 d, G heads, all S tokens} of one batch element (row = token * G + head in shared memory)
+static int make_tmap_bshd(CUtensorMap* m, const void* ptr, int B, int H, int S, int64_t sb, int64_t ss, int64_t sh, int G = 1) {
   static EncodeTiledFn4 enc = nullptr;
   if (!enc) {
     void* f = nullptr;
@@ -685,7 +719,7 @@ static int make_tmap_bshd(CUtensorMap* m, const void* ptr, int B, int H, int S, 
   }
   cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(B)};
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(sh) * 2, static_cast<cuuint64_t>(ss) * 2, static_cast<cuuint64_t>(sb) * 2};
-  cuuint32_t box[4] = {64, 1, kTile, 1};
+  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(G), static_cast<cuuint32_t>(G > 1 ? S : kTile), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -696,6 +730,13 @@ static int make_tmap_bshd(CUtensorMap* m, const void* ptr, int B, int H, int S, 
     return SIMSEG_ERR_CUDA;
   }
   return SIMSEG_OK;
+}
+
+// heads of one sequence packed per 128-row tile: largest power of two G with G * S <= 128 that divides H
+static int pack_factor(int H, int S) {
+  int G = 1;
+  while (G * 2 * S <= kTile && H % (G * 2) == 0 && G < 8) G *= 2;
+  return G;
 }
 
 // SIMSEG_ERR_UNSUPPORTED => caller uses the mma.sync kernel (S > 256, unaligned pointers, H == 1 with odd strides ...)
@@ -710,14 +751,18 @@ int attention_bwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v,
   if ((H > 1 && sh * 2 >= (int64_t(1) << 40)) || ss * 2 >= (int64_t(1) << 40)) return SIMSEG_ERR_UNSUPPORTED;
   CUtensorMap tq, tk, tv, tdo;
   int rc;
-  if ((rc = make_tmap_bshd(&tq, q, B, H, S, sb, ss, sh))) return rc;
-  if ((rc = make_tmap_bshd(&tk, k, B, H, S, sb, ss, sh))) return rc;
-  if ((rc = make_tmap_bshd(&tv, v, B, H, S, sb, ss, sh))) return rc;
-  if ((rc = make_tmap_bshd(&tdo, dout, B, H, S, static_cast<int64_t>(S) * H * 64, static_cast<int64_t>(H) * 64, 64))) return rc;
+  const int G = pack_factor(H, S);
+  if ((rc = make_tmap_bshd(&tq, q, B, H, S, sb, ss, sh, G))) return rc;
+  if ((rc = make_tmap_bshd(&tk, k, B, H, S, sb, ss, sh, G))) return rc;
+  if ((rc = make_tmap_bshd(&tv, v, B, H, S, sb, ss, sh, G))) return rc;
+  if ((rc = make_tmap_bshd(&tdo, dout, B, H, S, static_cast<int64_t>(S) * H * 64, static_cast<int64_t>(H) * 64, 64, G))) return rc;
   AttnBwdParams p{};
   p.B = B; p.H = H; p.S = S;
-  p.nqt = (S + kTile - 1) / kTile; p.nkt = p.nqt;
-  p.items = B * H;
+  p.G = G; p.HG = H / G; p.rows = S * G;
+  p.lg = G == 1 ? 0 : (G == 2 ? 1 : (G == 4 ? 2 : 3));
+  p.tile_tx = G > 1 ? p.rows * 128 : kTileBytes;
+  p.nqt = (p.rows + kTile - 1) / kTile; p.nkt = p.nqt;
+  p.items = B * p.HG;
   p.scale = scale; p.scale_log2e = scale * 1.44269504088896341f;
   p.key_len = key_len; p.lse = lse; p.out = reinterpret_cast<const __nv_bfloat16*>(out);
   p.dq = reinterpret_cast<__nv_bfloat16*>(dq); p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dv = reinterpret_cast<__nv_bfloat16*>(dv);
@@ -739,21 +784,28 @@ int attention_bwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v,
 int attention_fwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v, int64_t sb, int64_t ss, int64_t sh, int B, int H,
                           int S, const int32_t* key_len, float scale, void* out, float* lse, cudaStream_t st) {
   if (S > 224 || S < 1) return SIMSEG_ERR_UNSUPPORTED;
+  const int G = pack_factor(H, S);
+  // measured (B=4096, H=12, S=25): packed tcgen05 forward 0.21 ms vs 0.185 ms for the mma.sync kernel (the unit is
+  // latency-bound); backward is the opposite (0.58 vs 1.25 ms).  Forward keeps the small kernel unless forced.
+  if (S < 48 && getenv("SIMSEG_ATTN_FWD") == nullptr) return SIMSEG_ERR_UNSUPPORTED;
   const uintptr_t al = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
                        reinterpret_cast<uintptr_t>(out);
   if ((al & 15) || sb % 8 || ss % 8 || sh % 8) return SIMSEG_ERR_UNSUPPORTED;
   if ((H > 1 && sh * 2 >= (int64_t(1) << 40)) || ss * 2 >= (int64_t(1) << 40)) return SIMSEG_ERR_UNSUPPORTED;
   CUtensorMap tq, tk, tv;
   int rc;
-  if ((rc = make_tmap_bshd(&tq, q, B, H, S, sb, ss, sh))) return rc;
-  if ((rc = make_tmap_bshd(&tk, k, B, H, S, sb, ss, sh))) return rc;
-  if ((rc = make_tmap_bshd(&tv, v, B, H, S, sb, ss, sh))) return rc;
+  if ((rc = make_tmap_bshd(&tq, q, B, H, S, sb, ss, sh, G))) return rc;
+  if ((rc = make_tmap_bshd(&tk, k, B, H, S, sb, ss, sh, G))) return rc;
+  if ((rc = make_tmap_bshd(&tv, v, B, H, S, sb, ss, sh, G))) return rc;
   AttnFwdParams p{};
   p.B = B; p.H = H; p.S = S;
-  p.nqt = (S + kTile - 1) / kTile; p.nkt = p.nqt;
-  p.nkc = (S + 15) & ~15;
+  p.G = G; p.HG = H / G; p.rows = S * G;
+  p.lg = G == 1 ? 0 : (G == 2 ? 1 : (G == 4 ? 2 : 3));
+  p.tile_tx = G > 1 ? p.rows * 128 : kTileBytes;
+  p.nqt = (p.rows + kTile - 1) / kTile; p.nkt = p.nqt;
+  p.nkc = (p.rows + 15) & ~15;
   p.stride = (p.nkc + 31) & ~31;
-  p.items = B * H;
+  p.items = B * p.HG;
   p.kv_stages = p.nkt == 1 ? 4 : 2;
   p.scale_log2e = scale * 1.44269504088896341f;
   p.key_len = key_len; p.lse = lse; p.out = reinterpret_cast<__nv_bfloat16*>(out);

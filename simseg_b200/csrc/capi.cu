@@ -134,10 +134,10 @@ int simseg_attention_fwd(simseg_ctx* ctx, const void* q, const void* k, const vo
                          int64_t stride_h, int B, int H, int S, const int32_t* key_len, float scale, void* out, float* lse,
                          void* stream) {
   CTX_OR_FAIL();
-  // tcgen05 kernel for 64 <= S <= 224 (attention_sm100.cu); other shapes run the mma.sync kernel.
+  // tcgen05 kernel for S <= 224 (attention_sm100.cu); shapes it rejects run the mma.sync kernel.
   // SIMSEG_ATTN_FWD=mma|tc overrides the choice (tests exercise both).
   const char* force = getenv("SIMSEG_ATTN_FWD");
-  const bool want_tc = force ? (force[0] == 't') : (S >= 64);
+  const bool want_tc = force ? (force[0] == 't') : true;       // short sequences are packed several heads per tile
   if (want_tc) {
     const int rc = attention_fwd_tc_impl(c, q, k, v, stride_b, stride_s, stride_h, B, H, S, key_len, scale, out, lse, st);
     if (rc != SIMSEG_ERR_UNSUPPORTED) return rc;
@@ -151,7 +151,7 @@ int simseg_attention_bwd(simseg_ctx* ctx, const void* q, const void* k, const vo
   // tcgen05 kernel for S <= 256 (attention_sm100.cu); longer sequences and shapes it rejects run the mma.sync kernel.
   // SIMSEG_ATTN_BWD=mma|tc overrides the choice (tests exercise both).
   const char* force = getenv("SIMSEG_ATTN_BWD");
-  const bool want_tc = force ? (force[0] == 't') : (S >= 96);
+  const bool want_tc = force ? (force[0] == 't') : true;       // short sequences are packed several heads per tile
   if (want_tc) {
     const int rc = attention_bwd_tc_impl(c, q, k, v, out, dout, lse, stride_b, stride_s, stride_h, B, H, S, key_len, scale, dq, dk, dv, st);
     if (rc != SIMSEG_ERR_UNSUPPORTED) return rc;

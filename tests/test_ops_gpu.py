@@ -247,7 +247,8 @@ def test_attention(cuda, B, H, S, masked):
 
 @pytest.mark.parametrize("impl", ["tc", "mma"])
 @pytest.mark.parametrize("B,H,S,masked", [(3, 6, 197, False), (2, 12, 256, True), (7, 12, 25, True), (4, 12, 77, True),
-                                          (2, 2, 129, True), (40, 6, 197, False), (3, 1, 128, False)])
+                                          (2, 2, 129, True), (40, 6, 197, False), (3, 1, 128, False),
+                                          (5, 8, 30, True), (3, 12, 50, False), (4, 6, 25, True), (200, 12, 25, True), (9, 16, 16, True)])
 def test_attention_bwd_both_kernels(cuda, impl, B, H, S, masked):
     """Backward through the tcgen05 kernel (S <= 256) and through the mma.sync kernel, selected explicitly; more work
     items than SMs (40 x 6 heads) exercises the persistent loop, the buffer recycling and every barrier phase."""
@@ -332,7 +333,8 @@ def test_misc_elementwise(cuda):
 
 @pytest.mark.parametrize("impl", ["tc", "mma"])
 @pytest.mark.parametrize("B,H,S,masked", [(3, 6, 197, False), (2, 12, 224, True), (7, 12, 25, True), (4, 12, 77, True),
-                                          (2, 2, 129, True), (60, 6, 197, False), (3, 1, 128, False), (300, 2, 64, True)])
+                                          (2, 2, 129, True), (60, 6, 197, False), (3, 1, 128, False), (300, 2, 64, True),
+                                          (5, 8, 30, True), (3, 12, 50, False), (4, 6, 25, True), (200, 12, 25, True), (9, 16, 16, True)])
 def test_attention_fwd_both_kernels(cuda, impl, B, H, S, masked, monkeypatch):
     """Forward through the tcgen05 kernel (S <= 224: exact two-pass softmax out of TMEM, two alternating softmax
     groups) and through the mma.sync kernel, selected explicitly; more work items than SMs exercises the persistent
