@@ -214,6 +214,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       // belongs to the row's head
       const int klen = (p.key_len ? min(max(p.key_len[b], 1), p.S) : p.S) * p.G;
       const int gm = p.G - 1, rg = r & gm;
+      const bool need_mask = p.key_len != nullptr || p.G > 1;
       const int64_t base_b = static_cast<int64_t>(b) * p.sb;
       auto row_off = [&](int row) {                                   // (token, head) of a tile row -> q/k/v element offset
         return base_b + static_cast<int64_t>(row >> p.lg) * p.ss + static_cast<int64_t>(h0 + (row & gm)) * p.sh;
@@ -268,17 +269,31 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             tmem_ld_wait();
 
             uint32_t pp[16], dd[16];
+            if (need_mask || kt * kTile + col0 + 32 > p.rows) {    // padding keys: exp2(-lse) could overflow, mask them
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const int key = kt * kTile + col0 + j;
-              float p0 = ex2_approx(fmaf(__uint_as_float(sr[j]), p.scale_log2e, -Lq));
-              float p1 = ex2_approx(fmaf(__uint_as_float(sr[j + 1]), p.scale_log2e, -Lq));
-              p0 = (q_ok && key < klen && (key & gm) == rg) ? p0 : 0.f;
-              p1 = (q_ok && key + 1 < klen && ((key + 1) & gm) == rg) ? p1 : 0.f;
-              const float d0 = p0 * (__uint_as_float(dr[j]) - Dq);
-              const float d1 = p1 * (__uint_as_float(dr[j + 1]) - Dq);
-              pp[j >> 1] = pack_bf16(p0, p1);
-              dd[j >> 1] = pack_bf16(d0, d1);
+              for (int j = 0; j < 32; j += 2) {
+                const int key = kt * kTile + col0 + j;
+                float p0 = ex2_approx(fmaf(__uint_as_float(sr[j]), p.scale_log2e, -Lq));
+                float p1 = ex2_approx(fmaf(__uint_as_float(sr[j + 1]), p.scale_log2e, -Lq));
+                p0 = (q_ok && key < klen && (key & gm) == rg) ? p0 : 0.f;
+                p1 = (q_ok && key + 1 < klen && ((key + 1) & gm) == rg) ? p1 : 0.f;
+                const float d0 = p0 * (__uint_as_float(dr[j]) - Dq);
+                const float d1 = p1 * (__uint_as_float(dr[j + 1]) - Dq);
+                pp[j >> 1] = pack_bf16(p0, p1);
+                dd[j >> 1] = pack_bf16(d0, d1);
+              }
+            } else {
+              // dense, unmasked chunk of live keys: query rows past S come from zero-filled TMA rows (Q = dO = 0, lse := 0), so
+              // P = 1, dS = 0 there and every product they enter is exactly zero — no per-element predicates needed
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(sr[j]), p.scale_log2e, -Lq));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(sr[j + 1]), p.scale_log2e, -Lq));
+                const float d0 = p0 * (__uint_as_float(dr[j]) - Dq);
+                const float d1 = p1 * (__uint_as_float(dr[j + 1]) - Dq);
+                pp[j >> 1] = pack_bf16(p0, p1);
+                dd[j >> 1] = pack_bf16(d0, d1);
+              }
             }
             if (!waited_free) { mbar_wait(pds_free, (g - 1) & 1); waited_free = true; }
             // 32 keys = four 16-byte chunks of this row inside key atom (col0 / 64)
