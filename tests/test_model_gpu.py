@@ -191,3 +191,45 @@ def test_seg_map_through_reference_tool_calls(cuda):
     ref_sim, _ = O.patch_text_sim(O.simple_projection(tok[:, 1:], sd["image_projection.linear.weight"]), text)
     assert (sim.cpu() - ref_sim).abs().max().item() < 1e-2
     assert torch.equal(am.long(), sim.argmax(-1))
+
+
+def test_clip_vit_b_forward_backward_and_seg_map_vs_oracle(cuda):
+    """BASELINE configs[2]/[3] model (ViT-B/16 + BERT-base) at a batch the CPU oracle finishes in seconds: embeddings, loss,
+    a sample of parameter gradients, the 171-class patch-text map (CTA-pair kernel) and its argmax mask."""
+    from oracle import simseg_oracle as O
+    from simseg_b200 import ops
+    model, _ = _build(cuda, yaml="simseg.vit-b.yaml")
+    sd = O.make_state_dict(768, 12, seed=3)
+    model.load_state_dict(sd, strict=True)
+    batch = O.make_batch(4, 25, seed=4321)
+    gb = {k: v.to(cuda) for k, v in batch.items()}
+    with torch.no_grad():
+        img_e, txt_e = model(gb, embeddings="all")
+        feat = model.forward_image_feature(gb["image"])
+        proj = model.image_projection(feat)
+    tok = O.vit_forward(sd, batch["image"], 12, O.IMG_PREFIX)
+    assert feat.shape == (4, 196, 768)
+    assert (feat.cpu() - tok[:, 1:]).abs().max().item() < 0.15              # bf16 operands through 12 blocks, values ~ +-4
+    ref_proj = O.simple_projection(tok[:, 1:], sd["image_projection.linear.weight"])
+    text = torch.nn.functional.normalize(torch.randn(171, 512, generator=torch.Generator().manual_seed(5)), dim=-1)
+    sim, am = ops.patch_text_sim(proj.contiguous(), text.to(cuda))
+    ref_sim, _ = O.patch_text_sim(ref_proj, text)
+    assert (sim.cpu() - ref_sim).abs().max().item() < 1e-2
+    assert torch.equal(am.long(), sim.argmax(-1))
+    top2 = ref_sim.topk(2, -1)[0]
+    safe = (top2[..., 0] - top2[..., 1]) > 2e-2                                # mask is bit-exact wherever the oracle margin allows
+    assert torch.equal(am.cpu().long()[safe], ref_sim.argmax(-1)[safe])
+    # training step
+    model.zero_grad(set_to_none=True)
+    loss = model(gb)[0]["nce_loss"]
+    loss.backward()
+    torch.cuda.synchronize()
+    l_o, rows = _grad_table(model, sd, batch, 12)
+    assert abs(loss.item() - l_o) < 2e-2
+    big = [r for r in rows if r[3] > 1e-4]
+    assert len(big) > 100
+    cos = sorted(r[1] for r in big)
+    assert cos[len(cos) // 20] > 0.97, cos[:10]                                 # 95 % of the parameter gradients
+    ref_i, ref_t = O.clip_embeddings(sd, batch, 12) if hasattr(O, "clip_embeddings") else (None, None)
+    if ref_i is not None:
+        assert _cos(img_e.cpu(), ref_i) > 0.999 and _cos(txt_e.cpu(), ref_t) > 0.999
