@@ -204,6 +204,21 @@ int simseg_allpairs_sim(simseg_ctx* ctx, const float* left, const float* right, 
 int simseg_retrieval_rank(simseg_ctx* ctx, const float* sim, int M, int Nr, const int64_t* left_gid,
                           const int64_t* right_gid, int32_t* rank, void* stream);
 
+/* ---- zero-shot segmentation glue around the map (tools/seg_evaluation.py) ---- */
+/* class embedding of the zero-shot classifier (seg_evaluation.py:71-72): out[c,:] = mean_p prompt[c,p,:] / ||mean||
+ * (no eps).  prompt [C,P,E] fp32 = forward_text_project outputs of the P prompts of each class; E <= 1024. */
+int simseg_seg_class_embed(simseg_ctx* ctx, const float* prompt, int C, int P, int E, float* out, void* stream);
+/* image-level class selection (seg_evaluation.py:119-128,141-144): scores[b,c] = img[b,:] . text[c,:];
+ * top-`topk` scores; threshold[b] = mean + std (unbiased) of those; cand[b, 0..max_cand) = the classes among the first
+ * `max_cand` of the top-k, in order, skipping class ids 0 and 255, stopping at the first score < threshold; -1 pads.
+ * scores / threshold may be NULL.  C <= 1024. */
+int simseg_seg_select(simseg_ctx* ctx, const float* img_emb, const float* text_emb, int B, int C, int E, int topk,
+                      int max_cand, float* scores, int32_t* cand, float* threshold, void* stream);
+/* per (image, candidate): column cand[b,k] of sim [B,N,C] reshaped (h,w), nearest x`scale` up-sampling, min-max
+ * normalisation (seg_evaluation.py:136-139,146-147) -> out [B,K,h*scale,w*scale] fp32 (zeros where cand == -1). */
+int simseg_seg_upsample_norm(simseg_ctx* ctx, const float* sim, const int32_t* cand, int B, int N, int C, int K, int h,
+                             int w, int scale, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

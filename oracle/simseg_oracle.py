@@ -211,6 +211,44 @@ def image_level_scores(img_emb: Tensor, text_emb: Tensor) -> Tensor:
     return (img_emb[:, None, :] * text_emb[None]).sum(-1)
 
 
+def seg_select(img_emb: Tensor, text_emb: Tensor, top_cls_num: int, max_cand: int = 5):
+    """``tools/seg_evaluation.py:119-128,141-144`` for every image of a batch: image-level scores, top-k, threshold
+    ``mean + std`` (torch.std, unbiased), then the reference loop over the first ``max_cand`` classes of the top-k: ids 0
+    and 255 are skipped, the scan stops at the first score below the threshold.  Returns (scores, cand padded with -1,
+    threshold)."""
+    scores = image_level_scores(img_emb.float(), text_emb.float())
+    B = scores.shape[0]
+    cand = torch.full((B, max_cand), -1, dtype=torch.int32)
+    thr = torch.zeros(B)
+    for b in range(B):
+        tv, ti = scores[b].topk(top_cls_num)
+        thr[b] = tv.mean() + 1.0 * tv.std()
+        n = 0
+        for i, index in enumerate(ti[:max_cand]):
+            if int(index) in (0, 255):
+                continue
+            if float(scores[b, index]) < float(thr[b]):
+                break
+            cand[b, n] = int(index)
+            n += 1
+    return scores, cand, thr
+
+
+def seg_norm_maps(sim: Tensor, cand: Tensor, h: int, w: int, scale: int = 16) -> Tensor:
+    """``tools/seg_evaluation.py:131-139,146-147``: class column of the map -> (h,w) -> nearest x16 -> min-max normalisation."""
+    B, N, _ = sim.shape
+    K = cand.shape[1]
+    out = torch.zeros(B, K, h * scale, w * scale)
+    for b in range(B):
+        for k in range(K):
+            c = int(cand[b, k])
+            if c < 0:
+                continue
+            a = upsample_nearest(sim[b, :, c].reshape(h, w), scale)
+            out[b, k] = (a - a.min()) / (a.max() - a.min())
+    return out
+
+
 def upsample_nearest(sim_map: Tensor, scale: int = 16) -> Tensor:
     """``tools/seg_evaluation.py:137-139`` — (…,h,w) -> (…,h*scale,w*scale)."""
     return sim_map.repeat_interleave(scale, -2).repeat_interleave(scale, -1)

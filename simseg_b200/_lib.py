@@ -56,6 +56,9 @@ PROTOTYPES = {
     "simseg_patch_text_sim": (i32, [vp, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, i64, vp]),
     "simseg_allpairs_sim": (i32, [vp, vp, vp, i32, i32, i32, i32, vp, vp]),
     "simseg_retrieval_rank": (i32, [vp, vp, i32, i32, vp, vp, vp, vp]),
+    "simseg_seg_class_embed": (i32, [vp, vp, i32, i32, i32, vp, vp]),
+    "simseg_seg_select": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
+    "simseg_seg_upsample_norm": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
 }
 
 _lib = None

@@ -38,6 +38,9 @@ int row_argmax_impl(Ctx*, const float*, int64_t, int, int32_t*, cudaStream_t);
 int retrieval_rank_impl(Ctx*, const float*, int, int, const int64_t*, const int64_t*, int32_t*, cudaStream_t);
 int attention_bwd_tc_impl(Ctx*, const void*, const void*, const void*, const void*, const void*, const float*, int64_t, int64_t, int64_t, int, int, int, const int32_t*, float, void*, void*, void*, cudaStream_t);
 int attention_fwd_tc_impl(Ctx*, const void*, const void*, const void*, int64_t, int64_t, int64_t, int, int, int, const int32_t*, float, void*, float*, cudaStream_t);
+int seg_class_embed_impl(Ctx*, const float*, int, int, int, float*, cudaStream_t);
+int seg_select_impl(Ctx*, const float*, const float*, int, int, int, int, int, float*, int32_t*, float*, cudaStream_t);
+int seg_upsample_norm_impl(Ctx*, const float*, const int32_t*, int, int, int, int, int, int, int, float*, cudaStream_t);
 int patch_sim_fused_impl(Ctx*, const void*, int64_t, int, const void*, int, int, float*, int32_t*, cudaStream_t);
 
 // fp32 product in the requested precision: C[M,N] (+)= A(m,k) B(n,k)
@@ -264,6 +267,21 @@ int simseg_retrieval_rank(simseg_ctx* ctx, const float* sim, int M, int Nr, cons
                           const int64_t* right_gid, int32_t* rank, void* stream) {
   CTX_OR_FAIL();
   return retrieval_rank_impl(c, sim, M, Nr, left_gid, right_gid, rank, st);
+}
+
+int simseg_seg_class_embed(simseg_ctx* ctx, const float* prompt, int C, int P, int E, float* out, void* stream) {
+  CTX_OR_FAIL();
+  return seg_class_embed_impl(c, prompt, C, P, E, out, st);
+}
+int simseg_seg_select(simseg_ctx* ctx, const float* img_emb, const float* text_emb, int B, int C, int E, int topk, int max_cand,
+                      float* scores, int32_t* cand, float* threshold, void* stream) {
+  CTX_OR_FAIL();
+  return seg_select_impl(c, img_emb, text_emb, B, C, E, topk, max_cand, scores, cand, threshold, st);
+}
+int simseg_seg_upsample_norm(simseg_ctx* ctx, const float* sim, const int32_t* cand, int B, int N, int C, int K, int h, int w,
+                             int scale, float* out, void* stream) {
+  CTX_OR_FAIL();
+  return seg_upsample_norm_impl(c, sim, cand, B, N, C, K, h, w, scale, out, st);
 }
 
 }  // extern "C"

@@ -328,3 +328,40 @@ def retrieval_rank(sim: Tensor, left_gid: Tensor, right_gid: Tensor) -> Tensor:
     check(_lib.load().simseg_retrieval_rank(ctx(), _p(sim), M, Nr, _p(left_gid), _p(right_gid), _p(rank), _stream()),
           "retrieval_rank")
     return rank
+
+
+# --------------------------------------------------------------------------------------- zero-shot segmentation glue
+def seg_class_embed(prompt_emb: Tensor) -> Tensor:
+    """(C,P,E) fp32 prompt embeddings -> (C,E): mean over prompts, /= norm (``tools/seg_evaluation.py:71-72``)."""
+    Cn, P, E = prompt_emb.shape
+    x = prompt_emb.contiguous().float()
+    out = torch.empty((Cn, E), device=x.device, dtype=torch.float32)
+    check(_lib.load().simseg_seg_class_embed(ctx(), _p(x), Cn, P, E, _p(out), _stream()), "seg_class_embed")
+    return out
+
+
+def seg_select(img_emb: Tensor, text_emb: Tensor, top_cls_num: int, max_cand: int = 5):
+    """Image-level class scores, top-k threshold and candidate classes (``tools/seg_evaluation.py:119-128,141-144``).
+    Returns (scores [B,C], cand int32 [B,max_cand] padded with -1, threshold [B])."""
+    B, E = img_emb.shape
+    Cn = text_emb.shape[0]
+    x, t = img_emb.contiguous().float(), text_emb.contiguous().float()
+    scores = torch.empty((B, Cn), device=x.device, dtype=torch.float32)
+    cand = torch.empty((B, max_cand), device=x.device, dtype=torch.int32)
+    thr = torch.empty(B, device=x.device, dtype=torch.float32)
+    check(_lib.load().simseg_seg_select(ctx(), _p(x), _p(t), B, Cn, E, top_cls_num, max_cand, _p(scores), _p(cand), _p(thr),
+                                        _stream()), "seg_select")
+    return scores, cand, thr
+
+
+def seg_upsample_norm(sim: Tensor, cand: Tensor, h: int, w: int, scale: int = 16) -> Tensor:
+    """sim [B,N,C] fp32 + candidates [B,K] -> min-max normalised, nearest x`scale` up-sampled maps [B,K,h*scale,w*scale]
+    (``tools/seg_evaluation.py:136-139,146-147``)."""
+    B, N, Cn = sim.shape
+    K = cand.shape[1]
+    s = sim.contiguous()
+    assert s.dtype == torch.float32 and cand.dtype == torch.int32
+    out = torch.empty((B, K, h * scale, w * scale), device=s.device, dtype=torch.float32)
+    check(_lib.load().simseg_seg_upsample_norm(ctx(), _p(s), _p(cand.contiguous()), B, N, Cn, K, h, w, scale, _p(out), _stream()),
+          "seg_upsample_norm")
+    return out

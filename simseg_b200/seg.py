@@ -1,0 +1,45 @@
+"""Zero-shot segmentation around the patch-text map, in the call order of the reference tool
+(``tools/seg_evaluation.py:57-75`` ``zero_shot_classifier``; ``:84-150`` ``evaluate_benchmark``) — every step up to the CRF
+stays on the GPU (the reference fetches one class map at a time to the host).  CRF / dilate / erode post-processing is CPU
+code outside the hot path (out of scope)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+Tensor = torch.Tensor
+
+
+@torch.no_grad()
+def zero_shot_classifier(model, input_ids: Tensor, attention_mask: Tensor, chunk: int = 4096) -> Tensor:
+    """``input_ids`` / ``attention_mask`` (C, P, T) — P prompt captions per class (the reference tokenises 80 templates per
+    class, ``utils/prompt.py``) -> unit-norm class embeddings (C, 512).  All C*P captions go through the text tower in
+    batches of ``chunk`` instead of one 80-caption batch per class."""
+    Cn, P, T = input_ids.shape
+    ids, am = input_ids.reshape(Cn * P, T), attention_mask.reshape(Cn * P, T)
+    embs = []
+    for i in range(0, Cn * P, chunk):
+        feat = model.forward_text_feature(ids[i:i + chunk], am[i:i + chunk])
+        embs.append(model.forward_text_project(feat, am[i:i + chunk]).float())
+    return ops.seg_class_embed(torch.cat(embs).view(Cn, P, -1))
+
+
+@torch.no_grad()
+def segment(model, image: Tensor, class_emb: Tensor, top_cls_num: int, max_cand: int = 5, patch_size: int = 16):
+    """One pass of ``evaluate_benchmark`` for a batch of images: returns
+    ``sim`` (B, N, C) cosine map, ``argmax`` (B, N), ``scores`` (B, C) image-level class scores, ``cand`` (B, max_cand) the
+    classes the reference would send to the CRF (-1 padded) and ``maps`` (B, max_cand, H, W) their min-max normalised,
+    nearest-up-sampled attention maps."""
+    feat = model.forward_image_feature(image)                       # (B, N, D)
+    pooled = model.forward_image_project(feat)                      # (B, 512)  L2-normalised
+    proj = model.image_projection(feat)                             # (B, N, 512)
+    B, N, _ = proj.shape
+    hw = int(round(N ** 0.5))
+    text = class_emb.to(proj.dtype) if proj.dtype == torch.bfloat16 else class_emb
+    sim, am = ops.patch_text_sim(proj.contiguous(), text.contiguous())
+    scores, cand, _ = ops.seg_select(pooled.float(), class_emb.float(), top_cls_num, max_cand)
+    maps = ops.seg_upsample_norm(sim.view(B, N, -1), cand, hw, hw, patch_size)
+    return sim.view(B, N, -1), am.view(B, N), scores, cand, maps

@@ -228,3 +228,67 @@ def test_patch_text_sim_pair_equals_single(cuda, rows, C, monkeypatch):
     s2, a2 = ops.patch_text_sim(p, t)
     assert float((s1 - s2).abs().max()) < 1e-6
     assert torch.equal(a2.long(), s2.argmax(-1)) and torch.equal(a1.long(), s1.argmax(-1))
+
+
+def test_seg_glue_vs_oracle(cuda):
+    """zero-shot class embedding (mean over prompts, renorm), image-level class selection (top-k,
+    mean+std threshold, skip ids 0/255, stop below threshold) and the min-max normalised x16 nearest-up-sampled maps —
+    GPU kernels against the CPU restatement of tools/seg_evaluation.py:57-75,119-150."""
+    ops, O = _ops(), _O()
+    g = torch.Generator().manual_seed(9)
+    prompts = torch.randn(171, 80, 512, generator=g)
+    ce = ops.seg_class_embed(prompts.to(cuda))
+    ref_ce = O.zero_shot_class_embedding(prompts)
+    assert (ce.cpu() - ref_ce).abs().max().item() < 1e-6
+    img = torch.nn.functional.normalize(torch.randn(6, 512, generator=g) + 2.0 * ref_ce[[3, 0, 40, 255 % 171, 100, 7]], dim=-1)
+    for topk in (10, 20):
+        scores, cand, thr = ops.seg_select(img.to(cuda), ce, topk)
+        r_scores, r_cand, r_thr = O.seg_select(img, ref_ce, topk)
+        assert (scores.cpu() - r_scores).abs().max().item() < 1e-5
+        assert (thr.cpu() - r_thr).abs().max().item() < 1e-5
+        assert torch.equal(cand.cpu(), r_cand), (cand.cpu(), r_cand)
+    sim = torch.randn(6, 196, 171, generator=g)
+    maps = ops.seg_upsample_norm(sim.to(cuda), cand, 14, 14, 16)
+    ref_maps = O.seg_norm_maps(sim, r_cand, 14, 14, 16)
+    assert maps.shape == (6, 5, 224, 224)
+    assert (maps.cpu() - ref_maps).abs().max().item() < 1e-6
+
+
+def test_segment_pipeline_calls(cuda):
+    """simseg_b200.seg.zero_shot_classifier / segment: the tool-level flow end to end on a tiny synthetic problem."""
+    from oracle import simseg_oracle as O
+    from simseg_b200 import seg
+    from simseg_b200.config import load_cfg
+    from simseg_b200.pipeline import PIPELINE
+    cfg = load_cfg("simseg.vit-s.yaml", ["model.image_encoder.pretrained=False", "model.text_encoder.pretrained=False",
+                                          "transforms.input_size=224"])
+    model = PIPELINE["clip"](cfg).to(cuda).eval()
+    sd = O.make_state_dict(384, 6, seed=0)
+    model.load_state_dict(sd)
+    gen = torch.Generator().manual_seed(3)
+    Cn, P, T = 12, 4, 25
+    ids = torch.randint(0, 30522, (Cn, P, T), generator=gen)
+    ids[..., 0] = 101
+    am = torch.ones(Cn, P, T, dtype=torch.int64)
+    am[..., 17:] = 0
+    class_emb = seg.zero_shot_classifier(model, ids.to(cuda), am.to(cuda))
+    assert class_emb.shape == (Cn, 512)
+    assert (class_emb.norm(dim=-1) - 1).abs().max().item() < 1e-5
+    # oracle: text tower -> projection/pool/l2norm per caption -> mean over prompts -> renorm
+    tt = O.bert_forward(sd, ids.view(-1, T), am.view(-1, T), 12, O.TXT_PREFIX)
+    ref = O.zero_shot_class_embedding(O.text_embed(tt, sd["text_projection.linear.weight"], am.view(-1, T)).view(Cn, P, -1))
+    assert _cos_rows(class_emb.cpu(), ref) > 0.999
+    batch = O.make_batch(2, 25, seed=5)
+    sim, amax, scores, cand, maps = seg.segment(model, batch["image"].to(cuda), class_emb, top_cls_num=6)
+    assert sim.shape == (2, 196, Cn) and amax.shape == (2, 196) and scores.shape == (2, Cn)
+    assert cand.shape == (2, 5) and maps.shape == (2, 5, 224, 224)
+    assert torch.equal(amax.long(), sim.argmax(-1))
+    live = cand >= 0
+    if live.any():
+        m = maps[live]
+        assert float(m.min()) >= 0.0 and float(m.max()) <= 1.0 + 1e-6
+
+
+def _cos_rows(a, b):
+    a, b = a.double(), b.double()
+    return ((a * b).sum(-1) / (a.norm(dim=-1) * b.norm(dim=-1))).min().item()
