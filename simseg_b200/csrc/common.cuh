@@ -64,26 +64,31 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // erf-GELU (the reference's nn.GELU() default) and its derivative, fp32.  erf uses Abramowitz-Stegun 7.1.26
 // (|abs err| <= 1.5e-7, far below the bf16 resolution of every consumer) so one MUFU.RCP + one MUFU.EX2 serve both
 // gelu(x) = x*Phi(x) and gelu'(x) = Phi(x) + x*phi(x):  exp(-x^2/2) is shared between erf(x/sqrt2) and phi(x).
-__device__ __forceinline__ void gelu_erf_both(float x, float& gelu, float& dgelu) {
-  const float z = fabsf(x) * 0.70710678118654752f;
+// Instruction counts matter here: these run inside GEMM epilogues that are ALU-issue-bound.
+//   w(x) = 0.5 * erfc(|x|/sqrt2) = t*(a1' + t*(a2' + t*(a3' + t*(a4' + t*a5')))) * exp(-x^2/2),  t = 1/(1 + p|x|/sqrt2)
+//   (coefficients pre-multiplied by 0.5);   Phi(x) = x >= 0 ? 1 - w : w
+__device__ __forceinline__ float gelu_half_erfc(float x, float& e) {
   float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float e;                                             // exp(-z^2) = exp(-x^2/2)
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.44269504088896341f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float erfc_half = 0.5f * poly * e;             // 0.5 * erfc(|x|/sqrt2)
-  const float cdf = x >= 0.f ? 1.0f - erfc_half : erfc_half;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((x * x) * (-0.5f * 1.44269504088896341f)));   // exp(-x^2/2)
+  float q = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  q = fmaf(q, t, 0.5f * 1.421413741f);
+  q = fmaf(q, t, 0.5f * -0.284496736f);
+  q = fmaf(q, t, 0.5f * 0.254829592f);
+  return (q * t) * e;
+}
+__device__ __forceinline__ void gelu_erf_both(float x, float& gelu, float& dgelu) {
+  float e;
+  const float w = gelu_half_erfc(x, e);
+  const float cdf = x >= 0.f ? 1.0f - w : w;
   gelu = x * cdf;
   dgelu = fmaf(x * 0.3989422804014327f, e, cdf);
 }
+// gelu(x) = x*Phi(x) = max(x,0) - |x|*w(x): no select, no explicit Phi
 __device__ __forceinline__ float gelu_erf(float x) {
-  float g, d;
-  gelu_erf_both(x, g, d);
-  return g;
+  float e;
+  const float w = gelu_half_erfc(x, e);
+  return fmaf(-fabsf(x), w, fmaxf(x, 0.f));
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   float g, d;

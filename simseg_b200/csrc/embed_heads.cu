@@ -204,12 +204,7 @@ __global__ void topk_pool_l2norm_fwd_kernel(const void* __restrict__ x, int S, i
     int ti[kMaxK];
 #pragma unroll
     for (int j = 0; j < kMaxK; ++j) { tv[j] = -INFINITY; ti[j] = -1; }
-    for (int t = 0; t < ntok; ++t) {
-      const int s = tok_begin + t;
-      float v;
-      if (XBF16) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[(static_cast<int64_t>(b) * S + s) * E + e]);
-      else v = reinterpret_cast<const float*>(x)[(static_cast<int64_t>(b) * S + s) * E + e];
-      if (mask && mask[static_cast<int64_t>(b) * mask_ld + s] == 0) v = -10000.0f;       // pooling.py:60
+    auto insert = [&](float v, int s) {
       // insert into the descending list (strict > keeps the earliest token on ties, like a stable top-k)
       if (v > tv[k - 1]) {
         int pos = k - 1;
@@ -219,7 +214,23 @@ __global__ void topk_pool_l2norm_fwd_kernel(const void* __restrict__ x, int S, i
         }
         tv[pos] = v; ti[pos] = s;
       }
+    };
+    auto load = [&](int s) {
+      float v;
+      if (XBF16) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[(static_cast<int64_t>(b) * S + s) * E + e]);
+      else v = reinterpret_cast<const float*>(x)[(static_cast<int64_t>(b) * S + s) * E + e];
+      if (mask && mask[static_cast<int64_t>(b) * mask_ld + s] == 0) v = -10000.0f;       // pooling.py:60
+      return v;
+    };
+    int t = 0;
+    for (; t + 8 <= ntok; t += 8) {                         // eight independent loads in flight per thread
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = load(tok_begin + t + u);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) insert(v[u], tok_begin + t + u);
     }
+    for (; t < ntok; ++t) insert(load(tok_begin + t), tok_begin + t);
     float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < kMaxK; ++j) if (j < k) sum += tv[j];
