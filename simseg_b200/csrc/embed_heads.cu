@@ -192,27 +192,33 @@ int bert_embed_bwd_impl(Ctx* ctx, const int64_t* ids, const float* de, int B, in
 // channel (reads of x[b,t,:] are coalesced across channels).  k <= 8, kept as a sorted register list.
 constexpr int kMaxK = 8;
 
-template <bool XBF16>
-__global__ void topk_pool_l2norm_fwd_kernel(const void* __restrict__ x, int S, int E, int tok_begin, int ntok, int k,
+// K is a template parameter: with a run-time k the sorted list is indexed dynamically and lives in local memory
+// (measured: 1.1-1.5 ms for 4096 x 196 x 512; in registers the kernel is a stream of coalesced loads).
+template <bool XBF16, int K>
+__global__ void topk_pool_l2norm_fwd_kernel(const void* __restrict__ x, int S, int E, int tok_begin, int ntok,
                                             const int64_t* __restrict__ mask, int mask_ld, float eps,
                                             float* __restrict__ pooled, float* __restrict__ emb, int32_t* __restrict__ sel_idx) {
   const int b = blockIdx.x;
   __shared__ float warp_ss[32];
   float ssq = 0.f;
   for (int e = threadIdx.x; e < E; e += blockDim.x) {     // blockDim.x >= E in practice: one pass
-    float tv[kMaxK];
-    int ti[kMaxK];
+    float tv[K];
+    int ti[K];
 #pragma unroll
-    for (int j = 0; j < kMaxK; ++j) { tv[j] = -INFINITY; ti[j] = -1; }
+    for (int j = 0; j < K; ++j) { tv[j] = -INFINITY; ti[j] = -1; }
     auto insert = [&](float v, int s) {
-      // insert into the descending list (strict > keeps the earliest token on ties, like a stable top-k)
-      if (v > tv[k - 1]) {
-        int pos = k - 1;
+      // descending list; strict > keeps the earliest token ahead on ties, like a stable top-k
+      if (v > tv[K - 1]) {
+        float cur = v;
+        int ci = s;
 #pragma unroll
-        for (int j = kMaxK - 2; j >= 0; --j) {
-          if (j < k - 1 && v > tv[j]) { tv[j + 1] = tv[j]; ti[j + 1] = ti[j]; pos = j; }
+        for (int j = 0; j < K; ++j) {
+          const bool gt = cur > tv[j];
+          const float t0 = tv[j];
+          const int i0 = ti[j];
+          tv[j] = gt ? cur : t0; ti[j] = gt ? ci : i0;
+          cur = gt ? t0 : cur; ci = gt ? i0 : ci;
         }
-        tv[pos] = v; ti[pos] = s;
       }
     };
     auto load = [&](int s) {
@@ -233,12 +239,12 @@ __global__ void topk_pool_l2norm_fwd_kernel(const void* __restrict__ x, int S, i
     for (; t < ntok; ++t) insert(load(tok_begin + t), tok_begin + t);
     float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < kMaxK; ++j) if (j < k) sum += tv[j];
-    const float p = sum / static_cast<float>(k);
+    for (int j = 0; j < K; ++j) sum += tv[j];
+    const float p = sum / static_cast<float>(K);
     pooled[static_cast<int64_t>(b) * E + e] = p;
     if (sel_idx) {
 #pragma unroll
-      for (int j = 0; j < kMaxK; ++j) if (j < k) sel_idx[(static_cast<int64_t>(b) * k + j) * E + e] = ti[j];
+      for (int j = 0; j < K; ++j) sel_idx[(static_cast<int64_t>(b) * K + j) * E + e] = ti[j];
     }
     ssq += p * p;
   }
@@ -253,6 +259,13 @@ __global__ void topk_pool_l2norm_fwd_kernel(const void* __restrict__ x, int S, i
     emb[static_cast<int64_t>(b) * E + e] = pooled[static_cast<int64_t>(b) * E + e] * inv;
 }
 
+template <int K>
+static void launch_topk(bool bf16, int B, int threads, cudaStream_t st, const void* x, int S, int E, int tok_begin, int ntok,
+                        const int64_t* mask, int mask_ld, float eps, float* pooled, float* emb, int32_t* sel_idx) {
+  if (bf16) topk_pool_l2norm_fwd_kernel<true, K><<<B, threads, 0, st>>>(x, S, E, tok_begin, ntok, mask, mask_ld, eps, pooled, emb, sel_idx);
+  else topk_pool_l2norm_fwd_kernel<false, K><<<B, threads, 0, st>>>(x, S, E, tok_begin, ntok, mask, mask_ld, eps, pooled, emb, sel_idx);
+}
+
 int topk_pool_l2norm_fwd_impl(Ctx* ctx, const void* x, int x_dtype, int B, int S, int E, int tok_begin, int ntok, int k,
                               const int64_t* mask, int mask_ld, float eps, float* pooled, float* emb, int32_t* sel_idx,
                               cudaStream_t st) {
@@ -261,10 +274,12 @@ int topk_pool_l2norm_fwd_impl(Ctx* ctx, const void* x, int x_dtype, int B, int S
   SIMSEG_CHECK_ARG(pooled != nullptr, "topk_pool: pooled output required");
   int threads = ((E + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
-  if (x_dtype == SIMSEG_BF16)
-    topk_pool_l2norm_fwd_kernel<true><<<B, threads, 0, st>>>(x, S, E, tok_begin, ntok, k, mask, mask_ld, eps, pooled, emb, sel_idx);
-  else
-    topk_pool_l2norm_fwd_kernel<false><<<B, threads, 0, st>>>(x, S, E, tok_begin, ntok, k, mask, mask_ld, eps, pooled, emb, sel_idx);
+  const bool bf = x_dtype == SIMSEG_BF16;
+#define TOPK_CASE(KK) case KK: launch_topk<KK>(bf, B, threads, st, x, S, E, tok_begin, ntok, mask, mask_ld, eps, pooled, emb, sel_idx); break
+  switch (k) {
+    TOPK_CASE(1); TOPK_CASE(2); TOPK_CASE(3); TOPK_CASE(4); TOPK_CASE(5); TOPK_CASE(6); TOPK_CASE(7); TOPK_CASE(8);
+  }
+#undef TOPK_CASE
   ctx->launches++;
   SIMSEG_LAUNCH_CHECK();
   return SIMSEG_OK;
