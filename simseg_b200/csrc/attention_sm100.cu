@@ -625,6 +625,10 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                 m1 = fmaxf(m1, __uint_as_float(x[j + 1]));
               }
               m = fmaxf(m, fmaxf(m0, m1));
+            } else if (dense) {
+              const int nv = klen - c * 32;                                // live columns of this (last) chunk
+#pragma unroll
+              for (int j = 0; j < 32; ++j) m = (j < nv) ? fmaxf(m, __uint_as_float(x[j])) : m;
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
@@ -660,6 +664,17 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                 pp[(j >> 1) + 1] = pack_bf16(p2, p3);
               }
               sum += (s0 + s1) + (s2 + s3);
+            } else if (dense) {
+              const int nv = klen - c * 32;
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                float p0 = ex2_approx(fmaf(__uint_as_float(x[j]), p.scale_log2e, -ms));
+                float p1 = ex2_approx(fmaf(__uint_as_float(x[j + 1]), p.scale_log2e, -ms));
+                p0 = (j < nv) ? p0 : 0.f;
+                p1 = (j + 1 < nv) ? p1 : 0.f;
+                sum += p0 + p1;
+                pp[j >> 1] = pack_bf16(p0, p1);
+              }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; j += 2) {
