@@ -256,6 +256,13 @@ def run_ours(a):
             line["roofline"] = roof
             line["train_flops"] = train_flops(a, m, ms_step, tf_sus)
             line["patch_sim"] = patch_sim_bench(hbm, how)
+            if world == 1:
+                del trainer, model
+                torch.cuda.empty_cache()
+                try:
+                    line["inference"] = inference_extras(hbm, tf_sus)
+                except Exception as e:                       # never lose the headline line to an extra
+                    line["inference"] = {"error": repr(e)[:200]}
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -349,6 +356,69 @@ def patch_sim_bench(hbm_peak, how):
                          "traffic": 1328.5e6, "traffic_source": "ncu --set full, dram__bytes_read+write per launch at batch 4096 "
                                                                "(profiles/r01_ncu_patch_sim.txt); algorithmic 1374.4e6",
                          "peak_source": how, "algorithmic_bytes_per_map": bytes_per_map}}
+
+
+def inference_extras(hbm_peak, tf_peak):
+    """BASELINE.json configs[3] and configs[4] on one GPU (forward only, synthetic inputs, seeded random-init weights):
+    ViT-B/16 seg inference (batch 64 -> 196 x 171 map per image, encoder + projection + map) and the 5k x 25k all-pairs
+    retrieval similarity + first-match ranks."""
+    import torch
+    from simseg_b200 import ops
+    from simseg_b200.config import load_cfg
+    from simseg_b200.pipeline import PIPELINE
+    out = {}
+
+    def t_ms(fn, reps, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    g = torch.Generator(device="cuda").manual_seed(7)
+    cfg = load_cfg("simseg.vit-b.yaml", ["model.image_encoder.pretrained=False", "model.text_encoder.pretrained=False",
+                                          "transforms.input_size=224"])
+    torch.manual_seed(0)
+    model = PIPELINE["clip"](cfg).to("cuda").eval()
+    imgs = [torch.randn(64, 3, 224, 224, device="cuda", generator=g) for _ in range(4)]      # 154 MB of inputs cycled
+    text = torch.nn.functional.normalize(torch.randn(171, 512, device="cuda", generator=g), dim=-1).bfloat16()
+    state = {"i": 0}
+
+    def seg_step():
+        with torch.no_grad():
+            x = imgs[state["i"] % 4]
+            state["i"] += 1
+            feat = model.forward_image_feature(x)
+            proj = model.image_projection(feat)
+            ops.patch_text_sim(proj.contiguous(), text if proj.dtype == torch.bfloat16 else text.float())
+    ms = t_ms(seg_step, 10)
+    fl = 64 * (35.1e9 + 2 * 196 * 768 * 512 + 2 * 196 * 512 * 171)
+    out["seg_infer_vit_b_b64"] = {"workload": "ViT-B/16 224x224, batch 64, encoder + projection + 196x171 map", "value": 64 / (ms / 1e3),
+                                  "unit": "maps/s", "ms_per_batch": ms, "achieved_tflops": fl / (ms / 1e3) / 1e12,
+                                  "frac_of_sustained_bf16": fl / (ms / 1e3) / 1e12 / tf_peak}
+    del model, imgs
+    torch.cuda.empty_cache()
+    left = torch.nn.functional.normalize(torch.randn(5000, 512, device="cuda", generator=g), dim=-1)
+    right = torch.nn.functional.normalize(torch.randn(25000, 512, device="cuda", generator=g), dim=-1)
+    lg = torch.arange(5000, device="cuda", dtype=torch.int64)
+    rg = torch.arange(25000, device="cuda", dtype=torch.int64) // 5
+    holder = {}
+
+    def retr():
+        holder["sim"] = ops.allpairs_sim(left, right)
+        holder["rank"] = ops.retrieval_rank(holder["sim"], lg, rg)
+    ms = t_ms(retr, 5, warm=2)
+    by = (5000 + 25000) * 512 * 4 + 2 * 5000 * 25000 * 4
+    out["retrieval_5k_x_25k"] = {"workload": "5000 x 25000 all-pairs cosine (exact fp32 products) + first-match ranks", "ms": ms,
+                                 "value": 5000 * 25000 / (ms / 1e3), "unit": "pairs scored/s",
+                                 "achieved_gbs": by / (ms / 1e3) / 1e9, "frac_of_hbm": by / (ms / 1e3) / 1e9 / hbm_peak,
+                                 "achieved_tflops_fp32": 2.0 * 5000 * 25000 * 512 / (ms / 1e3) / 1e12}
+    return out
 
 
 def main():
