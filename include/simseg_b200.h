@@ -92,6 +92,17 @@ int simseg_gemm(simseg_ctx* ctx, const simseg_gemm_args* args, void* stream);
 /* fp32 -> bf16 cast, optionally also writing the transpose ([rows,cols] -> [cols,rows]). */
 int simseg_cast_bf16(simseg_ctx* ctx, const float* src, void* dst, void* dst_t, int64_t rows, int64_t cols,
                      void* stream);
+/* The same cast for many weights in one launch (the per-optimizer-step bf16 refresh of every Linear weight).  `items` is a
+ * DEVICE array; item i covers blocks [first_block, first_block + ceil(rows/32)*ceil(cols/32)) of the 1-D grid of
+ * `total_blocks` blocks (first_block ascending).  dst rows have pitch `ld` (>= cols), dst_t rows pitch `ld_t` (>= rows) so
+ * several weights can land side by side in one packed matrix (BERT q/k/v); dst or dst_t may be NULL. */
+typedef struct simseg_cast_item {
+  const float* src;
+  void* dst;
+  void* dst_t;
+  int64_t rows, cols, ld, ld_t, first_block;
+} simseg_cast_item;
+int simseg_cast_bf16_multi(simseg_ctx* ctx, const simseg_cast_item* items, int n_items, int64_t total_blocks, void* stream);
 /* bf16/f32 column sums: out[n] (+)= sum_m x[m,n]   (bias gradients) */
 int simseg_colsum(simseg_ctx* ctx, const void* x, int dtype, int64_t M, int64_t N, int64_t ldx, float* out,
                   int accumulate, void* stream);

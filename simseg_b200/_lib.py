@@ -36,6 +36,7 @@ PROTOTYPES = {
     "simseg_ctx_launch_count": (i64, [vp, i32]),
     "simseg_gemm": (i32, [vp, C.POINTER(GemmArgs), vp]),
     "simseg_cast_bf16": (i32, [vp, vp, vp, vp, i64, i64, vp]),
+    "simseg_cast_bf16_multi": (i32, [vp, vp, i32, i64, vp]),
     "simseg_colsum": (i32, [vp, vp, i32, i64, i64, i64, vp, i32, vp]),
     "simseg_gelu_fwd": (i32, [vp, vp, vp, i64, vp]),
     "simseg_layernorm_fwd": (i32, [vp, vp, i32, vp, vp, f32, i64, i32, vp, vp, vp, vp, vp]),

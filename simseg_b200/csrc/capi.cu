@@ -17,6 +17,7 @@ void set_error(const char* fmt, ...) {
 // implemented in the kernel translation units
 int gemm_impl(Ctx*, const simseg_gemm_args*, cudaStream_t);
 int cast_bf16_impl(Ctx*, const float*, void*, void*, int64_t, int64_t, cudaStream_t);
+int cast_bf16_multi_impl(Ctx*, const simseg_cast_item*, int, int64_t, cudaStream_t);
 int colsum_impl(Ctx*, const void*, int, int64_t, int64_t, int64_t, float*, int, cudaStream_t);
 int gelu_fwd_impl(Ctx*, const void*, void*, int64_t, cudaStream_t);
 int layernorm_fwd_impl(Ctx*, const void*, int, const float*, const float*, float, int64_t, int, void*, float*, float*, float*, const void*, float*, cudaStream_t);
@@ -101,6 +102,10 @@ int simseg_gemm(simseg_ctx* ctx, const simseg_gemm_args* args, void* stream) {
   CTX_OR_FAIL();
   if (!args) { set_error("null args"); return SIMSEG_ERR_INVALID; }
   return gemm_impl(c, args, st);
+}
+int simseg_cast_bf16_multi(simseg_ctx* ctx, const simseg_cast_item* items, int n_items, int64_t total_blocks, void* stream) {
+  CTX_OR_FAIL();
+  return cast_bf16_multi_impl(c, items, n_items, total_blocks, st);
 }
 int simseg_cast_bf16(simseg_ctx* ctx, const float* src, void* dst, void* dst_t, int64_t rows, int64_t cols, void* stream) {
   CTX_OR_FAIL();

@@ -40,6 +40,52 @@ int cast_bf16_impl(Ctx* ctx, const float* src, void* dst, void* dst_t, int64_t r
   return SIMSEG_OK;
 }
 
+// Many weights in ONE launch (the per-step bf16 refresh of every Linear weight: ~250 tiny launches otherwise).  The item
+// table lives in device memory; block -> item by binary search over the items' first block index.
+__global__ void cast_bf16_multi_kernel(const simseg_cast_item* __restrict__ items, int n_items) {
+  __shared__ float tile[32][33];
+  const int64_t blk = blockIdx.x;
+  int lo = 0, hi = n_items - 1;
+  while (lo < hi) {                                   // last item with first_block <= blk
+    const int mid = (lo + hi + 1) >> 1;
+    if (items[mid].first_block <= blk) lo = mid; else hi = mid - 1;
+  }
+  const simseg_cast_item it = items[lo];
+  const int64_t lb = blk - it.first_block;
+  const int64_t bx_n = (it.cols + 31) / 32;
+  const int64_t bx = lb % bx_n, by = lb / bx_n;
+  const float* src = it.src;
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(it.dst);
+  __nv_bfloat16* dst_t = reinterpret_cast<__nv_bfloat16*>(it.dst_t);
+  const int64_t c = bx * 32 + threadIdx.x;
+  const int64_t r0 = by * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int64_t r = r0 + i;
+    float v = 0.f;
+    if (r < it.rows && c < it.cols) {
+      v = src[r * it.cols + c];
+      if (dst) dst[r * it.ld + c] = __float2bfloat16(v);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  if (!dst_t) return;
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int64_t oc = bx * 32 + i;                   // original column = transposed row
+    const int64_t orow = r0 + threadIdx.x;
+    if (oc < it.cols && orow < it.rows) dst_t[oc * it.ld_t + orow] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+
+int cast_bf16_multi_impl(Ctx* ctx, const simseg_cast_item* items_dev, int n_items, int64_t total_blocks, cudaStream_t st) {
+  SIMSEG_CHECK_ARG(items_dev != nullptr && n_items > 0 && total_blocks > 0 && total_blocks < (int64_t(1) << 31),
+                   "cast_bf16_multi: bad table (n_items=%d, blocks=%lld)", n_items, static_cast<long long>(total_blocks));
+  cast_bf16_multi_kernel<<<static_cast<unsigned>(total_blocks), dim3(32, 8), 0, st>>>(items_dev, n_items);
+  ctx->launches++;
+  SIMSEG_LAUNCH_CHECK();
+  return SIMSEG_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // column sums: out[n] += sum_m x[m,n].  Block = 32 column-lanes x 8 row-lanes, each lane owns 4 columns.
 // bf16: 8 columns (one 16-byte load) per thread, 4 rows in flight per thread; fp32: 4 columns per thread.

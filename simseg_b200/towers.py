@@ -28,41 +28,142 @@ def _grad_of(p: Tensor) -> Tensor:
 
 
 class Bf16Weights:
-    """Per-step bf16 copies of the fp32 master weights (cast once in forward, reused in backward)."""
+    """bf16 copies of the fp32 master weights, refreshed once per optimizer step by ONE multi-tensor cast launch.
+
+    The destination buffers (plain [N,K], transposed [K,N] for dgrad, and the row-packed q/k/v matrices of BERT) are
+    allocated when a weight is first requested and then live as long as the model; ``clear()`` only marks them stale.
+    The next request re-casts every registered weight with a single ``simseg_cast_bf16_multi`` launch (the item table is
+    a device array rebuilt only when a new weight/buffer was registered or a parameter's storage moved)."""
 
     def __init__(self):
-        self._c: Dict[int, Tensor] = {}
+        self._items: Dict[tuple, dict] = {}        # (id(param), slot) -> item
+        self._views: Dict[object, Tensor] = {}     # what get/get_t/packed/packed_t hand out
+        self._stale = False
+        self._dirty = True                         # table must be rebuilt
+        self._table = None
+        self._nblocks = 0
+        self._keep = []
 
-    def get(self, p: Tensor) -> Tensor:
-        k = id(p)
-        if k not in self._c:
+    # ---- registration ------------------------------------------------------------------------
+    def _item(self, p: Tensor, slot) -> dict:
+        k = (id(p), slot)
+        it = self._items.get(k)
+        if it is None:
             w = p.detach()
-            self._c[k] = ops.cast_bf16(w.reshape(w.shape[0], -1))
-        return self._c[k]
+            rows = w.shape[0]
+            it = {"p": p, "rows": rows, "cols": w.numel() // rows, "dst": None, "dst_t": None, "ld": 0, "ld_t": 0, "ptr": 0}
+            self._items[k] = it
+            self._dirty = True
+        return it
+
+    def _fill_now(self, it: dict):
+        """First use inside a step: cast just this weight (later steps go through the batched refresh)."""
+        w = it["p"].detach().contiguous()
+        lib = ops._lib.load()
+        if it["ld"] in (0, it["cols"]) and it["ld_t"] in (0, it["rows"]):
+            ops.check(lib.simseg_cast_bf16(ops.ctx(), ops._p(w), ops._p(it["dst"]), ops._p(it["dst_t"]), it["rows"], it["cols"],
+                                           ops._stream()), "cast_bf16")
+        else:                                       # strided destination (packed matrices): use the table path for one item
+            self._launch([it])
+
+    def _launch(self, items):
+        import ctypes as C
+        n = len(items)
+        host = torch.empty((n, 8), dtype=torch.int64)
+        fb = 0
+        for i, it in enumerate(items):
+            w = it["p"].detach()
+            assert w.is_contiguous() and w.dtype == torch.float32
+            it["ptr"] = w.data_ptr()
+            host[i, 0] = w.data_ptr()
+            host[i, 1] = it["dst"].data_ptr() if it["dst"] is not None else 0
+            host[i, 2] = it["dst_t"].data_ptr() if it["dst_t"] is not None else 0
+            host[i, 3], host[i, 4] = it["rows"], it["cols"]
+            host[i, 5] = it["ld"] or it["cols"]
+            host[i, 6] = it["ld_t"] or it["rows"]
+            host[i, 7] = fb
+            fb += ((it["rows"] + 31) // 32) * ((it["cols"] + 31) // 32)
+        dev = next(iter(items))["p"].device
+        table = host.to(dev)
+        self._keep = [table]
+        ops.check(ops._lib.load().simseg_cast_bf16_multi(ops.ctx(), ops._p(table), n, fb, ops._stream()), "cast_bf16_multi")
+        return table, fb
+
+    def _refresh(self):
+        if not self._stale:
+            return
+        items = [it for it in self._items.values() if it["dst"] is not None or it["dst_t"] is not None]
+        if items:
+            moved = any(it["ptr"] != it["p"].detach().data_ptr() for it in items)
+            if self._dirty or moved or self._table is None:
+                self._table, self._nblocks = self._launch(items)
+                self._dirty = False
+            else:
+                ops.check(ops._lib.load().simseg_cast_bf16_multi(ops.ctx(), ops._p(self._table), len(items), self._nblocks,
+                                                                ops._stream()), "cast_bf16_multi")
+        self._stale = False
+
+    # ---- accessors ---------------------------------------------------------------------------
+    def get(self, p: Tensor) -> Tensor:
+        self._refresh()
+        it = self._item(p, "w")
+        if it["dst"] is None:
+            it["dst"] = torch.empty((it["rows"], it["cols"]), device=p.device, dtype=torch.bfloat16)
+            it["ld"] = it["cols"]
+            self._dirty = True
+            self._fill_now({**it, "dst_t": None, "ld_t": 0})
+        return it["dst"]
 
     def get_t(self, p: Tensor) -> Tensor:
         """bf16 W^T [K_in, N_out]: the K-major B operand of dgrad (dx = dy @ W), written by the same cast kernel."""
-        k = ("t", id(p))
-        if k not in self._c:
-            w = p.detach()
-            self._c[id(p)], self._c[k] = ops.cast_bf16(w.reshape(w.shape[0], -1), transpose_too=True)
-        return self._c[k]
+        self._refresh()
+        it = self._item(p, "w")
+        if it["dst_t"] is None:
+            it["dst_t"] = torch.empty((it["cols"], it["rows"]), device=p.device, dtype=torch.bfloat16)
+            it["ld_t"] = it["rows"]
+            self._dirty = True
+            self._fill_now({**it, "dst": None, "ld": 0})
+        return it["dst_t"]
 
     def packed(self, key: str, ps: List[Tensor]) -> Tensor:
         """Row-concatenation of several [n_i, K] weights as one bf16 matrix (BERT q/k/v -> one GEMM)."""
-        if key not in self._c:
-            self._c[key] = torch.cat([self.get(p) for p in ps], 0)
-        return self._c[key]
+        self._refresh()
+        buf = self._views.get(key)
+        if buf is None:
+            K = ps[0].shape[1]
+            buf = torch.empty((sum(p.shape[0] for p in ps), K), device=ps[0].device, dtype=torch.bfloat16)
+            self._views[key] = buf
+            r = 0
+            for p in ps:
+                it = self._item(p, ("pk", key))
+                it["dst"], it["ld"] = buf[r:r + p.shape[0]], K
+                r += p.shape[0]
+                self._fill_now({**it, "dst_t": None, "ld_t": 0})
+            self._dirty = True
+        return buf
 
     def packed_t(self, key: str, ps: List[Tensor]) -> Tensor:
         """Transpose of ``packed``: [K, sum n_i]."""
+        self._refresh()
         k = ("t", key)
-        if k not in self._c:
-            self._c[k] = torch.cat([self.get_t(p) for p in ps], 1).contiguous()
-        return self._c[k]
+        buf = self._views.get(k)
+        if buf is None:
+            K = ps[0].shape[1]
+            tot = sum(p.shape[0] for p in ps)
+            buf = torch.empty((K, tot), device=ps[0].device, dtype=torch.bfloat16)
+            self._views[k] = buf
+            c = 0
+            for p in ps:
+                it = self._item(p, ("pk", key))
+                it["dst_t"], it["ld_t"] = buf[:, c:c + p.shape[0]], tot
+                c += p.shape[0]
+                self._fill_now({**it, "dst": None, "ld": 0})
+            self._dirty = True
+        return buf
 
     def clear(self):
-        self._c.clear()
+        """Weights changed (optimizer step / state-dict load): every registered copy is re-cast on next use."""
+        self._stale = True
 
 
 # ------------------------------------------------------------------------------------------------ ViT
