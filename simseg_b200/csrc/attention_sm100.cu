@@ -729,6 +729,274 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   }
 }
 
+// ================================================================================================
+// Forward, variant "ts": P never leaves tensor memory.  S = Q K^T sits in one of two TMEM buffers; the softmax warps
+// overwrite the head of the SAME buffer with P as packed bf16 pairs (tcgen05.st) and O = P V is issued with the A
+// operand read from TMEM (tcgen05.mma [d], [a_tmem], b_desc).  No shared-memory P tile, no proxy fence, and — because P
+// is double-buffered for free — two groups of four warps (one thread = one query row, no row-pair exchange) work on
+// alternate units completely independently; only the MUFU rate couples them.
+//   warp 0      TMA (as above)          warp 1   MMA issue: QK^T of unit u+1, then P V of unit u
+//   warps 2-5   softmax + output of even units      warps 6-9   the same for odd units
+__global__ void __launch_bounds__(kAfThreads, 1)
+attention_fwd_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                        const __grid_constant__ CUtensorMap tm_v, const AttnFwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                          // [2 units][16 KB]
+  uint8_t* sK = sQ + 2 * kTileBytes;           // [kv_stages items][nkt tiles x 16 KB]
+  uint8_t* sV = sK + 4 * kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 4 * kTileBytes);
+  uint64_t* q_full = bars;            // [2]
+  uint64_t* q_empty = bars + 2;       // [2]
+  uint64_t* kv_full = bars + 4;       // [4]
+  uint64_t* kv_empty = bars + 8;      // [4]
+  uint64_t* s_full = bars + 12;       // [2] MMA -> group g : S of a unit is complete
+  uint64_t* p_ready = bars + 14;      // [2] group g -> MMA : P is in TMEM (4 warps)
+  uint64_t* pv_done = bars + 16;      // [2] MMA -> MMA     : P V has read buffer g, it may be overwritten by the next S
+  uint64_t* o_full = bars + 18;       // [2] MMA -> group g : O of one of ITS units is complete (per group: a group's first
+                                      //     wait must be a parity-0 wait, or it would pass before anything completed)
+  uint64_t* o_free = bars + 20;       // group -> MMA : O drained (4 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_q); prefetch_tmap(&tm_k); prefetch_tmap(&tm_v);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&pv_done[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(&o_full[0], 1); mbar_init(&o_full[1], 1); mbar_init(o_free, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (p.G > 1) {
+    uint4* z = reinterpret_cast<uint4*>(sQ);
+    for (int i = threadIdx.x; i < 10 * kTileBytes / 16; i += kAfThreads) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tO = tmem_base + 2 * p.stride;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    uint32_t u = 0, itc = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++itc) {
+      const int b = item / p.HG, h = (item - b * p.HG) * p.G;
+      const uint32_t kb = itc % p.kv_stages;
+      mbar_wait(&kv_empty[kb], ((itc / p.kv_stages) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&kv_full[kb], 2 * p.nkt * p.tile_tx);
+        for (int t = 0; t < p.nkt; ++t) {
+          tma_load_4d(sK + (p.nkt * kb + t) * kTileBytes, &tm_k, &kv_full[kb], 0, h, t * kTile, b);
+          tma_load_4d(sV + (p.nkt * kb + t) * kTileBytes, &tm_v, &kv_full[kb], 0, h, t * kTile, b);
+        }
+      }
+      __syncwarp();
+      for (int qt = 0; qt < p.nqt; ++qt, ++u) {
+        mbar_wait(&q_empty[u & 1], ((u >> 1) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&q_full[u & 1], p.tile_tx);
+          tma_load_4d(sQ + (u & 1) * kTileBytes, &tm_q, &q_full[u & 1], 0, h, qt * kTile, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    const uint32_t id_s = make_idesc(1u, 0u, 0u, kTile, static_cast<uint32_t>(p.nkc));   // A, B K-major, N = keys
+    const uint32_t id_o = make_idesc(1u, 0u, 1u, kTile, 64u);                            // A (TMEM) K-major, B MN-major (V)
+    const uint64_t kd = make_smem_desc_sw128(0, 16, 1024);
+    const uint64_t md = make_smem_desc_sw128(0, 16384, 1024);
+    const int ksteps = p.nkc >> 4;
+    struct Cur { int item, qt; uint32_t itc, u; };
+    auto valid = [&](const Cur& c) { return c.item < p.items; };
+    auto advance = [&](Cur& c) {
+      ++c.u;
+      if (++c.qt == p.nqt) { c.qt = 0; c.item += gridDim.x; ++c.itc; }
+    };
+    auto issue_qk = [&](const Cur& c) {
+      const uint32_t kb = c.itc % p.kv_stages, g = c.u & 1;
+      if (c.qt == 0) mbar_wait(&kv_full[kb], (c.itc / p.kv_stages) & 1);
+      mbar_wait(&q_full[g], (c.u >> 1) & 1);
+      mbar_wait(&pv_done[g], ((c.u >> 1) & 1) ^ 1);          // P V of unit u-2 has read this buffer (passes for u < 2)
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t aQ = smem_u32(sQ + g * kTileBytes) >> 4, aK = smem_u32(sK + p.nkt * kb * kTileBytes) >> 4;
+        const uint32_t tS = tmem_base + g * p.stride;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_f16(tS, kd + aQ + 2 * kk, kd + aK + 2 * kk, id_s, kk > 0 ? 1u : 0u);
+        umma_commit(&s_full[g]);
+        umma_commit(&q_empty[g]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](const Cur& c) {
+      const uint32_t kb = c.itc % p.kv_stages, g = c.u & 1;
+      mbar_wait(&p_ready[g], (c.u >> 1) & 1);
+      mbar_wait(o_free, (c.u & 1) ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t aV = smem_u32(sV + p.nkt * kb * kTileBytes) >> 4;
+        const uint32_t tP = tmem_base + g * p.stride;                        // bf16 pairs: 8 columns per 16-key k-step
+        for (int ks = 0; ks < ksteps; ++ks) umma_f16_ts(tO, tP + 8 * ks, md + aV + 128 * ks, id_o, ks > 0 ? 1u : 0u);
+        umma_commit(&o_full[g]);
+        umma_commit(&pv_done[g]);
+        if (c.qt == p.nqt - 1) umma_commit(&kv_empty[kb]);
+      }
+      __syncwarp();
+    };
+    Cur cq{static_cast<int>(blockIdx.x), 0, 0u, 0u}, cp = cq;
+    if (valid(cq)) { issue_qk(cq); advance(cq); }
+    while (valid(cp)) {
+      if (valid(cq)) { issue_qk(cq); advance(cq); }
+      issue_pv(cp);
+      advance(cp);
+    }
+  } else {
+    // =============================== softmax + output: group g owns units u = g (mod 2) ===============================
+    const int g = (warp - 2) >> 2;
+    const int quarter = warp & 3;              // TMEM lane quarter
+    const int r = quarter * 32 + lane;         // row inside the tile
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    uint32_t u = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int b = item / p.HG, h0 = (item - b * p.HG) * p.G;
+      const int klen = (p.key_len ? min(max(p.key_len[b], 1), p.S) : p.S) * p.G;      // live key columns
+      const int nch = (klen + 31) >> 5;
+      const int gm = p.G - 1, rg = r & gm;
+      const bool dense = p.G == 1;
+      for (int qt = 0; qt < p.nqt; ++qt, ++u) {
+        if ((u & 1) != static_cast<uint32_t>(g)) continue;
+        const int qrow = qt * kTile + r;
+        const bool q_ok = qrow < p.rows;
+        const bool warp_live = qt * kTile + quarter * 32 < p.rows;
+        const uint32_t tS = tmem_base + g * p.stride + lane_off;
+        mbar_wait(&s_full[g], (u >> 1) & 1);
+        tc_fence_after();
+        float m = -INFINITY, sum = 0.f;
+        if (warp_live) {
+          // ---- pass 1: row max
+          for (int c = 0; c < nch; ++c) {
+            uint32_t x[32];
+            tmem_ld_32x32(tS + c * 32, x);
+            tmem_ld_wait();
+            if (dense && c * 32 + 32 <= klen) {
+              float m0 = fmaxf(__uint_as_float(x[0]), __uint_as_float(x[1]));
+              float m1 = fmaxf(__uint_as_float(x[2]), __uint_as_float(x[3]));
+#pragma unroll
+              for (int j = 4; j < 32; j += 2) {
+                m0 = fmaxf(m0, __uint_as_float(x[j]));
+                m1 = fmaxf(m1, __uint_as_float(x[j + 1]));
+              }
+              m = fmaxf(m, fmaxf(m0, m1));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                m = (c * 32 + j < klen && ((c * 32 + j) & gm) == rg) ? fmaxf(m, __uint_as_float(x[j])) : m;
+            }
+          }
+          const float ms = m * p.scale_log2e;
+          // ---- pass 2: P = exp2(s*scale*log2e - max) as bf16 pairs into the first columns of the same TMEM buffer.
+          //      Chunk c lands in columns [16c, 16c+16): always inside S columns this thread has already consumed.
+          for (int c = 0; c * 32 < p.nkc; ++c) {
+            uint32_t pp[16];
+            if (c < nch) {
+              uint32_t x[32];
+              tmem_ld_32x32(tS + c * 32, x);
+              tmem_ld_wait();
+              if (dense && c * 32 + 32 <= klen) {
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float p0 = ex2_approx(fmaf(__uint_as_float(x[j]), p.scale_log2e, -ms));
+                  const float p1 = ex2_approx(fmaf(__uint_as_float(x[j + 1]), p.scale_log2e, -ms));
+                  const float p2 = ex2_approx(fmaf(__uint_as_float(x[j + 2]), p.scale_log2e, -ms));
+                  const float p3 = ex2_approx(fmaf(__uint_as_float(x[j + 3]), p.scale_log2e, -ms));
+                  s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+                  pp[j >> 1] = pack_bf16(p0, p1);
+                  pp[(j >> 1) + 1] = pack_bf16(p2, p3);
+                }
+                sum += (s0 + s1) + (s2 + s3);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                  float p0 = ex2_approx(fmaf(__uint_as_float(x[j]), p.scale_log2e, -ms));
+                  float p1 = ex2_approx(fmaf(__uint_as_float(x[j + 1]), p.scale_log2e, -ms));
+                  p0 = (c * 32 + j < klen && ((c * 32 + j) & gm) == rg) ? p0 : 0.f;
+                  p1 = (c * 32 + j + 1 < klen && ((c * 32 + j + 1) & gm) == rg) ? p1 : 0.f;
+                  sum += p0 + p1;
+                  pp[j >> 1] = pack_bf16(p0, p1);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pp[j] = 0u;             // keys between the last live chunk and the MMA's K extent
+            }
+            tmem_st_32x16(tS + c * 16, pp);
+          }
+          tmem_st_wait();
+          m = ms;                                                  // keep the scaled max for the log-sum-exp
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[g]);
+        // ---- output: O / sum, log-sum-exp
+        mbar_wait(&o_full[g], (u >> 1) & 1);
+        tc_fence_after();
+        if (warp_live) {
+          uint32_t o0[32], o1[32];
+          tmem_ld_32x32(tO + lane_off, o0);
+          tmem_ld_32x32(tO + lane_off + 32, o1);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(o_free);                      // O is in registers: release it before the stores
+          if (q_ok) {
+            const float inv = 1.0f / sum;
+            const int tok = qrow >> p.lg, hh = h0 + (qrow & gm);
+            __nv_bfloat16* po = p.out + (static_cast<int64_t>(b) * p.S + tok) * (p.H * 64) + hh * 64;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 a, c2;
+              a.x = pack_bf16(__uint_as_float(o0[8 * j]) * inv, __uint_as_float(o0[8 * j + 1]) * inv);
+              a.y = pack_bf16(__uint_as_float(o0[8 * j + 2]) * inv, __uint_as_float(o0[8 * j + 3]) * inv);
+              a.z = pack_bf16(__uint_as_float(o0[8 * j + 4]) * inv, __uint_as_float(o0[8 * j + 5]) * inv);
+              a.w = pack_bf16(__uint_as_float(o0[8 * j + 6]) * inv, __uint_as_float(o0[8 * j + 7]) * inv);
+              c2.x = pack_bf16(__uint_as_float(o1[8 * j]) * inv, __uint_as_float(o1[8 * j + 1]) * inv);
+              c2.y = pack_bf16(__uint_as_float(o1[8 * j + 2]) * inv, __uint_as_float(o1[8 * j + 3]) * inv);
+              c2.z = pack_bf16(__uint_as_float(o1[8 * j + 4]) * inv, __uint_as_float(o1[8 * j + 5]) * inv);
+              c2.w = pack_bf16(__uint_as_float(o1[8 * j + 6]) * inv, __uint_as_float(o1[8 * j + 7]) * inv);
+              reinterpret_cast<uint4*>(po)[j] = a;
+              reinterpret_cast<uint4*>(po + 32)[j] = c2;
+            }
+            if (p.lse) p.lse[(static_cast<int64_t>(b) * p.H + hh) * p.S + tok] = (m + log2f(sum)) * 0.69314718055994531f;
+          }
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(o_free);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn4)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -815,9 +1083,7 @@ int attention_fwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v,
                           int S, const int32_t* key_len, float scale, void* out, float* lse, cudaStream_t st) {
   if (S > 224 || S < 1) return SIMSEG_ERR_UNSUPPORTED;
   const int G = pack_factor(H, S);
-  // measured (B=4096, H=12, S=25): packed tcgen05 forward 0.21 ms vs 0.185 ms for the mma.sync kernel (the unit is
-  // latency-bound); backward is the opposite (0.58 vs 1.25 ms).  Forward keeps the small kernel unless forced.
-  if (S < 48 && getenv("SIMSEG_ATTN_FWD") == nullptr) return SIMSEG_ERR_UNSUPPORTED;
+  if (G == 1 && S < 48 && getenv("SIMSEG_ATTN_FWD") == nullptr) return SIMSEG_ERR_UNSUPPORTED;   // mostly padding: mma.sync kernel
   const uintptr_t al = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
                        reinterpret_cast<uintptr_t>(out);
   if ((al & 15) || sb % 8 || ss % 8 || sh % 8) return SIMSEG_ERR_UNSUPPORTED;
@@ -839,6 +1105,22 @@ int attention_fwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v,
   p.kv_stages = p.nkt == 1 ? 4 : 2;
   p.scale_log2e = scale * 1.44269504088896341f;
   p.key_len = key_len; p.lse = lse; p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  // default: the "ts" variant (P stays in tensor memory; measured 0.895 vs 0.974 ms on 4096 x 6 x 197 and 0.174 vs 0.214 ms on
+  // the packed 4096 x 12 x 25 case); SIMSEG_ATTN_FWD=tc selects the shared-memory-P variant below
+  const char* var = getenv("SIMSEG_ATTN_FWD");
+  if (!(var != nullptr && var[0] == 't' && var[1] == 'c')) {
+    const int smem_ts = 1024 + 10 * kTileBytes + 256;
+    static bool ts_set = false;
+    if (!ts_set) {
+      SIMSEG_CUDA(cudaFuncSetAttribute(attention_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ts));
+      ts_set = true;
+    }
+    const int grid_ts = p.items < ctx->num_sms ? p.items : ctx->num_sms;
+    attention_fwd_ts_kernel<<<grid_ts, kAfThreads, smem_ts, st>>>(tq, tk, tv, p);
+    ctx->launches++;
+    SIMSEG_LAUNCH_CHECK();
+    return SIMSEG_OK;
+  }
   const int smem_bytes = 14 * kTileBytes + 2048 + 256;   // the dynamic segment itself is 1024-byte aligned (checked in-kernel)
   static bool attr_set = false;
   if (!attr_set) {

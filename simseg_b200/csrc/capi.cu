@@ -143,7 +143,7 @@ int simseg_attention_fwd(simseg_ctx* ctx, const void* q, const void* k, const vo
                          void* stream) {
   CTX_OR_FAIL();
   // tcgen05 kernel for S <= 224 (attention_sm100.cu); shapes it rejects run the mma.sync kernel.
-  // SIMSEG_ATTN_FWD=mma|tc overrides the choice (tests exercise both).
+  // SIMSEG_ATTN_FWD=mma|tc|ts overrides the choice (tests exercise all three; default ts = P kept in tensor memory).
   const char* force = getenv("SIMSEG_ATTN_FWD");
   const bool want_tc = force ? (force[0] == 't') : true;       // short sequences are packed several heads per tile
   if (want_tc) {

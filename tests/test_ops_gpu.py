@@ -331,7 +331,7 @@ def test_misc_elementwise(cuda):
     assert (ops.gelu_fwd(h).float() - gelu(h.float())).abs().max().item() < 2e-2
 
 
-@pytest.mark.parametrize("impl", ["tc", "mma"])
+@pytest.mark.parametrize("impl", ["tc", "mma", "ts"])
 @pytest.mark.parametrize("B,H,S,masked", [(3, 6, 197, False), (2, 12, 224, True), (7, 12, 25, True), (4, 12, 77, True),
                                           (2, 2, 129, True), (60, 6, 197, False), (3, 1, 128, False), (300, 2, 64, True),
                                           (5, 8, 30, True), (3, 12, 50, False), (4, 6, 25, True), (200, 12, 25, True), (9, 16, 16, True)])

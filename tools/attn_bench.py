@@ -27,8 +27,12 @@ def run(B, H, S, masked, reps=5):
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
-    fwd = t(lambda: ops.attention_fwd(q, k, v, B, H, S, strides, klen, 0.125, out=out, lse=lse))
-    res = [f"fwd {fwd:7.3f} ms ({4.0 * B * H * S * S * 64 / fwd / 1e9:6.1f} TF/s)"]
+    res = []
+    for impl in ("tc", "ts"):
+        os.environ["SIMSEG_ATTN_FWD"] = impl
+        fwd = t(lambda: ops.attention_fwd(q, k, v, B, H, S, strides, klen, 0.125, out=out, lse=lse))
+        res.append(f"fwd[{impl}] {fwd:7.3f} ms ({4.0 * B * H * S * S * 64 / fwd / 1e9:6.1f} TF/s)")
+    os.environ.pop("SIMSEG_ATTN_FWD", None)
     for impl in ("mma", "tc"):
         os.environ["SIMSEG_ATTN_BWD"] = impl
         ms = t(lambda: ops.attention_bwd(q, k, v, out, dout, lse, B, H, S, strides, klen, 0.125, dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2]))
