@@ -229,6 +229,11 @@ int simseg_seg_select(simseg_ctx* ctx, const float* img_emb, const float* text_e
  * normalisation (seg_evaluation.py:136-139,146-147) -> out [B,K,h*scale,w*scale] fp32 (zeros where cand == -1). */
 int simseg_seg_upsample_norm(simseg_ctx* ctx, const float* sim, const int32_t* cand, int B, int N, int C, int K, int h,
                              int w, int scale, float* out, void* stream);
+/* position-embedding resize at checkpoint load (utils/interpolate_pe.py:4-27, called from seg_evaluation.py:228-230):
+ * src [num_extra + grid_src^2, D] fp32 -> dst [num_extra + grid_dst^2, D] fp32; the extra (class) tokens are copied, the
+ * grid part is resized like F.interpolate(mode="bicubic", align_corners=False). */
+int simseg_pos_embed_bicubic(simseg_ctx* ctx, const float* src, float* dst, int grid_src, int grid_dst, int D, int num_extra,
+                             void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,6 +10,10 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsimseg_b200.so")
+# development knob for A/B timing of two builds (tools/): another build of the same library; symbols it lacks stay unbound
+_ALT_LIB = os.environ.get("SIMSEG_B200_LIB")
+if _ALT_LIB:
+    LIB_PATH = _ALT_LIB
 
 F32, BF16 = 0, 1
 EPI_NONE, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU, EPI_ROWSCALE = range(5)
@@ -60,6 +64,7 @@ PROTOTYPES = {
     "simseg_seg_class_embed": (i32, [vp, vp, i32, i32, i32, vp, vp]),
     "simseg_seg_select": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
     "simseg_seg_upsample_norm": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "simseg_pos_embed_bicubic": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
 }
 
 _lib = None
@@ -78,6 +83,8 @@ def load() -> C.CDLL:
                               "(or __graft_entry__.build()); there is no fallback path")
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in PROTOTYPES.items():
+            if _ALT_LIB and not hasattr(lib, name):
+                continue
             fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
             fn.restype, fn.argtypes = res, args
         _lib = lib

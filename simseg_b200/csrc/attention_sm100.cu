@@ -49,11 +49,7 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
 }
 
 __device__ __forceinline__ int ceil16(int x) { return (x + 15) & ~15; }
-__device__ __forceinline__ float ex2_approx(float x) {       // MUFU.EX2, 2 ulp; arguments here are <= 0 up to rounding
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
+// ex2_approx (common.cuh): MUFU.EX2, 2 ulp; arguments here are <= 0 up to rounding
 
 __global__ void __launch_bounds__(kAbThreads, 1)
 attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,

@@ -42,6 +42,7 @@ int attention_fwd_tc_impl(Ctx*, const void*, const void*, const void*, int64_t, 
 int seg_class_embed_impl(Ctx*, const float*, int, int, int, float*, cudaStream_t);
 int seg_select_impl(Ctx*, const float*, const float*, int, int, int, int, int, float*, int32_t*, float*, cudaStream_t);
 int seg_upsample_norm_impl(Ctx*, const float*, const int32_t*, int, int, int, int, int, int, int, float*, cudaStream_t);
+int pos_embed_bicubic_impl(Ctx*, const float*, float*, int, int, int, int, cudaStream_t);
 int patch_sim_fused_impl(Ctx*, const void*, int64_t, int, const void*, int, int, float*, int32_t*, cudaStream_t);
 
 // fp32 product in the requested precision: C[M,N] (+)= A(m,k) B(n,k)
@@ -287,6 +288,12 @@ int simseg_seg_upsample_norm(simseg_ctx* ctx, const float* sim, const int32_t* c
                              int scale, float* out, void* stream) {
   CTX_OR_FAIL();
   return seg_upsample_norm_impl(c, sim, cand, B, N, C, K, h, w, scale, out, st);
+}
+int simseg_pos_embed_bicubic(simseg_ctx* ctx, const float* src, float* dst, int grid_src, int grid_dst, int D, int num_extra,
+                             void* stream) {
+  CTX_OR_FAIL();
+  SIMSEG_CHECK_ARG(src && dst, "pos_embed_bicubic: null pointer");
+  return pos_embed_bicubic_impl(c, src, dst, grid_src, grid_dst, D, num_extra, st);
 }
 
 }  // extern "C"

@@ -96,6 +96,97 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return d;
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 — one issue slot and one FMA-pipe pass for two lanes) ------
+// The GELU epilogues are issue-bound: evaluating two adjacent columns per instruction halves the
+// FMA-pipe instruction count.  A value is two fp32 in one 64-bit register pair (.x = low word).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_splat(float a) { return f2_pack(a, a); }
+__device__ __forceinline__ void f2_unpack(f32x2 p, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p));
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// gelu of the two bf16 values in `u` -> packed fp32 pair.  One MUFU per value instead of two:
+//   0.5*erfc(z) = 1 / (2^(1/16) * (1 + a1 z + ... + a6 z^6))^16,  z = |x|/sqrt2      (Abramowitz-Stegun 7.1.28, |err| <= 3e-7)
+// evaluated in n = -|x| (sign bit OR-ed into the bf16 pair, odd coefficients negated) so that no negation is needed:
+//   gelu(x) = max(x, 0) + n * w(n).      Absolute error of gelu <= 1e-6 (fp32 rounding through the 16th power included).
+__device__ __forceinline__ f32x2 gelu_erf_x2(uint32_t u) {
+  const float s = 1.04427378242741384f;                         // 2^(1/16): folds the 0.5 into the polynomial
+  const float r2 = 0.70710678118654752f;
+  const uint32_t un = u | 0x80008000u;
+  const f32x2 n = f2_pack(bf16_lo(un), bf16_hi(un));            // -|x|
+  f32x2 pl = f2_fma(f2_splat(s * 0.0000430638f * r2 * r2 * r2 * r2 * r2 * r2), n, f2_splat(-s * 0.0002765672f * r2 * r2 * r2 * r2 * r2));
+  pl = f2_fma(pl, n, f2_splat(s * 0.0001520143f * r2 * r2 * r2 * r2));
+  pl = f2_fma(pl, n, f2_splat(-s * 0.0092705272f * r2 * r2 * r2));
+  pl = f2_fma(pl, n, f2_splat(s * 0.0422820123f * r2 * r2));
+  pl = f2_fma(pl, n, f2_splat(-s * 0.0705230784f * r2));
+  pl = f2_fma(pl, n, f2_splat(s));
+  float p0, p1;
+  f2_unpack(pl, p0, p1);
+  f32x2 w = f2_pack(rcp_approx(p0), rcp_approx(p1));
+  w = f2_mul(w, w);
+  w = f2_mul(w, w);
+  w = f2_mul(w, w);
+  w = f2_mul(w, w);                                              // 0.5 * erfc(|x|/sqrt2)
+  return f2_fma(n, w, f2_pack(fmaxf(bf16_lo(u), 0.f), fmaxf(bf16_hi(u), 0.f)));
+}
+
+// (gelu, gelu') of the two bf16 values in `u`: gelu_erf_both two columns per instruction.  Same arithmetic (Abramowitz-Stegun
+// 7.1.26, exp(-x^2/2) shared by erfc and the density), same number of FMA-pipe lane operations, half the issue slots; the
+// Phi(x) = x >= 0 ? 1 - w : w select stays scalar on the ALU pipe.
+__device__ __forceinline__ void gelu_erf_both_x2(uint32_t u, f32x2& gelu, f32x2& dgelu) {
+  const uint32_t ua = u & 0x7fff7fffu;
+  const float x0 = bf16_lo(u), x1 = bf16_hi(u);
+  const f32x2 x = f2_pack(x0, x1);
+  const f32x2 ax = f2_pack(bf16_lo(ua), bf16_hi(ua));
+  float t0, t1, e0, e1;
+  f2_unpack(f2_fma(f2_splat(0.3275911f * 0.70710678118654752f), ax, f2_splat(1.0f)), t0, t1);
+  f2_unpack(f2_mul(f2_mul(x, x), f2_splat(-0.5f * 1.44269504088896341f)), e0, e1);
+  const f32x2 t = f2_pack(rcp_approx(t0), rcp_approx(t1));
+  const f32x2 e = f2_pack(ex2_approx(e0), ex2_approx(e1));      // exp(-x^2/2)
+  f32x2 q = f2_fma(f2_splat(0.5f * 1.061405429f), t, f2_splat(0.5f * -1.453152027f));
+  q = f2_fma(q, t, f2_splat(0.5f * 1.421413741f));
+  q = f2_fma(q, t, f2_splat(0.5f * -0.284496736f));
+  q = f2_fma(q, t, f2_splat(0.5f * 0.254829592f));
+  const f32x2 w = f2_mul(f2_mul(q, t), e);                      // 0.5 * erfc(|x|/sqrt2)
+  const f32x2 omw = f2_fma(w, f2_splat(-1.0f), f2_splat(1.0f));
+  float w0, w1, m0, m1;
+  f2_unpack(w, w0, w1);
+  f2_unpack(omw, m0, m1);
+  const f32x2 cdf = f2_pack(x0 >= 0.f ? m0 : w0, x1 >= 0.f ? m1 : w1);
+  gelu = f2_mul(x, cdf);
+  dgelu = f2_fma(f2_mul(x, f2_splat(0.3989422804014327f)), e, cdf);
+}
+
 // 128-bit streaming loads/stores
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 r;

@@ -186,7 +186,8 @@ __device__ __forceinline__ void epilogue_tma(const GemmParams& p, const CUtensor
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const float4 bb = __ldg(b4 + k);
-            v[4 * k] += bb.x; v[4 * k + 1] += bb.y; v[4 * k + 2] += bb.z; v[4 * k + 3] += bb.w;
+            f2_unpack(f2_add(f2_pack(v[4 * k], v[4 * k + 1]), f2_pack(bb.x, bb.y)), v[4 * k], v[4 * k + 1]);
+            f2_unpack(f2_add(f2_pack(v[4 * k + 2], v[4 * k + 3]), f2_pack(bb.z, bb.w)), v[4 * k + 2], v[4 * k + 3]);
           }
         } else {
 #pragma unroll
@@ -205,8 +206,7 @@ __device__ __forceinline__ void epilogue_tma(const GemmParams& p, const CUtensor
 #pragma unroll
         for (int k = 0; k < 32; k += 2) {
           xo[k >> 1] = pack_bf16(v[k], v[k + 1]);                   // pre-activation, bf16 — exactly what backward reads
-          v[k] = gelu_erf(bf16_lo(xo[k >> 1]));
-          v[k + 1] = gelu_erf(bf16_hi(xo[k >> 1]));
+          f2_unpack(gelu_erf_x2(xo[k >> 1]), v[k], v[k + 1]);       // two columns per instruction (FFMA2), one MUFU each
         }
       } else if (EPI == SIMSEG_EPI_DGELU) {
         mbar_wait(&aux_full[f % 3], (f / 3) & 1);
@@ -216,11 +216,11 @@ __device__ __forceinline__ void epilogue_tma(const GemmParams& p, const CUtensor
           const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float g0, a0, g1, a1;
-            gelu_erf_both(bf16_lo(w[e]), a0, g0);
-            gelu_erf_both(bf16_hi(w[e]), a1, g1);
-            v[8 * q4 + 2 * e] *= g0;
-            v[8 * q4 + 2 * e + 1] *= g1;
+            f32x2 act, grad;
+            gelu_erf_both_x2(w[e], act, grad);
+            float a0, a1;
+            f2_unpack(act, a0, a1);
+            f2_unpack(f2_mul(f2_pack(v[8 * q4 + 2 * e], v[8 * q4 + 2 * e + 1]), grad), v[8 * q4 + 2 * e], v[8 * q4 + 2 * e + 1]);
             xo[4 * q4 + e] = pack_bf16(a0, a1);
           }
         }

@@ -4,6 +4,8 @@
 //   select        :119-150 image-level class scores -> top-k -> threshold mean + std (unbiased) -> up to 5 candidates
 //                          (classes 0 and 255 are skipped, the scan stops at the first score below the threshold)
 //   upsample_norm :136-150 per candidate: its column of the map, nearest x16 up-sampling, min-max normalisation
+//   pos_embed_bicubic :228-230 -> utils/interpolate_pe.py:4-27, the position-embedding resize done at checkpoint load
+//                          (224^2 checkpoints evaluated at 288^2: 14x14 -> 18x18 grid)
 #include "common.cuh"
 
 namespace simseg {
@@ -135,6 +137,52 @@ __global__ void __launch_bounds__(256) seg_upsample_norm_kernel(const float* __r
   }
 }
 
+// Bicubic resize of the grid part of a ViT position embedding (utils/interpolate_pe.py:16-22: F.interpolate(mode='bicubic',
+// align_corners=False) on the [1,D,g0,g0] view), the extra (class) tokens are copied.  Same arithmetic as torch's
+// upsample_bicubic2d: source = (dst+0.5)*g0/g1-0.5 (not clamped), Keys kernel with A=-0.75, border taps clamped.
+__device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {
+  const float A = -0.75f;
+  const float x0 = t + 1.0f, x3 = 2.0f - t, x2 = 1.0f - t;
+  c[0] = ((A * x0 - 5.0f * A) * x0 + 8.0f * A) * x0 - 4.0f * A;
+  c[1] = ((A + 2.0f) * t - (A + 3.0f)) * t * t + 1.0f;
+  c[2] = ((A + 2.0f) * x2 - (A + 3.0f)) * x2 * x2 + 1.0f;
+  c[3] = ((A * x3 - 5.0f * A) * x3 + 8.0f * A) * x3 - 4.0f * A;
+}
+__global__ void __launch_bounds__(128) pos_embed_bicubic_kernel(const float* __restrict__ src, float* __restrict__ dst, int g0, int g1,
+                                                               int D, int extra) {
+  const int tok = blockIdx.x;
+  float* o = dst + static_cast<int64_t>(tok) * D;
+  if (tok < extra) {
+    for (int d = threadIdx.x; d < D; d += 128) o[d] = src[static_cast<int64_t>(tok) * D + d];
+    return;
+  }
+  const int oy = (tok - extra) / g1, ox = (tok - extra) % g1;
+  const float scale = static_cast<float>(g0) / static_cast<float>(g1);
+  const float ry = scale * (oy + 0.5f) - 0.5f, rx = scale * (ox + 0.5f) - 0.5f;
+  const float fy = floorf(ry), fx = floorf(rx);
+  float cy[4], cx[4];
+  cubic_coeffs(ry - fy, cy);
+  cubic_coeffs(rx - fx, cx);
+  const int iy = static_cast<int>(fy), ix = static_cast<int>(fx);
+  int64_t row[4];
+  int col[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    row[i] = static_cast<int64_t>(extra + min(max(iy - 1 + i, 0), g0 - 1) * g0) * D;
+    col[i] = min(max(ix - 1 + i, 0), g0 - 1) * D;
+  }
+  for (int d = threadIdx.x; d < D; d += 128) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float* r = src + row[i] + d;
+      const float v = r[col[0]] * cx[0] + r[col[1]] * cx[1] + r[col[2]] * cx[2] + r[col[3]] * cx[3];
+      acc += v * cy[i];
+    }
+    o[d] = acc;
+  }
+}
+
 int seg_class_embed_impl(Ctx* ctx, const float* prompt, int C, int P, int E, float* out, cudaStream_t st) {
   SIMSEG_CHECK_ARG(C > 0 && P > 0 && E > 0 && E <= 1024, "class_embed: C=%d P=%d E=%d unsupported (E <= 1024)", C, P, E);
   class_embed_kernel<<<C, 256, 0, st>>>(prompt, P, E, out);
@@ -158,6 +206,14 @@ int seg_upsample_norm_impl(Ctx* ctx, const float* sim, const int32_t* cand, int 
                            float* out, cudaStream_t st) {
   SIMSEG_CHECK_ARG(B > 0 && K > 0 && h * w == N && scale > 0, "seg_upsample_norm: h*w must equal N (h=%d w=%d N=%d)", h, w, N);
   seg_upsample_norm_kernel<<<B * K, 256, 0, st>>>(sim, cand, N, C, K, h, w, scale, out);
+  ctx->launches++;
+  SIMSEG_LAUNCH_CHECK();
+  return SIMSEG_OK;
+}
+
+int pos_embed_bicubic_impl(Ctx* ctx, const float* src, float* dst, int g0, int g1, int D, int extra, cudaStream_t st) {
+  SIMSEG_CHECK_ARG(g0 > 0 && g1 > 0 && D > 0 && extra >= 0, "pos_embed_bicubic: bad sizes g0=%d g1=%d D=%d extra=%d", g0, g1, D, extra);
+  pos_embed_bicubic_kernel<<<extra + g1 * g1, 128, 0, st>>>(src, dst, g0, g1, D, extra);
   ctx->launches++;
   SIMSEG_LAUNCH_CHECK();
   return SIMSEG_OK;

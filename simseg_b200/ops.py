@@ -365,3 +365,16 @@ def seg_upsample_norm(sim: Tensor, cand: Tensor, h: int, w: int, scale: int = 16
     check(_lib.load().simseg_seg_upsample_norm(ctx(), _p(s), _p(cand.contiguous()), B, N, Cn, K, h, w, scale, _p(out), _stream()),
           "seg_upsample_norm")
     return out
+
+
+def pos_embed_bicubic(pos_embed: Tensor, grid_dst: int, num_extra: int = 1) -> Tensor:
+    """pos_embed [1, num_extra + g0*g0, D] fp32 -> [1, num_extra + grid_dst**2, D]: bicubic (align_corners=False) resize of the
+    grid part, extra tokens copied (``simseg/utils/interpolate_pe.py:14-24``)."""
+    assert pos_embed.dim() == 3 and pos_embed.shape[0] == 1 and pos_embed.dtype == torch.float32
+    src = pos_embed.contiguous()
+    D = src.shape[-1]
+    g0 = int((src.shape[-2] - num_extra) ** 0.5)
+    assert g0 * g0 + num_extra == src.shape[-2], "position embedding grid must be square"
+    out = torch.empty((1, num_extra + grid_dst * grid_dst, D), device=src.device, dtype=torch.float32)
+    check(_lib.load().simseg_pos_embed_bicubic(ctx(), _p(src), _p(out), g0, grid_dst, D, num_extra, _stream()), "pos_embed_bicubic")
+    return out

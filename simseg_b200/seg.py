@@ -43,3 +43,21 @@ def segment(model, image: Tensor, class_emb: Tensor, top_cls_num: int, max_cand:
     scores, cand, _ = ops.seg_select(pooled.float(), class_emb.float(), top_cls_num, max_cand)
     maps = ops.seg_upsample_norm(sim.view(B, N, -1), cand, hw, hw, patch_size)
     return sim.view(B, N, -1), am.view(B, N), scores, cand, maps
+
+
+def interpolate_pos_embed(pos_embed_checkpoint: Tensor, visual_encoder) -> Tensor:
+    """Same call as the reference's ``simseg.utils.interpolate_pe.interpolate_pos_embed`` (``utils/interpolate_pe.py:4-27``;
+    used at checkpoint load, ``tools/seg_evaluation.py:228-230``): resize a checkpoint's position embedding to the grid of
+    ``visual_encoder`` (``.patch_embed.num_patches``, ``.pos_embed``).  Returns the input unchanged when the grids agree.
+    The checkpoint tensor may live on the host (as ``torch.load(map_location='cpu')`` leaves it); the resize itself runs
+    on the encoder's device and the result comes back on the checkpoint tensor's device."""
+    num_patches = visual_encoder.patch_embed.num_patches
+    num_extra = visual_encoder.pos_embed.shape[-2] - num_patches
+    orig = int((pos_embed_checkpoint.shape[-2] - num_extra) ** 0.5)
+    new = int(num_patches ** 0.5)
+    if orig == new:
+        return pos_embed_checkpoint
+    dev = visual_encoder.pos_embed.device
+    out = ops.pos_embed_bicubic(pos_embed_checkpoint.to(device=dev, dtype=torch.float32), new, num_extra)
+    print("reshape position embedding from %d to %d" % (orig ** 2, new ** 2))
+    return out.to(pos_embed_checkpoint.device)

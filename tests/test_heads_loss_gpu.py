@@ -292,3 +292,58 @@ def test_segment_pipeline_calls(cuda):
 def _cos_rows(a, b):
     a, b = a.double(), b.double()
     return ((a * b).sum(-1) / (a.norm(dim=-1) * b.norm(dim=-1))).min().item()
+
+
+@pytest.mark.parametrize("g0,g1,D,extra", [(14, 18, 384, 1), (14, 18, 768, 1), (18, 14, 384, 1), (14, 32, 100, 2), (7, 7, 64, 1),
+                                           (2, 9, 8, 0)])
+def test_pos_embed_bicubic_vs_oracle(cuda, g0, g1, D, extra):
+    """utils/interpolate_pe.py:4-27 (checkpoint-load resize, 14x14 -> 18x18 for the 288^2 seg evaluation): the CUDA resize
+    against the oracle's F.interpolate(mode='bicubic', align_corners=False) restatement — up-, down-sampling, identity."""
+    ops, O = _ops(), _O()
+    pe = torch.randn(1, extra + g0 * g0, D, generator=torch.Generator().manual_seed(g0 * 100 + g1))
+    out = ops.pos_embed_bicubic(pe.to(cuda), g1, extra)
+    ref = O.interpolate_pos_embed(pe, g1 * g1, extra) if g0 != g1 else pe
+    assert out.shape == ref.shape
+    assert (out.cpu() - ref).abs().max().item() < 1e-5
+    assert torch.equal(out[:, :extra].cpu(), pe[:, :extra])
+
+
+def test_pos_embed_bicubic_vs_reference_fixture(cuda):
+    """The same resize against the output of the reference's own interpolate_pos_embed (tests/golden/heads_loss.npz)."""
+    z = np.load(os.path.join(GOLD, "heads_loss.npz"))
+    out = _ops().pos_embed_bicubic(torch.tensor(z["pe_in"]).to(cuda), 18, 1)
+    assert out.shape == (1, 325, 16)
+    assert np.abs(out.cpu().numpy() - z["pe_out"]).max() < 2e-5
+
+
+def test_interpolate_pos_embed_model_288(cuda):
+    """seg.interpolate_pos_embed has the reference's call signature; a 224^2 checkpoint loaded into a 288^2 model gives the
+    oracle's image tokens (S = 325, the geometry tools/seg_evaluation.py actually evaluates at)."""
+    from oracle import simseg_oracle as O
+    from simseg_b200 import seg
+    from simseg_b200.config import load_cfg
+    from simseg_b200.pipeline import PIPELINE
+    cfg = load_cfg("simseg.vit-s.yaml", ["model.image_encoder.pretrained=False", "model.text_encoder.pretrained=False",
+                                          "transforms.input_size=288"])
+    model = PIPELINE["clip"](cfg).to(cuda).eval()
+    sd = O.make_state_dict(384, 6, seed=0)                      # a 224^2 checkpoint: pos_embed (1, 197, 384)
+    key = "image_encoder.model.model.pos_embed"
+    vis = model.image_encoder.model.model
+    assert vis.patch_embed.num_patches == 324
+    same = seg.interpolate_pos_embed(model.state_dict()[key], vis)
+    assert same.shape == (1, 325, 384)                          # grids agree -> returned unchanged
+    new_pe = seg.interpolate_pos_embed(sd[key], vis)            # host tensor in, host tensor out
+    assert new_pe.shape == (1, 325, 384) and new_pe.device == sd[key].device
+    ref_pe = O.interpolate_pos_embed(sd[key], 324)
+    assert (new_pe - ref_pe).abs().max().item() < 1e-5
+    sd = dict(sd)
+    sd[key] = new_pe
+    model.load_state_dict(sd)
+    image = O.make_batch(2, 25, img_size=288, seed=11)["image"]
+    with torch.no_grad():
+        feat = model.forward_image_feature(image.to(cuda))
+    assert feat.shape == (2, 324, 384)
+    sd_ref = dict(sd)
+    sd_ref[key] = ref_pe
+    ref = O.vit_forward(sd_ref, image, 6, O.IMG_PREFIX)[:, 1:]
+    assert _cos_rows(feat.float().cpu().reshape(-1, 384), ref.reshape(-1, 384)) > 0.999
