@@ -6,12 +6,17 @@
 // once.  The class-text matrix ([C, E] bf16, C <= 256) is loaded once per CTA and stays resident in shared memory as
 // the B operand; the contraction runs on tcgen05 (128 x Cpad x 16 MMAs, fp32 accumulators in TMEM, two accumulator
 // stages) while four "norm" warps read the same smem stages to accumulate the row sums of squares, so the row
-// normalisation costs no extra HBM traffic.  The epilogue scales by 1/||patch||, takes the row argmax, transposes
-// 32x32 blocks through padded smem and stores 128-byte row segments (rows of sim are contiguous in HBM).
+// normalisation costs no extra HBM traffic.  The epilogue scales by 1/||patch||, takes the row argmax and writes the map:
+//   * C % 4 != 0 (171, 81, 21, 150 classes ...): rows of sim are not 16-byte aligned, but any 16 consecutive rows are one
+//     contiguous, 16-byte aligned range of 64*C bytes.  Each lane-quarter warp lays its rows out in shared memory exactly
+//     as they lie in HBM (row stride C words: conflict-free for odd C and C = 2 mod 4) and one bulk copy
+//     (cp.async.bulk.global.shared::cta) writes the range — no transposition, no per-row address arithmetic, full lines.
+//     Two passes of 16 rows per tile keep the staging at 64*C bytes per warp; the second pass re-reads TMEM.
+//   * C % 4 == 0: 32x32 blocks are transposed through padded smem and stored as 128-byte row segments.
 //
 // Persistent CTAs (one per SM, 14 warps):  warp 0 TMA producer | warp 1 MMA issuer | warps 2-5 row norms |
-// warps 6-13 epilogue (two per TMEM lane quarter, taking alternate 32-column chunks; the row argmax of the pair is
-// combined through shared memory).
+// warps 6-13 epilogue (transposing path: two per TMEM lane quarter, taking alternate 32-column chunks, the row argmax of
+// the pair is combined through shared memory; bulk path: warps 6-9 only, one per lane quarter).
 // Algorithmic HBM bytes per row: E*2 + C*4 + 4  (DESIGN.md).
 #include "common.cuh"
 #include "sm100.cuh"
@@ -31,6 +36,8 @@ constexpr int kPsMaxStages = 8;
 struct PatchSimParams {
   int64_t rows;
   int32_t C, E, npad, kblocks, stages, tiles, normalize;
+  int32_t bulk;            // 1: contiguous bulk-copy epilogue (C % 4 != 0), 0: transposing epilogue
+  int32_t staging_bytes;   // epilogue staging area (multiple of 128)
   uint32_t tmem_cols, acc_stride;
   float* sim;
   int32_t* argmax;
@@ -75,7 +82,7 @@ patch_sim_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_consta
   uint8_t* s_text = smem;
   uint8_t* s_ring = s_text + p.kblocks * text_kb_bytes;
   float* s_stage = reinterpret_cast<float*>(s_ring + p.stages * kPsStageBytes);
-  float* s_inv = s_stage + kPsStagingBytes / 4;                       // [2][128]
+  float* s_inv = s_stage + p.staging_bytes / 4;                       // [2][128]
   float* s_arg = s_inv + 2 * kPsBM;                                  // [4 quarters][32 rows][2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_arg + 4 * 64);
   uint64_t* full_bar = bars;                                         // [stages]  TMA -> MMA + norm (local data)
@@ -106,9 +113,9 @@ patch_sim_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 8);
+      mbar_init(&acc_empty[s], p.bulk ? 4 : 8);              // epilogue warps that take part
       mbar_init(&norm_full[s], 4);
-      mbar_init(&pair_empty[s], 16);
+      mbar_init(&pair_empty[s], p.bulk ? 8 : 16);
     }
     mbar_init(text_bar, 1);
     mbar_init(peer_text, 1);
@@ -241,8 +248,92 @@ patch_sim_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_consta
       if (lane == 0) mbar_arrive(&norm_full[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+  } else if (p.bulk) {
+    // =============================== epilogue, contiguous bulk stores (warps 6-9) ===============================
+    if (warp < 10) {
+      const int quarter = warp & 3;                           // TMEM lane quarter (rows quarter*32 .. +32 of the tile)
+      float* stg = s_stage + quarter * (16 * p.C);            // [16 rows][C] fp32, laid out as in HBM
+      float* my_row = stg + (lane & 15) * p.C;
+      const int row_in_tile = quarter * 32 + lane;
+      const int nchunks = (p.C + 31) >> 5;
+      const uint32_t r_pair_empty = (CTAS == 2) ? mapa_shared(smem_u32(&pair_empty[0]), 0) : 0u;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = first_tile; tile < p.tiles; tile += tile_stride) {
+        const int64_t m0 = static_cast<int64_t>(tile) * (kPsBM * CTAS) + static_cast<int64_t>(rank) * kPsBM;
+        const int64_t wrow0 = m0 + quarter * 32;              // first global row of this warp
+        mbar_wait(&norm_full[acc], acc_phase);
+        const float inv = s_inv[acc * kPsBM + row_in_tile];
+        mbar_wait(&acc_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + acc * p.acc_stride + (static_cast<uint32_t>(quarter * 32) << 16);
+        float best = -INFINITY;
+        int besti = 0;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+          const bool mine = (lane >> 4) == pass;              // lanes 0-15 stage their rows in pass 0, lanes 16-31 in pass 1
+          if (lane == 0) tma_store_wait_read<0>();            // the previous bulk copy has finished reading the staging rows
+          __syncwarp();
+          for (int c = 0; c < nchunks; ++c) {
+            const int c0 = c * 32;
+            uint32_t r[32];
+            tmem_ld_32x32(t_row + c0, r);
+            tmem_ld_wait();
+            if (pass == 1 && c == nchunks - 1) {
+              // the last TMEM read of this warp is in registers: hand the accumulator back before the stores
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                mbar_arrive(&acc_empty[acc]);
+                if (CTAS == 2) mbar_arrive_cluster(r_pair_empty + acc * 8);
+              }
+            }
+            if (c0 + 32 <= p.C) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float v = __uint_as_float(r[j]) * inv;
+                if (pass == 0 && v > best) { best = v; besti = c0 + j; }
+                if (mine) my_row[c0 + j] = v;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float v = __uint_as_float(r[j]) * inv;
+                if (c0 + j < p.C) {
+                  if (pass == 0 && v > best) { best = v; besti = c0 + j; }
+                  if (mine) my_row[c0 + j] = v;
+                }
+              }
+            }
+          }
+          const int64_t grow = wrow0 + pass * 16;
+          const int64_t left = p.rows - grow;
+          const int valid = left < 16 ? static_cast<int>(left) : 16;            // may be <= 0 in the ragged last tile
+          if (valid > 0) {
+            float* out = p.sim + grow * p.C;
+            const int n = valid * p.C;
+            if ((n & 3) == 0) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                bulk_store_1d(out, stg, static_cast<uint32_t>(n) * 4u);
+                tma_store_commit();
+              }
+            } else {
+              __syncwarp();                                   // ragged tail whose byte count is not a multiple of 16
+              for (int i = lane; i < n; i += 32) __stcs(out + i, stg[i]);
+            }
+          }
+          __syncwarp();
+        }
+        const int64_t rows_left = p.rows - wrow0;
+        if (p.argmax != nullptr && lane < rows_left) p.argmax[wrow0 + lane] = besti;
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (lane == 0) tma_store_wait<0>();
+    }
   } else {
-    // =============================== epilogue ===============================
+    // =============================== epilogue, transposing (C % 4 == 0) ===============================
     const int quarter = warp & 3;                             // TMEM lane quarter (rows quarter*32 .. +32 of the tile)
     const int half = (warp - 6) >> 2;                         // 0: even 32-column chunks, 1: odd chunks
     float* stg = s_stage + (warp - 6) * (32 * 33);
@@ -349,8 +440,11 @@ int patch_sim_fused_impl(Ctx* ctx, const void* patches, int64_t rows, int E, con
   p.tmem_cols = cols;
   p.sim = sim; p.argmax = argmax;
   const int kMaxSmem = 232448;
+  // contiguous bulk-copy epilogue whenever rows of the map are not 16-byte aligned (the staging then holds 4 x 16 rows)
+  p.bulk = (C % 4 != 0 && (reinterpret_cast<uintptr_t>(sim) & 15) == 0 && getenv("SIMSEG_PATCH_SIM_NO_BULK") == nullptr) ? 1 : 0;
+  p.staging_bytes = p.bulk ? ((4 * 16 * C * 4 + 127) / 128) * 128 : kPsStagingBytes;
   auto stages_for = [&](int ctas) {
-    const int fixed = 1024 + p.kblocks * (p.npad / ctas) * 128 + kPsStagingBytes + 2 * kPsBM * 4 + 1024 + 512;
+    const int fixed = 1024 + p.kblocks * (p.npad / ctas) * 128 + p.staging_bytes + 2 * kPsBM * 4 + 1024 + 512;
     int stages = (kMaxSmem - fixed) / kPsStageBytes;
     return stages > kPsMaxStages ? kPsMaxStages : stages;
   };
@@ -358,11 +452,18 @@ int patch_sim_fused_impl(Ctx* ctx, const void* patches, int64_t rows, int E, con
   const char* force = getenv("SIMSEG_PATCH_SIM_CTAS");
   int ctas = (stages_for(1) >= 5 || rows <= kPsBM) ? 1 : 2;
   if (force) ctas = atoi(force) == 2 ? 2 : 1;
+  if (p.bulk && stages_for(ctas) < 4) {
+    // many classes: the row-contiguous staging would starve the patch ring, keep the small transposing staging
+    p.bulk = 0;
+    p.staging_bytes = kPsStagingBytes;
+    ctas = (stages_for(1) >= 5 || rows <= kPsBM) ? 1 : 2;
+    if (force) ctas = atoi(force) == 2 ? 2 : 1;
+  }
   const int stages = stages_for(ctas);
   if (stages < 2) return SIMSEG_ERR_UNSUPPORTED;
   p.stages = stages;
   p.tiles = static_cast<int>(cdiv(rows, kPsBM * ctas));
-  const int smem_bytes = 1024 + p.kblocks * (p.npad / ctas) * 128 + kPsStagingBytes + 2 * kPsBM * 4 + 1024 + 512 + stages * kPsStageBytes;
+  const int smem_bytes = 1024 + p.kblocks * (p.npad / ctas) * 128 + p.staging_bytes + 2 * kPsBM * 4 + 1024 + 512 + stages * kPsStageBytes;
   CUtensorMap tp, tt;
   int rc = make_tmap(&tp, patches, 2, rows, E, E, 64, kPsBM);
   if (rc) return rc;
