@@ -386,8 +386,8 @@ def patch_sim_bench(hbm_peak, how):
             "batch64": {"value": 64 / (ms64 / 1e3), "unit": "maps/s", "ms_per_batch": ms64, "achieved_gbs": ach64,
                         "note": "BASELINE configs[3] batch: 21 MB per launch, launch/latency-bound"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                         "traffic": 1328.5e6, "traffic_source": "ncu --set full, dram__bytes_read+write per launch at batch 4096 "
-                                                               "(profiles/r01_ncu_patch_sim.txt); algorithmic 1374.4e6",
+                         "traffic": 1382.3e6, "traffic_source": "ncu --set full, dram__bytes_read+write per launch at batch 4096 "
+                                                               "(profiles/r01_ncu_patch_sim_v3.txt); algorithmic 1374.4e6",
                          "peak_source": how, "algorithmic_bytes_per_map": bytes_per_map}}
 
 

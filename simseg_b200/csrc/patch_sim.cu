@@ -11,12 +11,13 @@
 //     contiguous, 16-byte aligned range of 64*C bytes.  Each lane-quarter warp lays its rows out in shared memory exactly
 //     as they lie in HBM (row stride C words: conflict-free for odd C and C = 2 mod 4) and one bulk copy
 //     (cp.async.bulk.global.shared::cta) writes the range — no transposition, no per-row address arithmetic, full lines.
-//     Two passes of 16 rows per tile keep the staging at 64*C bytes per warp; the second pass re-reads TMEM.
-//   * C % 4 == 0: 32x32 blocks are transposed through padded smem and stored as 128-byte row segments.
+//     Two passes of 16 rows per tile keep the staging at 64*C bytes per lane quarter; the second pass re-reads TMEM.
+//     Selected for large maps with many classes (CTA-pair mode), where the transposing epilogue is the bottleneck.
+//   * otherwise: 32x32 blocks are transposed through padded smem and stored as 128-byte row segments.
 //
 // Persistent CTAs (one per SM, 14 warps):  warp 0 TMA producer | warp 1 MMA issuer | warps 2-5 row norms |
-// warps 6-13 epilogue (transposing path: two per TMEM lane quarter, taking alternate 32-column chunks, the row argmax of
-// the pair is combined through shared memory; bulk path: warps 6-9 only, one per lane quarter).
+// warps 6-13 epilogue (two per TMEM lane quarter, taking alternate 32-column chunks; the row argmax of the pair is
+// combined through shared memory).
 // Algorithmic HBM bytes per row: E*2 + C*4 + 4  (DESIGN.md).
 #include "common.cuh"
 #include "sm100.cuh"
@@ -113,9 +114,9 @@ patch_sim_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], p.bulk ? 4 : 8);              // epilogue warps that take part
+      mbar_init(&acc_empty[s], 8);
       mbar_init(&norm_full[s], 4);
-      mbar_init(&pair_empty[s], p.bulk ? 8 : 16);
+      mbar_init(&pair_empty[s], 16);
     }
     mbar_init(text_bar, 1);
     mbar_init(peer_text, 1);
@@ -249,89 +250,113 @@ patch_sim_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_consta
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (p.bulk) {
-    // =============================== epilogue, contiguous bulk stores (warps 6-9) ===============================
-    if (warp < 10) {
-      const int quarter = warp & 3;                           // TMEM lane quarter (rows quarter*32 .. +32 of the tile)
-      float* stg = s_stage + quarter * (16 * p.C);            // [16 rows][C] fp32, laid out as in HBM
-      float* my_row = stg + (lane & 15) * p.C;
-      const int row_in_tile = quarter * 32 + lane;
-      const int nchunks = (p.C + 31) >> 5;
-      const uint32_t r_pair_empty = (CTAS == 2) ? mapa_shared(smem_u32(&pair_empty[0]), 0) : 0u;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = first_tile; tile < p.tiles; tile += tile_stride) {
-        const int64_t m0 = static_cast<int64_t>(tile) * (kPsBM * CTAS) + static_cast<int64_t>(rank) * kPsBM;
-        const int64_t wrow0 = m0 + quarter * 32;              // first global row of this warp
-        mbar_wait(&norm_full[acc], acc_phase);
-        const float inv = s_inv[acc * kPsBM + row_in_tile];
-        mbar_wait(&acc_full[acc], acc_phase);
-        tc_fence_after();
-        const uint32_t t_row = tmem_base + acc * p.acc_stride + (static_cast<uint32_t>(quarter * 32) << 16);
-        float best = -INFINITY;
-        int besti = 0;
+    // =============================== epilogue, contiguous bulk stores ===============================
+    // The two warps of a TMEM lane quarter take alternate 32-column chunks and fill ONE [16 rows][C] staging block laid
+    // out as in HBM (two passes per tile: lanes 0-15 stage their rows in pass 0, lanes 16-31 in pass 1, which re-reads
+    // TMEM); warp `half == 0` then issues the bulk copy.  Named barrier 1+quarter (64 threads) orders the two warps.
+    // A bulk copy takes ~1.5 us to finish reading its block (measured: four passes of 8 rows through two alternating
+    // blocks ran 30 % slower), so the wait is paid twice per tile and hidden behind the next tile's MMAs; that needs
+    // many tiles per CTA, which is why the host selects this path for large maps only.
+    const int quarter = warp & 3;                             // TMEM lane quarter (rows quarter*32 .. +32 of the tile)
+    const int half = (warp - 6) >> 2;                         // 0: even 32-column chunks (and the stores), 1: odd chunks
+    float* stg = s_stage + quarter * (16 * p.C);              // [16 rows][C] fp32
+    float* my_row = stg + (lane & 15) * p.C;
+    float* s_best = s_arg + quarter * 64;                     // [32 rows][value, index bits] handed from half 1 to half 0
+    const int row_in_tile = quarter * 32 + lane;
+    const int nchunks = (p.C + 31) >> 5;
+    const uint32_t r_pair_empty = (CTAS == 2) ? mapa_shared(smem_u32(&pair_empty[0]), 0) : 0u;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = first_tile; tile < p.tiles; tile += tile_stride) {
+      const int64_t m0 = static_cast<int64_t>(tile) * (kPsBM * CTAS) + static_cast<int64_t>(rank) * kPsBM;
+      const int64_t wrow0 = m0 + quarter * 32;                // first global row of this quarter
+      mbar_wait(&norm_full[acc], acc_phase);
+      const float inv = s_inv[acc * kPsBM + row_in_tile];
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * p.acc_stride + (static_cast<uint32_t>(quarter * 32) << 16);
+      float best = -INFINITY;
+      int besti = 0;
 #pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-          const bool mine = (lane >> 4) == pass;              // lanes 0-15 stage their rows in pass 0, lanes 16-31 in pass 1
-          if (lane == 0) tma_store_wait_read<0>();            // the previous bulk copy has finished reading the staging rows
-          __syncwarp();
-          for (int c = 0; c < nchunks; ++c) {
-            const int c0 = c * 32;
-            uint32_t r[32];
-            tmem_ld_32x32(t_row + c0, r);
-            tmem_ld_wait();
-            if (pass == 1 && c == nchunks - 1) {
-              // the last TMEM read of this warp is in registers: hand the accumulator back before the stores
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) {
-                mbar_arrive(&acc_empty[acc]);
-                if (CTAS == 2) mbar_arrive_cluster(r_pair_empty + acc * 8);
-              }
+      for (int pass = 0; pass < 2; ++pass) {
+        const bool mine = (lane >> 4) == pass;
+        if (half == 0 && lane == 0) tma_store_wait_read<0>(); // the previous bulk copy has finished reading the block
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        bool released = pass == 0;
+        for (int c = half; c < nchunks; c += 2) {
+          const int c0 = c * 32;
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + c0, r);
+          tmem_ld_wait();
+          if (pass == 1 && c + 2 >= nchunks) {
+            // the last TMEM read of this warp is in registers: hand the accumulator back before the stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(&acc_empty[acc]);
+              if (CTAS == 2) mbar_arrive_cluster(r_pair_empty + acc * 8);
             }
-            if (c0 + 32 <= p.C) {
+            released = true;
+          }
+          if (c0 + 32 <= p.C) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float v = __uint_as_float(r[j]) * inv;
+            for (int j = 0; j < 32; ++j) {
+              const float v = __uint_as_float(r[j]) * inv;
+              if (pass == 0 && v > best) { best = v; besti = c0 + j; }
+              if (mine) my_row[c0 + j] = v;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = __uint_as_float(r[j]) * inv;
+              if (c0 + j < p.C) {
                 if (pass == 0 && v > best) { best = v; besti = c0 + j; }
                 if (mine) my_row[c0 + j] = v;
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float v = __uint_as_float(r[j]) * inv;
-                if (c0 + j < p.C) {
-                  if (pass == 0 && v > best) { best = v; besti = c0 + j; }
-                  if (mine) my_row[c0 + j] = v;
-                }
-              }
             }
           }
+        }
+        if (!released) {                                      // this warp had no chunk (C <= 32 and half == 1)
+          if (lane == 0) {
+            mbar_arrive(&acc_empty[acc]);
+            if (CTAS == 2) mbar_arrive_cluster(r_pair_empty + acc * 8);
+          }
+        }
+        if (pass == 1 && half == 1 && p.argmax != nullptr) {
+          s_best[2 * lane] = best;
+          s_best[2 * lane + 1] = __int_as_float(besti);
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");      // both warps' columns of this pass are staged
+        if (half == 0) {
           const int64_t grow = wrow0 + pass * 16;
           const int64_t left = p.rows - grow;
-          const int valid = left < 16 ? static_cast<int>(left) : 16;            // may be <= 0 in the ragged last tile
+          const int valid = left < 16 ? static_cast<int>(left) : 16;         // may be <= 0 in the ragged last tile
           if (valid > 0) {
             float* out = p.sim + grow * p.C;
             const int n = valid * p.C;
             if ((n & 3) == 0) {
-              fence_proxy_async_smem();
-              __syncwarp();
               if (lane == 0) {
                 bulk_store_1d(out, stg, static_cast<uint32_t>(n) * 4u);
                 tma_store_commit();
               }
-            } else {
-              __syncwarp();                                   // ragged tail whose byte count is not a multiple of 16
+            } else {                                          // ragged tail whose byte count is not a multiple of 16
               for (int i = lane; i < n; i += 32) __stcs(out + i, stg[i]);
+              __syncwarp();
             }
           }
-          __syncwarp();
         }
-        const int64_t rows_left = p.rows - wrow0;
-        if (p.argmax != nullptr && lane < rows_left) p.argmax[wrow0 + lane] = besti;
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (lane == 0) tma_store_wait<0>();
+      // first-max argmax over both halves of the row (half 1 handed its candidate over before the last barrier)
+      if (half == 0 && p.argmax != nullptr) {
+        const float ob = s_best[2 * lane];
+        const int oi = __float_as_int(s_best[2 * lane + 1]);
+        if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        if (lane < p.rows - wrow0) p.argmax[wrow0 + lane] = besti;
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (half == 0 && lane == 0) tma_store_wait<0>();
   } else {
     // =============================== epilogue, transposing (C % 4 == 0) ===============================
     const int quarter = warp & 3;                             // TMEM lane quarter (rows quarter*32 .. +32 of the tile)
@@ -440,9 +465,10 @@ int patch_sim_fused_impl(Ctx* ctx, const void* patches, int64_t rows, int E, con
   p.tmem_cols = cols;
   p.sim = sim; p.argmax = argmax;
   const int kMaxSmem = 232448;
-  // contiguous bulk-copy epilogue whenever rows of the map are not 16-byte aligned (the staging then holds 4 x 16 rows)
-  p.bulk = (C % 4 != 0 && (reinterpret_cast<uintptr_t>(sim) & 15) == 0 && getenv("SIMSEG_PATCH_SIM_NO_BULK") == nullptr) ? 1 : 0;
-  p.staging_bytes = p.bulk ? ((4 * 16 * C * 4 + 127) / 128) * 128 : kPsStagingBytes;
+  // contiguous bulk-copy epilogue: rows of the map not 16-byte aligned, many classes (CTA-pair mode, where the transposing
+  // epilogue limits the kernel) and enough tiles per CTA pair to hide the bulk copies' latency behind the next tiles
+  p.bulk = 0;
+  p.staging_bytes = kPsStagingBytes;
   auto stages_for = [&](int ctas) {
     const int fixed = 1024 + p.kblocks * (p.npad / ctas) * 128 + p.staging_bytes + 2 * kPsBM * 4 + 1024 + 512;
     int stages = (kMaxSmem - fixed) / kPsStageBytes;
@@ -452,12 +478,16 @@ int patch_sim_fused_impl(Ctx* ctx, const void* patches, int64_t rows, int E, con
   const char* force = getenv("SIMSEG_PATCH_SIM_CTAS");
   int ctas = (stages_for(1) >= 5 || rows <= kPsBM) ? 1 : 2;
   if (force) ctas = atoi(force) == 2 ? 2 : 1;
-  if (p.bulk && stages_for(ctas) < 4) {
-    // many classes: the row-contiguous staging would starve the patch ring, keep the small transposing staging
-    p.bulk = 0;
-    p.staging_bytes = kPsStagingBytes;
-    ctas = (stages_for(1) >= 5 || rows <= kPsBM) ? 1 : 2;
-    if (force) ctas = atoi(force) == 2 ? 2 : 1;
+  const char* force_bulk = getenv("SIMSEG_PATCH_SIM_BULK");            // 0 / 1 override the heuristic (tests, A/B timing)
+  bool want_bulk = ctas == 2 && cdiv(rows, kPsBM * 2) >= 8 * (ctx->num_sms / 2);
+  if (force_bulk) want_bulk = atoi(force_bulk) != 0;
+  if (want_bulk && C % 4 != 0 && (reinterpret_cast<uintptr_t>(sim) & 15) == 0) {
+    p.bulk = 1;
+    p.staging_bytes = ((4 * 16 * C * 4 + 127) / 128) * 128;
+    if (stages_for(ctas) < 4) {                                        // the row-contiguous staging would starve the patch ring
+      p.bulk = 0;
+      p.staging_bytes = kPsStagingBytes;
+    }
   }
   const int stages = stages_for(ctas);
   if (stages < 2) return SIMSEG_ERR_UNSUPPORTED;
