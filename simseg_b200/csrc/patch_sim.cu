@@ -44,31 +44,6 @@ struct PatchSimParams {
   int32_t* argmax;
 };
 
-// cluster-scope mbarrier ops for the CTA-pair variant (the peer's "data landed" signal is relayed to the leader)
-__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  const long long t0 = clock64();
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("simseg: cluster mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
-  }
-}
-
 // CTAS == 2: a CTA pair works on 256 patch rows; each CTA stages its own 128 rows and HALF of the class-text matrix
 // (so C = 171 leaves room for a 7-stage ring instead of 2), the leader issues 256 x Cpad x 16 MMAs (cta_group::2).
 // Each CTA's TMA loads signal its OWN barriers (its norm warps read the stages locally); the peer's otherwise idle
