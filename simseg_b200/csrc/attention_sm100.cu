@@ -203,6 +203,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     const int r = quarter * 32 + lane;         // row inside a tile
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const int sw = r & 7;
+    // drain staging: a thread owns a tile ROW, so storing straight from registers makes every store instruction touch 32
+    // different 128-byte lines (16 bytes each) — the L1 store path, not HBM, then paces the drains.  The warp's 32 rows x 64
+    // bytes go through a swizzled 2 KB block instead and leave as 8 rows x 64 contiguous bytes per instruction.
+    uint8_t* stg = reinterpret_cast<uint8_t*>(bars) + 256 + ew * 2048;
     uint32_t it = 0, g = 0, drains = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
       const int b = item / p.HG, h0 = (item - b * p.HG) * p.G;
@@ -214,6 +218,23 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       const int64_t base_b = static_cast<int64_t>(b) * p.sb;
       auto row_off = [&](int row) {                                   // (token, head) of a tile row -> q/k/v element offset
         return base_b + static_cast<int64_t>(row >> p.lg) * p.ss + static_cast<int64_t>(h0 + (row & gm)) * p.sh;
+      };
+      // w[16] = this thread's row (32 bf16 of d-columns half*32..) -> rows tile_row0 .. +32 of `dst`
+      auto store_rows = [&](const uint32_t (&w)[16], __nv_bfloat16* dst, int tile_row0) {
+        uint8_t* mine = stg + lane * 64;
+        const int swz = (lane >> 1) & 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(mine + ((j ^ swz) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = (lane >> 2) + 8 * i;
+          const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4));
+          const int row = tile_row0 + rr;
+          if (row < p.rows) *reinterpret_cast<uint4*>(dst + row_off(row) + half * 32 + (lane & 3) * 8) = val;
+        }
+        __syncwarp();
       };
       float Dv[2] = {0.f, 0.f}, L2v[2] = {0.f, 0.f};
       for (int kt = 0; kt < p.nkt; ++kt) {
@@ -321,24 +342,14 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(dkv_free);
-            const int key = kt * kTile + r;
-            if (key < p.rows) {
-              __nv_bfloat16* pv = p.dv + row_off(key) + half * 32;
-              __nv_bfloat16* pk = p.dk + row_off(key) + half * 32;
+            {
+              uint32_t w[16];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 u, w;
-                u.x = pack_bf16(__uint_as_float(a[8 * j]), __uint_as_float(a[8 * j + 1]));
-                u.y = pack_bf16(__uint_as_float(a[8 * j + 2]), __uint_as_float(a[8 * j + 3]));
-                u.z = pack_bf16(__uint_as_float(a[8 * j + 4]), __uint_as_float(a[8 * j + 5]));
-                u.w = pack_bf16(__uint_as_float(a[8 * j + 6]), __uint_as_float(a[8 * j + 7]));
-                w.x = pack_bf16(__uint_as_float(c2[8 * j]) * p.scale, __uint_as_float(c2[8 * j + 1]) * p.scale);
-                w.y = pack_bf16(__uint_as_float(c2[8 * j + 2]) * p.scale, __uint_as_float(c2[8 * j + 3]) * p.scale);
-                w.z = pack_bf16(__uint_as_float(c2[8 * j + 4]) * p.scale, __uint_as_float(c2[8 * j + 5]) * p.scale);
-                w.w = pack_bf16(__uint_as_float(c2[8 * j + 6]) * p.scale, __uint_as_float(c2[8 * j + 7]) * p.scale);
-                reinterpret_cast<uint4*>(pv)[j] = u;
-                reinterpret_cast<uint4*>(pk)[j] = w;
-              }
+              for (int j = 0; j < 16; ++j) w[j] = pack_bf16(__uint_as_float(a[2 * j]), __uint_as_float(a[2 * j + 1]));
+              store_rows(w, p.dv, kt * kTile + quarter * 32);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) w[j] = pack_bf16(__uint_as_float(c2[2 * j]) * p.scale, __uint_as_float(c2[2 * j + 1]) * p.scale);
+              store_rows(w, p.dk, kt * kTile + quarter * 32);
             }
             ++drains;
             if (kt == p.nkt - 1) {
@@ -364,16 +375,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(dq_free);
-              if (r < p.rows) {
-                uint4* pq = reinterpret_cast<uint4*>(p.dq + row_off(r) + half * 32);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) pq[j] = make_uint4(q0[4 * j], q0[4 * j + 1], q0[4 * j + 2], q0[4 * j + 3]);
-              }
-              if (p.nqt > 1 && kTile + r < p.rows) {
-                uint4* pq = reinterpret_cast<uint4*>(p.dq + row_off(kTile + r) + half * 32);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) pq[j] = make_uint4(q1[4 * j], q1[4 * j + 1], q1[4 * j + 2], q1[4 * j + 3]);
-              }
+              store_rows(q0, p.dq, quarter * 32);
+              if (p.nqt > 1) store_rows(q1, p.dq, kTile + quarter * 32);
             }
           }
         }
@@ -863,6 +866,7 @@ attention_fwd_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     const int quarter = warp & 3;              // TMEM lane quarter
     const int r = quarter * 32 + lane;         // row inside the tile
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    uint8_t* stg = reinterpret_cast<uint8_t*>(bars) + 256 + (warp - 2) * 4096;       // this warp's output staging block
     uint32_t u = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int b = item / p.HG, h0 = (item - b * p.HG) * p.G;
@@ -956,10 +960,13 @@ attention_fwd_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(o_free);                      // O is in registers: release it before the stores
-          if (q_ok) {
-            const float inv = 1.0f / sum;
-            const int tok = qrow >> p.lg, hh = h0 + (qrow & gm);
-            __nv_bfloat16* po = p.out + (static_cast<int64_t>(b) * p.S + tok) * (p.H * 64) + hh * 64;
+          {
+            // a thread owns a query ROW: stored straight from registers, every instruction would touch 32 different lines
+            // (16 bytes each).  The warp's 32 rows x 128 bytes go through a swizzled 4 KB block and leave as 4 full
+            // 128-byte rows per instruction.
+            const float inv = q_ok ? 1.0f / sum : 0.f;
+            uint8_t* mine = stg + lane * 128;
+            const int swz = lane & 7;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 a, c2;
@@ -971,10 +978,25 @@ attention_fwd_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
               c2.y = pack_bf16(__uint_as_float(o1[8 * j + 2]) * inv, __uint_as_float(o1[8 * j + 3]) * inv);
               c2.z = pack_bf16(__uint_as_float(o1[8 * j + 4]) * inv, __uint_as_float(o1[8 * j + 5]) * inv);
               c2.w = pack_bf16(__uint_as_float(o1[8 * j + 6]) * inv, __uint_as_float(o1[8 * j + 7]) * inv);
-              reinterpret_cast<uint4*>(po)[j] = a;
-              reinterpret_cast<uint4*>(po + 32)[j] = c2;
+              *reinterpret_cast<uint4*>(mine + ((j ^ swz) << 4)) = a;
+              *reinterpret_cast<uint4*>(mine + (((j + 4) ^ swz) << 4)) = c2;
             }
-            if (p.lse) p.lse[(static_cast<int64_t>(b) * p.H + hh) * p.S + tok] = (m + log2f(sum)) * 0.69314718055994531f;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = (lane >> 3) + 4 * i;
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+              const int row = qt * kTile + quarter * 32 + rr;
+              if (row < p.rows) {
+                const int tok2 = row >> p.lg, hh2 = h0 + (row & gm);
+                *reinterpret_cast<uint4*>(p.out + (static_cast<int64_t>(b) * p.S + tok2) * (p.H * 64) + hh2 * 64 + (lane & 7) * 8) = val;
+              }
+            }
+            __syncwarp();
+            if (q_ok && p.lse) {
+              const int tok = qrow >> p.lg, hh = h0 + (qrow & gm);
+              p.lse[(static_cast<int64_t>(b) * p.H + hh) * p.S + tok] = (m + log2f(sum)) * 0.69314718055994531f;
+            }
           }
         } else {
           tc_fence_before();
@@ -1061,7 +1083,7 @@ int attention_bwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v,
   p.key_len = key_len; p.lse = lse; p.out = reinterpret_cast<const __nv_bfloat16*>(out);
   p.dq = reinterpret_cast<__nv_bfloat16*>(dq); p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dv = reinterpret_cast<__nv_bfloat16*>(dv);
   p.sb = sb; p.ss = ss; p.sh = sh;
-  const int smem_bytes = 1024 + 8 * kTileBytes + 2 * kPBytes + 256;
+  const int smem_bytes = 1024 + 8 * kTileBytes + 2 * kPBytes + 256 + 8 * 2048;      // + per-warp drain staging
   static bool attr_set = false;
   if (!attr_set) {
     SIMSEG_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -1105,7 +1127,7 @@ int attention_fwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v,
   // the packed 4096 x 12 x 25 case); SIMSEG_ATTN_FWD=tc selects the shared-memory-P variant below
   const char* var = getenv("SIMSEG_ATTN_FWD");
   if (!(var != nullptr && var[0] == 't' && var[1] == 'c')) {
-    const int smem_ts = 1024 + 10 * kTileBytes + 256;
+    const int smem_ts = 1024 + 10 * kTileBytes + 256 + 8 * 4096;                  // + per-warp output staging
     static bool ts_set = false;
     if (!ts_set) {
       SIMSEG_CUDA(cudaFuncSetAttribute(attention_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ts));
