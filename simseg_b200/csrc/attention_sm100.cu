@@ -244,31 +244,43 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           const bool q_ok = qrow < p.rows;
           // D = rowsum(dO * O) and lse (log2 units) — once per (item, query tile).  The O row and lse are requested from
           // global here and first touched after the wait for S / dP below, which hides their latency.
+          // The loads are cooperative: 8 lanes fetch one 128-byte O row (4 full rows per instruction; a thread fetching ITS
+          // row would touch 32 lines per instruction), the partial dot products are reduced over those 8 lanes below and
+          // handed to the lane that owns the row.
           uint4 o[8];
           float l2raw = 0.f;
           if (kt == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = qt * kTile + quarter * 32 + (lane >> 3) + 4 * i;
+              if (row < p.rows) {
+                const int tok = row >> p.lg, hh = h0 + (row & gm);
+                o[i] = __ldg(reinterpret_cast<const uint4*>(p.out + (static_cast<int64_t>(b) * p.S + tok) * (p.H * 64) + hh * 64) + (lane & 7));
+              } else {
+                o[i] = make_uint4(0, 0, 0, 0);
+              }
+            }
             if (q_ok) {
               const int tok = qrow >> p.lg, hh = h0 + (qrow & gm);
-              const uint4* orow = reinterpret_cast<const uint4*>(p.out + (static_cast<int64_t>(b) * p.S + tok) * (p.H * 64) + hh * 64);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] = __ldg(orow + j);
               l2raw = __ldg(p.lse + (static_cast<int64_t>(b) * p.H + hh) * p.S + tok);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] = make_uint4(0, 0, 0, 0);
             }
           }
           mbar_wait(sdp_full, g & 1);                                  // implies the Q / dO tiles of this qt have landed
           tc_fence_after();
           if (kt == 0) {
             float d = 0.f;
-            const uint8_t* dorow = sdO + qt * kTileBytes + r * 128;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint4 a = *reinterpret_cast<const uint4*>(dorow + ((j ^ sw) << 4));
-              d += bf16_lo(a.x) * bf16_lo(o[j].x) + bf16_hi(a.x) * bf16_hi(o[j].x) + bf16_lo(a.y) * bf16_lo(o[j].y) +
-                   bf16_hi(a.y) * bf16_hi(o[j].y) + bf16_lo(a.z) * bf16_lo(o[j].z) + bf16_hi(a.z) * bf16_hi(o[j].z) +
-                   bf16_lo(a.w) * bf16_lo(o[j].w) + bf16_hi(a.w) * bf16_hi(o[j].w);
+            for (int i = 0; i < 8; ++i) {
+              const int rr = (lane >> 3) + 4 * i;                    // row of this warp's 32 that the lane helps with
+              const uint4 a = *reinterpret_cast<const uint4*>(sdO + qt * kTileBytes + (quarter * 32 + rr) * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+              float part = bf16_lo(a.x) * bf16_lo(o[i].x) + bf16_hi(a.x) * bf16_hi(o[i].x) + bf16_lo(a.y) * bf16_lo(o[i].y) +
+                           bf16_hi(a.y) * bf16_hi(o[i].y) + bf16_lo(a.z) * bf16_lo(o[i].z) + bf16_hi(a.z) * bf16_hi(o[i].z) +
+                           bf16_lo(a.w) * bf16_lo(o[i].w) + bf16_hi(a.w) * bf16_hi(o[i].w);
+              part += __shfl_xor_sync(0xffffffffu, part, 1);
+              part += __shfl_xor_sync(0xffffffffu, part, 2);
+              part += __shfl_xor_sync(0xffffffffu, part, 4);
+              const float mine = __shfl_sync(0xffffffffu, part, (lane & 3) * 8);      // row 4 i + (lane & 3)
+              if (i == (lane >> 2)) d = mine;
             }
             const float l2 = l2raw * 1.44269504088896341f;
             if (qt == 0) { Dv[0] = d; L2v[0] = l2; } else { Dv[1] = d; L2v[1] = l2; }
