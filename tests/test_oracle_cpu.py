@@ -145,3 +145,46 @@ def test_full_clip_vit_s_vs_reference_fixture():
         if key.startswith("grad_norm/"):
             g = sdg[key[len("grad_norm/"):]].grad
             assert abs(g.norm().item() - float(z[key])) <= 2e-3 * float(z[key]) + 1e-9, key
+
+
+def test_seg_glue_known_answers():
+    """The zero-shot segmentation glue of tools/seg_evaluation.py is a script (not importable: pydensecrf), so these
+    oracle functions cannot be pinned by running the reference; they are pinned by hand-worked cases of the rules the
+    script applies (lines cited in the oracle): class-embedding mean + renormalisation (:71-72), image-level scores,
+    top-k, threshold = mean + unbiased std (:119-124), the scan over the FIRST five of the top-k that skips ids 0 and 255
+    without replacing them and stops at the first score below the threshold (:131-147), nearest up-sampling and min-max
+    normalisation (:136-147)."""
+    # class embedding
+    pr = np.arange(24, dtype=np.float32).reshape(2, 3, 4) - 7.0
+    m = pr.mean(1)
+    want = m / np.linalg.norm(m, axis=-1, keepdims=True)
+    assert _max(O.zero_shot_class_embedding(torch.tensor(pr)), want) < 1e-6
+    # class selection: identity text matrix => scores = the image embedding itself
+    Cn = 300
+    text = torch.eye(Cn)
+    img = torch.linspace(-0.3, -0.2, Cn).repeat(2, 1)              # distinct, small background scores
+    for c, v in ((0, 0.9), (7, 0.8), (255, 0.7), (3, 0.6), (9, 0.5)):
+        img[:, c] = v
+    # (a) top-10: threshold lands between 0.8 and 0.6 -> class 0 skipped, 7 kept, 255 skipped, 3 below threshold: stop
+    scores, cand, thr = O.seg_select(img, text, 10)
+    top = np.sort(img[0].numpy())[::-1][:10]
+    assert abs(float(thr[0]) - (top.mean() + top.std(ddof=1))) < 1e-6
+    assert 0.6 < float(thr[0]) < 0.8
+    assert cand.tolist() == [[7, -1, -1, -1, -1]] * 2
+    assert _max(scores, img) == 0.0
+    # (b) top-50: low threshold -> all of the first five qualify, two of them are skipped ids: three candidates, in order
+    _, cand, thr = O.seg_select(img, text, 50)
+    assert float(thr[0]) < 0.5
+    assert cand.tolist() == [[7, 3, 9, -1, -1]] * 2
+    # (c) only the first max_cand of the top-k are ever looked at (class 11 ranks sixth here)
+    img2 = img.clone()
+    img2[:, 11] = 0.45
+    _, cand, _ = O.seg_select(img2, text, 50)
+    assert cand.tolist() == [[7, 3, 9, -1, -1]] * 2
+    # normalised, nearest-up-sampled maps
+    sim = torch.zeros(1, 4, 6)
+    sim[0, :, 2] = torch.tensor([1.0, 2.0, 3.0, 5.0])
+    maps = O.seg_norm_maps(sim, torch.tensor([[2, -1]], dtype=torch.int32), 2, 2, scale=2)
+    want = np.array([[0, 0, .25, .25], [0, 0, .25, .25], [.5, .5, 1, 1], [.5, .5, 1, 1]], dtype=np.float32)
+    assert maps.shape == (1, 2, 4, 4)
+    assert _max(maps[0, 0], want) < 1e-7 and float(maps[0, 1].abs().max()) == 0.0
