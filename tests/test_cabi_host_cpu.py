@@ -132,3 +132,20 @@ def test_model_forward_without_gpu_raises():
     model = PIPELINE["clip"](_cfg())
     with pytest.raises((SimsegError, AssertionError, RuntimeError)):
         model(O.make_batch(2, 25))
+
+
+def test_library_is_sm100a_tcgen05_and_tma_code(lib):
+    """The shipped library holds sm_100a cubins only, and the hot kernels really are tcgen05 / TMEM / TMA code
+    (SASS mnemonics per B200_PROFILING.md): a rebuild that silently lost them would still pass a parity test."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    so = os.path.join(ROOT, "simseg_b200", "lib", "libsimseg_b200.so")
+    elfs = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True, timeout=120).stdout
+    archs = set(re.findall(r"\.(sm_[0-9a-z]+)\.cubin", elfs))
+    assert archs == {"sm_100a"}, archs
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, timeout=300).stdout
+    for mnemonic, least in (("UTCHMMA", 100), ("UTMALDG", 100), ("UTMASTG", 20), ("LDTM", 50), ("UTCBAR", 20), ("UBLKCP", 1)):
+        assert sass.count(mnemonic) >= least, (mnemonic, sass.count(mnemonic))
+    assert "HMMA.16816" in sass            # the mma.sync attention kernels kept as the tested alternate (short sequences)
