@@ -300,9 +300,10 @@ def run_ours(a):
         dist.barrier()
     if rank == 0:
         if world == 1 and not a.no_extras:
-            v, dt, cores = cpu_pairs_per_s(a, a.cpu_sample)
+            v, dt, cores = cpu_pairs_per_s(a, a.cpu_sample, steps=4, warmup=1)      # ~10-15 s of host work
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"one {a.cpu_sample}-pair micro-batch fwd+bwd+AdamW of the same model, fp32, {dt:.1f} s"}
+                                    "sample": f"{a.cpu_sample}-pair micro-batches fwd+bwd+AdamW of the same model, fp32: mean of 4 "
+                                              f"steps after 1 warm-up, {dt:.1f} s per step"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
