@@ -310,6 +310,88 @@ def global_reduce_two_ranks():
     return out
 
 
+def seg_glue():
+    """Pin the zero-shot segmentation glue against the reference's OWN source lines.  ``tools/seg_evaluation.py`` is a
+    script that does not import here (pydensecrf, cv2 ...), so its code is read from /root/reference at run time and executed
+    piecewise: the whole ``zero_shot_classifier`` function (AST-extracted) with stub model / tokenizer objects, and the
+    per-image block of ``evaluate_benchmark`` from ``im_f_a = F.normalize(...)`` down to ``norm_attn = ...`` (the statements
+    before the CRF call), with a recording line appended to the candidate loop.  Nothing of it is copied into the repo."""
+    print("[zero-shot segmentation glue vs the lines of tools/seg_evaluation.py]")
+    import ast
+    import textwrap
+    src = open(os.path.join(REF, "tools", "seg_evaluation.py")).read()
+    out = {}
+    g = torch.Generator().manual_seed(21)
+
+    # ---- zero_shot_classifier(model, classnames, make_template, tokenizer, ENV)
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "zero_shot_classifier")
+    ns = {"torch": torch, "tqdm": lambda x: x}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "seg_evaluation.py", "exec"), ns)
+    Cn, P, T, E = 7, 5, 25, 64
+    prompt_emb = torch.randn(Cn, P, E, generator=g)
+
+    class _Text:                                   # stands in for model.module: returns the prepared prompt embeddings
+        def forward_text_feature(self, input_ids, attention_mask):
+            assert input_ids.shape == (P, T) and attention_mask.shape == (P, T)
+            return int(input_ids[0, 0])
+        def forward_text_project(self, feat, attention_mask):
+            return prompt_emb[feat].clone()
+    model = type("M", (), {"module": _Text()})()
+    tok = lambda texts, **kw: {"input_ids": [[int(texts[0])] * T for _ in texts], "attention_mask": [[1] * T for _ in texts]}
+    env = type("E", (), {"rank": "cpu"})()
+    cuda_attr = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self                    # the function ends with .cuda(); there is no GPU here
+    try:
+        ref_w = ns["zero_shot_classifier"](model, list(range(Cn)), lambda c: [str(c)] * P, tok, env)
+    finally:
+        torch.Tensor.cuda = cuda_attr
+    _check("zero_shot_classifier -> class embeddings", O.zero_shot_class_embedding(prompt_emb), ref_w, 1e-6)
+    out.update(zs_prompt=prompt_emb.numpy(), zs_weights=ref_w.numpy())
+
+    # ---- per-image block of evaluate_benchmark
+    lines = src.splitlines()
+    i0 = next(i for i, l in enumerate(lines) if "im_f_a = F.normalize(im_f_a" in l)
+    i1 = next(i for i, l in enumerate(lines) if "norm_attn = (attn_ai2at - min_value)" in l)
+    block = lines[i0:i1 + 1]
+    indent = len(lines[i1]) - len(lines[i1].lstrip())
+    block.append(" " * indent + "_rec.append((int(index), norm_attn.copy()))")
+    code = compile(textwrap.dedent("\n".join(block)), "seg_evaluation.py[block]", "exec")
+    B, hw, Cc, Ee = 4, 14, 300, 48
+    text = F.normalize(torch.randn(Cc, Ee, generator=g), dim=-1)
+    feats = torch.randn(B, hw * hw, Ee, generator=g)
+    favored = [[0, 7, 255, 3, 9, 11], [5, 6, 8, 10, 12, 13], [255, 0, 20, 21, 22, 23], [40]]
+    pooled = []
+    for b in range(B):
+        v = 0.05 * torch.randn(Ee, generator=g)
+        for rank_, c in enumerate(favored[b]):
+            v = v + (1.0 - 0.12 * rank_) * text[c]
+        pooled.append(F.normalize(v, dim=-1))
+    pooled = torch.stack(pooled)
+    for top_cls_num in (10, 50):
+        o_scores, o_cand, o_thr = O.seg_select(pooled, text, top_cls_num)
+        sim, _ = O.patch_text_sim(feats, text)
+        o_maps = O.seg_norm_maps(sim, o_cand, hw, hw, 16)
+        for b in range(B):
+            rec = []
+            nsb = {"torch": torch, "np": np, "F": F, "im_f_a": feats[b].clone(), "image_feature_pooled": pooled, "index": b,
+                   "label_text_feature": text, "top_cls_num": top_cls_num, "num_patch": hw, "patch_size": 16,
+                   "image_shape": (hw * 16, hw * 16), "seg_categories": list(range(Cc)), "_rec": rec}
+            exec(code, nsb)
+            _check(f"top{top_cls_num} img {b}: scores", o_scores[b], nsb["scores"], 1e-6)
+            _check(f"top{top_cls_num} img {b}: threshold", o_thr[b], nsb["threshold"], 1e-6)
+            ref_c = [c for c, _ in rec] + [-1] * (5 - len(rec))
+            assert o_cand[b].tolist() == ref_c, (o_cand[b].tolist(), ref_c)
+            for k, (_, m) in enumerate(rec):
+                _check(f"top{top_cls_num} img {b}: map {k}", o_maps[b, k], m, 1e-6)
+            out[f"sel{top_cls_num}_cand_{b}"] = np.array(ref_c, dtype=np.int32)
+            out[f"sel{top_cls_num}_thr_{b}"] = np.array(float(nsb["threshold"]), dtype=np.float32)
+            if rec:
+                out[f"sel{top_cls_num}_map0_{b}"] = rec[0][1][::16, ::16].astype(np.float32)
+        print(f"  top{top_cls_num}: candidates per image", [[c for c in o_cand[b].tolist() if c >= 0] for b in range(B)])
+    out.update(sel_text=text.numpy(), sel_pooled=pooled.numpy(), sel_feats=feats.numpy())
+    return out
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     os.makedirs(GOLD, exist_ok=True)
@@ -317,8 +399,12 @@ def main():
     encoders_cross_check()
     np.savez_compressed(os.path.join(GOLD, "global_reduce.npz"), **global_reduce_two_ranks())
     np.savez_compressed(os.path.join(GOLD, "clip_vit_s.npz"), **full_model())
+    np.savez_compressed(os.path.join(GOLD, "seg_glue.npz"), **seg_glue())
     print("golden vectors written to", GOLD)
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "seg_glue":          # regenerate this fixture alone
+        np.savez_compressed(os.path.join(GOLD, "seg_glue.npz"), **seg_glue())
+    else:
+        main()

@@ -28,9 +28,9 @@ GatherLayer semantics, EmbANN, full ``CLIPModel``), against
 implementation) and against the installed ``transformers`` ``BertModel``.  The
 outputs are committed under ``tests/golden/``.
 
-Parity unpinned: ``zero_shot_class_embedding``, ``seg_select`` and ``seg_norm_maps`` restate lines of
-``tools/seg_evaluation.py``, a script that cannot be imported here (``pydensecrf`` is absent); they are checked against
-hand-worked cases only (``tests/test_oracle_cpu.py::test_seg_glue_known_answers``).
+``zero_shot_class_embedding``, ``seg_select`` and ``seg_norm_maps`` restate lines of ``tools/seg_evaluation.py``, a
+script that cannot be imported here (``pydensecrf`` is absent): ``make_golden.py:seg_glue`` executes those lines read from
+the reference tree (``tests/golden/seg_glue.npz``).
 """
 from __future__ import annotations
 

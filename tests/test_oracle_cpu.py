@@ -148,9 +148,8 @@ def test_full_clip_vit_s_vs_reference_fixture():
 
 
 def test_seg_glue_known_answers():
-    """The zero-shot segmentation glue of tools/seg_evaluation.py is a script (not importable: pydensecrf), so these
-    oracle functions cannot be pinned by running the reference; they are pinned by hand-worked cases of the rules the
-    script applies (lines cited in the oracle): class-embedding mean + renormalisation (:71-72), image-level scores,
+    """Hand-worked cases of the rules tools/seg_evaluation.py applies (lines cited in the oracle; the outputs of the script's
+    own lines are checked in test_seg_glue_vs_reference_fixture): class-embedding mean + renormalisation (:71-72), image-level scores,
     top-k, threshold = mean + unbiased std (:119-124), the scan over the FIRST five of the top-k that skips ids 0 and 255
     without replacing them and stops at the first score below the threshold (:131-147), nearest up-sampling and min-max
     normalisation (:136-147)."""
@@ -188,3 +187,26 @@ def test_seg_glue_known_answers():
     want = np.array([[0, 0, .25, .25], [0, 0, .25, .25], [.5, .5, 1, 1], [.5, .5, 1, 1]], dtype=np.float32)
     assert maps.shape == (1, 2, 4, 4)
     assert _max(maps[0, 0], want) < 1e-7 and float(maps[0, 1].abs().max()) == 0.0
+
+
+def test_seg_glue_vs_reference_fixture():
+    """tests/golden/seg_glue.npz holds what the reference's OWN lines of tools/seg_evaluation.py produced
+    (oracle/make_golden.py:seg_glue executes ``zero_shot_classifier`` and the per-image block of ``evaluate_benchmark``
+    read from the reference tree): class embeddings, thresholds, the candidate lists (ids 0 / 255 skipped, stop below the
+    threshold, only the first five of the top-k) and the min-max normalised maps."""
+    z = np.load(os.path.join(GOLD, "seg_glue.npz"))
+    assert _max(O.zero_shot_class_embedding(torch.tensor(z["zs_prompt"])), z["zs_weights"]) < 1e-6
+    text, pooled, feats = torch.tensor(z["sel_text"]), torch.tensor(z["sel_pooled"]), torch.tensor(z["sel_feats"])
+    sim, _ = O.patch_text_sim(feats, text)
+    seen = set()
+    for k in (10, 50):
+        _, cand, thr = O.seg_select(pooled, text, k)
+        maps = O.seg_norm_maps(sim, cand, 14, 14, 16)
+        for b in range(pooled.shape[0]):
+            assert cand[b].tolist() == z[f"sel{k}_cand_{b}"].tolist()
+            assert abs(float(thr[b]) - float(z[f"sel{k}_thr_{b}"])) < 1e-6
+            if f"sel{k}_map0_{b}" in z:
+                assert _max(maps[b, 0, ::16, ::16], z[f"sel{k}_map0_{b}"]) < 1e-6
+                assert _max(maps[b, 0], O.upsample_nearest(torch.tensor(z[f"sel{k}_map0_{b}"]), 16)) < 1e-6
+            seen.update(c for c in cand[b].tolist() if c >= 0)
+    assert 0 not in seen and 255 not in seen and len(seen) >= 8
