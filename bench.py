@@ -225,6 +225,11 @@ def run_ours(a):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    # ---- dp_check (SURVEY §4 item 3 on hardware): every rank takes its slice of ONE fixed, seeded 64-pair global batch and
+    # runs forward + backward + gradient all-reduce (no optimizer step).  The global-mean loss and the norms of the reduced
+    # per-tower gradients must not depend on N: compare this block across the N = 1/2/4/8 lines.
+    dp = dp_check(trainer, dev, world, rank, a.seq_len)
+
     # ---- resident-input loop (value): inputs already in HBM
     for k in dev_bufs[0]:
         dev_bufs[0][k].copy_(host[0][k])
@@ -280,7 +285,8 @@ def run_ours(a):
                     "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
-            "loss": float(last.get("loss", float("nan")))}
+            "loss": float(last.get("loss", float("nan"))),
+            "dp_check": dp}
 
     if not a.no_extras:
         hbm, tf_sus, tf_burst, how = peaks()
@@ -289,13 +295,25 @@ def run_ours(a):
             line["roofline"] = roof
             line["train_flops"] = train_flops(a, m, ms_step, tf_sus)
             line["patch_sim"] = patch_sim_bench(hbm, how)
-            if world == 1:
-                del trainer, model
-                torch.cuda.empty_cache()
-                try:
-                    line["inference"] = inference_extras(hbm, tf_sus)
-                except Exception as e:                       # never lose the headline line to an extra
-                    line["inference"] = {"error": repr(e)[:200]}
+        del trainer, model, roof
+        torch.cuda.empty_cache()
+        if world == 8 and a.model == "vit-s" and a.global_batch == 4096:
+            # BASELINE configs[2]: ViT-B/16 contrastive pretrain, global batch 8192 on 8 GPUs (b = 1024 per GPU)
+            try:
+                cfg3 = train_leg("vit-b", 8192, a.seq_len, world, rank, dev, steps=4, warmup=3, tf_sus=tf_sus, how=how)
+            except Exception as e:
+                cfg3 = {"error": repr(e)[:300]}
+            if rank == 0:
+                line["cfg3_vit_b_gb8192"] = cfg3
+        if rank == 0 and world == 1:
+            try:
+                line["inference"] = inference_extras(hbm, tf_sus)
+            except Exception as e:                       # never lose the headline line to an extra
+                line["inference"] = {"error": repr(e)[:200]}
+            try:
+                line["cfg1_vit_s_b32_t77_c20"] = cfg1_forward(hbm, tf_sus)
+            except Exception as e:
+                line["cfg1_vit_s_b32_t77_c20"] = {"error": repr(e)[:200]}
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -309,12 +327,163 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def fwd_gflop_per_pair(m, T):
+    return m["fwd_gf_img"] + T * 12 * (24 * 768 ** 2 + 4 * T * 768) / 1e9 + (2 * 196 * m["dim"] * 512 + 2 * T * 768 * 512) / 1e9
+
+
 def train_flops(a, m, ms_step, tf_peak):
     """Whole-step algorithmic FLOPs per SURVEY.md §8d (train = 3x forward)."""
-    T = a.seq_len
-    fwd_pair = m["fwd_gf_img"] + T * 12 * (24 * 768 ** 2 + 4 * T * 768) / 1e9 + (2 * 196 * m["dim"] * 512 + 2 * T * 768 * 512) / 1e9
+    fwd_pair = fwd_gflop_per_pair(m, a.seq_len)
     tf = 3 * fwd_pair * a.global_batch / 1e3 / (ms_step / 1e3)
-    return {"gflop_per_pair_train": 3 * fwd_pair, "achieved_tflops_all_gpus": tf}
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return {"gflop_per_pair_train": 3 * fwd_pair, "achieved_tflops_all_gpus": tf,
+            "frac_of_sustained_bf16_per_gpu": tf / world / tf_peak}
+
+
+def dp_check(trainer, dev, world, rank, T, pairs=64):
+    import torch
+    import torch.distributed as dist
+    from simseg_b200.synthetic import make_batch
+    gb = make_batch(pairs, T, seed=4242)                         # the same global batch on every rank, whatever N is
+    b = pairs // world
+    mine = {k: v[rank * b:(rank + 1) * b].to(dev) for k, v in gb.items()}
+    loss, i2t, t2i = trainer.backward_only(mine)
+    stats = torch.stack([loss.float(), i2t.float(), t2i.float()])
+    if world > 1:
+        dist.all_reduce(stats)
+        stats /= world
+    torch.cuda.synchronize()
+    out = {"pairs": pairs, "loss": stats[0].item(), "i2t_acc": stats[1].item(), "t2i_acc": stats[2].item(),
+           "grad_norm": {k: f.flat.double().norm().item() for k, f in trainer.flat.items()},
+           "note": "global-mean loss and all-reduced gradient norms of one fixed 64-pair batch: must agree across N"}
+    trainer.zero_grad()
+    return out
+
+
+def train_leg(model_key, global_batch, T, world, rank, dev, steps, warmup, tf_sus, how):
+    """An extra timed training leg (its own model + Trainer), same timing rules as the headline: W warm-up steps, K steps
+    between barrier + synchronize, CUDA events, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from simseg_b200.config import load_cfg
+    from simseg_b200.pipeline import PIPELINE
+    from simseg_b200.synthetic import make_batch
+    from simseg_b200.train import Trainer
+    m = MODELS[model_key]
+    b = global_batch // world
+    cfg = load_cfg(m["yaml"], ["model.image_encoder.pretrained=False", "model.text_encoder.pretrained=False",
+                               "transforms.input_size=224", f"data.batch_size={global_batch}"])
+    torch.manual_seed(0)
+    model = PIPELINE["clip"](cfg).to(dev)
+    trainer = Trainer(model, cfg)
+    batch = {k: v.to(dev) for k, v in make_batch(b, T, seed=99 + rank).items()}
+    torch.cuda.reset_peak_memory_stats()
+    for _ in range(warmup):
+        out = trainer.step(batch)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = trainer.step(batch)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    roof = gemm_roofline(trainer, batch, tf_sus, how)
+    fwd = fwd_gflop_per_pair(m, T)
+    tf = 3 * fwd * global_batch / 1e3 / (ms / 1e3)
+    res = {"workload": f"ViT-{model_key[-1].upper()}/16 224x224 + BERT-base contrastive train step (fwd+bwd+AdamW), global batch "
+                       f"{global_batch}, {T} text tokens, bf16, dp{world} (per-GPU batch {b})",
+           "value": global_batch / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": warmup,
+           "loss": out[0].item(), "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+           "train_flops": {"gflop_per_pair_train": 3 * fwd, "achieved_tflops_all_gpus": tf,
+                           "frac_of_sustained_bf16_per_gpu": tf / world / tf_sus},
+           "roofline": roof}
+    del trainer, model, batch
+    torch.cuda.empty_cache()
+    return res
+
+
+def cfg1_forward(hbm_peak, tf_peak):
+    """BASELINE.json configs[0]: ViT-S/16 224x224 + 77-token text, batch 32, 20-class patch-text similarity map, one GPU,
+    forward only — image tower -> projection -> (32,196,20) map + argmax; text tower -> (32,512); image-text logits (32,32).
+    The reference's CPU path (oracle port, fp32, all host cores) is timed beside it on the same inputs."""
+    import torch
+    from oracle import simseg_oracle as O                         # cpu_baseline leg only
+    from simseg_b200 import ops
+    from simseg_b200.config import load_cfg
+    from simseg_b200.pipeline import PIPELINE
+    cfg = load_cfg("simseg.vit-s.yaml", ["model.image_encoder.pretrained=False", "model.text_encoder.pretrained=False",
+                                          "transforms.input_size=224"])
+    sd = O.make_state_dict(384, 6, seed=0)
+    model = PIPELINE["clip"](cfg).to("cuda").eval()
+    model.load_state_dict(sd)
+    hb = [O.make_batch(32, 77, seed=500 + i) for i in range(4)]
+    batches = [{k: v.cuda() for k, v in b.items()} for b in hb]
+    text = torch.nn.functional.normalize(torch.randn(20, 512, generator=torch.Generator().manual_seed(5)), dim=-1)
+    tdev = text.cuda()
+    state = {"i": 0, "out": None}
+
+    def step():
+        with torch.no_grad():
+            b = batches[state["i"] % 4]
+            state["i"] += 1
+            feat = model.forward_image_feature(b["image"])
+            img = model.forward_image_project(feat)
+            proj = model.image_projection(feat)
+            sim, am = ops.patch_text_sim(proj.contiguous(), tdev)
+            txt = model.forward_text_project(model.forward_text_feature(b["input_ids"], b["attention_mask"]), b["attention_mask"])
+            logits = (img @ txt.T) / 0.02                          # 32x32 glue, as mml_loss.py:73
+            state["out"] = (sim, am, logits)
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    # CPU port on the same batch (also a parity check of this very leg)
+    torch.set_num_threads(os.cpu_count())
+    b0 = hb[0]
+    state["i"] = 0
+    step()
+    torch.cuda.synchronize()
+    sim_g, am_g, logits_g = [t.cpu() for t in state["out"]]
+
+    def cpu():
+        with torch.no_grad():
+            tok = O.vit_forward(sd, b0["image"], 6, O.IMG_PREFIX)
+            rsim, ram = O.patch_text_sim(O.simple_projection(tok[:, 1:], sd["image_projection.linear.weight"]), text)
+            ie = O.image_embed(tok, sd["image_projection.linear.weight"], 5)
+            te = O.text_embed(O.bert_forward(sd, b0["input_ids"], b0["attention_mask"], 12, O.TXT_PREFIX),
+                              sd["text_projection.linear.weight"], b0["attention_mask"], 1)
+            return rsim, ram, ie @ te.T / 0.02
+    cpu()
+    t0 = time.perf_counter()
+    rsim, ram, rlog = cpu()
+    dt = time.perf_counter() - t0
+    top2 = rsim.topk(2, -1)[0]
+    safe = (top2[..., 0] - top2[..., 1]) > 2e-2
+    gf = 32 * (9.20 + 77 * 12 * (24 * 768 ** 2 + 4 * 77 * 768) / 1e9 + (2 * 2 * 196 * 384 * 512 + 2 * 77 * 768 * 512 + 2 * 196 * 512 * 20) / 1e9)
+    return {"workload": "ViT-S/16 224x224 + BERT-base 77 tokens, batch 32, forward only: 196x20 patch-text map + argmax, (32,512) "
+                        "embeddings, 32x32 logits", "ms_per_batch": ms, "maps_per_s": 32 / (ms / 1e3), "pairs_per_s": 32 / (ms / 1e3),
+            "achieved_tflops": gf / ms, "frac_of_sustained_bf16": gf / ms / tf_peak,
+            "cpu_baseline": {"ms_per_batch": dt * 1e3, "maps_per_s": 32 / dt, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "the same 32-pair batch, fp32, second of two runs"},
+            "parity_vs_cpu_port": {"sim_max_abs_diff": (sim_g - rsim).abs().max().item(),
+                                   "logits_max_abs_diff": (logits_g - rlog).abs().max().item(),
+                                   "argmax_equal_where_margin_gt_2e-2": bool(torch.equal(am_g.long()[safe], ram[safe])),
+                                   "argmax_mismatches_total": int((am_g.long() != ram).sum())},
+            "note": "latency-bound: ~600 kernel launches for 32 pairs; the host launch path, not the GPU, sets this number"}
 
 
 def gemm_roofline(trainer, batch, tf_peak, how):

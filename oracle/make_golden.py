@@ -74,6 +74,7 @@ def heads_and_loss():
     x_txt = torch.randn(6, 25, 768, generator=g)
     lens = torch.tensor([25, 8, 13, 1, 20, 9])
     mask = (torch.arange(25)[None] < lens[:, None]).long()
+    torch.manual_seed(7)                          # nn.Linear's default init draws from the global RNG: seed it so the fixture regenerates
     pi = SimpleProjection(None, 384, 512); pt = SimpleProjection(None, 768, 512)
     with torch.no_grad():
         r_pi = pi(x_img); r_pt = pt(x_txt)

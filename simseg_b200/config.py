@@ -47,8 +47,9 @@ def default_cfg() -> AttrDict:
         },
         "loss": {"name": "NCE", "global_reduce": True, "group_size": -1, "smoothing": 0.0,
                  "nce_loss": {"gather_backward": False}, "temperature": {"name": "constant", "value": 0.02}},
-        "optim": {"name": "torch.optim.AdamW", "param": {"betas": (0.9, 0.98), "eps": 1e-6, "weight_decay": 0.001},
-                  "lr": {"init": 1e-4}},
+        # tasks/clip/config.py:44-49 (the shipped YAMLs override weight_decay with 0.001, simseg.vit-s.yaml:36)
+        "optim": {"name": "torch.optim.AdamW", "param": {"betas": (0.9, 0.98), "eps": 1e-6, "weight_decay": 0.1},
+                  "lr": {"init": 1e-4}, "param_group_rules": {}, "grad_clip": {}},
         "data": {"batch_size": 1024},
         "dist": {"name": "torch", "fp16": True},
     })

@@ -35,30 +35,39 @@ def world_size() -> int:
     return dist.get_world_size() if is_initialized() else 1
 
 
+def _pg(group):
+    """``WORLD`` -> the default process group (None for torch.distributed); anything else is a ProcessGroup."""
+    return None if group is WORLD else group
+
+
 def all_gather_rows(x: Tensor, group) -> Tensor:
-    """(b,E) -> (W*b,E), rank-major row order (== torch.cat(all_gather(x)), utils/dist.py:338-342)."""
+    """(b,E) -> (W*b,E), rank-major row order (== torch.cat(all_gather(x)), utils/dist.py:338-342).
+    ``group``: None = no gather, ``WORLD`` = default process group, or a ``ProcessGroup`` (group-rank-major order)."""
     if group is None or world_size() == 1:
         return x
-    W = world_size()
+    pg = _pg(group)
+    W = dist.get_world_size(pg)
     out = torch.empty((W * x.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
     if x.is_cuda:
-        dist.all_gather_into_tensor(out, x.contiguous())
+        dist.all_gather_into_tensor(out, x.contiguous(), group=pg)
     else:                                            # gloo has no all_gather_into_tensor
         parts = list(out.chunk(W, 0))
-        dist.all_gather(parts, x.contiguous())
+        dist.all_gather(parts, x.contiguous(), group=pg)
     return out
 
 
 def reduce_scatter_rows(g: Tensor, r: int, b: int, group) -> Tensor:
-    """Sum the (W*b,E) gradients over ranks and return this rank's b rows (GatherLayer.backward semantics)."""
+    """Sum the (W*b,E) gradients over ranks and return this rank's b rows (GatherLayer.backward semantics);
+    ``r`` is the rank inside ``group``."""
     if group is None or world_size() == 1:
         return g
+    pg = _pg(group)
     if g.is_cuda:
         out = torch.empty((b,) + tuple(g.shape[1:]), device=g.device, dtype=g.dtype)
-        dist.reduce_scatter_tensor(out, g.contiguous(), op=dist.ReduceOp.SUM)
+        dist.reduce_scatter_tensor(out, g.contiguous(), op=dist.ReduceOp.SUM, group=pg)
         return out
     g = g.clone()                                    # gloo: all_reduce + slice (exactly the reference's path)
-    dist.all_reduce(g, op=dist.ReduceOp.SUM)
+    dist.all_reduce(g, op=dist.ReduceOp.SUM, group=pg)
     return g[r * b:(r + 1) * b]
 
 
@@ -67,6 +76,8 @@ class FlatGrads:
 
     def __init__(self, params: Iterable[torch.nn.Parameter]):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatGrads needs at least one trainable parameter (skip frozen groups)")
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, device=dev, dtype=torch.float32)

@@ -157,18 +157,30 @@ class _Shared:
         self.wc = towers.Bf16Weights()
         self.stash = {}          # side outputs of the autograd nodes (bf16 token copies)
         self.tower_done = None   # optional callback(name) fired when a tower's backward has been enqueued
+        # False (default): parameter gradients are handed back to autograd, so ``.grad`` accumulation, hooks and a torch
+        # DDP wrap (core/hooks/dist.py:48-51) behave as with the reference model.  True (set by train.Trainer): the wgrad
+        # kernels accumulate straight into ``param.grad`` (views of the Trainer's flat all-reduce buffers).
+        self.direct_grads = False
+
+
+def _once(ctx, what):
+    if getattr(ctx, "_simseg_consumed", False):
+        raise RuntimeError(f"simseg_b200: backward through {what} a second time — its saved activations are freed (and the "
+                           "InfoNCE workspace overwritten) by the first backward; retain_graph is not supported")
+    ctx._simseg_consumed = True
 
 
 class _VitFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, image, anchor, vit, shared, drop_cls, save):
+    def forward(ctx, image, vit, shared, drop_cls, save, *params):
         tok_f32, tok_bf16, sv = towers.vit_forward(vit, image, shared.wc, save)
-        ctx.vit, ctx.shared, ctx.sv, ctx.drop_cls = vit, shared, sv, drop_cls
+        ctx.vit, ctx.shared, ctx.sv, ctx.drop_cls, ctx.params = vit, shared, sv, drop_cls, params
         shared.stash["vit"] = tok_bf16               # full [B,S,D] bf16 copy for the projection GEMM
         return tok_f32[:, 1:] if drop_cls else tok_f32
 
     @staticmethod
     def backward(ctx, g):
+        _once(ctx, "the ViT tower")
         full = getattr(g, "_simseg_full", None)
         if full is None:                              # generic upstream: rebuild the [B,S,D] gradient
             if ctx.drop_cls:
@@ -176,28 +188,33 @@ class _VitFn(torch.autograd.Function):
                 full[:, 1:] = g
             else:
                 full = g.contiguous().float()
-        towers.vit_backward(ctx.vit, ctx.sv, full, ctx.shared.wc)
+        sink = None if ctx.shared.direct_grads else towers.ScratchGrads(ctx.params)
+        towers.vit_backward(ctx.vit, ctx.sv, full, ctx.shared.wc, grad_of=sink)
         ctx.sv = None
         if ctx.shared.tower_done is not None:
             ctx.shared.tower_done("vit")
-        return None, None, None, None, None, None
+        pg = sink.as_tuple() if sink is not None else (None,) * len(ctx.params)
+        return (None, None, None, None, None) + pg
 
 
 class _BertFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, input_ids, attention_mask, anchor, bert, shared, save):
+    def forward(ctx, input_ids, attention_mask, bert, shared, save, *params):
         h_f32, h_bf16, sv = towers.bert_forward(bert, input_ids, attention_mask, shared.wc, save)
-        ctx.bert, ctx.shared, ctx.sv = bert, shared, sv
+        ctx.bert, ctx.shared, ctx.sv, ctx.params = bert, shared, sv, params
         shared.stash["bert"] = h_bf16
         return h_f32
 
     @staticmethod
     def backward(ctx, g):
-        towers.bert_backward(ctx.bert, ctx.sv, g.contiguous(), ctx.shared.wc)
+        _once(ctx, "the BERT tower")
+        sink = None if ctx.shared.direct_grads else towers.ScratchGrads(ctx.params)
+        towers.bert_backward(ctx.bert, ctx.sv, g.contiguous(), ctx.shared.wc, grad_of=sink)
         ctx.sv = None
         if ctx.shared.tower_done is not None:
             ctx.shared.tower_done("bert")
-        return None, None, None, None, None, None
+        pg = sink.as_tuple() if sink is not None else (None,) * len(ctx.params)
+        return (None, None, None, None, None) + pg
 
 
 def _bf16_tokens(x: Tensor):
@@ -234,12 +251,17 @@ def _project_backward(ctx, gf_bf16: Tensor, xb: Tensor):
     B, S, D = xb.shape
     E = gf_bf16.shape[-1]
     w = ctx.weight
+    dw = None
     if w.requires_grad:
-        ops.linear_wgrad(gf_bf16.view(B * S, E), xb.view(B * S, D), towers._grad_of(w), accumulate=True)
+        if ctx.shared.direct_grads:
+            ops.linear_wgrad(gf_bf16.view(B * S, E), xb.view(B * S, D), towers.param_grad(w), accumulate=True)
+        else:                                         # handed back to autograd (AccumulateGrad / DDP hooks)
+            dw = torch.empty_like(w, dtype=torch.float32)
+            ops.linear_wgrad(gf_bf16.view(B * S, E), xb.view(B * S, D), dw, accumulate=False)
     dfull = ops.linear_dgrad(gf_bf16.view(B * S, E), ctx.shared.wc.get_t(w), out_dtype=torch.float32).view(B, S, D)
     dx = dfull[:, ctx.t0:ctx.t0 + ctx.nt]
     dx._simseg_full = dfull
-    return dx, None, None
+    return dx, dw, None
 
 
 class _ProjectPoolFn(torch.autograd.Function):
@@ -266,8 +288,8 @@ class _ProjectPoolFn(torch.autograd.Function):
         xb, pooled, idx = ctx.saved_tensors
         B, S, D = xb.shape
         gp = ops.topk_pool_l2norm_bwd(g.contiguous().float(), pooled, idx, S, ctx.k, l2norm=ctx.l2norm)
-        dx, _, _ = _project_backward(ctx, gp, xb)
-        return dx, None, None, None, None, None, None
+        dx, dw, _ = _project_backward(ctx, gp, xb)
+        return dx, dw, None, None, None, None, None
 
 
 class _NceFn(torch.autograd.Function):
@@ -288,6 +310,7 @@ class _NceFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gloss, _gacc):
+        _once(ctx, "the InfoNCE loss")                # infonce_bwd overwrites the saved cosine workspace in place
         f1, f2g, lse, cos = ctx.saved_tensors
         t = ctx.temperature
         dtemp = torch.zeros((), device=f1.device, dtype=torch.float32)
@@ -298,6 +321,48 @@ class _NceFn(torch.autograd.Function):
         df2 = sdist.reduce_scatter_rows(df2g, ctx.rank, ctx.b, ctx.group)
         gl = gloss.float()
         return df1 * gl, df2 * gl, (dtemp * gl).reshape(t.shape) if t.requires_grad else None, None, None, None
+
+
+# ======================================================================================= input validation
+# The reference gets these checks from PyTorch itself (nn.Embedding index errors, timm's PatchEmbed size assert, HF's
+# exact additive mask); raw-pointer kernels do not, so the host mirrors them.  SIMSEG_B200_CHECK_INPUTS=0 removes the one
+# device->host sync they cost (bench.py keeps them on).
+import os as _os
+
+_CHECK_INPUTS = _os.environ.get("SIMSEG_B200_CHECK_INPUTS", "1") != "0"
+
+
+def _check_image(x: Tensor, vit) -> None:
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError(f"image must be (B,3,H,W), got {tuple(x.shape)}")
+    if tuple(x.shape[-2:]) != tuple(vit.patch_embed.img_size):          # timm PatchEmbed asserts the same
+        raise ValueError(f"input image size {tuple(x.shape[-2:])} doesn't match model {tuple(vit.patch_embed.img_size)}")
+    if vit.pos_embed.shape[1] != vit.patch_embed.num_patches + 1:
+        raise ValueError("pos_embed does not match patch_embed.num_patches (interpolate_pos_embed the checkpoint first)")
+
+
+def _check_text(input_ids: Tensor, attention_mask: Tensor, bert) -> None:
+    emb = bert.embeddings
+    if input_ids.dim() != 2 or attention_mask.shape != input_ids.shape:
+        raise ValueError(f"input_ids / attention_mask must both be (B,T), got {tuple(input_ids.shape)} / {tuple(attention_mask.shape)}")
+    if input_ids.dtype != torch.int64 or attention_mask.dtype != torch.int64:
+        raise TypeError("input_ids and attention_mask must be int64 (as the reference's tokenizer output)")
+    T = input_ids.shape[1]
+    if T > emb.position_embeddings.weight.shape[0]:
+        raise IndexError(f"sequence length {T} exceeds max_position_embeddings {emb.position_embeddings.weight.shape[0]}")
+    if not _CHECK_INPUTS or input_ids.numel() == 0:
+        return
+    vocab = emb.word_embeddings.weight.shape[0]
+    m = attention_mask
+    prefix = (m[:, 1:] <= m[:, :-1]).all() & (m >= 0).all() & (m <= 1).all() if T > 1 else ((m >= 0).all() & (m <= 1).all())
+    ok = torch.stack([(input_ids >= 0).all() & (input_ids < vocab).all(), prefix, (m[:, 0] == 1).all()]).tolist()   # one sync
+    if not ok[0]:
+        raise IndexError(f"input_ids out of range [0, {vocab})")
+    if not ok[1]:
+        raise ValueError("attention_mask must be a left-aligned 0/1 prefix mask (ones, then zeros): the attention kernels take a "
+                         "per-caption key length; arbitrary masks are not on the B200 hot path")
+    if not ok[2]:
+        raise ValueError("attention_mask has an empty caption (no valid token)")
 
 
 # ======================================================================================= reference-named modules
@@ -399,8 +464,10 @@ class ViTModel(nn.Module):
         self._shared = shared
 
     def forward(self, x, drop_cls=False):
-        save = torch.is_grad_enabled() and self.model.cls_token.requires_grad
-        out = _VitFn.apply(x, self.model.cls_token, self.model, self._shared, drop_cls, save)
+        _check_image(x, self.model)
+        params = tuple(self.model.parameters())
+        save = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        out = _VitFn.apply(x, self.model, self._shared, drop_cls, save, *params)
         out._simseg_bf16 = self._shared.stash.pop("vit")        # rides along for forward_image_project
         out._simseg_tok_begin = 1 if drop_cls else 0
         return out
@@ -419,9 +486,10 @@ class HuggingFaceModel(nn.Module):
         self._shared = shared
 
     def forward(self, input_ids, attention_mask, **kwargs):
-        anchor = self.model.embeddings.LayerNorm.weight
-        save = torch.is_grad_enabled() and anchor.requires_grad
-        out = _BertFn.apply(input_ids, attention_mask, anchor, self.model, self._shared, save)
+        _check_text(input_ids, attention_mask, self.model)
+        params = tuple(self.model.parameters())
+        save = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        out = _BertFn.apply(input_ids, attention_mask, self.model, self._shared, save, *params)
         out._simseg_bf16 = self._shared.stash.pop("bert")
         out._simseg_tok_begin = 0
         return out
@@ -512,10 +580,12 @@ class CLIPModel(nn.Module):
         self._maybe_refresh()
         return self.text_encoder(input_ids=input_ids, attention_mask=attention_mask)   # [:, 0:, :] is the identity
 
-    def forward_text_project(self, text_features, attention_mask):
-        k = self.text_pool.k
-        if k > 1:
-            k = min(k, int(attention_mask.sum(1).min()))                  # pooling.py:61-63
+    def forward_text_project(self, text_features, attention_mask, k=None):
+        """``k`` (extension): the already clamped top-k; default = pooling.py:61-63's clamp over THIS batch."""
+        if k is None:
+            k = self.text_pool.k
+            if k > 1:
+                k = min(k, int(attention_mask.sum(1).min()))              # pooling.py:61-63
         return _ProjectPoolFn.apply(text_features, self.text_projection.linear.weight, attention_mask, k, True,
                                     self._shared, torch.is_grad_enabled())
 
@@ -555,4 +625,11 @@ def clip(cfg, rank: Optional[int] = None):
     return CLIPModel(cfg, sdist.rank() if rank is None else rank)
 
 
-PIPELINE: Dict[str, callable] = {"clip": clip}
+def clip_b200(cfg):
+    """The same entry under a name that does not collide with the reference's own ``clip``: the reference registry keys on
+    ``obj.__name__`` (``simseg/utils/registry.py:40-53``), so ``PIPELINE.register_obj(clip_b200)`` + ``model.name=clip_b200``
+    selects this implementation."""
+    return clip(cfg)
+
+
+PIPELINE: Dict[str, callable] = {"clip": clip, "clip_b200": clip_b200}

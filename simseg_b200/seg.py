@@ -17,14 +17,25 @@ Tensor = torch.Tensor
 def zero_shot_classifier(model, input_ids: Tensor, attention_mask: Tensor, chunk: int = 4096) -> Tensor:
     """``input_ids`` / ``attention_mask`` (C, P, T) — P prompt captions per class (the reference tokenises 80 templates per
     class, ``utils/prompt.py``) -> unit-norm class embeddings (C, 512).  All C*P captions go through the text tower in
-    batches of ``chunk`` instead of one 80-caption batch per class."""
+    batches of ``chunk`` instead of one 80-caption batch per class.  With ``text_k > 1`` the pooling clamps k to the
+    shortest caption of the batch it sees (``pooling.py:61-63``) and the reference's batch is ONE class, so the clamp is
+    taken per class here as well (classes with equal k share a launch)."""
     Cn, P, T = input_ids.shape
     ids, am = input_ids.reshape(Cn * P, T), attention_mask.reshape(Cn * P, T)
-    embs = []
-    for i in range(0, Cn * P, chunk):
-        feat = model.forward_text_feature(ids[i:i + chunk], am[i:i + chunk])
-        embs.append(model.forward_text_project(feat, am[i:i + chunk]).float())
-    return ops.seg_class_embed(torch.cat(embs).view(Cn, P, -1))
+    k0 = model.text_pool.k
+    if k0 > 1:
+        kc = torch.clamp(attention_mask.sum(-1).amin(1), max=k0).tolist()          # per-class k (one host read)
+    else:
+        kc = [k0] * Cn
+    out = torch.empty((Cn * P, model.text_projection.projection_dim), device=input_ids.device, dtype=torch.float32)
+    for k in sorted(set(kc)):
+        rows = torch.tensor([c for c in range(Cn) if kc[c] == k], device=ids.device)
+        sel = (rows[:, None] * P + torch.arange(P, device=ids.device)[None]).reshape(-1)
+        for i in range(0, sel.numel(), chunk):
+            j = sel[i:i + chunk]
+            feat = model.forward_text_feature(ids[j], am[j])
+            out[j] = model.forward_text_project(feat, am[j], k=k).float()
+    return ops.seg_class_embed(out.view(Cn, P, -1))
 
 
 @torch.no_grad()

@@ -2,10 +2,11 @@
 
 Precision contract (= the reference under bf16 autocast, ``simseg/tasks/clip/clip_runner.py:226-228``):
 fp32 master weights, bf16 tensor-core GEMM operands with fp32 accumulation, fp32 residual stream,
-fp32 LayerNorm / softmax statistics.  Activations that are cheap to rebuild (LayerNorm outputs, GELU
-outputs) are recomputed in backward instead of stored; what is stored per block is listed in ``_Blk``.
+fp32 LayerNorm / softmax statistics.  LayerNorm outputs and MLP pre-activations are stored for backward (bf16);
+GELU outputs are re-emitted by the dGELU epilogue of the fc2 dgrad GEMM; what is stored per block is listed in ``_Blk``.
 
-Gradients are written straight into ``param.grad`` (fp32, accumulated) by the wgrad GEMMs.
+Gradients are accumulated (fp32) by the wgrad GEMMs into the buffer ``grad_of(param)`` names: ``param.grad`` itself
+under ``train.Trainer`` (flat buffers), a scratch buffer handed back to autograd otherwise (``pipeline._VitFn``).
 """
 from __future__ import annotations
 
@@ -20,11 +21,36 @@ from ._lib import EPI_BIAS_GELU, EPI_DGELU, EPI_NONE
 Tensor = torch.Tensor
 
 
-def _grad_of(p: Tensor) -> Tensor:
+def param_grad(p: Tensor) -> Tensor:
     """fp32 gradient buffer of a parameter (allocated zeroed on first touch)."""
     if p.grad is None:
         p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
     return p.grad
+
+
+_grad_of = param_grad
+
+
+class ScratchGrads:
+    """Gradient sink for the autograd-visible path: one zeroed flat fp32 buffer with a view per trainable parameter.
+    The tower backward accumulates into the views; the autograd node returns them, so ``AccumulateGrad`` (and with it
+    torch DDP's bucket hooks, ``simseg/core/hooks/dist.py:48-51``) sees every parameter gradient."""
+
+    def __init__(self, params):
+        self.params = list(params)
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, device=self.params[0].device, dtype=torch.float32)
+        self.views, o = {}, 0
+        for p in self.params:
+            self.views[id(p)] = self.flat[o:o + p.numel()].view(p.shape)
+            o += p.numel()
+
+    def __call__(self, p: Tensor) -> Tensor:
+        return self.views[id(p)]
+
+    def as_tuple(self):
+        """One entry per parameter, in order; ``None`` for frozen ones."""
+        return tuple(self.views[id(p)] if p.requires_grad else None for p in self.params)
 
 
 class Bf16Weights:
@@ -240,8 +266,10 @@ def vit_forward(m, image: Tensor, wc: Bf16Weights, save: bool):
     return tok_f32.view(B, S, D), tok_bf16.view(B, S, D), sv
 
 
-def vit_backward(m, sv: VitSaved, dtok: Tensor, wc: Bf16Weights, dtok2: Optional[Tensor] = None):
-    """Backward of ``vit_forward``.  ``dtok`` [B,S,D] bf16|f32 (+ optional fp32 ``dtok2``) = dL/d tokens."""
+def vit_backward(m, sv: VitSaved, dtok: Tensor, wc: Bf16Weights, dtok2: Optional[Tensor] = None, grad_of=None):
+    """Backward of ``vit_forward``.  ``dtok`` [B,S,D] bf16|f32 (+ optional fp32 ``dtok2``) = dL/d tokens.
+    ``grad_of(param)`` names the fp32 buffer a parameter's gradient is ACCUMULATED into (default: ``param.grad``)."""
+    _grad_of = grad_of or param_grad
     B, S = sv.B, sv.S
     D, H = m.embed_dim, m.num_heads
     M = B * S
@@ -378,8 +406,10 @@ def bert_forward(m, input_ids: Tensor, attention_mask: Tensor, wc: Bf16Weights, 
     return hf.view(B, T, D), hb.view(B, T, D), sv
 
 
-def bert_backward(m, sv: BertSaved, dh: Tensor, wc: Bf16Weights, dh2: Optional[Tensor] = None):
-    """Backward of ``bert_forward``; ``dh`` [B,T,D] bf16|f32 (+ optional fp32 ``dh2``) = dL/d last_hidden_state."""
+def bert_backward(m, sv: BertSaved, dh: Tensor, wc: Bf16Weights, dh2: Optional[Tensor] = None, grad_of=None):
+    """Backward of ``bert_forward``; ``dh`` [B,T,D] bf16|f32 (+ optional fp32 ``dh2``) = dL/d last_hidden_state.
+    ``grad_of`` as in ``vit_backward``."""
+    _grad_of = grad_of or param_grad
     B, T = sv.B, sv.T
     emb = m.embeddings
     D = emb.word_embeddings.weight.shape[1]

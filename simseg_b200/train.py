@@ -4,14 +4,20 @@
 
 * gradients of each tower live in one flat fp32 buffer (``dist.FlatGrads``); its mean all-reduce is enqueued the
   moment that tower's backward has been issued, so it overlaps the other tower's backward over NVLink;
-* the optimizer is the one the YAML names (``optim.name: torch.optim.AdamW``) — host-side PyTorch, fused kernel;
+* the optimizer is the one the YAML names (``optim.name``, e.g. ``torch.optim.AdamW``) with the reference's grouping
+  rules (``tasks/clip/hooks/optimizer.py:18-36``: base lr / weight decay, per-regex overrides from
+  ``optim.param_group_rules``; groups with equal hyper-parameters are merged so the fused kernel sees few groups) and
+  ``optim.grad_clip`` (``core/hooks/optimizer.py:40-49``).  LR schedules stay with the caller (control plane);
 * optional micro-batching with an embedding cache (the reference's BSGS idea, ``tasks/clip/clip_bsgs_runner.py:
   309-451``): pass 1 embeds micro-batches without saving activations, the loss and the embedding gradients are
   computed on the full (gathered) batch, pass 2 re-runs each micro-batch with activations and back-propagates the
-  cached embedding gradient.  Mathematically identical to the single pass; trades 1 extra forward for memory.
+  cached embedding gradient.  Mathematically identical to the single pass (the text top-k clamp of
+  ``pooling.py:61-63`` is taken over the whole batch, as the single pass does); trades 1 extra forward for memory.
 """
 from __future__ import annotations
 
+import importlib
+import re
 from typing import Dict, Optional
 
 import torch
@@ -22,28 +28,61 @@ from .pipeline import CLIPModel
 Tensor = torch.Tensor
 
 
+def grouped_parameters(model: torch.nn.Module, cfg):
+    """``ClipOptimizerHook.get_optimizer_grouped_parameters`` (``tasks/clip/hooks/optimizer.py:18-36``); parameters
+    whose group settings are equal share one group."""
+    base = {"lr": cfg.optim.lr.init, "weight_decay": cfg.optim.param["weight_decay"]}
+    rules = list((cfg.optim.get("param_group_rules") or {}).values())
+    merged: Dict[tuple, dict] = {}
+    for key, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        g = dict(base)
+        for rule in rules:
+            if re.search(rule["regex"], key):
+                g.update(rule.get("param", {}))
+        k = tuple(sorted(g.items()))
+        merged.setdefault(k, {**g, "params": []})["params"].append(p)
+    return list(merged.values())
+
+
+def build_optimizer(model: torch.nn.Module, cfg) -> torch.optim.Optimizer:
+    """``optim.name`` is a dotted class path (``core/hooks/optimizer.py:21-28`` evaluates it the same way)."""
+    mod, _, cls = str(cfg.optim.name).rpartition(".")
+    ctor = getattr(importlib.import_module(mod or "torch.optim"), cls)
+    kw = {k: (tuple(v) if isinstance(v, list) else v) for k, v in dict(cfg.optim.param).items()}
+    kw.pop("weight_decay", None)                      # carried per group
+    if ctor in (torch.optim.AdamW, torch.optim.Adam, torch.optim.SGD):
+        kw.setdefault("fused", True)
+    return ctor(grouped_parameters(model, cfg), **kw)
+
+
 class Trainer:
     def __init__(self, model: CLIPModel, cfg, micro_batch: Optional[int] = None):
         self.model, self.cfg, self.micro_batch = model, cfg, micro_batch
         vit = list(model.image_encoder.parameters())
         bert = list(model.text_encoder.parameters())
         heads = [p for n, p in model.named_parameters() if not n.startswith(("image_encoder.", "text_encoder."))]
-        self.flat = {"vit": sdist.FlatGrads(vit), "bert": sdist.FlatGrads(bert), "heads": sdist.FlatGrads(heads)}
+        # a frozen tower (image_encoder.trainable / text_encoder.trainable = False) simply has no buffer
+        self.flat = {name: sdist.FlatGrads(ps) for name, ps in (("vit", vit), ("bert", bert), ("heads", heads))
+                     if any(p.requires_grad for p in ps)}
         model._shared.tower_done = self._tower_done
-        p = cfg.optim.param
-        self.opt = torch.optim.AdamW(model.parameters(), lr=cfg.optim.lr.init, betas=tuple(p.betas), eps=p.eps,
-                                     weight_decay=p.weight_decay, fused=True)
+        model._shared.direct_grads = True             # wgrad kernels accumulate straight into the flat buffers
+        self.opt = build_optimizer(model, cfg)
+        gc = cfg.optim.get("grad_clip") or {}
+        self.grad_clip = dict(gc) if len(gc) else None
         self._defer_reduce = False
 
     def _tower_done(self, name: str):
-        if not self._defer_reduce:
+        if not self._defer_reduce and name in self.flat:
             self.flat[name].all_reduce_async()
 
     def zero_grad(self):
         for f in self.flat.values():
             f.zero()
 
-    def step(self, batch: Dict[str, Tensor]):
+    def backward_only(self, batch: Dict[str, Tensor]):
+        """Forward + backward + gradient all-reduce, no optimizer step (tests, ``bench.py`` ``dp_check``)."""
         self.zero_grad()
         B = batch["image"].shape[0]
         if self.micro_batch and self.micro_batch < B:
@@ -53,9 +92,16 @@ class Trainer:
             loss = loss_dict["nce_loss"]
             loss.backward()
             out = (loss.detach(), i2t, t2i)
-        self.flat["heads"].all_reduce_async()
+        if "heads" in self.flat:
+            self.flat["heads"].all_reduce_async()
         for f in self.flat.values():
             f.wait()
+        return out
+
+    def step(self, batch: Dict[str, Tensor]):
+        out = self.backward_only(batch)
+        if self.grad_clip is not None:
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), **self.grad_clip)
         self.opt.step()
         return out
 
@@ -64,8 +110,19 @@ class Trainer:
         m, mb = self.model, self.micro_batch
         B = batch["image"].shape[0]
         chunks = [slice(i, min(i + mb, B)) for i in range(0, B, mb)]
+        # pooling.py:61-63 clamps k to the shortest caption of the BATCH: fix it once for all micro-batches
+        tk = m.text_pool.k
+        if tk > 1:
+            tk = min(tk, int(batch["attention_mask"].sum(1).min()))
+
+        def embed(c):
+            sub = {k: v[c] for k, v in batch.items()}
+            ie = m.forward_image_project(m.forward_image_feature(sub["image"]))
+            te = m.forward_text_project(m.forward_text_feature(sub["input_ids"], sub["attention_mask"]),
+                                        sub["attention_mask"], k=tk)
+            return ie, te
         with torch.no_grad():
-            embs = [m({k: v[c] for k, v in batch.items()}, embeddings="all") for c in chunks]
+            embs = [embed(c) for c in chunks]
         img = torch.cat([e[0] for e in embs]).requires_grad_(True)
         txt = torch.cat([e[1] for e in embs]).requires_grad_(True)
         loss_dict, i2t, t2i = m.forward_loss(img, txt)
@@ -76,7 +133,7 @@ class Trainer:
             for n, c in enumerate(chunks):
                 if n == len(chunks) - 1:
                     self._defer_reduce = False            # the last micro-batch completes the tower gradients
-                ie, te = m({k: v[c] for k, v in batch.items()}, embeddings="all")
+                ie, te = embed(c)
                 torch.autograd.backward([ie, te], [img.grad[c], txt.grad[c]])
         finally:
             self._defer_reduce = False

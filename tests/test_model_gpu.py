@@ -233,3 +233,45 @@ def test_clip_vit_b_forward_backward_and_seg_map_vs_oracle(cuda):
     ref_i, ref_t = O.clip_embeddings(sd, batch, 12) if hasattr(O, "clip_embeddings") else (None, None)
     if ref_i is not None:
         assert _cos(img_e.cpu(), ref_i) > 0.999 and _cos(txt_e.cpu(), ref_t) > 0.999
+
+
+def test_clip_vit_s_77_token_captions_vs_oracle(cuda):
+    """BASELINE configs[0] geometry at model level: 77-token captions (ragged lengths 8..77), ViT-S/16, 20-class map —
+    embeddings, image-text logits (1e-2 bf16 bar on cosines x 1/0.02 is the loss bar 2e-2 used elsewhere), loss and a
+    sample of BERT gradients (the T = 77 attention path packs fewer captions per tile than T = 25)."""
+    from oracle import simseg_oracle as O
+    from simseg_b200 import ops
+    model, _ = _build(cuda)
+    sd = O.make_state_dict(384, 6, seed=0)
+    model.load_state_dict(sd, strict=True)
+    batch = O.make_batch(6, 77, seed=2024)
+    batch["attention_mask"][0] = 1                                            # one full-length caption
+    gb = {k: v.to(cuda) for k, v in batch.items()}
+    with torch.no_grad():
+        img_e, txt_e = model(gb, embeddings="all")
+        tfeat = model.forward_text_feature(gb["input_ids"], gb["attention_mask"])
+        proj = model.image_projection(model.forward_image_feature(gb["image"]))
+    ref_i, ref_t = O.clip_embeddings(sd, batch, 6)
+    ref_tok = O.bert_forward(sd, batch["input_ids"], batch["attention_mask"], 12, O.TXT_PREFIX)
+    assert tfeat.shape == (6, 77, 768)
+    valid = batch["attention_mask"].bool()
+    assert (tfeat.cpu()[valid] - ref_tok[valid]).abs().max().item() < 0.1     # LayerNorm-ed hidden states, values ~ +-3
+    assert _cos(img_e.cpu(), ref_i) > 0.9995 and _cos(txt_e.cpu(), ref_t) > 0.9995
+    assert (txt_e.cpu() - ref_t).abs().max().item() < 4e-3
+    cos_ours, cos_ref = img_e.cpu() @ txt_e.cpu().T, ref_i @ ref_t.T
+    assert (cos_ours - cos_ref).abs().max().item() < 1e-2
+    text = torch.nn.functional.normalize(torch.randn(20, 512, generator=torch.Generator().manual_seed(1)), dim=-1)
+    sim, am = ops.patch_text_sim(proj.contiguous(), text.to(cuda))
+    tok = O.vit_forward(sd, batch["image"], 6, O.IMG_PREFIX)
+    ref_sim, _ = O.patch_text_sim(O.simple_projection(tok[:, 1:], sd["image_projection.linear.weight"]), text)
+    assert (sim.cpu() - ref_sim).abs().max().item() < 1e-2
+    model.zero_grad(set_to_none=True)
+    loss = model(gb)[0]["nce_loss"]
+    loss.backward()
+    torch.cuda.synchronize()
+    l_o, rows = _grad_table(model, sd, batch, 6)
+    assert abs(loss.item() - l_o) < 2e-2
+    txt_rows = [r for r in rows if r[0].startswith("text_") and r[3] > 1e-6]
+    assert len(txt_rows) > 150
+    cs = sorted(r[1] for r in txt_rows)
+    assert cs[len(cs) // 20] > 0.97, cs[:8]
