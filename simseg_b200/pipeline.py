@@ -10,6 +10,7 @@ sees five coarse ``torch.autograd.Function`` nodes whose backward passes are han
 """
 from __future__ import annotations
 
+import weakref
 from typing import Dict, Optional
 
 import numpy as np
@@ -150,11 +151,28 @@ class BertModel(nn.Module):
 
 
 # ======================================================================================= autograd nodes
+_LIVE_SHARED = weakref.WeakSet()
+
+
+def _after_any_optimizer_step(optimizer, args, kwargs):
+    """Global optimizer post-step hook: every live model's bf16 weight copies are stale now.  Needed because fused
+    optimizers (``torch.optim.AdamW(fused=True)``) update parameters without bumping ``Tensor._version``, which is what
+    ``CLIPModel._maybe_refresh`` watches for plain in-place updates and ``load_state_dict``."""
+    for sh in list(_LIVE_SHARED):
+        sh.wc.clear()
+
+
+from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_post_hook  # noqa: E402
+
+_reg_post_hook(_after_any_optimizer_step)
+
+
 class _Shared:
     """Per-model scratch shared by the autograd nodes of one step (bf16 weight cache)."""
 
     def __init__(self):
         self.wc = towers.Bf16Weights()
+        _LIVE_SHARED.add(self)
         self.stash = {}          # side outputs of the autograd nodes (bf16 token copies)
         self.tower_done = None   # optional callback(name) fired when a tower's backward has been enqueued
         # False (default): parameter gradients are handed back to autograd, so ``.grad`` accumulation, hooks and a torch

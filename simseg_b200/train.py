@@ -103,6 +103,7 @@ class Trainer:
         if self.grad_clip is not None:
             torch.nn.utils.clip_grad_norm_(self.model.parameters(), **self.grad_clip)
         self.opt.step()
+        self.model.new_step()                         # the bf16 weight copies are re-cast (one launch) on next use
         return out
 
     # ---- two-pass micro-batched step with an embedding cache ---------------------------------

