@@ -564,7 +564,7 @@ def patch_sim_bench(hbm_peak, how):
 def inference_extras(hbm_peak, tf_peak):
     """BASELINE.json configs[3] and configs[4] on one GPU (forward only, synthetic inputs, seeded random-init weights):
     ViT-B/16 seg inference (batch 64 -> 196 x 171 map per image, encoder + projection + map) and the 5k x 25k all-pairs
-    retrieval similarity + first-match ranks."""
+    retrieval ranks (fused tensor-core path)."""
     import torch
     from simseg_b200 import ops
     from simseg_b200.config import load_cfg
@@ -612,15 +612,27 @@ def inference_extras(hbm_peak, tf_peak):
     rg = torch.arange(25000, device="cuda", dtype=torch.int64) // 5
     holder = {}
 
-    def retr():
-        holder["sim"] = ops.allpairs_sim(left, right)
-        holder["rank"] = ops.retrieval_rank(holder["sim"], lg, rg)
-    ms = t_ms(retr, 5, warm=2)
-    by = (5000 + 25000) * 512 * 4 + 2 * 5000 * 25000 * 4
-    out["retrieval_5k_x_25k"] = {"workload": "5000 x 25000 all-pairs cosine (exact fp32 products) + first-match ranks", "ms": ms,
-                                 "value": 5000 * 25000 / (ms / 1e3), "unit": "pairs scored/s",
-                                 "achieved_gbs": by / (ms / 1e3) / 1e9, "frac_of_hbm": by / (ms / 1e3) / 1e9 / hbm_peak,
-                                 "achieved_tflops_fp32": 2.0 * 5000 * 25000 * 512 / (ms / 1e3) / 1e12}
+    def retr():                                      # both directions, as tools/retrieval_evaluation.py evaluates them
+        holder["i2t"] = ops.retrieval_rank_fused(left, right, lg, rg)
+        holder["t2i"] = ops.retrieval_rank_fused(right, left, rg, lg)
+    ms = t_ms(retr, 10, warm=3)
+    fl = 2 * 2 * 2.0 * 5000 * 25000 * 512 * 3        # 2 directions x (best-match pass ~ +5 % not counted, rank pass) x 3 split products
+    by = 2 * (5000 + 25000) * 512 * (4 + 4)          # fp32 read + bf16 hi/lo written, per direction (scores never reach HBM)
+
+    def retr_simt():
+        s = ops.allpairs_sim(left, right)
+        holder["simt"] = ops.retrieval_rank(s, lg, rg)
+    ms_simt = t_ms(retr_simt, 3, warm=1)
+    agree = (holder["simt"] == holder["i2t"]).float().mean().item()
+    out["retrieval_5k_x_25k"] = {"workload": "5000 x 25000 all-pairs cosine + first-match ranks, BOTH directions, split-bf16 tcgen05 "
+                                             "products (fp32-grade), scores consumed in the GEMM epilogue (never written)",
+                                 "ms": ms, "ms_per_direction": ms / 2, "value": 2 * 5000 * 25000 / (ms / 1e3), "unit": "pairs scored/s",
+                                 "achieved_tflops_bf16": fl / 2 / (ms / 1e3) / 1e12,
+                                 "frac_of_sustained_bf16": fl / 2 / (ms / 1e3) / 1e12 / tf_peak,
+                                 "hbm_bytes_algorithmic": by, "r1_i2t": (holder["i2t"] == 0).float().mean().item(),
+                                 "simt_fp32_one_direction_ms": ms_simt, "rank_agreement_with_simt_fp32": agree,
+                                 "note": "tensor-bound: 2 x 5000 x 25000 x 512 MACs x 3 products per direction = 384 GFLOP -> 0.27 ms at "
+                                         "the sustained bf16 peak; round 1 (fp32 SIMT GEMM + 500 MB matrix): 3.5 ms per direction"}
     return out
 
 

@@ -195,6 +195,21 @@ int simseg_infonce_bwd(simseg_ctx* ctx, const float* feat1, const float* feat2g,
                        const float* temperature, int row_offset, int precision, const float* lse, float grad_scale,
                        float* cos_ws, float* dfeat1, float* dfeat2g, float* dtemp, void* stream);
 
+/* The same loss on the tcgen05 tensor cores at fp32-grade accuracy, with the [b,Bg] score matrix consumed inside the
+ * GEMM epilogue instead of being written (mml_loss.py:56,73-77 + utils/misc.py:462-477 in one pass).  fp32 operands are
+ * split into bf16 hi + lo and multiplied as hi*hi + hi*lo + lo*hi (fp32 accumulate): cosine error <= ~1e-5, logits within
+ * the 1e-3 bar at temperature 0.02.  `workspace` (simseg_infonce_fused_workspace_bytes, 256-byte aligned, caller-owned)
+ * keeps the split operands and must be handed unchanged from _fwd to _bwd; _bwd recomputes the scores, emits
+ * dLoss/dcos as split bf16 operands into the workspace and runs the two gradient GEMMs.  Outputs as above:
+ * dfeat1 [b,E] written, dfeat2g [Bg,E] ACCUMULATED, dtemp ACCUMULATED (any of the three may be NULL). */
+int64_t simseg_infonce_fused_workspace_bytes(int b, int Bg, int E);
+int simseg_infonce_fused_fwd(simseg_ctx* ctx, const float* feat1, const float* feat2g, int b, int Bg, int E,
+                             const float* temperature, int row_offset, void* workspace, int64_t workspace_bytes,
+                             float* loss_rows, float* lse, int32_t* argmax, void* stream);
+int simseg_infonce_fused_bwd(simseg_ctx* ctx, int b, int Bg, int E, const float* temperature, int row_offset,
+                             const float* lse, float grad_scale, void* workspace, int64_t workspace_bytes, float* dfeat1,
+                             float* dfeat2g, float* dtemp, void* stream);
+
 /* ---- dense patch-text similarity map (tools/seg_evaluation.py:111-112,136-139) -------------- */
 /* patches [rows,E] (rows = B*N projected patch tokens; f32 or bf16), text [C,E] same dtype
  * (class embeddings, already unit norm — seg_evaluation.py:71-72).
@@ -214,6 +229,19 @@ int simseg_allpairs_sim(simseg_ctx* ctx, const float* left, const float* right, 
  * rank[i] = #{j : s_ij > s*_i} + #{j < j* : s_ij == s*_i}, (s*,j*) = best matching item. -1 if none. */
 int simseg_retrieval_rank(simseg_ctx* ctx, const float* sim, int M, int Nr, const int64_t* left_gid,
                           const int64_t* right_gid, int32_t* rank, void* stream);
+
+/* EmbANN._ann + RetrievalMetric's first-match rank (tasks/clip/hooks/utils.py:35-42,63-65) in one pass on the tensor
+ * cores: the [M,Nr] similarity matrix (500 MB at 5k x 25k) and the [M,Nr] int64 argsort (1 GB) are never materialised.
+ * Same split-bf16 products as simseg_infonce_fused_*; rank[i] as defined for simseg_retrieval_rank (-1: no right item
+ * shares the row's group id). */
+int64_t simseg_retrieval_fused_workspace_bytes(int M, int Nr, int E);
+int simseg_retrieval_rank_fused(simseg_ctx* ctx, const float* left, const float* right, int M, int Nr, int E,
+                                const int64_t* left_gid, const int64_t* right_gid, void* workspace, int64_t workspace_bytes,
+                                int32_t* rank, void* stream);
+/* out[M,Nr] fp32 = left @ right^T through the same split products (materialising variant of tasks/clip/hooks/utils.py:36;
+ * workspace as simseg_retrieval_fused_workspace_bytes). */
+int simseg_allpairs_sim_split(simseg_ctx* ctx, const float* left, const float* right, int M, int Nr, int E, void* workspace,
+                              int64_t workspace_bytes, float* out, void* stream);
 
 /* ---- zero-shot segmentation glue around the map (tools/seg_evaluation.py) ---- */
 /* class embedding of the zero-shot classifier (seg_evaluation.py:71-72): out[c,:] = mean_p prompt[c,p,:] / ||mean||

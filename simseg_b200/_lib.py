@@ -17,7 +17,7 @@ if _ALT_LIB:
 
 F32, BF16 = 0, 1
 EPI_NONE, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU, EPI_ROWSCALE = range(5)
-PREC_FP32, PREC_TF32 = 0, 1
+PREC_FP32, PREC_TF32, PREC_SPLIT_BF16 = 0, 1, 2     # PREC_SPLIT_BF16: host-side selector of the fused tcgen05 entry points
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
@@ -57,6 +57,12 @@ PROTOTYPES = {
     "simseg_topk_pool_l2norm_bwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, vp, vp]),
     "simseg_infonce_fwd": (i32, [vp, vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
     "simseg_infonce_bwd": (i32, [vp, vp, vp, i32, i32, i32, vp, i32, i32, vp, f32, vp, vp, vp, vp, vp]),
+    "simseg_infonce_fused_workspace_bytes": (i64, [i32, i32, i32]),
+    "simseg_infonce_fused_fwd": (i32, [vp, vp, vp, i32, i32, i32, vp, i32, vp, i64, vp, vp, vp, vp]),
+    "simseg_infonce_fused_bwd": (i32, [vp, i32, i32, i32, vp, i32, vp, f32, vp, i64, vp, vp, vp, vp]),
+    "simseg_retrieval_fused_workspace_bytes": (i64, [i32, i32, i32]),
+    "simseg_retrieval_rank_fused": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, i64, vp, vp]),
+    "simseg_allpairs_sim_split": (i32, [vp, vp, vp, i32, i32, i32, vp, i64, vp, vp]),
     "simseg_patch_text_sim_workspace_bytes": (i64, [i64]),
     "simseg_patch_text_sim": (i32, [vp, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, i64, vp]),
     "simseg_allpairs_sim": (i32, [vp, vp, vp, i32, i32, i32, i32, vp, vp]),

@@ -44,6 +44,12 @@ int seg_select_impl(Ctx*, const float*, const float*, int, int, int, int, int, f
 int seg_upsample_norm_impl(Ctx*, const float*, const int32_t*, int, int, int, int, int, int, int, float*, cudaStream_t);
 int pos_embed_bicubic_impl(Ctx*, const float*, float*, int, int, int, int, cudaStream_t);
 int patch_sim_fused_impl(Ctx*, const void*, int64_t, int, const void*, int, int, float*, int32_t*, cudaStream_t);
+int64_t infonce_fused_workspace_bytes(int, int, int);
+int infonce_fused_fwd_impl(Ctx*, const float*, const float*, int, int, int, const float*, int, void*, int64_t, float*, float*, int32_t*, cudaStream_t);
+int infonce_fused_bwd_impl(Ctx*, int, int, int, const float*, int, const float*, float, void*, int64_t, float*, float*, float*, cudaStream_t);
+int64_t retrieval_fused_workspace_bytes(int, int, int);
+int retrieval_rank_fused_impl(Ctx*, const float*, const float*, int, int, int, const int64_t*, const int64_t*, void*, int64_t, int32_t*, cudaStream_t);
+int allpairs_split_impl(Ctx*, const float*, const float*, int, int, int, void*, int64_t, float*, cudaStream_t);
 
 // fp32 product in the requested precision: C[M,N] (+)= A(m,k) B(n,k)
 static int fp32_matmul(Ctx* c, const float* A, const float* B, float* C, int M, int N, int K, int64_t lda, int64_t ldb,
@@ -232,6 +238,38 @@ int simseg_infonce_bwd(simseg_ctx* ctx, const float* feat1, const float* feat2g,
     if (rc) return rc;
   }
   return SIMSEG_OK;
+}
+
+int64_t simseg_infonce_fused_workspace_bytes(int b, int Bg, int E) { return infonce_fused_workspace_bytes(b, Bg, E); }
+int simseg_infonce_fused_fwd(simseg_ctx* ctx, const float* feat1, const float* feat2g, int b, int Bg, int E,
+                             const float* temperature, int row_offset, void* workspace, int64_t workspace_bytes,
+                             float* loss_rows, float* lse, int32_t* argmax, void* stream) {
+  CTX_OR_FAIL();
+  SIMSEG_CHECK_ARG(feat1 && feat2g && temperature && loss_rows && lse, "infonce_fused_fwd: null pointer");
+  return infonce_fused_fwd_impl(c, feat1, feat2g, b, Bg, E, temperature, row_offset, workspace, workspace_bytes, loss_rows, lse,
+                                argmax, st);
+}
+int simseg_infonce_fused_bwd(simseg_ctx* ctx, int b, int Bg, int E, const float* temperature, int row_offset,
+                             const float* lse, float grad_scale, void* workspace, int64_t workspace_bytes, float* dfeat1,
+                             float* dfeat2g, float* dtemp, void* stream) {
+  CTX_OR_FAIL();
+  SIMSEG_CHECK_ARG(temperature && lse, "infonce_fused_bwd: null pointer");
+  return infonce_fused_bwd_impl(c, b, Bg, E, temperature, row_offset, lse, grad_scale, workspace, workspace_bytes, dfeat1, dfeat2g,
+                                dtemp, st);
+}
+int64_t simseg_retrieval_fused_workspace_bytes(int M, int Nr, int E) { return retrieval_fused_workspace_bytes(M, Nr, E); }
+int simseg_retrieval_rank_fused(simseg_ctx* ctx, const float* left, const float* right, int M, int Nr, int E,
+                                const int64_t* left_gid, const int64_t* right_gid, void* workspace, int64_t workspace_bytes,
+                                int32_t* rank, void* stream) {
+  CTX_OR_FAIL();
+  SIMSEG_CHECK_ARG(left && right && left_gid && right_gid && rank, "retrieval_rank_fused: null pointer");
+  return retrieval_rank_fused_impl(c, left, right, M, Nr, E, left_gid, right_gid, workspace, workspace_bytes, rank, st);
+}
+int simseg_allpairs_sim_split(simseg_ctx* ctx, const float* left, const float* right, int M, int Nr, int E, void* workspace,
+                              int64_t workspace_bytes, float* out, void* stream) {
+  CTX_OR_FAIL();
+  SIMSEG_CHECK_ARG(left && right && out, "allpairs_sim_split: null pointer");
+  return allpairs_split_impl(c, left, right, M, Nr, E, workspace, workspace_bytes, out, st);
 }
 
 int64_t simseg_patch_text_sim_workspace_bytes(int64_t rows) { return ((rows * 4 + 255) / 256) * 256; }

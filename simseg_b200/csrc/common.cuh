@@ -35,6 +35,31 @@ struct Ctx {
   int launches;            // kernels launched through this ctx (bench's gpu_launches claim)
 };
 
+// split-bf16 ("fp32-grade") operands + similarity epilogues of the GEMM engine (gemm_sm100.cu / sim_loss.cu)
+struct GemmSim {
+  const void* a_lo;
+  const void* b_lo;
+  int epi;                   // 0 = plain GEMM over the three hi/lo products; 16 NCE fwd, 17 NCE bwd, 18 retrieval rank, 19 best match
+  const float* temperature;
+  int row_offset;
+  void* part;                // float4 [M][part_ld]
+  int part_ld;
+  float* zt;
+  const float* lse;
+  float grad_scale;
+  float* dtemp;
+  int64_t lo_off;
+  const float* best;
+  const int32_t* bestj;
+  const int64_t* lgid;
+  const int64_t* rgid;
+  int32_t* rank;
+  unsigned long long* bestkey;
+  const int32_t* tile_list;  // optional device list of mn tiles to visit (count in *tile_count); tile shape forced by the caller
+  const int32_t* tile_count;
+};
+int gemm_sim_impl(Ctx*, const simseg_gemm_args*, const GemmSim*, cudaStream_t);
+
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
 

@@ -33,7 +33,34 @@ constexpr int kEpiBoxBytes = 32 * 64;   // epilogue staging box: 32 rows x 32 bf
 constexpr int kGemmThreads = 32 * (2 + kNumEpiWarps);
 constexpr int kMaxSmem = 232448;
 
+// internal epilogues of the similarity family (fp32 scores never leave the SM; see sim_loss.cu for the entry points)
+constexpr int kEpiNceFwd = 16;    // per-(row, tile-half) online-softmax partials of acc / clamp(temp) + target logit
+constexpr int kEpiNceBwd = 17;    // G = gs * (softmax - onehot) / t as bf16 hi | lo operands; dtemp
+constexpr int kEpiRank = 18;      // rank[row] += #{col : acc beats the row's best matching score}
+constexpr int kEpiBest = 19;      // bestkey[row] = max over same-group columns of (ordered score, lowest column)
+__host__ __device__ constexpr bool is_sim_epi(int e) { return e >= kEpiNceFwd; }
+
 struct GemmParams {
+  // ---- similarity family ----------------------------------------------------------------------------------------
+  int32_t split3, kb_seg;          // split-bf16 operands: k-blocks [0,kb_seg) = Ahi*Bhi, then Ahi*Blo, then Alo*Bhi
+  const float* temperature;        // device scalar (clamped to [0.001, 0.5] at use)
+  int32_t row_offset;              // target column of row i = row_offset + i
+  float4* part;                    // NCE fwd: [M][part_ld] (max, sumexp, best, bitcast argmax)
+  int32_t part_ld;
+  float* zt;                       // NCE fwd: [M] target logit
+  const float* lse;                // NCE bwd: [M]
+  float grad_scale;
+  float* dtemp;
+  int64_t lo_off;                  // NCE bwd: G lo half at d + lo_off (bf16 elements)
+  const float* best;               // rank: [M] best matching score, bestj [M] its column (-1: none)
+  const int32_t* bestj;
+  const int64_t* lgid;
+  const int64_t* rgid;
+  int32_t* rank;
+  unsigned long long* bestkey;     // kEpiBest: [M] atomicMax keys
+  const int32_t* tile_list;        // optional: only these mn tiles are visited (count in *tile_count)
+  const int32_t* tile_count;
+  // ---------------------------------------------------------------------------------------------------------------
   int64_t M, N, K;
   int32_t a_mn, b_mn;
   int32_t elem_bytes;      // 2 (bf16) or 4 (tf32)
@@ -279,6 +306,153 @@ __device__ __forceinline__ void epilogue_tma(const GemmParams& p, const CUtensor
 }
 
 // ------------------------------------------------------------------------------------------------
+// Epilogues of the similarity family: the fp32 score tile is consumed straight out of TMEM and never written.
+// A thread owns one row (TMEM lane) and half of the tile's columns, so every per-row reduction is thread-local.
+//   kEpiNceFwd  NCE.forward (mml_loss.py:56,73-77 + utils/misc.py:462-477): z = acc / clamp(temp); one online-softmax partial
+//               (max, sum exp, best value, first-max column) per (row, n-tile, half) + the target logit z[row, row_offset+row]
+//   kEpiNceBwd  G = grad_scale * (exp(z - lse) - [col == target]) / t written as bf16 hi | lo (the split operands of the
+//               two gradient GEMMs); dtemp += -(1/t) sum G * acc  (inside the clamp range)
+//   kEpiRank    EmbANN/RetrievalMetric (tasks/clip/hooks/utils.py:35-42,63-65) without the sort: rank[row] += number of
+//               columns of another group whose score beats the row's best matching score (ties: lower column first)
+template <int BN, int EPI>
+__device__ __forceinline__ void sim_epilogue_tile(const GemmParams& p, uint32_t t_row, int half, int64_t row, bool row_ok,
+                                                  int n0, int nt, int lane) {
+  constexpr int kColsPerWarp = BN / 2;
+  constexpr int kChunks = kColsPerWarp / 32;
+  constexpr float kLog2e = 1.44269504088896341f;
+  float traw = 0.02f;
+  if (EPI != kEpiRank) traw = __ldg(p.temperature);
+  const float t = fminf(fmaxf(traw, 0.001f), 0.5f);
+  const float inv_t = 1.0f / t;
+  const int64_t tgt = p.row_offset + row;
+  // ---- per-row state
+  float m2 = -INFINITY, l = 0.f, best = -INFINITY, ztv = 0.f;     // NCE fwd (m2 in the log2 domain)
+  int besti = 0x7fffffff;
+  bool have_t = false;
+  float L2 = 0.f, dsum = 0.f;                                      // NCE bwd
+  if (EPI == kEpiNceBwd) L2 = (row_ok ? __ldg(p.lse + row) : 0.f) * kLog2e;
+  float thr = 0.f;                                                 // rank
+  int js = -1, cnt = 0;
+  long long gid = 0;
+  if (EPI == kEpiRank && row_ok) { thr = __ldg(p.best + row); js = __ldg(p.bestj + row); gid = __ldg(p.lgid + row); }
+  unsigned long long key = 0ull;                                   // best
+  if (EPI == kEpiBest && row_ok) gid = __ldg(p.lgid + row);
+#pragma unroll 1
+  for (int c = 0; c < kChunks; ++c) {
+    const int col_in_tile = half * kColsPerWarp + c * 32;
+    const int64_t col0 = n0 + col_in_tile;
+    uint32_t r[32];
+    tmem_ld_32x32(t_row + col_in_tile, r);
+    tmem_ld_wait();
+    if (col0 >= p.N) continue;                                     // whole chunk is N padding (warp-uniform)
+    const int nvalid = (col0 + 32 <= p.N) ? 32 : static_cast<int>(p.N - col0);
+    if (EPI == kEpiNceFwd) {
+      const float sc = inv_t * kLog2e;
+      float cm = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float s = __uint_as_float(r[j]);
+        if (j < nvalid) {
+          if (s > best) { best = s; besti = static_cast<int>(col0) + j; }      // first maximum (ascending columns)
+          cm = fmaxf(cm, s);
+          if (col0 + j == tgt) { ztv = s * inv_t; have_t = true; }
+        }
+      }
+      cm *= sc;
+      if (cm > m2) { l *= exp2f(m2 - cm); m2 = cm; }
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(__uint_as_float(r[j]), sc, -m2)));
+        acc += (j < nvalid) ? e : 0.f;
+      }
+      l += acc;
+    } else if (EPI == kEpiNceBwd) {
+      const float sc = inv_t * kLog2e;
+      const float gs = p.grad_scale * inv_t;
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        float g[2];
+#pragma unroll
+        for (int e2 = 0; e2 < 2; ++e2) {
+          const float s = __uint_as_float(r[j + e2]);
+          float pr;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pr) : "f"(fmaf(s, sc, -L2)));
+          if (col0 + j + e2 == tgt) pr -= 1.0f;
+          g[e2] = (row_ok && j + e2 < nvalid) ? gs * pr : 0.f;
+          dsum = fmaf(g[e2], s, dsum);
+        }
+        const uint32_t h = pack_bf16(g[0], g[1]);
+        hi[j >> 1] = h;
+        lo[j >> 1] = pack_bf16(g[0] - bf16_lo(h), g[1] - bf16_hi(h));
+      }
+      if (row_ok) {
+        __nv_bfloat16* dh = reinterpret_cast<__nv_bfloat16*>(p.d) + row * p.ldd + col0;
+        __nv_bfloat16* dl = dh + p.lo_off;
+        if (nvalid == 32) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            reinterpret_cast<uint4*>(dh)[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+            reinterpret_cast<uint4*>(dl)[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < nvalid) {
+              const uint32_t h = hi[j >> 1], w = lo[j >> 1];
+              reinterpret_cast<uint16_t*>(dh)[j] = static_cast<uint16_t>((j & 1) ? (h >> 16) : (h & 0xffffu));
+              reinterpret_cast<uint16_t*>(dl)[j] = static_cast<uint16_t>((j & 1) ? (w >> 16) : (w & 0xffffu));
+            }
+          }
+        }
+      }
+    } else if (EPI == kEpiBest) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < nvalid) {
+          const int col = static_cast<int>(col0) + j;
+          if (row_ok && __ldg(reinterpret_cast<const long long*>(p.rgid) + col) == gid) {
+            uint32_t u = r[j];
+            u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;                        // monotonic float -> uint
+            const unsigned long long k2 = (static_cast<unsigned long long>(u) << 32) | (0xffffffffu - static_cast<uint32_t>(col));
+            key = k2 > key ? k2 : key;
+          }
+        }
+      }
+    } else {   // kEpiRank
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < nvalid) {
+          const float s = __uint_as_float(r[j]);
+          const int col = static_cast<int>(col0) + j;
+          const bool beats = (s > thr) || (s == thr && col < js);
+          const bool same = __ldg(reinterpret_cast<const long long*>(p.rgid) + col) == gid;    // warp-uniform address
+          cnt += (beats && !same) ? 1 : 0;
+        }
+      }
+    }
+  }
+  if (EPI == kEpiNceFwd) {
+    if (row_ok) {
+      constexpr float kLn2 = 0.69314718055994531f;
+      p.part[row * p.part_ld + nt * 2 + half] = make_float4(m2 * kLn2, l, best * inv_t, __int_as_float(besti));
+      if (have_t) p.zt[row] = ztv;
+    }
+  } else if (EPI == kEpiNceBwd) {
+    if (p.dtemp != nullptr) {
+      dsum = warp_sum(dsum);
+      if (lane == 0 && dsum != 0.f && traw >= 0.001f && traw <= 0.5f) atomicAdd(p.dtemp, -dsum * inv_t);
+    }
+  } else if (EPI == kEpiBest) {
+    if (key) atomicMax(p.bestkey + row, key);
+  } else {
+    if (row_ok && js >= 0 && cnt) atomicAdd(p.rank + row, cnt);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 template <int BN, int EPI, int CTAS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -327,7 +501,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  const int total_tiles = p.tile_list ? __ldg(p.tile_count) : p.m_tiles * p.n_tiles * p.splits;
   const int tiles_mn = p.m_tiles * p.n_tiles;
   const int k_elems = kSwizzleBytes / p.elem_bytes;      // K elements per k-block: 64 (bf16) or 32 (tf32)
   const int first_tile = static_cast<int>(blockIdx.x) / CTAS;
@@ -345,7 +519,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int mn_atom = kSwizzleBytes / p.elem_bytes;              // 64 bf16 / 32 tf32 elements
       for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
         const int split = tile / tiles_mn;
-        const int mn = tile - split * tiles_mn;
+        const int mn = p.tile_list ? __ldg(p.tile_list + tile) : tile - split * tiles_mn;
         const int m0 = (mn / p.n_tiles) * (kBM * CTAS) + row_base;
         const int n0 = (mn % p.n_tiles) * BN + static_cast<int>(rank) * Cfg::kBRows;
         const int kb0 = split * p.kb_per_split;
@@ -360,27 +534,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             } else {
               if (leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * CTAS);
               const uint32_t fb = full0 + stage * 8;
-              const int k0 = kb * k_elems;
+              // split-bf16 products (fp32-grade similarity GEMMs): three K segments over (hi,hi), (hi,lo), (lo,hi)
+              const CUtensorMap* pa = &tmap_a;
+              const CUtensorMap* pb = &tmap_b;
+              int kk = kb;
+              if (p.split3) {
+                const int seg = kb / p.kb_seg;
+                kk = kb - seg * p.kb_seg;
+                if (seg == 2) pa = &tmap_x;
+                if (seg == 1) pb = &tmap_x2;
+              }
+              const int k0 = kk * k_elems;
               if (!p.a_mn) {
-                if (CTAS == 2) tma_load_2d_2sm(sa, &tmap_a, fb, k0, m0);
-                else tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
+                if (CTAS == 2) tma_load_2d_2sm(sa, pa, fb, k0, m0);
+                else tma_load_2d(sa, pa, &full_bar[stage], k0, m0);
               } else {
                 // MN-major: boxes of (swizzle-row of MN elements) x k rows; one 3-D box when the extent allows
                 const int nbox = kBM / mn_atom;
                 const int box_bytes = Cfg::kABytes / nbox;
                 if (p.a_3d) {
-                  if (CTAS == 2) tma_load_3d_2sm(sa, &tmap_a, fb, 0, k0, m0 / mn_atom);
-                  else tma_load_3d(sa, &tmap_a, &full_bar[stage], 0, k0, m0 / mn_atom);
+                  if (CTAS == 2) tma_load_3d_2sm(sa, pa, fb, 0, k0, m0 / mn_atom);
+                  else tma_load_3d(sa, pa, &full_bar[stage], 0, k0, m0 / mn_atom);
                 } else {
                   for (int j = 0; j < nbox; ++j) {
-                    if (CTAS == 2) tma_load_2d_2sm(sa + j * box_bytes, &tmap_a, fb, m0 + j * mn_atom, k0);
-                    else tma_load_2d(sa + j * box_bytes, &tmap_a, &full_bar[stage], m0 + j * mn_atom, k0);
+                    if (CTAS == 2) tma_load_2d_2sm(sa + j * box_bytes, pa, fb, m0 + j * mn_atom, k0);
+                    else tma_load_2d(sa + j * box_bytes, pa, &full_bar[stage], m0 + j * mn_atom, k0);
                   }
                 }
               }
               if (!p.b_mn) {
-                if (CTAS == 2) tma_load_2d_2sm(sb, &tmap_b, fb, k0, n0);
-                else tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
+                if (CTAS == 2) tma_load_2d_2sm(sb, pb, fb, k0, n0);
+                else tma_load_2d(sb, pb, &full_bar[stage], k0, n0);
               } else if (Cfg::kWide) {
                 // wide pair tile: per CTA two column groups (one per MMA), one 3-D box per 64-column atom
                 constexpr int kAtoms0 = 2, kAtoms1 = (BN - 256) / 128;      // atoms per CTA for MMA 0 (N=256) and MMA 1
@@ -389,18 +573,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 for (int a2 = 0; a2 < kAtoms0 + kAtoms1; ++a2) {
                   const int col = a2 < kAtoms0 ? nt0 + static_cast<int>(rank) * 128 + a2 * 64
                                                : nt0 + 256 + static_cast<int>(rank) * (kAtoms1 * 64) + (a2 - kAtoms0) * 64;
-                  tma_load_3d_2sm(sb + a2 * 8192, &tmap_b, fb, 0, k0, col / 64);
+                  tma_load_3d_2sm(sb + a2 * 8192, pb, fb, 0, k0, col / 64);
                 }
               } else {
                 const int nbox = Cfg::kBRows / mn_atom;
                 const int box_bytes = Cfg::kBBytes / nbox;
                 if (p.b_3d) {
-                  if (CTAS == 2) tma_load_3d_2sm(sb, &tmap_b, fb, 0, k0, n0 / mn_atom);
-                  else tma_load_3d(sb, &tmap_b, &full_bar[stage], 0, k0, n0 / mn_atom);
+                  if (CTAS == 2) tma_load_3d_2sm(sb, pb, fb, 0, k0, n0 / mn_atom);
+                  else tma_load_3d(sb, pb, &full_bar[stage], 0, k0, n0 / mn_atom);
                 } else {
                   for (int j = 0; j < nbox; ++j) {
-                    if (CTAS == 2) tma_load_2d_2sm(sb + j * box_bytes, &tmap_b, fb, n0 + j * mn_atom, k0);
-                    else tma_load_2d(sb + j * box_bytes, &tmap_b, &full_bar[stage], n0 + j * mn_atom, k0);
+                    if (CTAS == 2) tma_load_2d_2sm(sb + j * box_bytes, pb, fb, n0 + j * mn_atom, k0);
+                    else tma_load_2d(sb + j * box_bytes, pb, &full_bar[stage], n0 + j * mn_atom, k0);
                   }
                 }
               }
@@ -514,7 +698,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     uint32_t acc_phase = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
       const int split = tile / tiles_mn;
-      const int mn = tile - split * tiles_mn;
+      const int mn = p.tile_list ? __ldg(p.tile_list + tile) : tile - split * tiles_mn;
       const int m0 = (mn / p.n_tiles) * (kBM * CTAS) + row_base;
       const int n0 = (mn % p.n_tiles) * BN;
       const int64_t row = m0 + row_in_tile;
@@ -524,8 +708,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const uint32_t t_row = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
       float rs = 1.0f;
       if (EPI == SIMSEG_EPI_ROWSCALE) rs = row_ok ? p.row_scale[row] : 0.0f;
+      if (is_sim_epi(EPI)) sim_epilogue_tile<BN, EPI>(p, t_row, half, row, row_ok, n0, mn % p.n_tiles, lane);
 #pragma unroll 1
-      for (int c = 0; c < kChunks; ++c) {
+      for (int c = 0; c < (is_sim_epi(EPI) ? 0 : kChunks); ++c) {
         const int col_in_tile = half * kColsPerWarp + c * 32;
         const int64_t col0 = n0 + col_in_tile;
         uint32_t r[32];
@@ -814,9 +999,20 @@ static int dispatch_epi(Ctx* ctx, int epi, const CUtensorMap* tm, const GemmPara
   return SIMSEG_ERR_INVALID;
 }
 
+template <int EPI>
+static int dispatch_sim(Ctx* ctx, int bn, int ctas, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
+  if (ctas == 2) return launch_gemm<256, EPI, 2>(ctx, tm, p, grid, st);
+  if (bn == 128) return launch_gemm<128, EPI, 1>(ctx, tm, p, grid, st);
+  return launch_gemm<256, EPI, 1>(ctx, tm, p, grid, st);
+}
+
+int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) { return gemm_sim_impl(ctx, a, nullptr, st); }
+
 // `reserved` bits (bench / debug only): 1 = no TMA, 2 = no MMA, 4 = 2-D boxes for MN-major operands, 8 = direct-store
 // epilogue, 16 = force single-CTA tiles, 32 = force CTA pairs, 128 = no wide (256 x 384|512) split-K tiles.
-int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
+// `sim` != NULL: split-bf16 operands (a / b are the hi halves, sim->a_lo / b_lo the lo halves, K counts ONE segment) and
+// optionally one of the similarity epilogues (sim->epi = 0 keeps a->epilogue).
+int gemm_sim_impl(Ctx* ctx, const simseg_gemm_args* a, const GemmSim* sim, cudaStream_t st) {
   SIMSEG_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "gemm: empty problem M=%lld N=%lld K=%lld", (long long)a->M,
                    (long long)a->N, (long long)a->K);
   SIMSEG_CHECK_ARG(a->in_dtype == SIMSEG_BF16 || a->in_dtype == SIMSEG_F32, "gemm: bad in_dtype %d", a->in_dtype);
@@ -836,8 +1032,17 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
 
   const int mn_atom = kSwizzleBytes / eb;
   const int k_elems = kSwizzleBytes / eb;
-  const int kb_total = static_cast<int>(cdiv(a->K, k_elems));
-  const bool can_split = a->epilogue == SIMSEG_EPI_NONE && a->out_dtype == SIMSEG_F32 && a->col_sum == nullptr;
+  const int kb_seg = static_cast<int>(cdiv(a->K, k_elems));
+  const int kb_total = sim ? 3 * kb_seg : kb_seg;
+  const int sim_epi = sim ? sim->epi : 0;
+  if (sim) {
+    SIMSEG_CHECK_ARG(eb == 2 && sim->a_lo && sim->b_lo, "gemm: split operands need bf16 hi/lo pairs");
+    SIMSEG_CHECK_ARG((reinterpret_cast<uintptr_t>(sim->a_lo) & 15) == 0 && (reinterpret_cast<uintptr_t>(sim->b_lo) & 15) == 0,
+                     "gemm: lo operands must be 16-byte aligned");
+    SIMSEG_CHECK_ARG(sim_epi == 0 || (!a->a_major && !a->b_major && a->epilogue == SIMSEG_EPI_NONE),
+                     "gemm: similarity epilogues take K-major operands");
+  }
+  const bool can_split = !sim_epi && a->epilogue == SIMSEG_EPI_NONE && a->out_dtype == SIMSEG_F32 && a->col_sum == nullptr;
 
   // ---- tile shape: BN in {128,192,256}, single CTA (128 rows) or CTA pair (256 rows)
   int bn = a->tile_n;
@@ -859,11 +1064,13 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
       for (int n : {192, 128}) if (padded(n) < padded(auto_bn)) auto_bn = n;
     }
     if (bn == 0) bn = auto_bn;
+    if (sim_epi && bn == 192) bn = 256;                        // the similarity epilogues are instantiated for 128 / 256
     if (ctas == 0) {
       const int64_t pair_tiles = cdiv(a->M, 2 * kBM) * cdiv(a->N, bn);
       ctas = (eb == 2 && !mn_major && pair_ok(bn) && pair_tiles >= ctx->num_sms / 2) ? 2 : 1;
       if (ctas == 1 && a->tile_n == 0 && !can_split) {
         while (bn > 128 && cdiv(a->M, kBM) * cdiv(a->N, bn) < ctx->num_sms) bn -= 64;
+        if (sim_epi && bn == 192) bn = 128;
       }
     }
   }
@@ -873,6 +1080,7 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
   // 128 x 256 single-CTA tiles, which are pinned at the ~11 TB/s L2 fabric limit because no two units of a split-K
   // GEMM ever read the same bytes.  dW or dW^T is computed, whichever wastes fewer padded rows/columns.
   simseg_gemm_args sw;
+  GemmSim sim_sw;
   int wide_bn = 0, d_trans = 0;
   const bool wide_ok = eb == 2 && a->a_major && a->b_major && can_split && a->bias == nullptr && a->tile_n == 0 &&
                        (a->reserved & (16 | 128)) == 0 && a->M % 64 == 0 && a->N % 64 == 0 && kb_total >= 64 &&
@@ -895,6 +1103,7 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
         sw = *a;
         sw.a = a->b; sw.b = a->a; sw.M = a->N; sw.N = a->M; sw.lda = a->ldb; sw.ldb = a->lda;
         a = &sw;
+        if (sim) { sim_sw = *sim; sim_sw.a_lo = sim->b_lo; sim_sw.b_lo = sim->a_lo; sim = &sim_sw; }   // the three products are symmetric
         d_trans = 1;
         wide_bn = bn_t;
       } else {
@@ -906,6 +1115,14 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
   }
 
   GemmParams p{};
+  if (sim) {
+    p.split3 = 1; p.kb_seg = kb_seg;
+    p.temperature = sim->temperature; p.row_offset = sim->row_offset; p.part = reinterpret_cast<float4*>(sim->part);
+    p.part_ld = sim->part_ld; p.zt = sim->zt; p.lse = sim->lse; p.grad_scale = sim->grad_scale; p.dtemp = sim->dtemp;
+    p.lo_off = sim->lo_off; p.best = sim->best; p.bestj = sim->bestj; p.lgid = sim->lgid; p.rgid = sim->rgid; p.rank = sim->rank;
+    p.bestkey = sim->bestkey; p.tile_list = sim->tile_list; p.tile_count = sim->tile_count;
+    if (sim_epi == kEpiNceFwd) SIMSEG_CHECK_ARG(sim->part_ld >= 2 * cdiv(a->N, bn), "gemm: partial buffer too narrow for %d-wide tiles", bn);
+  }
   p.d_trans = d_trans;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.a_mn = a->a_major ? 1 : 0; p.b_mn = a->b_major ? 1 : 0;
@@ -967,6 +1184,7 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
   if (a->bias) tma_epi = tma_epi && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0;
   if (a->epilogue != SIMSEG_EPI_DGELU && a->col_sum) tma_epi = false;
   SIMSEG_CHECK_ARG(!(a->aux2 && !tma_epi), "gemm: aux2 needs the bf16 TMA epilogue (DGELU, bf16 out, 16-byte aligned rows)");
+  if (sim) tma_epi = false;                                  // tm[3] / tm[4] carry the lo operands
   p.tma_epi = tma_epi ? 1 : 0;
   p.aux2 = a->aux2;
   if (tma_epi) {
@@ -990,6 +1208,17 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
   else if (p.b_3d) rc = make_tmap_mn3d(&tb, a->b, eb, a->K, a->N, a->ldb, k_elems, b_rows / mn_atom);
   else rc = make_tmap(&tb, a->b, eb, a->K, a->N, a->ldb, mn_atom, k_elems);
   if (rc) return rc;
+  if (sim) {                                                 // same geometry, lo halves
+    if (!p.a_mn) rc = make_tmap(&tm[3], sim->a_lo, eb, a->M, a->K, a->lda, k_elems, kBM);
+    else if (p.a_3d) rc = make_tmap_mn3d(&tm[3], sim->a_lo, eb, a->K, a->M, a->lda, k_elems, kBM / mn_atom);
+    else rc = make_tmap(&tm[3], sim->a_lo, eb, a->K, a->M, a->lda, mn_atom, k_elems);
+    if (rc) return rc;
+    if (!p.b_mn) rc = make_tmap(&tm[4], sim->b_lo, eb, a->N, a->K, a->ldb, k_elems, b_rows);
+    else if (wide_bn) rc = make_tmap_mn3d(&tm[4], sim->b_lo, eb, a->K, a->N, a->ldb, k_elems, 1);
+    else if (p.b_3d) rc = make_tmap_mn3d(&tm[4], sim->b_lo, eb, a->K, a->N, a->ldb, k_elems, b_rows / mn_atom);
+    else rc = make_tmap(&tm[4], sim->b_lo, eb, a->K, a->N, a->ldb, mn_atom, k_elems);
+    if (rc) return rc;
+  }
 
   // persistent grid: one unit (CTA or CTA pair) per SM (pair); with fused column sums keep every unit on ONE n-tile
   // (unit count a multiple of n_tiles) so the sums stay in registers until the unit is done
@@ -998,6 +1227,10 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) {
   if (tma_epi && a->col_sum && p.n_tiles <= units) units = (units / p.n_tiles) * p.n_tiles;
   const int grid = units * ctas;
 
+  if (sim_epi == kEpiNceFwd) return dispatch_sim<kEpiNceFwd>(ctx, bn, ctas, tm, p, grid, st);
+  if (sim_epi == kEpiNceBwd) return dispatch_sim<kEpiNceBwd>(ctx, bn, ctas, tm, p, grid, st);
+  if (sim_epi == kEpiRank) return dispatch_sim<kEpiRank>(ctx, bn, ctas, tm, p, grid, st);
+  if (sim_epi == kEpiBest) return dispatch_sim<kEpiBest>(ctx, bn, ctas, tm, p, grid, st);
   if (wide_bn == 384) return launch_gemm<384, SIMSEG_EPI_NONE, 2>(ctx, tm, p, grid, st);
   if (wide_bn == 512) return launch_gemm<512, SIMSEG_EPI_NONE, 2>(ctx, tm, p, grid, st);
   if (ctas == 2) {

@@ -3,6 +3,8 @@
 // norms + argmax, retrieval first-match rank.
 #include "common.cuh"
 
+#include <cstring>
+
 namespace simseg {
 
 // ------------------------------------------------------------------------------------------------
@@ -379,6 +381,314 @@ int retrieval_rank_impl(Ctx* ctx, const float* sim, int M, int Nr, const int64_t
   ctx->launches++;
   SIMSEG_LAUNCH_CHECK();
   return SIMSEG_OK;
+}
+
+
+// =================================================================================================================
+// Tensor-core similarity family (round 2): InfoNCE and retrieval ranking on the tcgen05 GEMM engine at fp32-grade
+// accuracy, with the score matrix consumed inside the GEMM epilogue instead of being written to HBM.
+//
+// fp32 operands are split x = hi + lo (two bf16 numbers, |x - hi - lo| <= 2^-18 |x|) and the product is evaluated as
+// hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM (three K segments of one kind::f16 GEMM; the dropped lo*lo term
+// is <= 2^-18 relative).  On unit-norm embeddings the cosine error is <= ~1e-5 worst case / ~5e-7 typical, i.e. logits
+// (x 1/0.02) within the 1e-3 bar of the north star, where single-pass tf32 (2^-11) misses it by 50x.
+//
+// forward   split(feat1), split(feat2g) -> GEMM[kEpiNceFwd] (partials) -> nce_merge (lse, CE, first-max argmax)
+// backward  GEMM[kEpiNceBwd] recomputes the scores and emits G as bf16 hi|lo -> dfeat1 = G @ feat2g, dfeat2g += G^T @ feat1
+// retrieval split(left), split(right) -> best_match (SIMT, the <= few matching columns) -> GEMM[kEpiRank] (counts)
+
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, int64_t n4, uint2* __restrict__ hi,
+                                                         uint2* __restrict__ lo) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    const uint32_t h0 = pack_bf16(v.x, v.y), h1 = pack_bf16(v.z, v.w);
+    hi[i] = make_uint2(h0, h1);
+    lo[i] = make_uint2(pack_bf16(v.x - bf16_lo(h0), v.y - bf16_hi(h0)), pack_bf16(v.z - bf16_lo(h1), v.w - bf16_hi(h1)));
+  }
+}
+
+static int split_bf16(Ctx* ctx, const float* x, int64_t n, void* hi, void* lo, cudaStream_t st) {
+  SIMSEG_CHECK_ARG(n % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "split_bf16: need 16-byte aligned rows");
+  const int64_t n4 = n / 4;
+  const int grid = static_cast<int>(imin64(cdiv(n4, 256), static_cast<int64_t>(ctx->num_sms) * 8));
+  split_bf16_kernel<<<grid, 256, 0, st>>>(x, n4, reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo));
+  ctx->launches++;
+  SIMSEG_LAUNCH_CHECK();
+  return SIMSEG_OK;
+}
+
+// one warp per row: merge the (max, sum exp, best, argmax) partials of the row's tile halves
+__global__ void __launch_bounds__(256) nce_merge_kernel(const float4* __restrict__ part, int part_ld, int nparts, int b,
+                                                        const float* __restrict__ zt, float* __restrict__ loss_rows,
+                                                        float* __restrict__ lse_out, int32_t* __restrict__ argmax_out) {
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= b) return;
+  float m = -INFINITY, l = 0.f, best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int k = lane; k < nparts; k += 32) {
+    const float4 q = part[static_cast<int64_t>(row) * part_ld + k];
+    const int qi = __float_as_int(q.w);
+    if (q.y > 0.f) {                                    // a half whose columns were all padding wrote nothing sensible: l == 0
+      const float mm = fmaxf(m, q.x);
+      l = l * __expf(m - mm) + q.y * __expf(q.x - mm);
+      m = mm;
+      if (q.z > best || (q.z == best && qi < bi)) { best = q.z; bi = qi; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), l2 = __shfl_xor_sync(0xffffffffu, l, o);
+    const float b2 = __shfl_xor_sync(0xffffffffu, best, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+    const float mm = fmaxf(m, m2);
+    l = (mm == -INFINITY) ? 0.f : l * __expf(m - mm) + l2 * __expf(m2 - mm);
+    m = mm;
+    if (b2 > best || (b2 == best && i2 < bi)) { best = b2; bi = i2; }
+  }
+  if (lane == 0) {
+    const float lse = m + logf(l);
+    loss_rows[row] = lse - zt[row];
+    lse_out[row] = lse;
+    if (argmax_out) argmax_out[row] = bi;
+  }
+}
+
+// partial slots of tile halves that lie entirely in the N padding are never written: clear l (= .y) so the merge skips them
+__global__ void clear_parts_kernel(float4* part, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    part[i] = make_float4(-INFINITY, 0.f, -INFINITY, __int_as_float(0x7fffffff));
+}
+
+static inline int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
+struct NceWs {
+  int64_t f1h, f1l, f2h, f2l, part, zt, g, total;
+  int part_ld;
+  int64_t ldg, lo_off;
+};
+static NceWs nce_ws_layout(int b, int Bg, int E) {
+  NceWs w;
+  int64_t o = 0;
+  w.f1h = o; o += align256(static_cast<int64_t>(b) * E * 2);
+  w.f1l = o; o += align256(static_cast<int64_t>(b) * E * 2);
+  w.f2h = o; o += align256(static_cast<int64_t>(Bg) * E * 2);
+  w.f2l = o; o += align256(static_cast<int64_t>(Bg) * E * 2);
+  w.part_ld = 2 * static_cast<int>(cdiv(Bg, 128));
+  w.part = o; o += align256(static_cast<int64_t>(b) * w.part_ld * 16);
+  w.zt = o; o += align256(static_cast<int64_t>(b) * 4);
+  w.lo_off = cdiv(Bg, 8) * 8;
+  w.ldg = 2 * w.lo_off;
+  w.g = o; o += align256(static_cast<int64_t>(b) * w.ldg * 2);
+  w.total = o;
+  return w;
+}
+int64_t infonce_fused_workspace_bytes(int b, int Bg, int E) { return nce_ws_layout(b, Bg, E).total; }
+
+static void sim_gemm_args(simseg_gemm_args& g, const void* a, const void* bm, void* d, int64_t M, int64_t N, int64_t K,
+                          int64_t lda, int64_t ldb, int64_t ldd, int a_major, int b_major, int accumulate) {
+  memset(&g, 0, sizeof(g));
+  g.a = a; g.b = bm; g.d = d; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldd = ldd;
+  g.a_major = a_major; g.b_major = b_major; g.in_dtype = SIMSEG_BF16; g.out_dtype = SIMSEG_F32;
+  g.epilogue = SIMSEG_EPI_NONE; g.accumulate = accumulate;
+}
+
+int infonce_fused_fwd_impl(Ctx* ctx, const float* feat1, const float* feat2g, int b, int Bg, int E, const float* temperature,
+                           int row_offset, void* ws, int64_t ws_bytes, float* loss_rows, float* lse, int32_t* argmax,
+                           cudaStream_t st) {
+  SIMSEG_CHECK_ARG(b > 0 && Bg > 0 && row_offset >= 0 && row_offset + b <= Bg, "infonce_fused_fwd: bad shape b=%d Bg=%d off=%d", b, Bg, row_offset);
+  SIMSEG_CHECK_ARG(E % 8 == 0, "infonce_fused: E must be a multiple of 8");
+  const NceWs w = nce_ws_layout(b, Bg, E);
+  SIMSEG_CHECK_ARG(ws != nullptr && ws_bytes >= w.total && (reinterpret_cast<uintptr_t>(ws) & 255) == 0,
+                   "infonce_fused: workspace needs %lld bytes, 256-byte aligned", static_cast<long long>(w.total));
+  uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+  int rc;
+  if ((rc = split_bf16(ctx, feat1, static_cast<int64_t>(b) * E, base + w.f1h, base + w.f1l, st))) return rc;
+  if ((rc = split_bf16(ctx, feat2g, static_cast<int64_t>(Bg) * E, base + w.f2h, base + w.f2l, st))) return rc;
+  const int64_t nparts = static_cast<int64_t>(b) * w.part_ld;
+  clear_parts_kernel<<<static_cast<int>(imin64(cdiv(nparts, 256), 1184)), 256, 0, st>>>(reinterpret_cast<float4*>(base + w.part), nparts);
+  ctx->launches++;
+  SIMSEG_LAUNCH_CHECK();
+  simseg_gemm_args g;
+  sim_gemm_args(g, base + w.f1h, base + w.f2h, nullptr, b, Bg, E, E, E, 0, 0, 0, 0);
+  GemmSim s;
+  memset(&s, 0, sizeof(s));
+  s.a_lo = base + w.f1l; s.b_lo = base + w.f2l; s.epi = 16;
+  s.temperature = temperature; s.row_offset = row_offset;
+  s.part = base + w.part; s.part_ld = w.part_ld; s.zt = reinterpret_cast<float*>(base + w.zt);
+  if ((rc = gemm_sim_impl(ctx, &g, &s, st))) return rc;
+  nce_merge_kernel<<<static_cast<int>(cdiv(b, 8)), 256, 0, st>>>(reinterpret_cast<const float4*>(base + w.part), w.part_ld, w.part_ld,
+                                                                 b, reinterpret_cast<const float*>(base + w.zt), loss_rows, lse, argmax);
+  ctx->launches++;
+  SIMSEG_LAUNCH_CHECK();
+  return SIMSEG_OK;
+}
+
+int infonce_fused_bwd_impl(Ctx* ctx, int b, int Bg, int E, const float* temperature, int row_offset, const float* lse,
+                           float grad_scale, void* ws, int64_t ws_bytes, float* dfeat1, float* dfeat2g, float* dtemp,
+                           cudaStream_t st) {
+  SIMSEG_CHECK_ARG(b > 0 && Bg > 0 && row_offset >= 0 && row_offset + b <= Bg, "infonce_fused_bwd: bad shape");
+  const NceWs w = nce_ws_layout(b, Bg, E);
+  SIMSEG_CHECK_ARG(ws != nullptr && ws_bytes >= w.total, "infonce_fused_bwd: workspace too small");
+  uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+  __nv_bfloat16* G = reinterpret_cast<__nv_bfloat16*>(base + w.g);
+  int rc;
+  simseg_gemm_args g;
+  GemmSim s;
+  // scores again (the split operands are still in the workspace), G = dLoss/dcos out of the epilogue
+  sim_gemm_args(g, base + w.f1h, base + w.f2h, G, b, Bg, E, E, E, w.ldg, 0, 0, 0);
+  memset(&s, 0, sizeof(s));
+  s.a_lo = base + w.f1l; s.b_lo = base + w.f2l; s.epi = 17;
+  s.temperature = temperature; s.row_offset = row_offset; s.lse = lse; s.grad_scale = grad_scale; s.dtemp = dtemp;
+  s.lo_off = w.lo_off;
+  if ((rc = gemm_sim_impl(ctx, &g, &s, st))) return rc;
+  if (dfeat1) {      // dfeat1[b,E] = G[b,Bg] @ feat2g[Bg,E]      (A K-major, B stored [K,N])
+    sim_gemm_args(g, G, base + w.f2h, dfeat1, b, E, Bg, w.ldg, E, E, 0, 1, 0);
+    memset(&s, 0, sizeof(s));
+    s.a_lo = G + w.lo_off; s.b_lo = base + w.f2l;
+    if ((rc = gemm_sim_impl(ctx, &g, &s, st))) return rc;
+  }
+  if (dfeat2g) {     // dfeat2g[Bg,E] += G^T[Bg,b] @ feat1[b,E]   (A stored [K,M], B stored [K,N])
+    sim_gemm_args(g, G, base + w.f1h, dfeat2g, Bg, E, b, w.ldg, E, E, 1, 1, 1);
+    memset(&s, 0, sizeof(s));
+    s.a_lo = G + w.lo_off; s.b_lo = base + w.f1l;
+    if ((rc = gemm_sim_impl(ctx, &g, &s, st))) return rc;
+  }
+  return SIMSEG_OK;
+}
+
+// ---- retrieval ---------------------------------------------------------------------------------------------------
+// Two passes of the same split-product GEMM, so every comparison is between numbers produced by the SAME arithmetic (rows
+// with identical data get identical scores and the lower-column tie rule holds exactly):
+//   pass 1 (kEpiBest)  (s*, j*) of every left row = its best-scoring right item of the same group, ties -> lowest column;
+//                      only the tiles whose group-id ranges intersect are visited (a short device-built tile list: with
+//                      the usual id-sorted layout — 5 captions per image — that is ~1/20 of the tiles)
+//   pass 2 (kEpiRank)  rank[i] = #{j of another group : s_ij > s*  or  (s_ij == s* and j < j*)}
+__global__ void __launch_bounds__(1024) gid_tile_list_kernel(const int64_t* __restrict__ lgid, int M, int tile_m,
+                                                             const int64_t* __restrict__ rgid, int Nr, int tile_n,
+                                                             long long* __restrict__ range, int32_t* __restrict__ list,
+                                                             int32_t* __restrict__ count) {
+  const int mt = (M + tile_m - 1) / tile_m, nt = (Nr + tile_n - 1) / tile_n;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  if (threadIdx.x == 0) *count = 0;
+  for (int t = warp; t < mt + nt; t += nwarps) {
+    const bool is_row = t < mt;
+    const int64_t* g = is_row ? lgid : rgid;
+    const int lo = (is_row ? t : t - mt) * (is_row ? tile_m : tile_n);
+    const int hi = min(lo + (is_row ? tile_m : tile_n), is_row ? M : Nr);
+    long long mn = 0x7fffffffffffffffll, mx = -0x7fffffffffffffffll - 1;
+    for (int i = lo + lane; i < hi; i += 32) {
+      const long long v = g[i];
+      mn = v < mn ? v : mn;
+      mx = v > mx ? v : mx;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const long long a = __shfl_xor_sync(0xffffffffu, mn, o), c = __shfl_xor_sync(0xffffffffu, mx, o);
+      mn = a < mn ? a : mn;
+      mx = c > mx ? c : mx;
+    }
+    if (lane == 0) { range[2 * t] = mn; range[2 * t + 1] = mx; }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < mt * nt; k += blockDim.x) {
+    const int im = k / nt, in = k - im * nt;
+    if (range[2 * im] <= range[2 * (mt + in) + 1] && range[2 * (mt + in)] <= range[2 * im + 1]) list[atomicAdd(count, 1)] = k;
+  }
+}
+
+__global__ void best_decode_kernel(const unsigned long long* __restrict__ key, int M, float* __restrict__ best,
+                                   int32_t* __restrict__ bestj, int32_t* __restrict__ rank) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const unsigned long long k = key[i];
+  if (k == 0ull) { best[i] = INFINITY; bestj[i] = -1; rank[i] = -1; return; }
+  uint32_t u = static_cast<uint32_t>(k >> 32);
+  u ^= (u >> 31) ? 0x80000000u : 0xffffffffu;
+  best[i] = __uint_as_float(u);
+  bestj[i] = static_cast<int32_t>(0xffffffffu - static_cast<uint32_t>(k & 0xffffffffu));
+  rank[i] = 0;
+}
+
+struct RetrWs { int64_t lh, ll, rh, rl, best, bestj, key, range, list, count, total; };
+static RetrWs retr_ws_layout(int M, int Nr, int E) {
+  RetrWs w;
+  int64_t o = 0;
+  w.lh = o; o += align256(static_cast<int64_t>(M) * E * 2);
+  w.ll = o; o += align256(static_cast<int64_t>(M) * E * 2);
+  w.rh = o; o += align256(static_cast<int64_t>(Nr) * E * 2);
+  w.rl = o; o += align256(static_cast<int64_t>(Nr) * E * 2);
+  w.best = o; o += align256(static_cast<int64_t>(M) * 4);
+  w.bestj = o; o += align256(static_cast<int64_t>(M) * 4);
+  w.key = o; o += align256(static_cast<int64_t>(M) * 8);
+  const int64_t mt = cdiv(M, 128), nt = cdiv(Nr, 128);
+  w.range = o; o += align256((mt + nt) * 16);
+  w.list = o; o += align256(mt * nt * 4);
+  w.count = o; o += 256;
+  w.total = o;
+  return w;
+}
+int64_t retrieval_fused_workspace_bytes(int M, int Nr, int E) { return retr_ws_layout(M, Nr, E).total; }
+
+int retrieval_rank_fused_impl(Ctx* ctx, const float* left, const float* right, int M, int Nr, int E, const int64_t* left_gid,
+                              const int64_t* right_gid, void* ws, int64_t ws_bytes, int32_t* rank, cudaStream_t st) {
+  SIMSEG_CHECK_ARG(M > 0 && Nr > 0 && E % 8 == 0, "retrieval_rank_fused: bad shape M=%d Nr=%d E=%d", M, Nr, E);
+  const RetrWs w = retr_ws_layout(M, Nr, E);
+  SIMSEG_CHECK_ARG(ws != nullptr && ws_bytes >= w.total && (reinterpret_cast<uintptr_t>(ws) & 255) == 0,
+                   "retrieval_rank_fused: workspace needs %lld bytes, 256-byte aligned", static_cast<long long>(w.total));
+  uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+  float* best = reinterpret_cast<float*>(base + w.best);
+  int32_t* bestj = reinterpret_cast<int32_t*>(base + w.bestj);
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(base + w.key);
+  int32_t* list = reinterpret_cast<int32_t*>(base + w.list);
+  int32_t* count = reinterpret_cast<int32_t*>(base + w.count);
+  int rc;
+  if ((rc = split_bf16(ctx, left, static_cast<int64_t>(M) * E, base + w.lh, base + w.ll, st))) return rc;
+  if ((rc = split_bf16(ctx, right, static_cast<int64_t>(Nr) * E, base + w.rh, base + w.rl, st))) return rc;
+  // one tile shape for both passes (the tile list is built for it): CTA pairs on 256 x 256 when they fill the machine
+  const bool pairs = cdiv(M, 256) * cdiv(Nr, 256) >= ctx->num_sms / 2;
+  const int tile_m = pairs ? 256 : 128, tile_n = pairs ? 256 : 128;
+  SIMSEG_CUDA(cudaMemsetAsync(key, 0, static_cast<size_t>(M) * 8, st));
+  gid_tile_list_kernel<<<1, 1024, 0, st>>>(left_gid, M, tile_m, right_gid, Nr, tile_n, reinterpret_cast<long long*>(base + w.range),
+                                           list, count);
+  ctx->launches++;
+  SIMSEG_LAUNCH_CHECK();
+  simseg_gemm_args g;
+  sim_gemm_args(g, base + w.lh, base + w.rh, nullptr, M, Nr, E, E, E, 0, 0, 0, 0);
+  g.tile_n = tile_n;
+  g.reserved = pairs ? 32 : 16;
+  GemmSim s;
+  memset(&s, 0, sizeof(s));
+  s.a_lo = base + w.ll; s.b_lo = base + w.rl; s.epi = 19;
+  s.lgid = left_gid; s.rgid = right_gid; s.bestkey = key; s.tile_list = list; s.tile_count = count;
+  if ((rc = gemm_sim_impl(ctx, &g, &s, st))) return rc;
+  best_decode_kernel<<<static_cast<int>(cdiv(M, 256)), 256, 0, st>>>(key, M, best, bestj, rank);
+  ctx->launches++;
+  SIMSEG_LAUNCH_CHECK();
+  s.epi = 18;
+  s.bestkey = nullptr; s.tile_list = nullptr; s.tile_count = nullptr;
+  s.best = best; s.bestj = bestj; s.rank = rank;
+  return gemm_sim_impl(ctx, &g, &s, st);
+}
+
+// out[M,Nr] fp32 = left @ right^T through the same split products (materialising variant, e.g. for top-k inspection)
+int allpairs_split_impl(Ctx* ctx, const float* left, const float* right, int M, int Nr, int E, void* ws, int64_t ws_bytes,
+                        float* out, cudaStream_t st) {
+  SIMSEG_CHECK_ARG(M > 0 && Nr > 0 && E % 8 == 0, "allpairs_split: bad shape");
+  const RetrWs w = retr_ws_layout(M, Nr, E);
+  SIMSEG_CHECK_ARG(ws != nullptr && ws_bytes >= w.total && (reinterpret_cast<uintptr_t>(ws) & 255) == 0,
+                   "allpairs_split: workspace too small");
+  uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+  uint8_t *lh = base + w.lh, *ll = base + w.ll, *rh = base + w.rh, *rl = base + w.rl;
+  int rc;
+  if ((rc = split_bf16(ctx, left, static_cast<int64_t>(M) * E, lh, ll, st))) return rc;
+  if ((rc = split_bf16(ctx, right, static_cast<int64_t>(Nr) * E, rh, rl, st))) return rc;
+  simseg_gemm_args g;
+  sim_gemm_args(g, lh, rh, out, M, Nr, E, E, E, Nr, 0, 0, 0);
+  GemmSim s;
+  memset(&s, 0, sizeof(s));
+  s.a_lo = ll; s.b_lo = rl;
+  return gemm_sim_impl(ctx, &g, &s, st);
 }
 
 }  // namespace simseg

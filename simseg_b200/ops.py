@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 from ._lib import (BF16, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU, EPI_NONE, EPI_ROWSCALE, F32,
-                   PREC_FP32, PREC_TF32, GemmArgs, check)
+                   PREC_FP32, PREC_SPLIT_BF16, PREC_TF32, GemmArgs, check)
 
 Tensor = torch.Tensor
 _ctx = {}
@@ -293,6 +293,67 @@ def infonce_bwd(feat1: Tensor, feat2g: Tensor, temperature: Tensor, row_offset: 
                                          _p(lse), grad_scale, _p(cos), _p(dfeat1), _p(dfeat2g), _p(dtemp), _stream()),
           "infonce_bwd")
     return dfeat1
+
+
+def _workspace(nbytes: int, device) -> Tensor:
+    """256-byte aligned caller-owned scratch (torch's caching allocator hands out 512-byte aligned blocks)."""
+    ws = torch.empty(max(int(nbytes), 256), device=device, dtype=torch.uint8)
+    assert ws.data_ptr() % 256 == 0
+    return ws
+
+
+def infonce_fused_fwd(feat1: Tensor, feat2g: Tensor, temperature: Tensor, row_offset: int):
+    """NCE.forward on the tensor cores (split-bf16 products, scores consumed in the GEMM epilogue): returns
+    (loss_rows [b], lse [b], argmax [b] int32, workspace) — hand the workspace to ``infonce_fused_bwd`` unchanged."""
+    b, E = feat1.shape
+    Bg = feat2g.shape[0]
+    assert feat1.dtype == torch.float32 and feat2g.dtype == torch.float32 and feat1.is_contiguous() and feat2g.is_contiguous()
+    dev = feat1.device
+    lib = _lib.load()
+    ws = _workspace(lib.simseg_infonce_fused_workspace_bytes(b, Bg, E), dev)
+    loss_rows = torch.empty(b, device=dev, dtype=torch.float32)
+    lse = torch.empty(b, device=dev, dtype=torch.float32)
+    argmax = torch.empty(b, device=dev, dtype=torch.int32)
+    check(lib.simseg_infonce_fused_fwd(ctx(), _p(feat1), _p(feat2g), b, Bg, E, _p(temperature), row_offset, _p(ws), ws.numel(),
+                                       _p(loss_rows), _p(lse), _p(argmax), _stream()), "infonce_fused_fwd")
+    return loss_rows, lse, argmax, ws
+
+
+def infonce_fused_bwd(b: int, Bg: int, E: int, temperature: Tensor, row_offset: int, lse: Tensor, grad_scale: float,
+                      ws: Tensor, dfeat2g: Optional[Tensor], dtemp: Optional[Tensor], want_dfeat1: bool = True):
+    """dfeat1 [b,E] (returned), dfeat2g [Bg,E] accumulated, dtemp accumulated; consumes the forward's workspace."""
+    dfeat1 = torch.empty((b, E), device=ws.device, dtype=torch.float32) if want_dfeat1 else None
+    check(_lib.load().simseg_infonce_fused_bwd(ctx(), b, Bg, E, _p(temperature), row_offset, _p(lse), grad_scale, _p(ws),
+                                               ws.numel(), _p(dfeat1), _p(dfeat2g), _p(dtemp), _stream()), "infonce_fused_bwd")
+    return dfeat1
+
+
+def retrieval_rank_fused(left: Tensor, right: Tensor, left_gid: Tensor, right_gid: Tensor) -> Tensor:
+    """First-match rank of every left row (``EmbANN._ann`` + ``RetrievalMetric``, tasks/clip/hooks/utils.py:35-42,63-65) in one
+    tensor-core pass; neither the [M,Nr] similarity matrix nor its argsort is materialised.  -1 where no right item matches."""
+    M, E = left.shape
+    Nr = right.shape[0]
+    assert left.dtype == torch.float32 and right.dtype == torch.float32 and left.is_contiguous() and right.is_contiguous()
+    assert left_gid.dtype == torch.int64 and right_gid.dtype == torch.int64 and left_gid.numel() == M and right_gid.numel() == Nr
+    lib = _lib.load()
+    ws = _workspace(lib.simseg_retrieval_fused_workspace_bytes(M, Nr, E), left.device)
+    rank = torch.empty(M, device=left.device, dtype=torch.int32)
+    check(lib.simseg_retrieval_rank_fused(ctx(), _p(left), _p(right), M, Nr, E, _p(left_gid.contiguous()), _p(right_gid.contiguous()),
+                                          _p(ws), ws.numel(), _p(rank), _stream()), "retrieval_rank_fused")
+    return rank
+
+
+def allpairs_sim_split(left: Tensor, right: Tensor) -> Tensor:
+    """left @ right^T (fp32 out) through the split-bf16 tensor-core products (|err| <= ~1e-5 on unit-norm rows)."""
+    M, E = left.shape
+    Nr = right.shape[0]
+    assert left.dtype == torch.float32 and right.dtype == torch.float32 and left.is_contiguous() and right.is_contiguous()
+    lib = _lib.load()
+    ws = _workspace(lib.simseg_retrieval_fused_workspace_bytes(M, Nr, E), left.device)
+    out = torch.empty((M, Nr), device=left.device, dtype=torch.float32)
+    check(lib.simseg_allpairs_sim_split(ctx(), _p(left), _p(right), M, Nr, E, _p(ws), ws.numel(), _p(out), _stream()),
+          "allpairs_sim_split")
+    return out
 
 
 def patch_text_sim(patches: Tensor, text: Tensor, normalize: bool = True, want_argmax: bool = True):

@@ -19,7 +19,7 @@ import torch.nn as nn
 
 from . import dist as sdist
 from . import ops, towers
-from ._lib import PREC_FP32
+from ._lib import PREC_FP32, PREC_SPLIT_BF16
 
 Tensor = torch.Tensor
 
@@ -311,15 +311,23 @@ class _ProjectPoolFn(torch.autograd.Function):
 
 
 class _NceFn(torch.autograd.Function):
-    """One ``NCE.forward`` direction (``mml_loss.py:51-96``) incl. the gather of feat2 (``utils/dist.py:323-354``)."""
+    """One ``NCE.forward`` direction (``mml_loss.py:51-96``) incl. the gather of feat2 (``utils/dist.py:323-354``).
+    ``precision``: ``PREC_SPLIT_BF16`` (default) = tcgen05 split-bf16 products with the scores consumed in the GEMM
+    epilogue; ``PREC_FP32`` = the exact-fp32 SIMT path that materialises the cosine matrix (kept as a cross-check)."""
 
     @staticmethod
     def forward(ctx, feat1, feat2, temperature, rank, group, precision):
         f1 = feat1.contiguous().float()
         f2g = sdist.all_gather_rows(feat2.contiguous().float(), group)
         b = f1.shape[0]
-        loss_rows, lse, argmax, cos, _ = ops.infonce_fwd(f1, f2g, temperature.detach().reshape(()), rank * b, precision)
-        ctx.save_for_backward(f1, f2g, lse, cos)
+        t0 = temperature.detach().reshape(())
+        if precision == PREC_SPLIT_BF16:
+            loss_rows, lse, argmax, ws = ops.infonce_fused_fwd(f1, f2g, t0, rank * b)
+            ctx.save_for_backward(lse, ws)
+            ctx.shape = (b, f2g.shape[0], f1.shape[1])
+        else:
+            loss_rows, lse, argmax, cos, _ = ops.infonce_fwd(f1, f2g, t0, rank * b, precision)
+            ctx.save_for_backward(f1, f2g, lse, cos)
         ctx.temperature, ctx.rank, ctx.group, ctx.precision, ctx.b = temperature, rank, group, precision, b
         targets = torch.arange(rank * b, (rank + 1) * b, device=f1.device, dtype=torch.int32)
         acc = (argmax == targets).float().sum() / b
@@ -328,14 +336,22 @@ class _NceFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gloss, _gacc):
-        _once(ctx, "the InfoNCE loss")                # infonce_bwd overwrites the saved cosine workspace in place
-        f1, f2g, lse, cos = ctx.saved_tensors
+        _once(ctx, "the InfoNCE loss")                # the backward overwrites the saved workspace in place
         t = ctx.temperature
-        dtemp = torch.zeros((), device=f1.device, dtype=torch.float32)
-        df2g = torch.zeros_like(f2g)
+        t0 = t.detach().reshape(())
         # loss = mean_i CE_i  ->  dCE_i = gloss / b   (gloss is a device scalar: fold it in afterwards)
-        df1 = ops.infonce_bwd(f1, f2g, t.detach().reshape(()), ctx.rank * ctx.b, lse, 1.0 / ctx.b, cos, df2g,
-                              dtemp if t.requires_grad else None, ctx.precision)
+        if ctx.precision == PREC_SPLIT_BF16:
+            lse, ws = ctx.saved_tensors
+            b, Bg, E = ctx.shape
+            dtemp = torch.zeros((), device=ws.device, dtype=torch.float32)
+            df2g = torch.zeros((Bg, E), device=ws.device, dtype=torch.float32)
+            df1 = ops.infonce_fused_bwd(b, Bg, E, t0, ctx.rank * b, lse, 1.0 / b, ws, df2g, dtemp if t.requires_grad else None)
+        else:
+            f1, f2g, lse, cos = ctx.saved_tensors
+            dtemp = torch.zeros((), device=f1.device, dtype=torch.float32)
+            df2g = torch.zeros_like(f2g)
+            df1 = ops.infonce_bwd(f1, f2g, t0, ctx.rank * ctx.b, lse, 1.0 / ctx.b, cos, df2g,
+                                  dtemp if t.requires_grad else None, ctx.precision)
         df2 = sdist.reduce_scatter_rows(df2g, ctx.rank, ctx.b, ctx.group)
         gl = gloss.float()
         return df1 * gl, df2 * gl, (dtemp * gl).reshape(t.shape) if t.requires_grad else None, None, None, None
@@ -451,7 +467,7 @@ class NCE(nn.Module):
             raise NotImplementedError
         if cfg.loss.smoothing > 0:
             raise NotImplementedError("label smoothing is outside the B200 hot path (shipped configs use 0)")
-        self.precision = PREC_FP32
+        self.precision = PREC_SPLIT_BF16          # PREC_FP32 selects the exact-fp32 SIMT cross-check path
 
     def forward(self, feat1, feat2, label=None, ignore_mask=None):
         if ignore_mask is not None:
