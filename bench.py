@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--micro-batch", type=int, default=0, help="0 = whole per-rank batch in one pass")
     ap.add_argument("--cpu-sample", type=int, default=32, help="pairs in the CPU-baseline sample")
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / patch-sim / cpu_baseline legs")
+    ap.add_argument("--no-graph", action="store_true", help="issue every kernel from the host instead of replaying the CUDA graph of the step")
     return ap.parse_args()
 
 
@@ -197,7 +198,8 @@ def run_ours(a):
                                "transforms.input_size=224", f"data.batch_size={a.global_batch}"])
     torch.manual_seed(0)                            # same random-init weights on every rank (DDP broadcast not needed)
     model = PIPELINE["clip"](cfg).to(dev)
-    trainer = Trainer(model, cfg, micro_batch=a.micro_batch or None)
+    use_graph = not a.no_graph and not a.micro_batch
+    trainer = Trainer(model, cfg, micro_batch=a.micro_batch or None, capturable=use_graph)
 
     # synthetic per-rank shard, pinned on the host (two rotating host batches so every step copies fresh bytes)
     host = []
@@ -230,24 +232,42 @@ def run_ours(a):
     # per-tower gradients must not depend on N: compare this block across the N = 1/2/4/8 lines.
     dp = dp_check(trainer, dev, world, rank, a.seq_len)
 
-    # ---- resident-input loop (value): inputs already in HBM
+    # ---- the step: one CUDA-graph launch (forward, backward, all-reduces, AdamW, bf16 weight re-cast recorded once); the
+    # eager path (every kernel issued from the host) is kept behind --no-graph and as the fallback if capture fails
     for k in dev_bufs[0]:
         dev_bufs[0][k].copy_(host[0][k])
+    graphed, graph_note = None, "off (--no-graph / micro-batching)"
+    launches_per_step = None
+    if use_graph:
+        try:
+            graphed = trainer.capture(dev_bufs[0], warmup=max(a.warmup, 2))
+            launches_per_step = graphed.launches_per_replay
+            graph_note = "whole step replayed as one CUDA graph"
+        except Exception as e:                               # noqa: BLE001 - report and fall back, never lose the line
+            graphed, graph_note = None, f"capture failed, eager fallback: {repr(e)[:160]}"
+            torch.cuda.synchronize()
     last = {}
 
+    def do_step(batch, resident_inputs=False):
+        if graphed is None:
+            return trainer.step(batch)
+        return graphed(None if resident_inputs else batch)    # None: the static input buffers already hold the batch
+
+    # ---- resident-input loop (value): inputs already in HBM
     def resident(steps):
         for _ in range(steps):
-            last["out"] = trainer.step(dev_bufs[0])
+            last["out"] = do_step(dev_bufs[0], resident_inputs=True)
 
     resident(a.warmup)
     ops.launch_count(reset=True)
     with ClockSampler(local) as cs:
         ms_total = timed(resident, a.steps)
-    launches = ops.launch_count()
+    launches = ops.launch_count() if graphed is None else launches_per_step * a.steps
     ms_step = ms_total / a.steps
     value = a.global_batch / (ms_step / 1e3)
 
-    # ---- end-to-end loop: pinned host batch -> H2D (prefetched on a copy stream) -> step -> loss.item()
+    # ---- end-to-end loop: pinned host batch -> H2D (prefetched on a copy stream into a staging buffer) -> step -> loss.item()
+    # (a graph reads fixed addresses: the staged batch is copied device-to-device into the step's static input buffers)
     def e2e(steps):
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         done = [None, None]
@@ -266,7 +286,7 @@ def run_ours(a):
             if i + 1 < steps:
                 issue(i + 1)
             torch.cuda.current_stream().wait_event(ready[s])
-            loss, _, _ = trainer.step(dev_bufs[s])
+            loss, _, _ = do_step(dev_bufs[s])
             done[s] = torch.cuda.Event()
             done[s].record()
             last["loss"] = loss.item()                        # D2H read of the step result
@@ -279,6 +299,7 @@ def run_ours(a):
             "data": "synthetic",
             "config": {"workload": workload_name(a), "global_batch": a.global_batch, "per_gpu_batch": b,
                        "seq_len": a.seq_len, "parallelism": f"dp{world}", "micro_batch": a.micro_batch or b,
+                       "cuda_graph": graph_note,
                        "l2": "per-step working set (>10 GB of activations) is far larger than the 126 MB L2"},
             "clocks": cs.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": 4 * world,
@@ -290,6 +311,9 @@ def run_ours(a):
 
     if not a.no_extras:
         hbm, tf_sus, tf_burst, how = peaks()
+        graphed = None                                               # the graph's memory pool goes back before the extra legs
+        last.clear()
+        torch.cuda.empty_cache()
         roof = gemm_roofline(trainer, dev_bufs[0], tf_sus, how)      # a training step: EVERY rank takes part in its collectives
         if rank == 0:
             line["roofline"] = roof

@@ -384,8 +384,8 @@ def _check_text(input_ids: Tensor, attention_mask: Tensor, bert) -> None:
     T = input_ids.shape[1]
     if T > emb.position_embeddings.weight.shape[0]:
         raise IndexError(f"sequence length {T} exceeds max_position_embeddings {emb.position_embeddings.weight.shape[0]}")
-    if not _CHECK_INPUTS or input_ids.numel() == 0:
-        return
+    if not _CHECK_INPUTS or input_ids.numel() == 0 or (input_ids.is_cuda and torch.cuda.is_current_stream_capturing()):
+        return                                        # (a CUDA-graph capture cannot read values back; warm-up steps did)
     vocab = emb.word_embeddings.weight.shape[0]
     m = attention_mask
     prefix = (m[:, 1:] <= m[:, :-1]).all() & (m >= 0).all() & (m <= 1).all() if T > 1 else ((m >= 0).all() & (m <= 1).all())

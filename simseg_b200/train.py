@@ -46,19 +46,29 @@ def grouped_parameters(model: torch.nn.Module, cfg):
     return list(merged.values())
 
 
-def build_optimizer(model: torch.nn.Module, cfg) -> torch.optim.Optimizer:
-    """``optim.name`` is a dotted class path (``core/hooks/optimizer.py:21-28`` evaluates it the same way)."""
+def build_optimizer(model: torch.nn.Module, cfg, capturable: bool = False) -> torch.optim.Optimizer:
+    """``optim.name`` is a dotted class path (``core/hooks/optimizer.py:21-28`` evaluates it the same way).
+    ``capturable``: optimizer state (step counters, learning rates) lives on the device so ``step()`` can be recorded
+    into a CUDA graph; the learning rate of every group becomes a device scalar a scheduler may update in place."""
     mod, _, cls = str(cfg.optim.name).rpartition(".")
     ctor = getattr(importlib.import_module(mod or "torch.optim"), cls)
     kw = {k: (tuple(v) if isinstance(v, list) else v) for k, v in dict(cfg.optim.param).items()}
     kw.pop("weight_decay", None)                      # carried per group
     if ctor in (torch.optim.AdamW, torch.optim.Adam, torch.optim.SGD):
         kw.setdefault("fused", True)
-    return ctor(grouped_parameters(model, cfg), **kw)
+    groups = grouped_parameters(model, cfg)
+    if capturable:
+        if ctor not in (torch.optim.AdamW, torch.optim.Adam):
+            raise NotImplementedError("CUDA-graph capture of the step is wired for Adam/AdamW (capturable=True)")
+        kw["capturable"] = True
+        dev = groups[0]["params"][0].device
+        for g in groups:
+            g["lr"] = torch.tensor(float(g["lr"]), device=dev, dtype=torch.float32)
+    return ctor(groups, **kw)
 
 
 class Trainer:
-    def __init__(self, model: CLIPModel, cfg, micro_batch: Optional[int] = None):
+    def __init__(self, model: CLIPModel, cfg, micro_batch: Optional[int] = None, capturable: bool = False):
         self.model, self.cfg, self.micro_batch = model, cfg, micro_batch
         vit = list(model.image_encoder.parameters())
         bert = list(model.text_encoder.parameters())
@@ -68,7 +78,8 @@ class Trainer:
                      if any(p.requires_grad for p in ps)}
         model._shared.tower_done = self._tower_done
         model._shared.direct_grads = True             # wgrad kernels accumulate straight into the flat buffers
-        self.opt = build_optimizer(model, cfg)
+        self.opt = build_optimizer(model, cfg, capturable)
+        self.capturable = capturable
         gc = cfg.optim.get("grad_clip") or {}
         self.grad_clip = dict(gc) if len(gc) else None
         self._defer_reduce = False
@@ -106,6 +117,11 @@ class Trainer:
         self.model.new_step()                         # the bf16 weight copies are re-cast (one launch) on next use
         return out
 
+    def capture(self, batch: Dict[str, Tensor], warmup: int = 2) -> "GraphedStep":
+        """Record one whole training step (forward, backward, gradient all-reduces, optimizer, weight re-cast) into a CUDA
+        graph; see ``GraphedStep``."""
+        return GraphedStep(self, batch, warmup)
+
     # ---- two-pass micro-batched step with an embedding cache ---------------------------------
     def _step_cached(self, batch):
         m, mb = self.model, self.micro_batch
@@ -139,3 +155,47 @@ class Trainer:
         finally:
             self._defer_reduce = False
         return loss.detach(), i2t, t2i
+
+
+class GraphedStep:
+    """One training step as a single CUDA-graph launch.
+
+    A step is ~520 kernel launches through the C ABI plus ~300 small torch kernels; at the per-GPU batch of an 8-GPU run
+    (512 pairs: ~35 ms of GPU work) the host needs ~15 ms to issue them and the GPU idles in between.  Everything in the step
+    is static — shapes, buffers (the graph's private memory pool), tensor maps (encoded on the host at capture time with the
+    pool's addresses), collectives (NCCL kernels are captured like any other) — so it is recorded once and replayed.
+
+    ``warmup`` real steps run first on the capture stream (they DO train: lazily created buffers, bf16 weight tables and
+    ``cudaFuncSetAttribute`` calls must exist before recording).  ``__call__(batch)`` copies the batch into the static input
+    buffers (device-to-device, or host-to-device for a pinned host batch) and launches the graph; it returns the static
+    ``(loss, i2t_acc, t2i_acc)`` tensors, overwritten by the next call."""
+
+    def __init__(self, trainer: Trainer, batch: Dict[str, Tensor], warmup: int = 2):
+        if not trainer.capturable:
+            raise ValueError("build the Trainer with capturable=True to record its step into a CUDA graph")
+        from . import ops
+        self.trainer = trainer
+        dev = next(trainer.model.parameters()).device
+        self.static = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in batch.items()}
+        for k, v in batch.items():
+            self.static[k].copy_(v)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                trainer.step(self.static)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        torch.cuda.empty_cache()                      # hand the warm-up's blocks back so the graph pool can have them
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = ops.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.out = trainer.step(self.static)
+        self.launches_per_replay = ops.launch_count() - n0      # kernels of the library inside one replay
+
+    def __call__(self, batch: Optional[Dict[str, Tensor]] = None):
+        if batch is not None and batch is not self.static:
+            for k, v in batch.items():
+                self.static[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.out

@@ -290,3 +290,41 @@ def test_torch_ddp_wrap_reduces_tower_gradients(cuda):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_cuda_graph_step_equals_eager_steps(cuda):
+    """``Trainer.capture``: the whole step (forward, backward, optimizer, bf16 weight re-cast) replayed as one CUDA graph must
+    train exactly like the eager step: 2 warm-up + 3 replayed steps vs 5 eager steps from the same weights, a new batch every
+    step (the static input buffers are refilled), losses and final weights compared (split-K atomics reorder fp32 sums, so
+    the bar is 1e-4 relative on the weight DELTAS, not bitwise)."""
+    from oracle import simseg_oracle as O
+    from simseg_b200.train import Trainer
+    sd = O.make_state_dict(384, 6, seed=0)
+    batches = [{k: v.to(cuda) for k, v in O.make_batch(8, 25, seed=100 + i).items()} for i in range(5)]
+    eager, cfg = _build(cuda)
+    eager.load_state_dict(sd)
+    te = Trainer(eager, cfg, capturable=True)
+    le = [te.step(b)[0].item() for b in batches]
+    model, cfg = _build(cuda)
+    model.load_state_dict(sd)
+    tg = Trainer(model, cfg, capturable=True)
+    # warm-up steps inside capture() train on the batch they are given: feed batches 0 and 1 by hand, then capture with 1
+    lg = [tg.step(batches[0])[0].item()]
+    gs = tg.capture(batches[1], warmup=1)
+    assert gs.launches_per_replay > 400
+    for b in batches[2:]:
+        loss, i2t, t2i = gs(b)
+        lg.append(loss.item())
+    torch.cuda.synchronize()
+    print("eager", le, "graph", lg)
+    assert len(lg) == 4
+    for a, b in zip([le[0]] + le[2:], lg):
+        assert abs(a - b) < 2e-3, (le, lg)
+    w0 = {k: v.to(cuda) for k, v in sd.items()}
+    worst = 0.0
+    for (k, pe), (_, pg) in zip(eager.named_parameters(), model.named_parameters()):
+        de, dg = pe.detach() - w0[k], pg.detach() - w0[k]
+        if de.norm().item() > 1e-9:
+            worst = max(worst, ((de - dg).norm() / de.norm()).item())
+    print("worst relative difference of the 5-step weight deltas:", worst)
+    assert worst < 5e-2
