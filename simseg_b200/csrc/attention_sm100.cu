@@ -8,7 +8,9 @@
 //                 S  = Q_qt K_kt^T   [128 q x 128 keys]  cols   0..127      dP = dO_qt V_kt^T         cols 128..255
 //                 dV_kt += P^T dO_qt [128 keys x 64]     cols 256..319      dK_kt += dS^T Q_qt        cols 320..383
 //                 dQ_qt += dS K_kt   [128 q x 64]        cols 384 + 64 qt
-//   warps 2..9  elementwise: tcgen05.ld S and dP, P = exp2(S*scale*log2e - lse*log2e), dS = P * (dP - D), written as bf16
+//   warps 2..9  elementwise, two phases per block (A: tcgen05.ld S, P = exp2(S*scale*log2e - lse*log2e); B: tcgen05.ld dP,
+//               dS = P * (dP - D)) so the tensor pipe computes S of the NEXT block under phase B and dP of the next block under
+//               its phase A (software-pipelined issue order, see the MMA warp); P and dS are written as bf16
 //               into smem in the [key atom][q row][128 B] swizzled layout that serves BOTH as the K-major A operand of
 //               dQ = dS K and as the MN-major A operand of dK = dS^T Q / dV = P^T dO (no transposes anywhere);
 //               the same warps drain dK/dV after the last query tile of a key tile and dQ after the last key tile.
@@ -68,14 +70,17 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   uint64_t* qdo_empty = bars + 2;     // [2]
   uint64_t* kv_full = bars + 4;       // [2]
   uint64_t* kv_empty = bars + 6;      // [2]
-  uint64_t* sdp_full = bars + 8;      // MMA -> EW : S and dP are in TMEM
-  uint64_t* ew_done = bars + 9;       // EW -> MMA : S/dP consumed, P/dS written to smem        (8 warps)
-  uint64_t* pds_free = bars + 10;     // MMA -> EW : the MMAs reading P/dS have completed
-  uint64_t* dkv_full = bars + 11;     // MMA -> EW : dK/dV of a key tile complete
-  uint64_t* dkv_free = bars + 12;     // EW -> MMA : dK/dV drained                               (8 warps)
-  uint64_t* dq_full = bars + 13;
-  uint64_t* dq_free = bars + 14;      //                                                          (8 warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* s_full = bars + 8;        // MMA -> EW : S of block g is in TMEM
+  uint64_t* dp_full = bars + 9;       // MMA -> EW : dP of block g is in TMEM
+  uint64_t* p_ready = bars + 10;      // EW -> MMA : S consumed, P written to smem               (8 warps)
+  uint64_t* ds_ready = bars + 11;     // EW -> MMA : dP consumed, dS written to smem             (8 warps)
+  uint64_t* p_free = bars + 12;       // MMA -> EW : dV = P^T dO has read P
+  uint64_t* ds_free = bars + 13;      // MMA -> EW : dK = dS^T Q and dQ = dS K have read dS
+  uint64_t* dkv_full = bars + 14;     // MMA -> EW : dK/dV of a key tile complete
+  uint64_t* dkv_free = bars + 15;     // EW -> MMA : dK/dV drained                               (8 warps)
+  uint64_t* dq_full = bars + 16;
+  uint64_t* dq_free = bars + 17;      //                                                          (8 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -86,7 +91,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1);
       mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
     }
-    mbar_init(sdp_full, 1); mbar_init(ew_done, 8); mbar_init(pds_free, 1);
+    mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_ready, 8); mbar_init(ds_ready, 8);
+    mbar_init(p_free, 1); mbar_init(ds_free, 1);
     mbar_init(dkv_full, 1); mbar_init(dkv_free, 8); mbar_init(dq_full, 1); mbar_init(dq_free, 8);
     fence_barrier_init();
   }
@@ -119,11 +125,15 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           tma_load_4d(sK + buf * kTileBytes, &tm_k, &kv_full[buf], 0, h, kt * kTile, b);
           tma_load_4d(sV + buf * kTileBytes, &tm_v, &kv_full[buf], 0, h, kt * kTile, b);
           if (kt == 0) {
+            // Q / dO slots: one per query tile; single-tile items alternate between the two slots, so the next item's
+            // tiles load while the current item is still being worked on (the MMA issue runs one block ahead)
             for (int qt = 0; qt < p.nqt; ++qt) {
-              mbar_wait(&qdo_empty[qt], (it & 1) ^ 1);
-              mbar_arrive_expect_tx(&qdo_full[qt], 2 * p.tile_tx);
-              tma_load_4d(sQ + qt * kTileBytes, &tm_q, &qdo_full[qt], 0, h, qt * kTile, b);
-              tma_load_4d(sdO + qt * kTileBytes, &tm_do, &qdo_full[qt], 0, h, qt * kTile, b);
+              const uint32_t slot = (p.nqt == 1) ? (it & 1) : static_cast<uint32_t>(qt);
+              const uint32_t use = (p.nqt == 1) ? (it >> 1) : it;
+              mbar_wait(&qdo_empty[slot], (use & 1) ^ 1);
+              mbar_arrive_expect_tx(&qdo_full[slot], 2 * p.tile_tx);
+              tma_load_4d(sQ + slot * kTileBytes, &tm_q, &qdo_full[slot], 0, h, qt * kTile, b);
+              tma_load_4d(sdO + slot * kTileBytes, &tm_do, &qdo_full[slot], 0, h, qt * kTile, b);
             }
           }
         }
@@ -134,65 +144,105 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     // Warp-uniform loops, one elected lane issues (values stay in uniform registers; a descriptor is a 64-bit add away
     // from two constants).  Issued from inside `if (lane == 0)` this thread — ~45 instructions per MMA — was the
     // slowest stage of the kernel.
+    // Software pipeline over the flattened block sequence (item, key tile, query tile): the elementwise warps work in two
+    // phases per block — A: S -> P, B: dP -> dS — and the tensor pipe is fed in the order
+    //     [A(g) done] dV(g), S(g+1)      [B(g) done] dK(g), dQ(g), dP(g+1)
+    // so S(g+1) is computed under phase B of block g and dP(g+1) under phase A of block g+1: the elementwise warps, not the
+    // commit -> wait -> ld -> st -> fence -> arrive round trips, set the pace (round 1 ran the five products and the
+    // elementwise pass of a block strictly one after the other: 70 % of the kernel was hand-off latency).
     {
-      uint32_t kvc = 0, it = 0, g = 0, drains = 0;
       const uint32_t id_sdp_base = make_idesc(1u, 0u, 0u, kTile, 16u) & ~(0x3Fu << 17);     // N filled per key tile
       const uint32_t id_dkv = make_idesc(1u, 1u, 1u, kTile, 64u);                           // A, B MN-major
       const uint32_t id_dq = make_idesc(1u, 0u, 1u, kTile, 64u);                            // A K-major, B MN-major
       const uint64_t kd = make_smem_desc_sw128(0, 16, 1024);                                // K-major operand template
       const uint64_t md = make_smem_desc_sw128(0, 16384, 1024);                             // MN-major operand template
       const uint32_t aP = smem_u32(sP) >> 4, adS = smem_u32(sdS) >> 4;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-        for (int kt = 0; kt < p.nkt; ++kt, ++kvc) {
-          const uint32_t buf = kvc & 1;
-          const int nkc = min(kTile, ceil16(p.rows - kt * kTile));            // key columns of this tile (multiple of 16)
-          const uint32_t id_sdp = id_sdp_base | (static_cast<uint32_t>(nkc >> 3) << 17);
-          mbar_wait(&kv_full[buf], (kvc >> 1) & 1);
-          const uint32_t aK = smem_u32(sK + buf * kTileBytes) >> 4, aV = smem_u32(sV + buf * kTileBytes) >> 4;
-          for (int qt = 0; qt < p.nqt; ++qt, ++g) {
-            if (kt == 0) mbar_wait(&qdo_full[qt], it & 1);
-            tc_fence_after();
-            const uint32_t aQ = smem_u32(sQ + qt * kTileBytes) >> 4, adO = smem_u32(sdO + qt * kTileBytes) >> 4;
-            // ---- S = Q K^T, dP = dO V^T   (K = d = 64: four K-steps inside one 128-byte swizzle row)
-            if (elect_one()) {
+      struct Cur { int item, kt, qt; uint32_t it, kvc, g; };
+      auto valid = [&](const Cur& c) { return c.item < p.items; };
+      auto advance = [&](Cur& c) {
+        ++c.g;
+        if (++c.qt == p.nqt) {
+          c.qt = 0; ++c.kvc;
+          if (++c.kt == p.nkt) { c.kt = 0; c.item += gridDim.x; ++c.it; }
+        }
+      };
+      auto nkc_of = [&](const Cur& c) { return min(kTile, ceil16(p.rows - c.kt * kTile)); };
+      auto slot_of = [&](const Cur& c) { return (p.nqt == 1) ? (c.it & 1) : static_cast<uint32_t>(c.qt); };
+      auto use_of = [&](const Cur& c) { return (p.nqt == 1) ? (c.it >> 1) : c.it; };
+      auto idesc_sdp = [&](const Cur& c) { return id_sdp_base | (static_cast<uint32_t>(nkc_of(c) >> 3) << 17); };
+      auto issue_s = [&](const Cur& c) {              // S = Q K^T   (K = d = 64: four K-steps inside one 128-byte swizzle row)
+        const uint32_t buf = c.kvc & 1;
+        if (c.qt == 0) mbar_wait(&kv_full[buf], (c.kvc >> 1) & 1);
+        if (c.kt == 0) mbar_wait(&qdo_full[slot_of(c)], use_of(c) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t aQ = smem_u32(sQ + slot_of(c) * kTileBytes) >> 4, aK = smem_u32(sK + buf * kTileBytes) >> 4;
+          const uint32_t id = idesc_sdp(c);
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) umma_f16(tS, kd + aQ + 2 * kk, kd + aK + 2 * kk, id_sdp, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk) umma_f16(tS, kd + aQ + 2 * kk, kd + aK + 2 * kk, id, kk > 0 ? 1u : 0u);
+          umma_commit(s_full);
+        }
+        __syncwarp();
+      };
+      auto issue_dp = [&](const Cur& c) {             // dP = dO V^T  (operands were waited for by issue_s of the same block)
+        const uint32_t buf = c.kvc & 1;
+        if (elect_one()) {
+          const uint32_t adO = smem_u32(sdO + slot_of(c) * kTileBytes) >> 4, aV = smem_u32(sV + buf * kTileBytes) >> 4;
+          const uint32_t id = idesc_sdp(c);
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) umma_f16(tdP, kd + adO + 2 * kk, kd + aV + 2 * kk, id_sdp, kk > 0 ? 1u : 0u);
-              umma_commit(sdp_full);
-            }
-            __syncwarp();
-            // ---- wait for P / dS
-            mbar_wait(ew_done, g & 1);
-            if (qt == 0 && drains > 0) mbar_wait(dkv_free, (drains - 1) & 1);
-            if (kt == 0 && qt == 0 && it > 0) mbar_wait(dq_free, (it - 1) & 1);
-            tc_fence_after();
-            const int qsteps = min(kTile, ceil16(p.rows - qt * kTile)) >> 4;   // K-steps over query rows
-            const int ksteps = nkc >> 4;                                       // K-steps over keys
-            if (elect_one()) {
-              // dV += P^T dO ; dK += dS^T Q      (A MN-major: key atoms 16 KB apart; K-step = 16 q rows = 2048 B)
-              for (int ks = 0; ks < qsteps; ++ks)
-                umma_f16(tdV, md + aP + 128 * ks, md + adO + 128 * ks, id_dkv, (qt > 0 || ks > 0) ? 1u : 0u);
-              for (int ks = 0; ks < qsteps; ++ks)
-                umma_f16(tdK, md + adS + 128 * ks, md + aQ + 128 * ks, id_dkv, (qt > 0 || ks > 0) ? 1u : 0u);
-              // dQ += dS K                        (A K-major: 4 K-steps per 64-key atom; B MN-major: K-step = 16 key rows)
-              for (int ks = 0; ks < ksteps; ++ks)
-                umma_f16(tdQ + 64 * qt, kd + adS + (ks >> 2) * (kTileBytes >> 4) + (ks & 3) * 2, md + aK + 128 * ks, id_dq,
-                         (kt > 0 || ks > 0) ? 1u : 0u);
-              umma_commit(pds_free);
-              if (qt == p.nqt - 1) {
-                umma_commit(dkv_full);
-                umma_commit(&kv_empty[buf]);
-              }
-              if (kt == p.nkt - 1) {
-                umma_commit(&qdo_empty[qt]);
-                if (qt == p.nqt - 1) umma_commit(dq_full);
-              }
-            }
-            __syncwarp();
-            if (qt == p.nqt - 1) ++drains;
+          for (int kk = 0; kk < 4; ++kk) umma_f16(tdP, kd + adO + 2 * kk, kd + aV + 2 * kk, id, kk > 0 ? 1u : 0u);
+          umma_commit(dp_full);
+        }
+        __syncwarp();
+      };
+      uint32_t drains = 0;
+      Cur c{static_cast<int>(blockIdx.x), 0, 0, 0u, 0u, 0u}, n = c;
+      if (valid(n)) { issue_s(n); issue_dp(n); advance(n); }
+      while (valid(c)) {
+        const uint32_t buf = c.kvc & 1;
+        const uint32_t slot = slot_of(c);
+        const uint32_t aQ = smem_u32(sQ + slot * kTileBytes) >> 4, adO = smem_u32(sdO + slot * kTileBytes) >> 4;
+        const uint32_t aK = smem_u32(sK + buf * kTileBytes) >> 4;
+        const int qsteps = min(kTile, ceil16(p.rows - c.qt * kTile)) >> 4;   // K-steps over query rows
+        const int ksteps = nkc_of(c) >> 4;                                   // K-steps over keys
+        // ---- phase A of block c is done: P is in smem, the S buffer is free
+        mbar_wait(p_ready, c.g & 1);
+        if (c.qt == 0 && drains > 0) mbar_wait(dkv_free, (drains - 1) & 1);  // dV/dK accumulators drained (first MMA overwrites)
+        tc_fence_after();
+        if (elect_one()) {
+          // dV += P^T dO      (A MN-major: key atoms 16 KB apart; K-step = 16 q rows = 2048 B)
+          for (int ks = 0; ks < qsteps; ++ks)
+            umma_f16(tdV, md + aP + 128 * ks, md + adO + 128 * ks, id_dkv, (c.qt > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(p_free);
+        }
+        __syncwarp();
+        if (valid(n)) issue_s(n);                                            // runs under phase B of block c
+        // ---- phase B of block c is done: dS is in smem, the dP buffer is free
+        mbar_wait(ds_ready, c.g & 1);
+        if (c.kt == 0 && c.qt == 0 && c.it > 0) mbar_wait(dq_free, (c.it - 1) & 1);
+        tc_fence_after();
+        if (valid(n)) { issue_dp(n); advance(n); }                           // ahead of dK / dQ: phase B of the next block waits for it
+        if (elect_one()) {
+          // dK += dS^T Q
+          for (int ks = 0; ks < qsteps; ++ks)
+            umma_f16(tdK, md + adS + 128 * ks, md + aQ + 128 * ks, id_dkv, (c.qt > 0 || ks > 0) ? 1u : 0u);
+          // dQ += dS K        (A K-major: 4 K-steps per 64-key atom; B MN-major: K-step = 16 key rows)
+          for (int ks = 0; ks < ksteps; ++ks)
+            umma_f16(tdQ + 64 * c.qt, kd + adS + (ks >> 2) * (kTileBytes >> 4) + (ks & 3) * 2, md + aK + 128 * ks, id_dq,
+                     (c.kt > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(ds_free);
+          if (c.qt == p.nqt - 1) {
+            umma_commit(dkv_full);
+            umma_commit(&kv_empty[buf]);
+          }
+          if (c.kt == p.nkt - 1) {
+            umma_commit(&qdo_empty[slot]);
+            if (c.qt == p.nqt - 1) umma_commit(dq_full);
           }
         }
+        __syncwarp();
+        if (c.qt == p.nqt - 1) ++drains;
+        advance(c);
       }
     }
   } else {
@@ -242,6 +292,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         for (int qt = 0; qt < p.nqt; ++qt, ++g) {
           const int qrow = qt * kTile + r;
           const bool q_ok = qrow < p.rows;
+          const int qslot = (p.nqt == 1) ? static_cast<int>(it & 1) : qt;     // Q / dO slot (single-tile items alternate slots)
           // D = rowsum(dO * O) and lse (log2 units) — once per (item, query tile).  The O row and lse are requested from
           // global here and first touched after the wait for S / dP below, which hides their latency.
           // The loads are cooperative: 8 lanes fetch one 128-byte O row (4 full rows per instruction; a thread fetching ITS
@@ -265,14 +316,16 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
               l2raw = __ldg(p.lse + (static_cast<int64_t>(b) * p.H + hh) * p.S + tok);
             }
           }
-          mbar_wait(sdp_full, g & 1);                                  // implies the Q / dO tiles of this qt have landed
+          // ---- phase A: S -> P (kept as packed bf16 in registers for phase B), P into smem
+          mbar_wait(s_full, g & 1);                                    // implies the Q / dO tiles of this qt have landed
           tc_fence_after();
+          // ---- D = rowsum(dO * O) of this query tile (first key tile only; the O rows were requested before the wait)
           if (kt == 0) {
             float d = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rr = (lane >> 3) + 4 * i;                    // row of this warp's 32 that the lane helps with
-              const uint4 a = *reinterpret_cast<const uint4*>(sdO + qt * kTileBytes + (quarter * 32 + rr) * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+              const uint4 a = *reinterpret_cast<const uint4*>(sdO + qslot * kTileBytes + (quarter * 32 + rr) * 128 + (((lane & 7) ^ (rr & 7)) << 4));
               float part = bf16_lo(a.x) * bf16_lo(o[i].x) + bf16_hi(a.x) * bf16_hi(o[i].x) + bf16_lo(a.y) * bf16_lo(o[i].y) +
                            bf16_hi(a.y) * bf16_hi(o[i].y) + bf16_lo(a.z) * bf16_lo(o[i].z) + bf16_hi(a.z) * bf16_hi(o[i].z) +
                            bf16_lo(a.w) * bf16_lo(o[i].w) + bf16_hi(a.w) * bf16_hi(o[i].w);
@@ -282,22 +335,18 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
               const float mine = __shfl_sync(0xffffffffu, part, (lane & 3) * 8);      // row 4 i + (lane & 3)
               if (i == (lane >> 2)) d = mine;
             }
-            const float l2 = l2raw * 1.44269504088896341f;
-            if (qt == 0) { Dv[0] = d; L2v[0] = l2; } else { Dv[1] = d; L2v[1] = l2; }
+            if (qt == 0) Dv[0] = d; else Dv[1] = d;
           }
-          const float Dq = qt == 0 ? Dv[0] : Dv[1];
-          const float Lq = qt == 0 ? L2v[0] : L2v[1];
-          bool waited_free = (g == 0);
-#pragma unroll 1
+          const float Lq = (kt == 0) ? l2raw * 1.44269504088896341f : (qt == 0 ? L2v[0] : L2v[1]);
+          if (kt == 0) { if (qt == 0) L2v[0] = Lq; else L2v[1] = Lq; }
+          uint32_t pp[2][16];
+#pragma unroll
           for (int c = 0; c < 2; ++c) {
             const int col0 = half * 64 + c * 32;
-            if (col0 >= nkc) break;                                   // warp-uniform: nothing of this chunk is ever read
-            uint32_t sr[32], dr[32];
+            if (col0 >= nkc) continue;                                // warp-uniform: nothing of this chunk is ever read
+            uint32_t sr[32];
             tmem_ld_32x32(tS + lane_off + col0, sr);
-            tmem_ld_32x32(tdP + lane_off + col0, dr);
             tmem_ld_wait();
-
-            uint32_t pp[16], dd[16];
             if (need_mask || kt * kTile + col0 + 32 > p.rows) {    // padding keys: exp2(-lse) could overflow, mask them
 #pragma unroll
               for (int j = 0; j < 32; j += 2) {
@@ -306,40 +355,65 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                 float p1 = ex2_approx(fmaf(__uint_as_float(sr[j + 1]), p.scale_log2e, -Lq));
                 p0 = (q_ok && key < klen && (key & gm) == rg) ? p0 : 0.f;
                 p1 = (q_ok && key + 1 < klen && ((key + 1) & gm) == rg) ? p1 : 0.f;
-                const float d0 = p0 * (__uint_as_float(dr[j]) - Dq);
-                const float d1 = p1 * (__uint_as_float(dr[j + 1]) - Dq);
-                pp[j >> 1] = pack_bf16(p0, p1);
-                dd[j >> 1] = pack_bf16(d0, d1);
+                pp[c][j >> 1] = pack_bf16(p0, p1);
               }
             } else {
               // dense, unmasked chunk of live keys: query rows past S come from zero-filled TMA rows (Q = dO = 0, lse := 0), so
               // P = 1, dS = 0 there and every product they enter is exactly zero — no per-element predicates needed
 #pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(sr[j]), p.scale_log2e, -Lq));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(sr[j + 1]), p.scale_log2e, -Lq));
-                const float d0 = p0 * (__uint_as_float(dr[j]) - Dq);
-                const float d1 = p1 * (__uint_as_float(dr[j + 1]) - Dq);
-                pp[j >> 1] = pack_bf16(p0, p1);
-                dd[j >> 1] = pack_bf16(d0, d1);
-              }
+              for (int j = 0; j < 32; j += 2)
+                pp[c][j >> 1] = pack_bf16(ex2_approx(fmaf(__uint_as_float(sr[j]), p.scale_log2e, -Lq)),
+                                          ex2_approx(fmaf(__uint_as_float(sr[j + 1]), p.scale_log2e, -Lq)));
             }
-            if (!waited_free) { mbar_wait(pds_free, (g - 1) & 1); waited_free = true; }
+          }
+          if (g > 0) mbar_wait(p_free, (g - 1) & 1);                   // dV of the previous block has read sP
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int col0 = half * 64 + c * 32;
+            if (col0 >= nkc) continue;
             // 32 keys = four 16-byte chunks of this row inside key atom (col0 / 64)
             const uint32_t rowoff = (col0 >> 6) * kTileBytes + r * 128;
             const int ch0 = (col0 & 63) >> 3;
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const uint32_t off = rowoff + (((ch0 + q4) ^ sw) << 4);
-              *reinterpret_cast<uint4*>(sP + off) = make_uint4(pp[4 * q4], pp[4 * q4 + 1], pp[4 * q4 + 2], pp[4 * q4 + 3]);
-              *reinterpret_cast<uint4*>(sdS + off) = make_uint4(dd[4 * q4], dd[4 * q4 + 1], dd[4 * q4 + 2], dd[4 * q4 + 3]);
-            }
+            for (int q4 = 0; q4 < 4; ++q4)
+              *reinterpret_cast<uint4*>(sP + rowoff + (((ch0 + q4) ^ sw) << 4)) =
+                  make_uint4(pp[c][4 * q4], pp[c][4 * q4 + 1], pp[c][4 * q4 + 2], pp[c][4 * q4 + 3]);
           }
-          if (!waited_free) mbar_wait(pds_free, (g - 1) & 1);         // keep every waiter in phase lock-step
           tc_fence_before();
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(ew_done);
+          if (lane == 0) mbar_arrive(p_ready);
+
+          const float Dq = qt == 0 ? Dv[0] : Dv[1];
+
+          // ---- phase B: dP -> dS = P * (dP - D), dS into smem
+          mbar_wait(dp_full, g & 1);
+          tc_fence_after();
+          if (g > 0) mbar_wait(ds_free, (g - 1) & 1);                  // dK / dQ of the previous block have read sdS (issued a
+                                                                       // whole phase A ago: this wait does not stall)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int col0 = half * 64 + c * 32;
+            if (col0 >= nkc) continue;
+            uint32_t dr[32], dd[16];
+            tmem_ld_32x32(tdP + lane_off + col0, dr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const uint32_t pk = pp[c][j >> 1];                       // masked entries are exactly 0 -> dS = 0
+              dd[j >> 1] = pack_bf16(bf16_lo(pk) * (__uint_as_float(dr[j]) - Dq), bf16_hi(pk) * (__uint_as_float(dr[j + 1]) - Dq));
+            }
+            const uint32_t rowoff = (col0 >> 6) * kTileBytes + r * 128;
+            const int ch0 = (col0 & 63) >> 3;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              *reinterpret_cast<uint4*>(sdS + rowoff + (((ch0 + q4) ^ sw) << 4)) =
+                  make_uint4(dd[4 * q4], dd[4 * q4 + 1], dd[4 * q4 + 2], dd[4 * q4 + 3]);
+          }
+          tc_fence_before();
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ds_ready);
 
           if (qt == p.nqt - 1) {
             // ---- drain dV, dK of key tile kt: thread = key row, this warp's 32 of the 64 d-columns

@@ -294,37 +294,43 @@ def test_torch_ddp_wrap_reduces_tower_gradients(cuda):
 
 def test_cuda_graph_step_equals_eager_steps(cuda):
     """``Trainer.capture``: the whole step (forward, backward, optimizer, bf16 weight re-cast) replayed as one CUDA graph must
-    train exactly like the eager step: 2 warm-up + 3 replayed steps vs 5 eager steps from the same weights, a new batch every
-    step (the static input buffers are refilled), losses and final weights compared (split-K atomics reorder fp32 sums, so
-    the bar is 1e-4 relative on the weight DELTAS, not bitwise)."""
+    train exactly like the eager step: 2 eager + 3 replayed steps vs 5 eager steps from the same weights, a new batch every
+    step (the static input buffers are refilled).  Split-K atomics reorder fp32 sums and AdamW's sign-like early updates
+    amplify that, so the yardstick is a SECOND eager run: the graph run may differ from eager run A by no more than 3x what
+    eager run B differs from A (+ a small floor)."""
     from oracle import simseg_oracle as O
     from simseg_b200.train import Trainer
     sd = O.make_state_dict(384, 6, seed=0)
     batches = [{k: v.to(cuda) for k, v in O.make_batch(8, 25, seed=100 + i).items()} for i in range(5)]
-    eager, cfg = _build(cuda)
-    eager.load_state_dict(sd)
-    te = Trainer(eager, cfg, capturable=True)
-    le = [te.step(b)[0].item() for b in batches]
-    model, cfg = _build(cuda)
-    model.load_state_dict(sd)
-    tg = Trainer(model, cfg, capturable=True)
-    # warm-up steps inside capture() train on the batch they are given: feed batches 0 and 1 by hand, then capture with 1
-    lg = [tg.step(batches[0])[0].item()]
-    gs = tg.capture(batches[1], warmup=1)
-    assert gs.launches_per_replay > 400
-    for b in batches[2:]:
-        loss, i2t, t2i = gs(b)
-        lg.append(loss.item())
-    torch.cuda.synchronize()
-    print("eager", le, "graph", lg)
-    assert len(lg) == 4
-    for a, b in zip([le[0]] + le[2:], lg):
-        assert abs(a - b) < 2e-3, (le, lg)
     w0 = {k: v.to(cuda) for k, v in sd.items()}
-    worst = 0.0
-    for (k, pe), (_, pg) in zip(eager.named_parameters(), model.named_parameters()):
-        de, dg = pe.detach() - w0[k], pg.detach() - w0[k]
-        if de.norm().item() > 1e-9:
-            worst = max(worst, ((de - dg).norm() / de.norm()).item())
-    print("worst relative difference of the 5-step weight deltas:", worst)
-    assert worst < 5e-2
+
+    def run(graph):
+        model, cfg = _build(cuda)
+        model.load_state_dict(sd)
+        tr = Trainer(model, cfg, capturable=True)
+        if not graph:
+            losses = [tr.step(b)[0].item() for b in batches]
+        else:
+            # capture()'s warm-up steps are real steps: batch 0 by hand, batch 1 as the single warm-up step, then 3 replays
+            losses = [tr.step(batches[0])[0].item(), None]
+            gs = tr.capture(batches[1], warmup=1)
+            assert gs.launches_per_replay > 400
+            for b in batches[2:]:
+                losses.append(gs(b)[0].item())
+        torch.cuda.synchronize()
+        return losses, {k: p.detach() - w0[k] for k, p in model.named_parameters()}
+
+    def worst(d1, d2):
+        return max(((d1[k] - d2[k]).norm() / d1[k].norm()).item() for k in d1 if d1[k].norm().item() > 1e-9)
+
+    la, da = run(False)
+    lb, db = run(False)
+    lg, dg = run(True)
+    print("eager A", la, "eager B", lb, "graph", lg)
+    noise_l = max(abs(x - y) for x, y in zip(la, lb))
+    noise_w = worst(da, db)
+    diff_l = max(abs(x - y) for x, y in zip(la, lg) if y is not None)
+    diff_w = worst(da, dg)
+    print(f"eager-vs-eager: loss {noise_l:.2e}, weight deltas {noise_w:.2e}; graph-vs-eager: loss {diff_l:.2e}, weight deltas {diff_w:.2e}")
+    assert diff_l <= 3 * noise_l + 5e-3
+    assert diff_w <= 3 * noise_w + 2e-2
