@@ -263,6 +263,12 @@ int simseg_seg_upsample_norm(simseg_ctx* ctx, const float* sim, const int32_t* c
 int simseg_pos_embed_bicubic(simseg_ctx* ctx, const float* src, float* dst, int grid_src, int grid_dst, int D, int num_extra,
                              void* stream);
 
+/* ---- debug (measurement only; synchronises the device) -------------------------------------------------------- */
+/* Per-warp event trace of CTA 0 of the tcgen05 attention-backward kernel: 5 warps x 2048 events of (clock64 << 8 | id).
+ * enable(1) clears and arms it, read() copies it to the host and returns the number of words written. */
+int simseg_debug_trace_enable(int on);
+int simseg_debug_trace_read(uint64_t* host, int n);
+
 #ifdef __cplusplus
 }
 #endif

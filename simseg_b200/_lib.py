@@ -57,6 +57,8 @@ PROTOTYPES = {
     "simseg_topk_pool_l2norm_bwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, vp, vp]),
     "simseg_infonce_fwd": (i32, [vp, vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
     "simseg_infonce_bwd": (i32, [vp, vp, vp, i32, i32, i32, vp, i32, i32, vp, f32, vp, vp, vp, vp, vp]),
+    "simseg_debug_trace_enable": (i32, [i32]),
+    "simseg_debug_trace_read": (i32, [vp, i32]),
     "simseg_infonce_fused_workspace_bytes": (i64, [i32, i32, i32]),
     "simseg_infonce_fused_fwd": (i32, [vp, vp, vp, i32, i32, i32, vp, i32, vp, i64, vp, vp, vp, vp]),
     "simseg_infonce_fused_bwd": (i32, [vp, i32, i32, i32, vp, i32, vp, f32, vp, i64, vp, vp, vp, vp]),

@@ -26,7 +26,8 @@ namespace simseg {
 
 using namespace sm100;
 
-constexpr int kAbThreads = 320;
+constexpr int kAbEwWarps = 16;                       // elementwise warps: four per TMEM lane quarter
+constexpr int kAbThreads = 32 * (2 + kAbEwWarps);
 constexpr int kTile = 128;                 // query rows / key rows per tile
 constexpr int kTileBytes = kTile * 128;    // [128 rows][64 bf16]
 constexpr int kPBytes = 2 * kTileBytes;    // P or dS: [2 key atoms][128 q rows][128 B]
@@ -51,7 +52,52 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
 }
 
 __device__ __forceinline__ int ceil16(int x) { return (x + 15) & ~15; }
-// ex2_approx (common.cuh): MUFU.EX2, 2 ulp; arguments here are <= 0 up to rounding
+
+// ---- debug: per-warp phase timing of CTA 0, read back with simseg_debug_trace_read (tools/attn_trace.py) ----------------
+// Only in builds with -DSIMSEG_ATTN_TRACE (the register cost perturbs the kernel: use for RELATIVE shares only), armed with
+// simseg_debug_trace_enable(1).  Slot 0 = MMA warp, slots 1.. = elementwise warps 2, 3, 6, 10.
+constexpr int kTraceIds = 24;
+constexpr int kTraceWarps = 5;
+constexpr int kTraceLen = 2 * kTraceIds;                    // per slot: clocks per event id, then counts
+__device__ unsigned long long g_attn_trace[kTraceWarps * kTraceLen];
+__device__ int g_attn_trace_on = 0;
+// Non-perturbing: clock deltas are summed in registers per event id ("time spent reaching this event from the previous
+// one") and written out once at the end of the kernel — no memory traffic inside the loops.
+#ifdef SIMSEG_ATTN_TRACE
+struct Tracer {
+  uint32_t acc[kTraceIds], cnt[kTraceIds], last;
+  int slot;
+  __device__ __forceinline__ Tracer(int slot_, bool active) : last(0), slot(-1) {
+    if (active && g_attn_trace_on && blockIdx.x == 0 && slot_ >= 0) slot = slot_;
+#pragma unroll
+    for (int i = 0; i < kTraceIds; ++i) { acc[i] = 0; cnt[i] = 0; }
+    last = static_cast<uint32_t>(clock64());
+  }
+  __device__ __forceinline__ void operator()(int id) {       // id must be a compile-time constant at every call site
+    if (slot >= 0) {
+      const uint32_t now = static_cast<uint32_t>(clock64());
+      acc[id] += now - last;
+      cnt[id] += 1;
+      last = now;
+    }
+  }
+  __device__ __forceinline__ void flush() {
+    if (slot >= 0) {
+#pragma unroll
+      for (int i = 0; i < kTraceIds; ++i) {
+        g_attn_trace[slot * kTraceLen + i] = acc[i];
+        g_attn_trace[slot * kTraceLen + kTraceIds + i] = cnt[i];
+      }
+    }
+  }
+};
+#else
+struct Tracer {                                              // compiled out: the accumulators cost ~48 registers per thread
+  __device__ __forceinline__ Tracer(int, bool) {}
+  __device__ __forceinline__ void operator()(int) {}
+  __device__ __forceinline__ void flush() {}
+};
+#endif
 
 __global__ void __launch_bounds__(kAbThreads, 1)
 attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -91,9 +137,9 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1);
       mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
     }
-    mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_ready, 8); mbar_init(ds_ready, 8);
+    mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_ready, kAbEwWarps); mbar_init(ds_ready, kAbEwWarps);
     mbar_init(p_free, 1); mbar_init(ds_free, 1);
-    mbar_init(dkv_full, 1); mbar_init(dkv_free, 8); mbar_init(dq_full, 1); mbar_init(dq_free, 8);
+    mbar_init(dkv_full, 1); mbar_init(dkv_free, kAbEwWarps); mbar_init(dq_full, 1); mbar_init(dq_free, kAbEwWarps);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -196,9 +242,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         __syncwarp();
       };
       uint32_t drains = 0;
+      Tracer tr(0, lane == 0);
       Cur c{static_cast<int>(blockIdx.x), 0, 0, 0u, 0u, 0u}, n = c;
       if (valid(n)) { issue_s(n); issue_dp(n); advance(n); }
       while (valid(c)) {
+        tr(1);
         const uint32_t buf = c.kvc & 1;
         const uint32_t slot = slot_of(c);
         const uint32_t aQ = smem_u32(sQ + slot * kTileBytes) >> 4, adO = smem_u32(sdO + slot * kTileBytes) >> 4;
@@ -207,7 +255,9 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         const int ksteps = nkc_of(c) >> 4;                                   // K-steps over keys
         // ---- phase A of block c is done: P is in smem, the S buffer is free
         mbar_wait(p_ready, c.g & 1);
+        tr(2);
         if (c.qt == 0 && drains > 0) mbar_wait(dkv_free, (drains - 1) & 1);  // dV/dK accumulators drained (first MMA overwrites)
+        tr(3);
         tc_fence_after();
         if (elect_one()) {
           // dV += P^T dO      (A MN-major: key atoms 16 KB apart; K-step = 16 q rows = 2048 B)
@@ -216,9 +266,12 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           umma_commit(p_free);
         }
         __syncwarp();
+        tr(4);
         if (valid(n)) issue_s(n);                                            // runs under phase B of block c
+        tr(5);
         // ---- phase B of block c is done: dS is in smem, the dP buffer is free
         mbar_wait(ds_ready, c.g & 1);
+        tr(6);
         if (c.kt == 0 && c.qt == 0 && c.it > 0) mbar_wait(dq_free, (c.it - 1) & 1);
         tc_fence_after();
         if (valid(n)) { issue_dp(n); advance(n); }                           // ahead of dK / dQ: phase B of the next block waits for it
@@ -241,23 +294,105 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           }
         }
         __syncwarp();
+        tr(7);
         if (c.qt == p.nqt - 1) ++drains;
         advance(c);
       }
+      tr.flush();
     }
   } else {
     // =============================== elementwise + drains ===============================
-    const int ew = warp - 2;                   // 0..7
+    // 16 warps: four per TMEM lane quarter (a warp may only touch lanes 32 * (warp % 4) ..), each owning ONE 32-key chunk of
+    // a block.  The pass is latency-bound (dependent MUFU / FMA / pack chains, smem round trips), so it is spread over four
+    // warps per scheduler instead of two; per block a thread handles 32 S and 32 dP values of its query row.
+    const int ew = warp - 2;                   // 0..15
     const int quarter = warp & 3;              // TMEM lane quarter
-    const int half = ew >> 2;                  // column half
+    const int cq = ew >> 2;                    // 32-column chunk of a block handled by this warp
     const int r = quarter * 32 + lane;         // row inside a tile
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const int sw = r & 7;
+    const int col0 = cq * 32;
     // drain staging: a thread owns a tile ROW, so storing straight from registers makes every store instruction touch 32
     // different 128-byte lines (16 bytes each) — the L1 store path, not HBM, then paces the drains.  The warp's 32 rows x 64
     // bytes go through a swizzled 2 KB block instead and leave as 8 rows x 64 contiguous bytes per instruction.
     uint8_t* stg = reinterpret_cast<uint8_t*>(bars) + 256 + ew * 2048;
+    float* sD = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256 + kAbEwWarps * 2048);   // [2 slots][128 rows]
     uint32_t it = 0, g = 0, drains = 0;
+    Tracer tr(warp == 2 ? 1 : warp == 3 ? 2 : warp == 6 ? 3 : warp == 10 ? 4 : -1, lane == 0);
+    const int gm0 = p.G - 1;
+    // w[16] = this thread's row (32 bf16 of d-columns dcol0..dcol0+31) -> rows tile_row0 .. +32 of `dst` of item (sb, sh0)
+    auto store_rows = [&](const uint32_t (&w)[16], __nv_bfloat16* dst, int sb_idx, int sh0, int tile_row0, int dcol0) {
+      uint8_t* mine = stg + lane * 64;
+      const int swz = (lane >> 1) & 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(mine + ((j ^ swz) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+      __syncwarp();
+      const int64_t base_b = static_cast<int64_t>(sb_idx) * p.sb;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = (lane >> 2) + 8 * i;
+        const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4));
+        const int row = tile_row0 + rr;
+        if (row < p.rows)
+          *reinterpret_cast<uint4*>(dst + base_b + static_cast<int64_t>(row >> p.lg) * p.ss +
+                                    static_cast<int64_t>(sh0 + (row & gm0)) * p.sh + dcol0 + (lane & 3) * 8) = val;
+      }
+      __syncwarp();
+    };
+    // Deferred drains: the accumulators of a key tile (dK / dV) and of an item (dQ) complete ~a block's worth of MMAs after
+    // this warp's last contribution; draining right away would idle the elementwise warps for that long (20 % of their
+    // time).  The drain is parked and done after phase A of the NEXT block instead, when the accumulators have long landed.
+    bool pend_kv = false, pend_q = false;
+    int pend_b = 0, pend_h0 = 0, pend_kt = 0;
+    uint32_t pend_it = 0;
+    auto drain_pending = [&]() {
+      const bool is_dk = cq >= 2;
+      const int dcol0 = (cq & 1) * 32;
+      if (pend_kv) {
+        // dV (warps cq = 0, 1) and dK (warps cq = 2, 3) of key tile pend_kt: thread = key row, 32 of the 64 d-columns
+        mbar_wait(dkv_full, drains & 1);
+        tr(19);
+        tc_fence_after();
+        uint32_t a[32];
+        tmem_ld_32x32((is_dk ? tdK : tdV) + lane_off + dcol0, a);
+        tmem_ld_wait();
+        // the accumulator is in registers: release it BEFORE the global stores (an mbarrier arrive has release
+        // semantics — placed after the stores it would wait for them to drain)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dkv_free);
+        const float sc = is_dk ? p.scale : 1.0f;
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = pack_bf16(__uint_as_float(a[2 * j]) * sc, __uint_as_float(a[2 * j + 1]) * sc);
+        store_rows(w, is_dk ? p.dk : p.dv, pend_b, pend_h0, pend_kt * kTile + quarter * 32, dcol0);
+        ++drains;
+        pend_kv = false;
+        tr(20);
+      }
+      if (pend_q) {
+        // dQ: warp cq takes query tile cq >> 1, d-columns 32 (cq & 1) ..
+        mbar_wait(dq_full, pend_it & 1);
+        tr(21);
+        tc_fence_after();
+        const int dqt = cq >> 1;
+        uint32_t w[16];
+        if (dqt < p.nqt) {
+          uint32_t a2[32];
+          tmem_ld_32x32(tdQ + 64 * dqt + lane_off + dcol0, a2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] = pack_bf16(__uint_as_float(a2[2 * j]) * p.scale, __uint_as_float(a2[2 * j + 1]) * p.scale);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dq_free);
+        if (dqt < p.nqt) store_rows(w, p.dq, pend_b, pend_h0, dqt * kTile + quarter * 32, dcol0);
+        pend_q = false;
+        tr(22);
+      }
+    };
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
       const int b = item / p.HG, h0 = (item - b * p.HG) * p.G;
       // klen = live key COLUMNS (packed: key tokens * G, column = token * G + head); a column is live for a row iff it
@@ -265,45 +400,27 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       const int klen = (p.key_len ? min(max(p.key_len[b], 1), p.S) : p.S) * p.G;
       const int gm = p.G - 1, rg = r & gm;
       const bool need_mask = p.key_len != nullptr || p.G > 1;
-      const int64_t base_b = static_cast<int64_t>(b) * p.sb;
-      auto row_off = [&](int row) {                                   // (token, head) of a tile row -> q/k/v element offset
-        return base_b + static_cast<int64_t>(row >> p.lg) * p.ss + static_cast<int64_t>(h0 + (row & gm)) * p.sh;
-      };
-      // w[16] = this thread's row (32 bf16 of d-columns half*32..) -> rows tile_row0 .. +32 of `dst`
-      auto store_rows = [&](const uint32_t (&w)[16], __nv_bfloat16* dst, int tile_row0) {
-        uint8_t* mine = stg + lane * 64;
-        const int swz = (lane >> 1) & 3;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(mine + ((j ^ swz) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = (lane >> 2) + 8 * i;
-          const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4));
-          const int row = tile_row0 + rr;
-          if (row < p.rows) *reinterpret_cast<uint4*>(dst + row_off(row) + half * 32 + (lane & 3) * 8) = val;
-        }
-        __syncwarp();
-      };
       float Dv[2] = {0.f, 0.f}, L2v[2] = {0.f, 0.f};
       for (int kt = 0; kt < p.nkt; ++kt) {
         const int nkc = min(kTile, ceil16(p.rows - kt * kTile));
+        const bool chunk_live = col0 < nkc;                           // warp-uniform: columns >= nkc are never read by an MMA
         for (int qt = 0; qt < p.nqt; ++qt, ++g) {
           const int qrow = qt * kTile + r;
           const bool q_ok = qrow < p.rows;
+          // rows of this quarter that no MMA reads (K extent over query rows = ceil16(live rows)): skip the whole pass
+          const bool rows_live = qt * kTile + quarter * 32 < ceil16(p.rows);
           const int qslot = (p.nqt == 1) ? static_cast<int>(it & 1) : qt;     // Q / dO slot (single-tile items alternate slots)
-          // D = rowsum(dO * O) and lse (log2 units) — once per (item, query tile).  The O row and lse are requested from
-          // global here and first touched after the wait for S / dP below, which hides their latency.
-          // The loads are cooperative: 8 lanes fetch one 128-byte O row (4 full rows per instruction; a thread fetching ITS
-          // row would touch 32 lines per instruction), the partial dot products are reduced over those 8 lanes below and
-          // handed to the lane that owns the row.
-          uint4 o[8];
+          // D = rowsum(dO * O) and lse (log2 units) — once per (item, query tile), shared by the four warps of a quarter:
+          // warp cq takes rows 8 cq .. 8 cq + 7 of the quarter (8 lanes fetch one 128-byte O row; a thread fetching ITS row
+          // would touch 32 lines per instruction), the sums go through shared memory.  The loads are issued before the wait
+          // for S so that their latency is hidden.
+          tr(8);
+          uint4 o[2];
           float l2raw = 0.f;
           if (kt == 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int row = qt * kTile + quarter * 32 + (lane >> 3) + 4 * i;
+            for (int i = 0; i < 2; ++i) {
+              const int row = qt * kTile + quarter * 32 + (lane >> 3) + 4 * (2 * cq + i);
               if (row < p.rows) {
                 const int tok = row >> p.lg, hh = h0 + (row & gm);
                 o[i] = __ldg(reinterpret_cast<const uint4*>(p.out + (static_cast<int64_t>(b) * p.S + tok) * (p.H * 64) + hh * 64) + (lane & 7));
@@ -317,14 +434,14 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             }
           }
           // ---- phase A: S -> P (kept as packed bf16 in registers for phase B), P into smem
+          tr(10);
           mbar_wait(s_full, g & 1);                                    // implies the Q / dO tiles of this qt have landed
+          tr(11);
           tc_fence_after();
-          // ---- D = rowsum(dO * O) of this query tile (first key tile only; the O rows were requested before the wait)
           if (kt == 0) {
-            float d = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = (lane >> 3) + 4 * i;                    // row of this warp's 32 that the lane helps with
+            for (int i = 0; i < 2; ++i) {
+              const int rr = (lane >> 3) + 4 * (2 * cq + i);         // row of the quarter's 32 that the lane helps with
               const uint4 a = *reinterpret_cast<const uint4*>(sdO + qslot * kTileBytes + (quarter * 32 + rr) * 128 + (((lane & 7) ^ (rr & 7)) << 4));
               float part = bf16_lo(a.x) * bf16_lo(o[i].x) + bf16_hi(a.x) * bf16_hi(o[i].x) + bf16_lo(a.y) * bf16_lo(o[i].y) +
                            bf16_hi(a.y) * bf16_hi(o[i].y) + bf16_lo(a.z) * bf16_lo(o[i].z) + bf16_hi(a.z) * bf16_hi(o[i].z) +
@@ -332,18 +449,18 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
               part += __shfl_xor_sync(0xffffffffu, part, 1);
               part += __shfl_xor_sync(0xffffffffu, part, 2);
               part += __shfl_xor_sync(0xffffffffu, part, 4);
-              const float mine = __shfl_sync(0xffffffffu, part, (lane & 3) * 8);      // row 4 i + (lane & 3)
-              if (i == (lane >> 2)) d = mine;
+              if ((lane & 7) == 0) sD[qslot * kTile + quarter * 32 + rr] = part;
             }
-            if (qt == 0) Dv[0] = d; else Dv[1] = d;
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");    // the four warps of this quarter
+            const float d = sD[qslot * kTile + r];
+            const float l2 = l2raw * 1.44269504088896341f;
+            if (qt == 0) { Dv[0] = d; L2v[0] = l2; } else { Dv[1] = d; L2v[1] = l2; }
           }
-          const float Lq = (kt == 0) ? l2raw * 1.44269504088896341f : (qt == 0 ? L2v[0] : L2v[1]);
-          if (kt == 0) { if (qt == 0) L2v[0] = Lq; else L2v[1] = Lq; }
-          uint32_t pp[2][16];
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int col0 = half * 64 + c * 32;
-            if (col0 >= nkc) continue;                                // warp-uniform: nothing of this chunk is ever read
+          const float Lq = qt == 0 ? L2v[0] : L2v[1];
+          const float Dq = qt == 0 ? Dv[0] : Dv[1];
+          tr(12);
+          uint32_t pp[16];
+          if (chunk_live && rows_live) {
             uint32_t sr[32];
             tmem_ld_32x32(tS + lane_off + col0, sr);
             tmem_ld_wait();
@@ -355,56 +472,52 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                 float p1 = ex2_approx(fmaf(__uint_as_float(sr[j + 1]), p.scale_log2e, -Lq));
                 p0 = (q_ok && key < klen && (key & gm) == rg) ? p0 : 0.f;
                 p1 = (q_ok && key + 1 < klen && ((key + 1) & gm) == rg) ? p1 : 0.f;
-                pp[c][j >> 1] = pack_bf16(p0, p1);
+                pp[j >> 1] = pack_bf16(p0, p1);
               }
             } else {
               // dense, unmasked chunk of live keys: query rows past S come from zero-filled TMA rows (Q = dO = 0, lse := 0), so
               // P = 1, dS = 0 there and every product they enter is exactly zero — no per-element predicates needed
 #pragma unroll
               for (int j = 0; j < 32; j += 2)
-                pp[c][j >> 1] = pack_bf16(ex2_approx(fmaf(__uint_as_float(sr[j]), p.scale_log2e, -Lq)),
-                                          ex2_approx(fmaf(__uint_as_float(sr[j + 1]), p.scale_log2e, -Lq)));
+                pp[j >> 1] = pack_bf16(ex2_approx(fmaf(__uint_as_float(sr[j]), p.scale_log2e, -Lq)),
+                                       ex2_approx(fmaf(__uint_as_float(sr[j + 1]), p.scale_log2e, -Lq)));
             }
           }
+          tr(13);
           if (g > 0) mbar_wait(p_free, (g - 1) & 1);                   // dV of the previous block has read sP
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int col0 = half * 64 + c * 32;
-            if (col0 >= nkc) continue;
-            // 32 keys = four 16-byte chunks of this row inside key atom (col0 / 64)
-            const uint32_t rowoff = (col0 >> 6) * kTileBytes + r * 128;
-            const int ch0 = (col0 & 63) >> 3;
+          tr(14);
+          // 32 keys = four 16-byte chunks of this row inside key atom (col0 / 64)
+          const uint32_t rowoff = (col0 >> 6) * kTileBytes + r * 128;
+          const int ch0 = (col0 & 63) >> 3;
+          if (chunk_live && rows_live) {
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4)
               *reinterpret_cast<uint4*>(sP + rowoff + (((ch0 + q4) ^ sw) << 4)) =
-                  make_uint4(pp[c][4 * q4], pp[c][4 * q4 + 1], pp[c][4 * q4 + 2], pp[c][4 * q4 + 3]);
+                  make_uint4(pp[4 * q4], pp[4 * q4 + 1], pp[4 * q4 + 2], pp[4 * q4 + 3]);
           }
           tc_fence_before();
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(p_ready);
-
-          const float Dq = qt == 0 ? Dv[0] : Dv[1];
+          tr(15);
+          drain_pending();                                             // accumulators of the previous key tile / item
 
           // ---- phase B: dP -> dS = P * (dP - D), dS into smem
           mbar_wait(dp_full, g & 1);
+          tr(16);
           tc_fence_after();
-          if (g > 0) mbar_wait(ds_free, (g - 1) & 1);                  // dK / dQ of the previous block have read sdS (issued a
+          if (g > 0) mbar_wait(ds_free, (g - 1) & 1);
+          tr(17);                  // dK / dQ of the previous block have read sdS (issued a
                                                                        // whole phase A ago: this wait does not stall)
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int col0 = half * 64 + c * 32;
-            if (col0 >= nkc) continue;
+          if (chunk_live && rows_live) {
             uint32_t dr[32], dd[16];
             tmem_ld_32x32(tdP + lane_off + col0, dr);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
-              const uint32_t pk = pp[c][j >> 1];                       // masked entries are exactly 0 -> dS = 0
+              const uint32_t pk = pp[j >> 1];                          // masked entries are exactly 0 -> dS = 0
               dd[j >> 1] = pack_bf16(bf16_lo(pk) * (__uint_as_float(dr[j]) - Dq), bf16_hi(pk) * (__uint_as_float(dr[j + 1]) - Dq));
             }
-            const uint32_t rowoff = (col0 >> 6) * kTileBytes + r * 128;
-            const int ch0 = (col0 & 63) >> 3;
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4)
               *reinterpret_cast<uint4*>(sdS + rowoff + (((ch0 + q4) ^ sw) << 4)) =
@@ -414,60 +527,17 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(ds_ready);
+          tr(18);
 
-          if (qt == p.nqt - 1) {
-            // ---- drain dV, dK of key tile kt: thread = key row, this warp's 32 of the 64 d-columns
-            mbar_wait(dkv_full, drains & 1);
-            tc_fence_after();
-            uint32_t a[32], c2[32];
-            tmem_ld_32x32(tdV + lane_off + half * 32, a);
-            tmem_ld_32x32(tdK + lane_off + half * 32, c2);
-            tmem_ld_wait();
-            // dK / dV are in registers: release the accumulators BEFORE the global stores (an mbarrier arrive has release
-            // semantics — placed after the stores it would wait for them to drain)
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(dkv_free);
-            {
-              uint32_t w[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) w[j] = pack_bf16(__uint_as_float(a[2 * j]), __uint_as_float(a[2 * j + 1]));
-              store_rows(w, p.dv, kt * kTile + quarter * 32);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) w[j] = pack_bf16(__uint_as_float(c2[2 * j]) * p.scale, __uint_as_float(c2[2 * j + 1]) * p.scale);
-              store_rows(w, p.dk, kt * kTile + quarter * 32);
-            }
-            ++drains;
-            if (kt == p.nkt - 1) {
-              // ---- drain dQ of both query tiles
-              mbar_wait(dq_full, it & 1);
-              tc_fence_after();
-              // both query tiles are pulled out of TMEM (the first one packed to bf16 right away to save registers),
-              // then the accumulator is released BEFORE the global stores (see above)
-              uint32_t q0[16], q1[16];
-              {
-                uint32_t a2[32];
-                tmem_ld_32x32(tdQ + lane_off + half * 32, a2);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) q0[j] = pack_bf16(__uint_as_float(a2[2 * j]) * p.scale, __uint_as_float(a2[2 * j + 1]) * p.scale);
-                if (p.nqt > 1) {
-                  tmem_ld_32x32(tdQ + 64 + lane_off + half * 32, a2);
-                  tmem_ld_wait();
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) q1[j] = pack_bf16(__uint_as_float(a2[2 * j]) * p.scale, __uint_as_float(a2[2 * j + 1]) * p.scale);
-                }
-              }
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(dq_free);
-              store_rows(q0, p.dq, quarter * 32);
-              if (p.nqt > 1) store_rows(q1, p.dq, kTile + quarter * 32);
-            }
+          if (qt == p.nqt - 1) {                                      // park the drains (see drain_pending)
+            pend_kv = true; pend_b = b; pend_h0 = h0; pend_kt = kt;
+            if (kt == p.nkt - 1) { pend_q = true; pend_it = it; }
           }
         }
       }
     }
+    drain_pending();
+    tr.flush();
   }
 
   tc_fence_before();
@@ -1134,6 +1204,22 @@ static int make_tmap_bshd(CUtensorMap* m, const void* ptr, int B, int H, int S, 
   return SIMSEG_OK;
 }
 
+int debug_trace_enable_impl(int on) {
+  SIMSEG_CUDA(cudaMemcpyToSymbol(g_attn_trace_on, &on, sizeof(int)));
+  if (on) {
+    void* ptr = nullptr;
+    SIMSEG_CUDA(cudaGetSymbolAddress(&ptr, g_attn_trace));
+    SIMSEG_CUDA(cudaMemset(ptr, 0, sizeof(unsigned long long) * kTraceWarps * kTraceLen));
+  }
+  return SIMSEG_OK;
+}
+int debug_trace_read_impl(unsigned long long* host, int n) {
+  const int total = kTraceWarps * kTraceLen;
+  SIMSEG_CUDA(cudaDeviceSynchronize());
+  SIMSEG_CUDA(cudaMemcpyFromSymbol(host, g_attn_trace, sizeof(unsigned long long) * (n < total ? n : total)));
+  return n < total ? n : total;
+}
+
 // heads of one sequence packed per 128-row tile: largest power of two G with G * S <= 128 that divides H
 static int pack_factor(int H, int S) {
   int G = 1;
@@ -1169,7 +1255,7 @@ int attention_bwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v,
   p.key_len = key_len; p.lse = lse; p.out = reinterpret_cast<const __nv_bfloat16*>(out);
   p.dq = reinterpret_cast<__nv_bfloat16*>(dq); p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dv = reinterpret_cast<__nv_bfloat16*>(dv);
   p.sb = sb; p.ss = ss; p.sh = sh;
-  const int smem_bytes = 1024 + 8 * kTileBytes + 2 * kPBytes + 256 + 8 * 2048;      // + per-warp drain staging
+  const int smem_bytes = 1024 + 8 * kTileBytes + 2 * kPBytes + 256 + kAbEwWarps * 2048 + 1024;   // + per-warp drain staging + D exchange
   static bool attr_set = false;
   if (!attr_set) {
     SIMSEG_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));

@@ -44,6 +44,8 @@ int seg_select_impl(Ctx*, const float*, const float*, int, int, int, int, int, f
 int seg_upsample_norm_impl(Ctx*, const float*, const int32_t*, int, int, int, int, int, int, int, float*, cudaStream_t);
 int pos_embed_bicubic_impl(Ctx*, const float*, float*, int, int, int, int, cudaStream_t);
 int patch_sim_fused_impl(Ctx*, const void*, int64_t, int, const void*, int, int, float*, int32_t*, cudaStream_t);
+int debug_trace_enable_impl(int);
+int debug_trace_read_impl(unsigned long long*, int);
 int64_t infonce_fused_workspace_bytes(int, int, int);
 int infonce_fused_fwd_impl(Ctx*, const float*, const float*, int, int, int, const float*, int, void*, int64_t, float*, float*, int32_t*, cudaStream_t);
 int infonce_fused_bwd_impl(Ctx*, int, int, int, const float*, int, const float*, float, void*, int64_t, float*, float*, float*, cudaStream_t);
@@ -239,6 +241,9 @@ int simseg_infonce_bwd(simseg_ctx* ctx, const float* feat1, const float* feat2g,
   }
   return SIMSEG_OK;
 }
+
+int simseg_debug_trace_enable(int on) { return debug_trace_enable_impl(on); }
+int simseg_debug_trace_read(uint64_t* host, int n) { return debug_trace_read_impl(reinterpret_cast<unsigned long long*>(host), n); }
 
 int64_t simseg_infonce_fused_workspace_bytes(int b, int Bg, int E) { return infonce_fused_workspace_bytes(b, Bg, E); }
 int simseg_infonce_fused_fwd(simseg_ctx* ctx, const float* feat1, const float* feat2g, int b, int Bg, int E,
