@@ -348,7 +348,14 @@ def run_ours(a):
                                               f"steps after 1 warm-up, {dt:.1f} s per step"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # The line is out.  Tearing down NCCL communicators that a captured CUDA graph still references blocked for minutes
+        # (seen at N = 2: the run printed its line and then sat in destroy_process_group until the harness killed it), so
+        # every rank synchronises once more and leaves without the teardown.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def fwd_gflop_per_pair(m, T):
