@@ -568,6 +568,9 @@ constexpr int kAfThreads = 320;
 
 struct AttnFwdParams {
   int32_t B, H, S, nqt, nkt, nkc, stride, items, kv_stages;
+  int32_t nbuf;        // S accumulators in TMEM: 2 (alternating units) while 2 * stride + 64 <= 512, else 1 (long sequences)
+  int32_t kv_tiles;    // 16 KB tiles per K (and per V) array = nkt * kv_stages
+  int32_t p_atoms;     // 64-key atoms of the P tile in smem (tc variant) = ceil(nkc / 64)
   int32_t G, lg, HG, rows, tile_tx;   // packed mode (G > 1): G heads of one sequence share a 128-row tile, row = token * G + head
   float scale_log2e;
   const int32_t* key_len;
@@ -586,9 +589,9 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   }
   uint8_t* sQ = smem;                          // [2 units][16 KB]
   uint8_t* sK = sQ + 2 * kTileBytes;           // [kv_stages items][nkt tiles x 16 KB]  rows = keys, contiguous over the tiles
-  uint8_t* sV = sK + 4 * kTileBytes;           // (2 stages of 2 tiles, or 4 stages of 1 tile when S <= 128)
-  uint8_t* sP = sV + 4 * kTileBytes;           // [4 key atoms][128 rows][128 B]
-  float* s_xchg = reinterpret_cast<float*>(sP + 4 * kTileBytes);     // [256 row sums | 256 row maxima] exchanged between the two warps of a row
+  uint8_t* sV = sK + p.kv_tiles * kTileBytes;  // (2 stages of 2 tiles, 4 stages of 1 tile when S <= 128, 1 stage of 3 tiles when S > 256)
+  uint8_t* sP = sV + p.kv_tiles * kTileBytes;  // [p_atoms key atoms][128 rows][128 B]
+  float* s_xchg = reinterpret_cast<float*>(sP + p.p_atoms * kTileBytes);     // [256 row sums | 256 row maxima] exchanged between the two warps of a row
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_xchg + 512);
   uint64_t* q_full = bars;            // [2]
   uint64_t* q_empty = bars + 2;       // [2]
@@ -629,7 +632,9 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tO = tmem_base + 2 * p.stride;
+  const uint32_t tO = tmem_base + p.nbuf * p.stride;
+  const uint32_t bmask = static_cast<uint32_t>(p.nbuf - 1);        // S buffer of unit u = u & bmask, its phase = (u / nbuf) & 1
+  const uint32_t bshift = bmask;                                    // nbuf = 2 -> 1, nbuf = 1 -> 0
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -657,7 +662,10 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    const uint32_t id_s = make_idesc(1u, 0u, 0u, kTile, static_cast<uint32_t>(p.nkc));   // A, B K-major, N = keys
+    // A, B K-major, N = keys; one instruction covers at most 256 keys, longer sequences (S = 325 at 288 x 288) take a second one
+    const uint32_t n0 = static_cast<uint32_t>(p.nkc > 256 ? 256 : p.nkc), n1 = static_cast<uint32_t>(p.nkc) - n0;
+    const uint32_t id_s = make_idesc(1u, 0u, 0u, kTile, n0);
+    const uint32_t id_s1 = make_idesc(1u, 0u, 0u, kTile, n1 ? n1 : 16u);
     const uint32_t id_o = make_idesc(1u, 0u, 1u, kTile, 64u);                            // A K-major (P), B MN-major (V)
     const uint32_t aP = smem_u32(sP);
     const int ksteps = p.nkc >> 4;
@@ -678,30 +686,41 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       }
       __syncwarp();
     };
+    bool pv_owed = false;                        // P V of unit u-1 not issued yet
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++itc) {
       const uint32_t kb = itc % p.kv_stages;
       for (int qt = 0; qt < p.nqt; ++qt, ++u) {
+        // single-stage K/V (long sequences): the next item's keys can only load once the LAST P V of this item has released
+        // the buffer, so that P V must be issued before waiting for them (it is normally deferred behind the next S = Q K^T)
+        if (qt == 0 && p.kv_stages == 1 && pv_owed) { issue_pv(u - 1, prev_kb, prev_last); pv_owed = false; }
         if (qt == 0) mbar_wait(&kv_full[kb], (itc / p.kv_stages) & 1);
         mbar_wait(&q_full[u & 1], (u >> 1) & 1);
-        mbar_wait(&s_empty[u & 1], ((u >> 1) & 1) ^ 1);
+        mbar_wait(&s_empty[u & bmask], ((u >> bshift) & 1) ^ 1);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t aQ = smem_u32(sQ + (u & 1) * kTileBytes), aK = smem_u32(sK + p.nkt * kb * kTileBytes);
-          const uint32_t tS = tmem_base + (u & 1) * p.stride;
+          const uint32_t tS = tmem_base + (u & bmask) * p.stride;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             umma_f16(tS, make_smem_desc_sw128(aQ + kk * 32, 16, 1024), make_smem_desc_sw128(aK + kk * 32, 16, 1024), id_s,
                      kk > 0 ? 1u : 0u);
-          umma_commit(&s_full[u & 1]);
+          if (n1) {                                  // keys 256.. : K rows two tiles further, accumulator columns 256..
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16(tS + 256, make_smem_desc_sw128(aQ + kk * 32, 16, 1024),
+                       make_smem_desc_sw128(aK + 2 * kTileBytes + kk * 32, 16, 1024), id_s1, kk > 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[u & bmask]);
           umma_commit(&q_empty[u & 1]);            // Q is only read by these MMAs: reload its buffer as early as possible
         }
         __syncwarp();
-        if (u > 0) issue_pv(u - 1, prev_kb, prev_last);
+        if (pv_owed) issue_pv(u - 1, prev_kb, prev_last);
+        pv_owed = true;
         prev_kb = kb;
         prev_last = (qt == p.nqt - 1) ? 1u : 0u;
       }
     }
-    if (u > 0) issue_pv(u - 1, prev_kb, prev_last);
+    if (pv_owed) issue_pv(u - 1, prev_kb, prev_last);
   } else {
     // =============================== softmax + output (8 warps on every unit) ===============================
     // Two warps share a TMEM lane quarter (32 query rows) and take alternate 32-key chunks; the row max and the row
@@ -761,8 +780,8 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         const int qrow = qt * kTile + r;                                    // packed: row = token * G + head
         const bool q_ok = qrow < p.rows;
         const bool warp_live = qt * kTile + quarter * 32 < p.rows;          // any live row in this warp
-        const uint32_t tS = tmem_base + (u & 1) * p.stride + lane_off;
-        mbar_wait(&s_full[u & 1], (u >> 1) & 1);
+        const uint32_t tS = tmem_base + (u & bmask) * p.stride + lane_off;
+        mbar_wait(&s_full[u & bmask], (u >> bshift) & 1);
         tc_fence_after();
         // ---- pass 1: row max over this warp's chunks (chunk = half + 2k), exchanged with the mate warp
         float m = -INFINITY;
@@ -864,7 +883,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
         sum += s_xchg[mate];
         asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-        if (lane == 0) { mbar_arrive(p_ready); mbar_arrive(&s_empty[u & 1]); }
+        if (lane == 0) { mbar_arrive(p_ready); mbar_arrive(&s_empty[u & bmask]); }
         pv_pending = true; p_q_ok = q_ok; p_live = warp_live; p_sum = sum; p_ms = ms;
         {
           const int tok = qrow >> p.lg, hh = h0 + (qrow & gm);
@@ -899,8 +918,8 @@ attention_fwd_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                          // [2 units][16 KB]
   uint8_t* sK = sQ + 2 * kTileBytes;           // [kv_stages items][nkt tiles x 16 KB]
-  uint8_t* sV = sK + 4 * kTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 4 * kTileBytes);
+  uint8_t* sV = sK + p.kv_tiles * kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + p.kv_tiles * kTileBytes);
   uint64_t* q_full = bars;            // [2]
   uint64_t* q_empty = bars + 2;       // [2]
   uint64_t* kv_full = bars + 4;       // [4]
@@ -1268,10 +1287,13 @@ int attention_bwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v,
   return SIMSEG_OK;
 }
 
-// SIMSEG_ERR_UNSUPPORTED => caller uses the mma.sync kernel (S > 224, unaligned pointers ...)
+// SIMSEG_ERR_UNSUPPORTED => caller uses the mma.sync kernel (S > 384, unaligned pointers ...)
+// S <= 224: two S accumulators in TMEM, "ts" variant by default.  224 < S <= 384 (the reference's seg evaluation runs 288 x 288
+// images = 325 tokens, configs/clip/simseg.vit-s.yaml:70-77): the shared-memory-P variant with ONE S accumulator (up to 384
+// columns + 64 for O), all keys of a sequence in smem (3 K + 3 V tiles, single stage) and two MMAs per S = Q K^T (N <= 256 each).
 int attention_fwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v, int64_t sb, int64_t ss, int64_t sh, int B, int H,
                           int S, const int32_t* key_len, float scale, void* out, float* lse, cudaStream_t st) {
-  if (S > 224 || S < 1) return SIMSEG_ERR_UNSUPPORTED;
+  if (S > 384 || S < 1) return SIMSEG_ERR_UNSUPPORTED;
   const int G = pack_factor(H, S);
   if (G == 1 && S < 48 && getenv("SIMSEG_ATTN_FWD") == nullptr) return SIMSEG_ERR_UNSUPPORTED;   // mostly padding: mma.sync kernel
   const uintptr_t al = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
@@ -1292,13 +1314,16 @@ int attention_fwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v,
   p.nkc = (p.rows + 15) & ~15;
   p.stride = (p.nkc + 31) & ~31;
   p.items = B * p.HG;
-  p.kv_stages = p.nkt == 1 ? 4 : 2;
+  p.kv_stages = p.nkt == 1 ? 4 : (p.nkt == 2 ? 2 : 1);
+  p.kv_tiles = p.nkt * p.kv_stages;
+  p.nbuf = (2 * p.stride + 64 <= 512) ? 2 : 1;
+  p.p_atoms = (p.nkc + 63) / 64 < 4 ? 4 : (p.nkc + 63) / 64;
   p.scale_log2e = scale * 1.44269504088896341f;
   p.key_len = key_len; p.lse = lse; p.out = reinterpret_cast<__nv_bfloat16*>(out);
   // default: the "ts" variant (P stays in tensor memory; measured 0.895 vs 0.974 ms on 4096 x 6 x 197 and 0.174 vs 0.214 ms on
   // the packed 4096 x 12 x 25 case); SIMSEG_ATTN_FWD=tc selects the shared-memory-P variant below
   const char* var = getenv("SIMSEG_ATTN_FWD");
-  if (!(var != nullptr && var[0] == 't' && var[1] == 'c')) {
+  if (p.nbuf == 2 && !(var != nullptr && var[0] == 't' && var[1] == 'c')) {
     const int smem_ts = 1024 + 10 * kTileBytes + 256 + 8 * 4096;                  // + per-warp output staging
     static bool ts_set = false;
     if (!ts_set) {
@@ -1311,10 +1336,11 @@ int attention_fwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v,
     SIMSEG_LAUNCH_CHECK();
     return SIMSEG_OK;
   }
-  const int smem_bytes = 14 * kTileBytes + 2048 + 256;   // the dynamic segment itself is 1024-byte aligned (checked in-kernel)
+  const int smem_bytes = (2 + 2 * p.kv_tiles + p.p_atoms) * kTileBytes + 2048 + 256;   // the dynamic segment itself is 1024-byte aligned (checked in-kernel)
+  if (smem_bytes > 14 * kTileBytes + 2048 + 256) return SIMSEG_ERR_UNSUPPORTED;
   static bool attr_set = false;
   if (!attr_set) {
-    SIMSEG_CUDA(cudaFuncSetAttribute(attention_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    SIMSEG_CUDA(cudaFuncSetAttribute(attention_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 14 * kTileBytes + 2048 + 256));
     attr_set = true;
   }
   const int grid = p.items < ctx->num_sms ? p.items : ctx->num_sms;

@@ -10,6 +10,7 @@ sees five coarse ``torch.autograd.Function`` nodes whose backward passes are han
 """
 from __future__ import annotations
 
+import warnings
 import weakref
 from typing import Dict, Optional
 
@@ -518,6 +519,19 @@ class HuggingFaceModel(nn.Module):
             raise RuntimeError("pretrained HF weights cannot be downloaded here: load a checkpoint with load_state_dict")
         self.model = BertModel()
         self._shared = shared
+        # bert-base-uncased ships hidden_dropout_prob = attention_probs_dropout_prob = 0.1, active under model.train() in
+        # the reference.  The B200 kernels implement p = 0 only (parity is defined at p = 0, SURVEY 8d "Dropout p forced to
+        # 0"): a deliberate, documented deviation — train() warns once instead of silently differing.
+        self.hidden_dropout_prob = 0.0
+        self.attention_probs_dropout_prob = 0.0
+        self._warned_dropout = False
+
+    def train(self, mode: bool = True):
+        if mode and not self._warned_dropout and any(p.requires_grad for p in self.parameters()):
+            warnings.warn("simseg_b200: the text tower trains WITHOUT BERT's dropout (reference: hidden / attention-probability "
+                          "dropout 0.1 under model.train()); see INTEGRATION.md section 3", stacklevel=2)
+            self._warned_dropout = True
+        return super().train(mode)
 
     def forward(self, input_ids, attention_mask, **kwargs):
         _check_text(input_ids, attention_mask, self.model)

@@ -381,3 +381,42 @@ def test_gemm_wgrad_wide_pair_tiles(cuda, T, Do, Di):
     assert _rel(out, 2 * ref) < 1e-4
     legacy = ops.gemm(dy, x, M=Do, N=Di, K=T, a_major=1, b_major=1, out_dtype=torch.float32, _dbg=128)
     assert _rel(legacy, ref) < 1e-4
+
+
+@pytest.mark.parametrize("B,H,S,masked", [(2, 12, 325, False), (64, 12, 325, False), (3, 6, 325, True), (2, 6, 384, True), (5, 6, 257, False),
+                                          (4, 12, 256, True), (3, 6, 225, False), (200, 6, 325, False)])
+def test_attention_fwd_long_sequences_on_tcgen05(cuda, B, H, S, masked, monkeypatch):
+    """224 < S <= 384 — the geometry the reference's segmentation tool runs (288 x 288 -> 325 tokens,
+    configs/clip/simseg.vit-s.yaml:70-77, tools/seg_evaluation.py:228-231) — through the tcgen05 forward (one S accumulator
+    of up to 384 TMEM columns, two MMAs per S = Q K^T, three K / V tiles in smem) and bit-compared in value with the
+    mma.sync kernel that used to take these shapes."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(S + B)
+    D = H * 64
+    qkv = (torch.randn(B, S, 3, H, 64, device=cuda, generator=g)).bfloat16()
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    strides = (S * 3 * D, 3 * D, 64)
+    klen = None
+    if masked:
+        klen = torch.randint(1, S + 1, (B,), device=cuda, generator=g, dtype=torch.int32)
+        klen[0] = S
+    res = {}
+    for impl in ("tc", "mma"):
+        monkeypatch.setenv("SIMSEG_ATTN_FWD", impl)
+        out = torch.full((B, S, D), float("nan"), device=cuda, dtype=torch.bfloat16)
+        lse = torch.full((B, H, S), float("nan"), device=cuda)
+        n0 = ops.launch_count()
+        ops.attention_fwd(q, k, v, B, H, S, strides, klen, 0.125, out=out, lse=lse)
+        assert ops.launch_count() == n0 + 1
+        res[impl] = (out, lse)
+    qf, kf, vf = [t.float().permute(0, 2, 1, 3) for t in (q, k, v)]
+    s = (qf @ kf.transpose(-1, -2)) * 0.125
+    if masked:
+        km = torch.arange(S, device=cuda)[None] >= klen[:, None]
+        s = s.masked_fill(km[:, None, None, :], float("-inf"))
+    ref_o = (torch.softmax(s, -1) @ vf).permute(0, 2, 1, 3).reshape(B, S, D)
+    for impl, (out, lse) in res.items():
+        assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all(), impl
+        assert (out.float() - ref_o).abs().max().item() < 3e-2, impl
+        assert (lse - torch.logsumexp(s, -1)).abs().max().item() < 2e-3, impl
+    assert (res["tc"][0].float() - res["mma"][0].float()).abs().max().item() < 2e-2
