@@ -532,6 +532,10 @@ def gemm_roofline(trainer, batch, tf_peak, how):
         e1.record()
         rec.append((2.0 * kw["M"] * kw["N"] * kw["K"], e0, e1))
         return out
+    # one untimed eager step first: the caching allocator is empty here (the CUDA graph's pool was just handed back), and a
+    # cudaMalloc between e0.record() and the launch would idle the GPU inside the bracket
+    trainer.step(batch)
+    torch.cuda.synchronize()
     ops.gemm = timed_gemm
     try:
         trainer.step(batch)
