@@ -28,9 +28,7 @@ using namespace sm100;
 
 constexpr int kBM = 128;            // tile rows per CTA = TMEM lanes
 constexpr int kSwizzleBytes = 128;  // one swizzle atom row = one K block (K-major) / 64 MN elements (bf16)
-constexpr int kNumEpiWarps = 8;
 constexpr int kEpiBoxBytes = 32 * 64;   // epilogue staging box: 32 rows x 32 bf16 columns, SWIZZLE_64B (TMA store/load box)
-constexpr int kGemmThreads = 32 * (2 + kNumEpiWarps);
 constexpr int kMaxSmem = 232448;
 
 // internal epilogues of the similarity family (fp32 scores never leave the SM; see sim_loss.cu for the entry points)
@@ -85,16 +83,27 @@ struct GemmParams {
   int32_t d_trans;         // fp32 atomic output stored transposed: element (m, n) at d[n * ldd + m]  (wgrad computed as dW^T)
 };
 
-template <int BN, int EPI, int CTAS>
+// NEW = number of epilogue warps: 8 (two per TMEM lane quarter), or 16 for the activation epilogues (GELU / dGELU), whose
+// per-element work (MUFU + a dozen FMA-pipe instructions in dependent chains) needs four warps per scheduler to fill the
+// issue slots — with two, the epilogue of a 128 x 256 tile took ~2x the tile's MMA time (profiles/r01_ncu_gemm.txt).
+template <int BN, int EPI, int CTAS, int NEW = 8>
 struct GemmCfg {
+  static constexpr int kEpiWarps = NEW;
+  static constexpr int kThreads = 32 * (2 + NEW);
+  static constexpr int kGroups = NEW / 4;                      // warps per TMEM lane quarter = column groups of a tile
+  static_assert(NEW == 8 || NEW == 16, "8 or 16 epilogue warps");
+  static constexpr bool kGroupsOk = (BN / 32) % kGroups == 0 || BN > 256;   // 32-column chunks divide evenly among the groups
   static constexpr int kABytes = kBM * kSwizzleBytes;          // 16 KB: this CTA's 128 rows of A, one k-block
   static constexpr int kBRows = BN / CTAS;                     // B columns staged by this CTA
   static constexpr int kBBytes = kBRows * kSwizzleBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  // per-warp epilogue staging: EPI_NONE rotates 2 boxes; BIAS_GELU 2 x (out, aux); DGELU 3 aux-in boxes + 1 out box
-  static constexpr int kStgPerWarp = (BN > 256) ? 0 : ((EPI == SIMSEG_EPI_BIAS_GELU || EPI == SIMSEG_EPI_DGELU) ? 4 : 2) * kEpiBoxBytes;
-  static constexpr int kStagingBytes = kNumEpiWarps * kStgPerWarp;
-  static constexpr int kBarBytes = 512;
+  // per-warp epilogue staging, 8 warps: EPI_NONE rotates 2 boxes; BIAS_GELU 2 x (out, aux); DGELU 3 aux-in boxes + 1 out box
+  //                             16 warps: BIAS_GELU (out, aux) single-buffered; DGELU 2 aux-in boxes + 1 out box
+  static constexpr bool kAct = (EPI == SIMSEG_EPI_BIAS_GELU || EPI == SIMSEG_EPI_DGELU);
+  static constexpr int kStgBoxes = (BN > 256) ? 0 : (NEW == 16 ? (EPI == SIMSEG_EPI_DGELU ? 3 : 2) : (kAct ? 4 : 2));
+  static constexpr int kStgPerWarp = kStgBoxes * kEpiBoxBytes;
+  static constexpr int kStagingBytes = NEW * kStgPerWarp;
+  static constexpr int kBarBytes = 1024;
   static constexpr int kStagesFit = (kMaxSmem - 1024 - kStagingBytes - kBarBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   // BN <= 256: two accumulator stages (epilogue of tile i overlaps the MMAs of tile i+1).  BN = 384 / 512 ("wide", CTA
@@ -107,7 +116,7 @@ struct GemmCfg {
   static constexpr int kTmemCols = kWide ? 512 : 2 * kAccStride;                // 256 or 512 (power of two)
   static_assert(!kWide || CTAS == 2, "wide tiles are a CTA-pair configuration");
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + kBarBytes;
-  static_assert(kStages >= 3, "ring too shallow");
+  static constexpr bool kFits = kStages >= 3 && kGroupsOk;       // checked where the kernel is instantiated
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -306,6 +315,182 @@ __device__ __forceinline__ void epilogue_tma(const GemmParams& p, const CUtensor
 }
 
 // ------------------------------------------------------------------------------------------------
+// Activation epilogues (BIAS_GELU, DGELU) on SIXTEEN warps: four per TMEM lane quarter, warp (quarter, grp) takes the
+// 32-column chunks grp, grp + 4, ... of the tile.  The math per element is the same as in epilogue_tma; what changes is how
+// its latency is hidden: not by software-pipelining inside a warp (next chunk's tcgen05.ld in flight, double-buffered
+// staging — 140-170 registers) but by four warps per scheduler, each a plain load -> math -> stage -> TMA-store sequence that
+// fits 112 registers.  Staging per warp: GELU one (aux, out) pair; DGELU two aux-in boxes (next chunk's pre-activation is
+// TMA-loaded while the current one is processed) + one out box.  A box is rewritten only after the bulk-group that last read
+// it has finished reading (cp.async.bulk.wait_group.read 0, issued a whole chunk later: it does not stall).
+template <int BN, int EPI, int CTAS>
+__device__ __forceinline__ void epilogue_act16(const GemmParams& p, const CUtensorMap& tmap_d, const CUtensorMap& tmap_x,
+                                               const CUtensorMap& tmap_x2, uint8_t* stg, uint64_t* acc_full,
+                                               uint32_t acc_empty_addr, uint64_t* aux_full, uint32_t tmem_base, int first_tile,
+                                               int tile_stride, int total_tiles, int tiles_mn, int row_base, int warp, int lane) {
+  using Cfg = GemmCfg<BN, EPI, CTAS, 16>;
+  constexpr int kG = 4;
+  constexpr int kCw = BN / 32 / kG;                                 // chunks per warp and tile (2 for BN = 256)
+  const int quarter = warp & 3;
+  const int grp = (warp - 2) >> 2;
+  const int sw = (lane >> 1) & 3;                                   // SWIZZLE_64B: 16-byte chunk ^= (row >> 1) & 3
+  const uint32_t row_off = static_cast<uint32_t>(lane) * 64;
+  const bool has_bias = p.bias != nullptr;
+  const bool want_cs = (EPI == SIMSEG_EPI_DGELU) && p.col_sum != nullptr;
+  uint32_t f = 0;                                                   // flat chunk counter over (tile, chunk)
+  float cs[kCw];
+  int cs_n0 = -1;
+#pragma unroll
+  for (int j = 0; j < kCw; ++j) cs[j] = 0.f;
+
+  auto coords = [&](uint32_t ff, int& row0, int& col0) -> bool {
+    const int tile = first_tile + static_cast<int>(ff / kCw) * tile_stride;
+    if (tile >= total_tiles) return false;
+    const int mn = tile % tiles_mn;
+    row0 = (mn / p.n_tiles) * (kBM * CTAS) + row_base + quarter * 32;
+    col0 = (mn % p.n_tiles) * BN + (grp + kG * static_cast<int>(ff % kCw)) * 32;
+    return true;
+  };
+  auto flush_cs = [&]() {
+    if (cs_n0 < 0) return;
+#pragma unroll
+    for (int j = 0; j < kCw; ++j) {
+      const int c = cs_n0 + (grp + kG * j) * 32 + lane;
+      if (c < p.N) atomicAdd(p.col_sum + c, cs[j]);
+      cs[j] = 0.f;
+    }
+  };
+  if (EPI == SIMSEG_EPI_DGELU && lane == 0) {
+    int r0, c0;
+    if (coords(0, r0, c0)) {
+      mbar_arrive_expect_tx(&aux_full[0], kEpiBoxBytes);
+      tma_load_2d(stg, &tmap_x, &aux_full[0], c0, r0);
+    }
+  }
+
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+    const int mn = tile % tiles_mn;
+    const int n0 = (mn % p.n_tiles) * BN;
+    const int row0 = (mn / p.n_tiles) * (kBM * CTAS) + row_base + quarter * 32;
+    if (want_cs && n0 != cs_n0) {
+      flush_cs();
+      cs_n0 = n0;
+    }
+    mbar_wait(&acc_full[acc], acc_phase);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll
+    for (int j = 0; j < kCw; ++j, ++f) {
+      const int col = n0 + (grp + kG * j) * 32;
+      uint32_t r[32];
+      tmem_ld_32x32(t_row + (grp + kG * j) * 32, r);
+      tmem_ld_wait();
+      if (j + 1 == kCw) {
+        // every TMEM read of this warp has landed in registers: hand the accumulator stage back to the MMA issuer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc_empty_addr + acc * 8);
+      }
+      float v[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+      if (has_bias) {
+        if (col + 32 <= p.N) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float4 bb = __ldg(b4 + k);
+            f2_unpack(f2_add(f2_pack(v[4 * k], v[4 * k + 1]), f2_pack(bb.x, bb.y)), v[4 * k], v[4 * k + 1]);
+            f2_unpack(f2_add(f2_pack(v[4 * k + 2], v[4 * k + 3]), f2_pack(bb.z, bb.w)), v[4 * k + 2], v[4 * k + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] += (col + k < p.N) ? __ldg(p.bias + col + k) : 0.f;
+        }
+      }
+      uint8_t* sx;                                                  // aux box (GELU: aux out; DGELU: aux in, then aux2 out)
+      uint8_t* so;                                                  // out box
+      if (EPI == SIMSEG_EPI_BIAS_GELU) { sx = stg; so = stg + kEpiBoxBytes; }
+      else { sx = stg + (f & 1) * kEpiBoxBytes; so = stg + 2 * kEpiBoxBytes; }
+      sx += row_off;
+      so += row_off;
+      uint32_t xo[16];
+      if (EPI == SIMSEG_EPI_BIAS_GELU) {
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) {
+          xo[k >> 1] = pack_bf16(v[k], v[k + 1]);                   // pre-activation, bf16 — exactly what backward reads
+          f2_unpack(gelu_erf_x2(xo[k >> 1]), v[k], v[k + 1]);
+        }
+      } else {
+        mbar_wait(&aux_full[f & 1], (f >> 1) & 1);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const uint4 u = *reinterpret_cast<const uint4*>(sx + ((q4 ^ sw) << 4));
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            f32x2 act, grad;
+            gelu_erf_both_x2(w[e], act, grad);
+            float a0, a1;
+            f2_unpack(act, a0, a1);
+            f2_unpack(f2_mul(f2_pack(v[8 * q4 + 2 * e], v[8 * q4 + 2 * e + 1]), grad), v[8 * q4 + 2 * e], v[8 * q4 + 2 * e + 1]);
+            xo[4 * q4 + e] = pack_bf16(a0, a1);
+          }
+        }
+      }
+      uint32_t o[16];
+#pragma unroll
+      for (int k = 0; k < 32; k += 2) o[k >> 1] = pack_bf16(v[k], v[k + 1]);
+      if (want_cs) {
+        // column sums over this warp's 32 rows (butterfly transpose-reduce): lane l ends up with column l
+#pragma unroll
+        for (int o2 = 16; o2 >= 1; o2 >>= 1) {
+          const bool upper = (lane & o2) != 0;
+#pragma unroll
+          for (int k = 0; k < o2; ++k) {
+            const float mine = upper ? v[k + o2] : v[k];
+            const float send = upper ? v[k] : v[k + o2];
+            v[k] = mine + __shfl_xor_sync(0xffffffffu, send, o2);
+          }
+        }
+        cs[j] += v[0];
+      }
+      // ---- the boxes written below must have been read by the bulk group of the previous chunk
+      if (lane == 0) {
+        tma_store_wait_read<0>();
+        if (EPI == SIMSEG_EPI_DGELU) {
+          int r2, c2;
+          if (coords(f + 1, r2, c2)) {                               // slot (f+1)&1 == (f-1)&1: its aux2 store has been read
+            mbar_arrive_expect_tx(&aux_full[(f + 1) & 1], kEpiBoxBytes);
+            tma_load_2d(stg + ((f + 1) & 1) * kEpiBoxBytes, &tmap_x, &aux_full[(f + 1) & 1], c2, r2);
+          }
+        }
+      }
+      __syncwarp();
+      const bool two = (EPI == SIMSEG_EPI_BIAS_GELU && p.aux != nullptr) || (EPI == SIMSEG_EPI_DGELU && p.aux2 != nullptr);
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const uint32_t off = (q4 ^ sw) << 4;
+        *reinterpret_cast<uint4*>(so + off) = make_uint4(o[4 * q4], o[4 * q4 + 1], o[4 * q4 + 2], o[4 * q4 + 3]);
+        if (two) *reinterpret_cast<uint4*>(sx + off) = make_uint4(xo[4 * q4], xo[4 * q4 + 1], xo[4 * q4 + 2], xo[4 * q4 + 3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tmap_d, so - row_off, col, row0);
+        if (EPI == SIMSEG_EPI_BIAS_GELU && p.aux != nullptr) tma_store_2d(&tmap_x, sx - row_off, col, row0);
+        if (EPI == SIMSEG_EPI_DGELU && p.aux2 != nullptr) tma_store_2d(&tmap_x2, sx - row_off, col, row0);
+        tma_store_commit();
+      }
+    }
+    if (++acc == Cfg::kAccStages) { acc = 0; acc_phase ^= 1; }
+  }
+  if (want_cs) flush_cs();
+  if (lane == 0) tma_store_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Epilogues of the similarity family: the fp32 score tile is consumed straight out of TMEM and never written.
 // A thread owns one row (TMEM lane) and half of the tile's columns, so every per-row reduction is thread-local.
 //   kEpiNceFwd  NCE.forward (mml_loss.py:56,73-77 + utils/misc.py:462-477): z = acc / clamp(temp); one online-softmax partial
@@ -453,12 +638,13 @@ __device__ __forceinline__ void sim_epilogue_tile(const GemmParams& p, uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int BN, int EPI, int CTAS>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN, int EPI, int CTAS, int NEW = 8>
+__global__ void __launch_bounds__(32 * (2 + NEW), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_x,
             const __grid_constant__ CUtensorMap tmap_x2, const GemmParams p) {
-  using Cfg = GemmCfg<BN, EPI, CTAS>;
+  using Cfg = GemmCfg<BN, EPI, CTAS, NEW>;
+  static_assert(Cfg::kFits, "operand ring too shallow, or chunks do not divide among the epilogue warps");
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B (descriptor base_offset = 0); the dynamic-smem base offset is the
   // same in both CTAs of a pair, so every carved address below is at the same offset in the peer.
@@ -469,8 +655,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* empty_bar = bars + 8;                  // [8]   MMA -> TMA            (multicast to both CTAs of a pair)
   uint64_t* acc_full = bars + 16;                  // [2]   MMA -> epilogue       (multicast)
   uint64_t* acc_empty = bars + 18;                 // [2]   epilogue -> MMA       (leader's; both CTAs' warps arrive)
-  uint64_t* aux_full = bars + 20;                  // [8 warps][3]  TMA (aux-in boxes of the DGELU epilogue) -> warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 44);
+  uint64_t* aux_full = bars + 20;                  // [NEW warps][3]  TMA (aux-in boxes of the DGELU epilogue) -> warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20 + 3 * 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -486,9 +672,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], kNumEpiWarps * CTAS);
+      mbar_init(&acc_empty[s], NEW * CTAS);
     }
-    for (int s = 0; s < 3 * kNumEpiWarps; ++s) mbar_init(&aux_full[s], 1);
+    for (int s = 0; s < 3 * NEW; ++s) mbar_init(&aux_full[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -683,16 +869,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // the leader's acc_empty barriers (a shared::cta address is a valid shared::cluster address of the own CTA)
     const uint32_t acc_empty_addr = (CTAS == 2) ? mapa_shared(smem_u32(&acc_empty[0]), 0) : smem_u32(&acc_empty[0]);
     if (p.tma_epi) {
-      epilogue_tma<BN, EPI, CTAS>(p, tmap_d, tmap_x, tmap_x2, stg + (warp - 2) * Cfg::kStgPerWarp, acc_full, acc_empty_addr,
-                                  aux_full + 3 * (warp - 2), tmem_base, first_tile, tile_stride, total_tiles, tiles_mn, row_base,
-                                  warp, lane);
+      if constexpr (NEW == 16)
+        epilogue_act16<BN, EPI, CTAS>(p, tmap_d, tmap_x, tmap_x2, stg + (warp - 2) * Cfg::kStgPerWarp, acc_full, acc_empty_addr,
+                                      aux_full + 3 * (warp - 2), tmem_base, first_tile, tile_stride, total_tiles, tiles_mn,
+                                      row_base, warp, lane);
+      else
+        epilogue_tma<BN, EPI, CTAS>(p, tmap_d, tmap_x, tmap_x2, stg + (warp - 2) * Cfg::kStgPerWarp, acc_full, acc_empty_addr,
+                                    aux_full + 3 * (warp - 2), tmem_base, first_tile, tile_stride, total_tiles, tiles_mn, row_base,
+                                    warp, lane);
     } else {
-    const int ew = warp - 2;                 // 0..7
+    const int ew = warp - 2;                 // 0..NEW-1
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = ew >> 2;                // column half handled by this warp
-    constexpr int kColsPerWarp = BN / 2;
+    const int half = ew >> 2;                // column group handled by this warp (two groups = halves with 8 warps)
+    constexpr int kColsPerWarp = BN / Cfg::kGroups;
     constexpr int kChunks = kColsPerWarp / 32;
-    static_assert(kColsPerWarp % 32 == 0, "BN must be a multiple of 64");
+    static_assert(kColsPerWarp % 32 == 0, "BN must be a multiple of 32 x column groups");
     const int row_in_tile = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -957,21 +1148,21 @@ int make_tmap_mn3d(CUtensorMap* m, const void* ptr, int elem_bytes, int64_t k_ro
   return SIMSEG_OK;
 }
 
-template <int BN, int EPI, int CTAS>
+template <int BN, int EPI, int CTAS, int NEW = 8>
 static int launch_gemm(Ctx* ctx, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
-  using Cfg = GemmCfg<BN, EPI, CTAS>;
+  using Cfg = GemmCfg<BN, EPI, CTAS, NEW>;
   static bool attr_set = false;
-  auto kfn = gemm_kernel<BN, EPI, CTAS>;
+  auto kfn = gemm_kernel<BN, EPI, CTAS, NEW>;
   if (!attr_set) {
     SIMSEG_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   if (CTAS == 1) {
-    kfn<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
+    kfn<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kGemmThreads);
+    cfg.blockDim = dim3(Cfg::kThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -987,7 +1178,15 @@ static int launch_gemm(Ctx* ctx, const CUtensorMap* tm, const GemmParams& p, int
 }
 
 template <int BN, int CTAS>
-static int dispatch_epi(Ctx* ctx, int epi, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
+static int dispatch_epi(Ctx* ctx, int epi, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st, bool act16) {
+  // activation epilogues on 16 warps (four per scheduler) wherever the larger staging area leaves a >= 3-stage operand
+  // ring; `reserved & 64` keeps the 8-warp version for A/B timing
+  if constexpr (GemmCfg<BN, SIMSEG_EPI_BIAS_GELU, CTAS, 16>::kFits) {
+    if (act16 && epi == SIMSEG_EPI_BIAS_GELU) return launch_gemm<BN, SIMSEG_EPI_BIAS_GELU, CTAS, 16>(ctx, tm, p, grid, st);
+  }
+  if constexpr (GemmCfg<BN, SIMSEG_EPI_DGELU, CTAS, 16>::kFits) {
+    if (act16 && epi == SIMSEG_EPI_DGELU) return launch_gemm<BN, SIMSEG_EPI_DGELU, CTAS, 16>(ctx, tm, p, grid, st);
+  }
   switch (epi) {
     case SIMSEG_EPI_NONE: return launch_gemm<BN, SIMSEG_EPI_NONE, CTAS>(ctx, tm, p, grid, st);
     case SIMSEG_EPI_BIAS_GELU: return launch_gemm<BN, SIMSEG_EPI_BIAS_GELU, CTAS>(ctx, tm, p, grid, st);
@@ -1009,7 +1208,8 @@ static int dispatch_sim(Ctx* ctx, int bn, int ctas, const CUtensorMap* tm, const
 int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) { return gemm_sim_impl(ctx, a, nullptr, st); }
 
 // `reserved` bits (bench / debug only): 1 = no TMA, 2 = no MMA, 4 = 2-D boxes for MN-major operands, 8 = direct-store
-// epilogue, 16 = force single-CTA tiles, 32 = force CTA pairs, 128 = no wide (256 x 384|512) split-K tiles.
+// epilogue, 16 = force single-CTA tiles, 32 = force CTA pairs, 64 = activation epilogues on 8 warps (the round-1 version),
+// 128 = no wide (256 x 384|512) split-K tiles, 256 = 16-warp GELU epilogue regardless of K.
 // `sim` != NULL: split-bf16 operands (a / b are the hi halves, sim->a_lo / b_lo the lo halves, K counts ONE segment) and
 // optionally one of the similarity epilogues (sim->epi = 0 keeps a->epilogue).
 int gemm_sim_impl(Ctx* ctx, const simseg_gemm_args* a, const GemmSim* sim, cudaStream_t st) {
@@ -1233,17 +1433,21 @@ int gemm_sim_impl(Ctx* ctx, const simseg_gemm_args* a, const GemmSim* sim, cudaS
   if (sim_epi == kEpiBest) return dispatch_sim<kEpiBest>(ctx, bn, ctas, tm, p, grid, st);
   if (wide_bn == 384) return launch_gemm<384, SIMSEG_EPI_NONE, 2>(ctx, tm, p, grid, st);
   if (wide_bn == 512) return launch_gemm<512, SIMSEG_EPI_NONE, 2>(ctx, tm, p, grid, st);
+  // measured (profiles/r02_gemm_act16_ab.txt): dGELU gains 7-16 % on every shape of the step; the forward GELU gains 22 % at
+  // K = 384 (ViT-S fc1: the epilogue, not the MMAs, paces the tile) and loses 3-10 % at K = 768, where the 8-warp epilogue
+  // already hides under twice as many MMAs
+  const bool act16 = tma_epi && (a->reserved & 64) == 0 && (a->epilogue == SIMSEG_EPI_DGELU || a->K <= 512 || (a->reserved & 256));
   if (ctas == 2) {
     switch (bn) {
-      case 128: return dispatch_epi<128, 2>(ctx, a->epilogue, tm, p, grid, st);
-      case 192: return dispatch_epi<192, 2>(ctx, a->epilogue, tm, p, grid, st);
-      default: return dispatch_epi<256, 2>(ctx, a->epilogue, tm, p, grid, st);
+      case 128: return dispatch_epi<128, 2>(ctx, a->epilogue, tm, p, grid, st, act16);
+      case 192: return dispatch_epi<192, 2>(ctx, a->epilogue, tm, p, grid, st, act16);
+      default: return dispatch_epi<256, 2>(ctx, a->epilogue, tm, p, grid, st, act16);
     }
   }
   switch (bn) {
-    case 128: return dispatch_epi<128, 1>(ctx, a->epilogue, tm, p, grid, st);
-    case 192: return dispatch_epi<192, 1>(ctx, a->epilogue, tm, p, grid, st);
-    default: return dispatch_epi<256, 1>(ctx, a->epilogue, tm, p, grid, st);
+    case 128: return dispatch_epi<128, 1>(ctx, a->epilogue, tm, p, grid, st, act16);
+    case 192: return dispatch_epi<192, 1>(ctx, a->epilogue, tm, p, grid, st, act16);
+    default: return dispatch_epi<256, 1>(ctx, a->epilogue, tm, p, grid, st, act16);
   }
 }
 

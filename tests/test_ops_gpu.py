@@ -132,7 +132,7 @@ def test_gemm_tma_epilogue_bf16(cuda, M, N, K, tile_n, mode):
     legacy = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, tile_n=tile_n, _dbg=mode | 8)          # direct-store epilogue
     assert torch.equal(out, legacy)
     aux = torch.full((M, N), float("nan"), device=cuda, dtype=torch.bfloat16)
-    act = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, epilogue=EPI_BIAS_GELU, aux=aux, tile_n=tile_n, _dbg=mode)
+    act = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, epilogue=EPI_BIAS_GELU, aux=aux, tile_n=tile_n, _dbg=mode | 256)   # 256: 16-warp epilogue at any K
     assert torch.equal(aux, out)                                                  # same rounding of the pre-activation
     assert (act.float() - gelu(aux.float())).abs().max().item() < 2e-2
     act_noaux = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, epilogue=EPI_BIAS_GELU, tile_n=tile_n, _dbg=mode)
@@ -147,6 +147,15 @@ def test_gemm_tma_epilogue_bf16(cuda, M, N, K, tile_n, mode):
     assert _rel(cs, h.grad.sum(0)) < 2e-3
     assert (a2.float() - gelu(aux.float())).abs().max().item() < 2e-2 and torch.isfinite(a2.float()).all()
     assert (a2.float() - act.float()).abs().max().item() < 1e-6 + 8e-3 * act.float().abs().max().item()
+    # 16-warp activation epilogues (default where the staging area fits) == the 8-warp version (reserved bit 64), bit for bit
+    aux8 = torch.empty_like(aux)
+    act8 = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, epilogue=EPI_BIAS_GELU, aux=aux8, tile_n=tile_n, _dbg=mode | 64)
+    assert torch.equal(act8, act) and torch.equal(aux8, aux)
+    cs8 = torch.zeros(N, device=cuda)
+    a28 = torch.empty_like(a2)
+    dh8 = ops.gemm(a, b, M=M, N=N, K=K, epilogue=EPI_DGELU, aux=aux, aux2=a28, col_sum=cs8, tile_n=tile_n, _dbg=mode | 64)
+    assert torch.equal(dh8, dh) and torch.equal(a28, a2)
+    assert _rel(cs8, cs) < 1e-5
 
 
 @pytest.mark.parametrize("D", [384, 768])

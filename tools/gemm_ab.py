@@ -22,6 +22,9 @@ if epi == EPI_DGELU:
 if epi == 0:
     kw["bias"] = torch.randn(N, device="cuda")
 cfgs = [(tn, mode) for mode in (16, 32) for tn in (128, 192, 256)]
+if epi in (EPI_BIAS_GELU, EPI_DGELU):
+    # A/B of the activation epilogue: 16 warps (default) vs the round-1 8-warp version (reserved bit 64), CTA pairs, auto tile
+    cfgs = [(0, 256), (0, 64), (256, 32 + 256), (256, 32 + 64), (128, 32 + 256), (128, 32 + 64)]
 res = {c: [] for c in cfgs}
 for r in range(rounds + 1):
     for c in cfgs:
@@ -35,4 +38,5 @@ for r in range(rounds + 1):
             res[c].append(e0.elapsed_time(e1) / 5)
 for c in cfgs:
     v = sorted(res[c])
-    print(f"{'c1' if c[1] == 16 else 'c2'}/{c[0]}: min {v[0]:.3f} med {v[len(v) // 2]:.3f} ms  {2.0 * M * N * K / v[len(v) // 2] / 1e9:.0f} TF/s")
+    tag = ("c1" if c[1] & 16 else "c2" if c[1] & 32 else "auto") + ("/8w" if c[1] & 64 else "")
+    print(f"{tag}/{c[0]}: min {v[0]:.3f} med {v[len(v) // 2]:.3f} ms  {2.0 * M * N * K / v[len(v) // 2] / 1e9:.0f} TF/s")
