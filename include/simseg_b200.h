@@ -177,6 +177,25 @@ int simseg_topk_pool_l2norm_bwd(simseg_ctx* ctx, const float* demb, const float*
                                 int B, int S, int E, int tok_begin, int k, float eps, int has_l2norm, void* dx,
                                 void* stream);
 
+/* Fused LoDA head: image_pool(image_projection(feat)) / text_pool(text_projection(feat), mask) of
+ * pipelines/clip.py:87-93,111-120 = SimpleProjection (components/projection.py:45-46, y = x W^T, no bias) followed by
+ * TopKPooling (components/pooling.py:57-65) [+ L2norm, components/normalization.py:6-11] as ONE tensor-core GEMM whose
+ * epilogue keeps, per (sample, channel), the k largest bf16-rounded projections over tokens [tok_begin, tok_begin+ntok)
+ * (earliest token first on ties; masked tokens = -10000): the [B,S,E] projection is never written.
+ *   x  bf16 [B,S,D] (all S tokens of every sample, contiguous), w bf16 [E,D]; S <= 256, D % 64 == 0, E % 128 == 0, k <= 8
+ *   pooled f32 [B,E]; emb f32 [B,E] or NULL (no L2norm); sel_idx int32 [B,k,E] or NULL (absolute token positions) */
+int simseg_proj_topk_fwd(simseg_ctx* ctx, const void* x, const void* w, int B, int S, int D, int E, int tok_begin,
+                         int ntok, int k, const int64_t* attention_mask, int mask_ld, float eps, float* pooled,
+                         float* emb, int32_t* sel_idx, void* stream);
+/* Backward of the fused head without the dense [B,S,E] gradient: demb [B,E] -> gy = dL/dpooled / k (workspace f32
+ * [B,E], written), then   dx f32 [B,S,D] = dY W   (every row written; tokens nobody selected get zeros; NULL = skip;
+ * needs wt = bf16 [D,E], the transposed weight copy)   and   dw f32 [E,D] += dY^T x   (NULL = skip; ACCUMULATES),
+ * where dY[b,s,e] = gy[b,e] for the k selected tokens s of (b,e) and 0 elsewhere is generated tile by tile in shared
+ * memory as the tcgen05 operand.  D % 128 == 0. */
+int simseg_proj_topk_bwd(simseg_ctx* ctx, const float* demb, const float* pooled, const int32_t* sel_idx, const void* x,
+                         const void* wt, int B, int S, int D, int E, int k, float eps, int has_l2norm, float* gy,
+                         float* dx, float* dw, void* stream);
+
 /* ---- InfoNCE (criteria/losses/mml_loss.py:51-96, driven twice by clip.py:123-149) ------------ */
 #define SIMSEG_PREC_FP32 0 /* exact fp32 FFMA products                       */
 #define SIMSEG_PREC_TF32 1 /* tcgen05 kind::tf32 products, fp32 accumulation */

@@ -55,6 +55,8 @@ PROTOTYPES = {
     "simseg_bert_embed_bwd": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]),
     "simseg_topk_pool_l2norm_fwd": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, f32, vp, vp, vp, vp]),
     "simseg_topk_pool_l2norm_bwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, vp, vp]),
+    "simseg_proj_topk_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, f32, vp, vp, vp, vp]),
+    "simseg_proj_topk_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, vp, vp, vp, vp]),
     "simseg_infonce_fwd": (i32, [vp, vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
     "simseg_infonce_bwd": (i32, [vp, vp, vp, i32, i32, i32, vp, i32, i32, vp, f32, vp, vp, vp, vp, vp]),
     "simseg_debug_trace_enable": (i32, [i32]),

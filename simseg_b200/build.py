@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libsimseg_b200.so")
-SOURCES = ["capi.cu", "gemm_sm100.cu", "norm_act.cu", "embed_heads.cu", "sim_loss.cu", "attention.cu", "patch_sim.cu", "attention_sm100.cu", "seg_post.cu"]
+SOURCES = ["capi.cu", "gemm_sm100.cu", "norm_act.cu", "embed_heads.cu", "sim_loss.cu", "attention.cu", "patch_sim.cu", "attention_sm100.cu", "seg_post.cu", "head_fused.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -31,6 +31,8 @@ int bert_embed_fwd_impl(Ctx*, const int64_t*, const float*, const float*, const 
 int bert_embed_bwd_impl(Ctx*, const int64_t*, const float*, int, int, int, float*, float*, float*, cudaStream_t);
 int topk_pool_l2norm_fwd_impl(Ctx*, const void*, int, int, int, int, int, int, int, const int64_t*, int, float, float*, float*, int32_t*, cudaStream_t);
 int topk_pool_l2norm_bwd_impl(Ctx*, const float*, const float*, const int32_t*, int, int, int, int, float, int, void*, cudaStream_t);
+int proj_topk_fwd_impl(Ctx*, const void*, const void*, int, int, int, int, int, int, int, const int64_t*, int, float, float*, float*, int32_t*, cudaStream_t);
+int proj_topk_bwd_impl(Ctx*, const float*, const float*, const int32_t*, const void*, const void*, int, int, int, int, int, float, int, float*, float*, float*, cudaStream_t);
 int sgemm_impl(Ctx*, const float*, const float*, float*, int, int, int, int64_t, int64_t, int64_t, int, int, int, cudaStream_t);
 int nce_rows_fwd_impl(Ctx*, const float*, int, int, int64_t, const float*, int, float*, float*, float*, int32_t*, cudaStream_t);
 int nce_rows_bwd_impl(Ctx*, float*, int, int, int64_t, const float*, int, const float*, float, float*, cudaStream_t);
@@ -211,6 +213,19 @@ int simseg_topk_pool_l2norm_bwd(simseg_ctx* ctx, const float* demb, const float*
   CTX_OR_FAIL();
   (void)tok_begin;   // sel_idx already holds absolute token positions
   return topk_pool_l2norm_bwd_impl(c, demb, pooled, sel_idx, B, S, E, k, eps, has_l2norm, dx, st);
+}
+
+int simseg_proj_topk_fwd(simseg_ctx* ctx, const void* x, const void* w, int B, int S, int D, int E, int tok_begin, int ntok,
+                         int k, const int64_t* attention_mask, int mask_ld, float eps, float* pooled, float* emb,
+                         int32_t* sel_idx, void* stream) {
+  CTX_OR_FAIL();
+  return proj_topk_fwd_impl(c, x, w, B, S, D, E, tok_begin, ntok, k, attention_mask, mask_ld, eps, pooled, emb, sel_idx, st);
+}
+int simseg_proj_topk_bwd(simseg_ctx* ctx, const float* demb, const float* pooled, const int32_t* sel_idx, const void* x,
+                         const void* wt, int B, int S, int D, int E, int k, float eps, int has_l2norm, float* gy, float* dx,
+                         float* dw, void* stream) {
+  CTX_OR_FAIL();
+  return proj_topk_bwd_impl(c, demb, pooled, sel_idx, x, wt, B, S, D, E, k, eps, has_l2norm, gy, dx, dw, st);
 }
 
 int simseg_infonce_fwd(simseg_ctx* ctx, const float* feat1, const float* feat2g, int b, int Bg, int E,

@@ -207,13 +207,17 @@ __global__ void topk_pool_l2norm_fwd_kernel(const void* __restrict__ x, int S, i
 #pragma unroll
     for (int j = 0; j < K; ++j) { tv[j] = -INFINITY; ti[j] = -1; }
     auto insert = [&](float v, int s) {
-      // descending list; strict > keeps the earliest token ahead on ties, like a stable top-k
+      // descending list; strict > keeps the earliest token ahead on ties, like a stable top-k.  Once the new value has
+      // displaced an entry, that entry travels down and must also pass entries EQUAL to it (they came later) — with a
+      // strict compare there the order among equal values flipped and the earlier token could be the one dropped
       if (v > tv[K - 1]) {
         float cur = v;
         int ci = s;
+        bool moved = false;
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-          const bool gt = cur > tv[j];
+          const bool gt = moved ? (cur >= tv[j]) : (cur > tv[j]);
+          moved = moved || gt;
           const float t0 = tv[j];
           const int i0 = ti[j];
           tv[j] = gt ? cur : t0; ti[j] = gt ? ci : i0;

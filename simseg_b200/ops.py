@@ -266,6 +266,45 @@ def topk_pool_l2norm_bwd(demb: Tensor, pooled: Tensor, idx: Tensor, S: int, k: i
     return dx
 
 
+def proj_topk_supported(S: int, D: int, E: int, k: int) -> bool:
+    """Shapes the fused projection + top-k head (``simseg_proj_topk_*``) takes; others use the two-kernel path."""
+    return S <= 256 and D % 128 == 0 and E % 128 == 0 and 1 <= k <= 8
+
+
+def proj_topk_fwd(x: Tensor, w: Tensor, k: int, tok_begin: int, ntok: int, attention_mask: Optional[Tensor] = None,
+                  eps: float = 1e-8, l2norm: bool = True, save_idx: bool = True):
+    """x bf16 [B,S,D] (all tokens), w bf16 [E,D] -> (pooled, emb | None, idx | None) without the [B,S,E] projection."""
+    B, S, D = x.shape
+    E = w.shape[0]
+    assert x.is_contiguous() and w.is_contiguous() and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    pooled = torch.empty((B, E), device=x.device, dtype=torch.float32)
+    emb = torch.empty((B, E), device=x.device, dtype=torch.float32) if l2norm else None
+    idx = torch.empty((B, k, E), device=x.device, dtype=torch.int32) if save_idx else None
+    mask_ld = 0
+    if attention_mask is not None:
+        assert attention_mask.dtype == torch.int64 and attention_mask.stride(1) == 1
+        mask_ld = attention_mask.stride(0)
+    check(_lib.load().simseg_proj_topk_fwd(ctx(), _p(x), _p(w), B, S, D, E, tok_begin, ntok, k, _p(attention_mask), mask_ld,
+                                           eps, _p(pooled), _p(emb), _p(idx), _stream()), "proj_topk_fwd")
+    return pooled, emb, idx
+
+
+def proj_topk_bwd(demb: Tensor, pooled: Tensor, idx: Tensor, x: Tensor, wt: Optional[Tensor], k: int, eps: float = 1e-8,
+                  l2norm: bool = True, dw: Optional[Tensor] = None, want_dx: bool = True):
+    """Backward of ``proj_topk_fwd``: returns dx f32 [B,S,D] (or None); ``dw`` f32 [E,D] is ACCUMULATED into when given.
+    ``wt`` = bf16 [D,E] transposed weight copy (needed for dx)."""
+    B, S, D = x.shape
+    E = demb.shape[1]
+    assert x.is_contiguous() and demb.is_contiguous() and demb.dtype == torch.float32
+    gy = torch.empty((B, E), device=x.device, dtype=torch.float32)
+    dx = torch.empty((B, S, D), device=x.device, dtype=torch.float32) if want_dx else None
+    if dw is not None:
+        assert dw.dtype == torch.float32 and dw.is_contiguous() and tuple(dw.shape) == (E, D)
+    check(_lib.load().simseg_proj_topk_bwd(ctx(), _p(demb), _p(pooled), _p(idx), _p(x), _p(wt), B, S, D, E, k, eps,
+                                           1 if l2norm else 0, _p(gy), _p(dx), _p(dw), _stream()), "proj_topk_bwd")
+    return dx
+
+
 # --------------------------------------------------------------------------------------- loss / similarity
 def infonce_fwd(feat1: Tensor, feat2g: Tensor, temperature: Tensor, row_offset: int, precision: int = PREC_FP32,
                 want_logits: bool = False):

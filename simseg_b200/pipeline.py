@@ -284,31 +284,56 @@ def _project_backward(ctx, gf_bf16: Tensor, xb: Tensor):
 
 
 class _ProjectPoolFn(torch.autograd.Function):
-    """projection -> TopKPooling -> L2norm fused at the kernel level (``clip.py:87-93`` / ``:111-120``)."""
+    """projection -> TopKPooling -> L2norm (``clip.py:87-93`` / ``:111-120``).  Default: ONE tensor-core GEMM whose epilogue
+    is the per-channel top-k pooling (``simseg_proj_topk_fwd``) and a backward whose sparse dY operand is generated in
+    shared memory (``simseg_proj_topk_bwd``) — the (B,S,E) projection exists in neither direction.  Shapes outside the
+    fused kernels' range (S > 256, e.g. the 288 px evaluation geometry) and ``SIMSEG_B200_FUSED_HEAD=0`` take the
+    two-kernel path (GEMM -> bf16 (B,S,E) -> pooling kernel; dense dY -> dgrad / wgrad GEMMs)."""
 
     @staticmethod
     def forward(ctx, x, weight, attention_mask, k, l2norm, shared, save):
         xb, t0, nt = _bf16_tokens(x)
         B, S, D = xb.shape
-        p = ops.linear_fwd(xb.view(B * S, D), shared.wc.get(weight)).view(B, S, -1)        # bf16 [B,S,E]
         mask = None
         if attention_mask is not None:
             mask = attention_mask.contiguous()
             if t0:                                   # mask columns are indexed by absolute token position
                 pad = torch.ones((B, t0), device=mask.device, dtype=mask.dtype)
                 mask = torch.cat([pad, mask], 1).contiguous()
-        pooled, emb, idx = ops.topk_pool_l2norm_fwd(p, k, t0, nt, attention_mask=mask, l2norm=l2norm, save_idx=save)
+        fused = _FUSED_HEAD and xb.is_contiguous() and ops.proj_topk_supported(S, D, weight.shape[0], k)
+        if fused:
+            pooled, emb, idx = ops.proj_topk_fwd(xb, shared.wc.get(weight), k, t0, nt, attention_mask=mask, l2norm=l2norm,
+                                                 save_idx=save)
+        else:
+            p = ops.linear_fwd(xb.view(B * S, D), shared.wc.get(weight)).view(B, S, -1)        # bf16 [B,S,E]
+            pooled, emb, idx = ops.topk_pool_l2norm_fwd(p, k, t0, nt, attention_mask=mask, l2norm=l2norm, save_idx=save)
         ctx.save_for_backward(xb, pooled, idx)
-        ctx.weight, ctx.shared, ctx.t0, ctx.nt, ctx.k, ctx.l2norm = weight, shared, t0, nt, k, l2norm
+        ctx.weight, ctx.shared, ctx.t0, ctx.nt, ctx.k, ctx.l2norm, ctx.fused = weight, shared, t0, nt, k, l2norm, fused
         return emb if l2norm else pooled
 
     @staticmethod
     def backward(ctx, g):
         xb, pooled, idx = ctx.saved_tensors
         B, S, D = xb.shape
-        gp = ops.topk_pool_l2norm_bwd(g.contiguous().float(), pooled, idx, S, ctx.k, l2norm=ctx.l2norm)
-        dx, dw, _ = _project_backward(ctx, gp, xb)
-        return dx, dw, None, None, None, None, None
+        if not ctx.fused:
+            gp = ops.topk_pool_l2norm_bwd(g.contiguous().float(), pooled, idx, S, ctx.k, l2norm=ctx.l2norm)
+            dx, dw, _ = _project_backward(ctx, gp, xb)
+            return dx, dw, None, None, None, None, None
+        w = ctx.weight
+        dw_ret, dw_buf = None, None
+        if w.requires_grad:
+            if ctx.shared.direct_grads:
+                dw_buf = towers.param_grad(w)                  # accumulated in place (views of the Trainer's flat buffers)
+            else:                                             # handed back to autograd (AccumulateGrad / DDP hooks)
+                dw_buf = dw_ret = torch.zeros_like(w, dtype=torch.float32, memory_format=torch.contiguous_format)
+        want_dx = ctx.needs_input_grad[0]
+        dfull = ops.proj_topk_bwd(g.contiguous().float(), pooled, idx, xb, ctx.shared.wc.get_t(w) if want_dx else None, ctx.k,
+                                  l2norm=ctx.l2norm, dw=dw_buf, want_dx=want_dx)
+        dx = None
+        if want_dx:
+            dx = dfull[:, ctx.t0:ctx.t0 + ctx.nt]
+            dx._simseg_full = dfull
+        return dx, dw_ret, None, None, None, None, None
 
 
 class _NceFn(torch.autograd.Function):
@@ -365,6 +390,7 @@ class _NceFn(torch.autograd.Function):
 import os as _os
 
 _CHECK_INPUTS = _os.environ.get("SIMSEG_B200_CHECK_INPUTS", "1") != "0"
+_FUSED_HEAD = _os.environ.get("SIMSEG_B200_FUSED_HEAD", "1") != "0"     # development knob: 0 = two-kernel head path
 
 
 def _check_image(x: Tensor, vit) -> None:

@@ -60,6 +60,93 @@ def test_topk_pool_with_cls_offset_bf16(cuda):
     assert (emb.cpu() - ref).abs().max().item() < 1e-5
 
 
+def _head_case(cuda, B, S, D, E, k, t0, masked, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.randn(B, S, D, generator=g) * 0.7).bfloat16().to(cuda).contiguous()
+    w = (torch.randn(E, D, generator=g) * 0.05).bfloat16().to(cuda).contiguous()
+    mask = None
+    if masked:
+        lens = torch.randint(max(k, 1) + t0, S + 1, (B,), generator=g)
+        lens[0] = S
+        mask = (torch.arange(S)[None, :] < lens[:, None]).long().to(cuda).contiguous()
+    demb = torch.randn(B, E, generator=g).to(cuda)
+    return x, w, mask, demb
+
+
+@pytest.mark.parametrize("B,S,D,E,k,t0,masked", [(5, 197, 384, 512, 5, 1, False),       # ViT-S image head (clip.py:87-93)
+                                                  (3, 197, 768, 512, 5, 1, False),       # ViT-B
+                                                  (23, 25, 768, 512, 1, 1, True),        # text head, T = 25, k = 1, masks
+                                                  (7, 77, 768, 512, 3, 1, True),         # T = 77, clamped k
+                                                  (9, 25, 768, 256, 8, 0, False),        # k = 8 (two samples per tile)
+                                                  (301, 197, 384, 512, 5, 1, False)])    # more work items than SMs
+def test_fused_projection_topk_head_equals_two_kernel_path(cuda, B, S, D, E, k, t0, masked):
+    """f1: projection GEMM with the top-k pooling as its epilogue, and the backward with the dY operand generated in shared
+    memory, against the two-kernel path (tcgen05 GEMM -> bf16 [B,S,E] -> ``topk_pool_l2norm`` / dense dgrad + wgrad) and the
+    oracle (``pooling.py:57-65``, ``normalization.py:6-11``) on the same bf16 inputs."""
+    ops, O = _ops(), _O()
+    x, w, mask, demb = _head_case(cuda, B, S, D, E, k, t0, masked, 100 + B + S)
+    ntok = S - t0
+    # two-kernel path
+    proj = ops.linear_fwd(x.view(B * S, D), w).view(B, S, E)
+    pooled0, emb0, idx0 = ops.topk_pool_l2norm_fwd(proj, k, t0, ntok, attention_mask=mask)
+    # fused
+    pooled1, emb1, idx1 = ops.proj_topk_fwd(x, w, k, t0, ntok, attention_mask=mask)
+    assert (pooled1 - pooled0).abs().max().item() <= 1e-6 + 4e-3 * pooled0.abs().max().item()
+    assert (emb1 - emb0).abs().max().item() < 2e-3
+    # selected tokens: the k largest bf16 projections, earliest token first among equal values (a stable descending sort) —
+    # exactly, in both paths (the two GEMM tile shapes give bit-identical fp32-accumulated products)
+    pm = proj.float().clone()
+    if mask is not None:
+        pm[mask == 0] = -10000.0
+    stable = pm[:, t0:].sort(dim=1, descending=True, stable=True).indices[:, :k] + t0
+    assert torch.equal(idx1.long(), stable)
+    assert torch.equal(idx0.long(), stable)
+    # oracle on the fp32 product of the same bf16 operands
+    pf = (x.float().cpu() @ w.float().cpu().T)
+    if mask is not None:
+        pf = pf.clone()
+        pf[mask.cpu() == 0] = -10000.0
+    ref = O.l2norm(O.topk_pooling(pf[:, t0:], k))
+    assert (emb1.cpu() - ref).abs().max().item() < 1e-2                       # bf16 rounding of the projection (north_star 1e-2)
+    assert idx1.min().item() >= t0 and idx1.max().item() < S
+
+    # ---- backward from the FUSED forward's own selection (so both paths see the same sparse dY)
+    dy = ops.topk_pool_l2norm_bwd(demb, pooled1, idx1, S, k)                   # dense bf16 [B,S,E]
+    wt = w.t().contiguous()
+    dx0 = ops.linear_dgrad(dy.view(B * S, E), wt, out_dtype=torch.float32).view(B, S, D)
+    dw0 = torch.zeros(E, D, device=cuda)
+    ops.linear_wgrad(dy.view(B * S, E), x.view(B * S, D), dw0, accumulate=False)
+    dw1 = torch.full((E, D), 0.25, device=cuda)                                # accumulates
+    dx1 = ops.proj_topk_bwd(demb, pooled1, idx1, x, wt, k, dw=dw1)
+    assert (dx1 - dx0).abs().max().item() <= 1e-6 + 2e-3 * dx0.abs().max().item()
+    assert (dx1[:, :t0] == 0).all()
+    assert ((dw1 - 0.25) - dw0).abs().max().item() <= 1e-6 + 2e-3 * dw0.abs().max().item()
+    # and against fp32 autograd through the oracle: which of several bf16-EQUAL projections carries the gradient is a
+    # tie-break (torch.topk's differs from "earliest token"), but the gradient summed over the tokens of a sample is not:
+    # sum_s dx[b, s, :] = dL/dpooled[b, :] @ W
+    pl = pooled1.cpu().clone().requires_grad_(True)
+    O.l2norm(pl).backward(demb.cpu())
+    dx_sum_ref = pl.grad @ w.float().cpu()
+    assert (dx1.sum(1).cpu() - dx_sum_ref).abs().max().item() < 1e-2 * dx_sum_ref.abs().max().item() + 1e-6
+
+
+def test_fused_head_vs_reference_fixture(cuda):
+    """The fused head on the reference's own fixture (``tests/golden/heads_loss.npz``: SimpleProjection + TopKPooling + L2norm
+    of ``clip.py:87-93,111-120`` run by the reference's modules), bf16 operands -> 1e-2."""
+    ops = _ops()
+    gold = np.load(os.path.join(GOLD, "heads_loss.npz"))
+    g = torch.Generator().manual_seed(int(gold["heads_seed"]))
+    x_img = torch.randn(6, 196, 384, generator=g)
+    x_txt = torch.randn(6, 25, 768, generator=g)
+    wi, wt = torch.tensor(gold["heads_wi"]), torch.tensor(gold["heads_wt"])
+    mask = torch.tensor(gold["heads_mask"])
+    _, emb_i, _ = ops.proj_topk_fwd(x_img.bfloat16().to(cuda).contiguous(), wi.bfloat16().to(cuda).contiguous(), 5, 0, 196)
+    _, emb_t, _ = ops.proj_topk_fwd(x_txt.bfloat16().to(cuda).contiguous(), wt.bfloat16().to(cuda).contiguous(), 1, 0, 25,
+                                    attention_mask=mask.to(cuda))
+    assert np.abs(emb_i.cpu().numpy() - gold["heads_img_emb"]).max() < 1e-2
+    assert np.abs(emb_t.cpu().numpy() - gold["heads_txt_emb"]).max() < 1e-2
+
+
 @pytest.mark.parametrize("prec", [0, 1])
 def test_infonce_vs_golden_and_oracle(cuda, prec):
     ops, O = _ops(), _O()
