@@ -24,11 +24,23 @@ def run(B, N=196, C=171, E=512, reps=20):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / (reps * nset)
     gbs = B * bytes_per_map / ms / 1e6
-    print(json.dumps({"B": B, "N": N, "C": C, "ms": ms, "maps_per_s": B / ms * 1e3, "GBps": gbs, "nset": nset}), flush=True)
+    # device time per launch: the same nset launches replayed as one CUDA graph (no host issue path in the measurement)
+    from simseg_b200.graph import replay_sequence
+    gr = replay_sequence([(lambda x=x: ops.patch_text_sim(x, t)) for x in ps])
+    gr.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        gr.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    msg = e0.elapsed_time(e1) / (reps * nset)
+    print(json.dumps({"B": B, "N": N, "C": C, "ms": ms, "maps_per_s": B / ms * 1e3, "GBps": gbs, "nset": nset,
+                      "ms_graph": msg, "GBps_graph": B * bytes_per_map / msg / 1e6}), flush=True)
 
 
 if __name__ == "__main__":
     C = int(sys.argv[1]) if len(sys.argv) > 1 else 171
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-    for B in (64, 512, 4096):
+    for B in (64, 128, 256, 512, 4096):
         run(B, C=C, reps=reps if B < 4096 else max(2, reps // 4))
