@@ -27,7 +27,7 @@ namespace simseg {
 using namespace sm100;
 
 constexpr int kAbEwWarps = 16;                       // elementwise warps: four per TMEM lane quarter
-constexpr int kAbThreads = 32 * (2 + kAbEwWarps);
+constexpr int kAbThreads = 32 * (2 + kAbEwWarps + 2);   // + two D / lse warps
 constexpr int kTile = 128;                 // query rows / key rows per tile
 constexpr int kTileBytes = kTile * 128;    // [128 rows][64 bf16]
 constexpr int kPBytes = 2 * kTileBytes;    // P or dS: [2 key atoms][128 q rows][128 B]
@@ -39,6 +39,7 @@ struct AttnBwdParams {
   const int32_t* key_len;
   const float* lse;                 // [B,H,S]
   const __nv_bfloat16* out;         // [B,S,H*64]
+  const __nv_bfloat16* dout;        // [B,S,H*64]
   __nv_bfloat16 *dq, *dk, *dv;      // strides as q/k/v
   int64_t sb, ss, sh;
 };
@@ -126,7 +127,15 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   uint64_t* dkv_free = bars + 15;     // EW -> MMA : dK/dV drained                               (8 warps)
   uint64_t* dq_full = bars + 16;
   uint64_t* dq_free = bars + 17;      //                                                          (8 warps)
+  uint64_t* d_full = bars + 18;       // [2] producer -> EW : D = rowsum(dO * O) and lse * log2(e) of a Q / dO slot are in smem
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  // per Q / dO slot and tile row: {D, lse * log2 e}, written by the producer warp (it has the dO tile in smem and 31 idle
+  // lanes) one item ahead of the elementwise warps — their only global loads and a 4-warp exchange used to sit here
+  float2* sDL = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 256 + kAbEwWarps * 2048);   // [2 slots][128 rows]
+  if (threadIdx.x == 0 && static_cast<uint32_t>(smem - smem_raw) > 768u) {
+    printf("simseg: attention_bwd dynamic shared memory base is not 256-byte aligned\n");
+    __trap();
+  }
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -140,6 +149,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_ready, kAbEwWarps); mbar_init(ds_ready, kAbEwWarps);
     mbar_init(p_free, 1); mbar_init(ds_free, 1);
     mbar_init(dkv_full, 1); mbar_init(dkv_free, kAbEwWarps); mbar_init(dq_full, 1); mbar_init(dq_free, kAbEwWarps);
+    mbar_init(&d_full[0], 1); mbar_init(&d_full[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -300,7 +310,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       }
       tr.flush();
     }
-  } else {
+  } else if (warp < 2 + kAbEwWarps) {
     // =============================== elementwise + drains ===============================
     // 16 warps: four per TMEM lane quarter (a warp may only touch lanes 32 * (warp % 4) ..), each owning ONE 32-key chunk of
     // a block.  The pass is latency-bound (dependent MUFU / FMA / pack chains, smem round trips), so it is spread over four
@@ -316,7 +326,6 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     // different 128-byte lines (16 bytes each) — the L1 store path, not HBM, then paces the drains.  The warp's 32 rows x 64
     // bytes go through a swizzled 2 KB block instead and leave as 8 rows x 64 contiguous bytes per instruction.
     uint8_t* stg = reinterpret_cast<uint8_t*>(bars) + 256 + ew * 2048;
-    float* sD = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256 + kAbEwWarps * 2048);   // [2 slots][128 rows]
     uint32_t it = 0, g = 0, drains = 0;
     Tracer tr(warp == 2 ? 1 : warp == 3 ? 2 : warp == 6 ? 3 : warp == 10 ? 4 : -1, lane == 0);
     const int gm0 = p.G - 1;
@@ -400,7 +409,6 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       const int klen = (p.key_len ? min(max(p.key_len[b], 1), p.S) : p.S) * p.G;
       const int gm = p.G - 1, rg = r & gm;
       const bool need_mask = p.key_len != nullptr || p.G > 1;
-      float Dv[2] = {0.f, 0.f}, L2v[2] = {0.f, 0.f};
       for (int kt = 0; kt < p.nkt; ++kt) {
         const int nkc = min(kTile, ceil16(p.rows - kt * kTile));
         const bool chunk_live = col0 < nkc;                           // warp-uniform: columns >= nkc are never read by an MMA
@@ -410,54 +418,16 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           // rows of this quarter that no MMA reads (K extent over query rows = ceil16(live rows)): skip the whole pass
           const bool rows_live = qt * kTile + quarter * 32 < ceil16(p.rows);
           const int qslot = (p.nqt == 1) ? static_cast<int>(it & 1) : qt;     // Q / dO slot (single-tile items alternate slots)
-          // D = rowsum(dO * O) and lse (log2 units) — once per (item, query tile), shared by the four warps of a quarter:
-          // warp cq takes rows 8 cq .. 8 cq + 7 of the quarter (8 lanes fetch one 128-byte O row; a thread fetching ITS row
-          // would touch 32 lines per instruction), the sums go through shared memory.  The loads are issued before the wait
-          // for S so that their latency is hidden.
-          tr(8);
-          uint4 o[2];
-          float l2raw = 0.f;
-          if (kt == 0) {
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const int row = qt * kTile + quarter * 32 + (lane >> 3) + 4 * (2 * cq + i);
-              if (row < p.rows) {
-                const int tok = row >> p.lg, hh = h0 + (row & gm);
-                o[i] = __ldg(reinterpret_cast<const uint4*>(p.out + (static_cast<int64_t>(b) * p.S + tok) * (p.H * 64) + hh * 64) + (lane & 7));
-              } else {
-                o[i] = make_uint4(0, 0, 0, 0);
-              }
-            }
-            if (q_ok) {
-              const int tok = qrow >> p.lg, hh = h0 + (qrow & gm);
-              l2raw = __ldg(p.lse + (static_cast<int64_t>(b) * p.H + hh) * p.S + tok);
-            }
-          }
+          const uint32_t quse = (p.nqt == 1) ? (it >> 1) : it;
           // ---- phase A: S -> P (kept as packed bf16 in registers for phase B), P into smem
           tr(10);
           mbar_wait(s_full, g & 1);                                    // implies the Q / dO tiles of this qt have landed
           tr(11);
           tc_fence_after();
-          if (kt == 0) {
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const int rr = (lane >> 3) + 4 * (2 * cq + i);         // row of the quarter's 32 that the lane helps with
-              const uint4 a = *reinterpret_cast<const uint4*>(sdO + qslot * kTileBytes + (quarter * 32 + rr) * 128 + (((lane & 7) ^ (rr & 7)) << 4));
-              float part = bf16_lo(a.x) * bf16_lo(o[i].x) + bf16_hi(a.x) * bf16_hi(o[i].x) + bf16_lo(a.y) * bf16_lo(o[i].y) +
-                           bf16_hi(a.y) * bf16_hi(o[i].y) + bf16_lo(a.z) * bf16_lo(o[i].z) + bf16_hi(a.z) * bf16_hi(o[i].z) +
-                           bf16_lo(a.w) * bf16_lo(o[i].w) + bf16_hi(a.w) * bf16_hi(o[i].w);
-              part += __shfl_xor_sync(0xffffffffu, part, 1);
-              part += __shfl_xor_sync(0xffffffffu, part, 2);
-              part += __shfl_xor_sync(0xffffffffu, part, 4);
-              if ((lane & 7) == 0) sD[qslot * kTile + quarter * 32 + rr] = part;
-            }
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");    // the four warps of this quarter
-            const float d = sD[qslot * kTile + r];
-            const float l2 = l2raw * 1.44269504088896341f;
-            if (qt == 0) { Dv[0] = d; L2v[0] = l2; } else { Dv[1] = d; L2v[1] = l2; }
-          }
-          const float Lq = qt == 0 ? L2v[0] : L2v[1];
-          const float Dq = qt == 0 ? Dv[0] : Dv[1];
+          // D = rowsum(dO * O) and lse (log2 units) of this row: written by the producer warp, long before S is ready
+          mbar_wait(&d_full[qslot], quse & 1);
+          const float2 dl = sDL[qslot * kTile + r];
+          const float Dq = dl.x, Lq = dl.y;
           tr(12);
           uint32_t pp[16];
           if (chunk_live && rows_live) {
@@ -477,10 +447,13 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             } else {
               // dense, unmasked chunk of live keys: query rows past S come from zero-filled TMA rows (Q = dO = 0, lse := 0), so
               // P = 1, dS = 0 there and every product they enter is exactly zero — no per-element predicates needed
+              const f32x2 sc2 = f2_splat(p.scale_log2e), nl2 = f2_splat(-Lq);
 #pragma unroll
-              for (int j = 0; j < 32; j += 2)
-                pp[j >> 1] = pack_bf16(ex2_approx(fmaf(__uint_as_float(sr[j]), p.scale_log2e, -Lq)),
-                                       ex2_approx(fmaf(__uint_as_float(sr[j + 1]), p.scale_log2e, -Lq)));
+              for (int j = 0; j < 32; j += 2) {
+                float e0, e1;
+                f2_unpack(f2_fma(f2_pack(__uint_as_float(sr[j]), __uint_as_float(sr[j + 1])), sc2, nl2), e0, e1);
+                pp[j >> 1] = pack_bf16(ex2_approx(e0), ex2_approx(e1));
+              }
             }
           }
           tr(13);
@@ -513,10 +486,14 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             uint32_t dr[32], dd[16];
             tmem_ld_32x32(tdP + lane_off + col0, dr);
             tmem_ld_wait();
+            const f32x2 nd2 = f2_splat(-Dq);
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               const uint32_t pk = pp[j >> 1];                          // masked entries are exactly 0 -> dS = 0
-              dd[j >> 1] = pack_bf16(bf16_lo(pk) * (__uint_as_float(dr[j]) - Dq), bf16_hi(pk) * (__uint_as_float(dr[j + 1]) - Dq));
+              float d0, d1;
+              f2_unpack(f2_mul(f2_pack(bf16_lo(pk), bf16_hi(pk)),
+                               f2_add(f2_pack(__uint_as_float(dr[j]), __uint_as_float(dr[j + 1])), nd2)), d0, d1);
+              dd[j >> 1] = pack_bf16(d0, d1);
             }
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4)
@@ -538,6 +515,68 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     }
     drain_pending();
     tr.flush();
+  } else {
+    // =============================== D / lse rows (warps 18, 19) ===============================
+    // D_i = sum_d dO[i,d] O[i,d] and lse_i * log2(e) for the 128 rows of Q / dO slot `w` — one warp per slot, both operands
+    // straight from HBM / L2 (8 lanes fetch one 128-byte row, so a load instruction covers four full lines; 16 of them in
+    // flight), results parked in registers: the warp runs a whole item AHEAD of the elementwise warps and only has to drop its
+    // 128 {D, lse} pairs into shared memory when the slot's previous use has been released.  (Computed by the elementwise
+    // warps at the head of every query tile, these loads were the longest exposed latency of the kernel.)
+    const int w = warp - 2 - kAbEwWarps;                        // slot served by this warp
+    const int sub = lane >> 3, c8 = lane & 7;
+    const int gm = p.G - 1;
+    float2* dl = sDL + w * kTile;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      if (p.nqt == 1 ? (static_cast<int>(it & 1) != w) : (w >= p.nqt)) continue;
+      const int qt = (p.nqt == 1) ? 0 : w;
+      const uint32_t use = (p.nqt == 1) ? (it >> 1) : it;
+      const int b = item / p.HG, h = (item - b * p.HG) * p.G;
+      const int nrows = min(kTile, p.rows - qt * kTile);
+      float dv[4], lv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {                              // this lane keeps rows (8 i + c8) * 4 + sub
+        const int r = (8 * i + c8) * 4 + sub;
+        lv[i] = 0.f;
+        dv[i] = 0.f;
+        if (r < nrows) {
+          const int row = qt * kTile + r;
+          lv[i] = __ldg(p.lse + (static_cast<int64_t>(b) * p.H + h + (row & gm)) * p.S + (row >> p.lg));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (32 * i >= nrows) break;                              // warp-uniform
+        uint4 o[8], a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = (8 * i + j) * 4 + sub;
+          o[j] = make_uint4(0, 0, 0, 0);
+          a[j] = make_uint4(0, 0, 0, 0);
+          if (r < nrows) {
+            const int row = qt * kTile + r;
+            const int64_t off = (static_cast<int64_t>(b) * p.S + (row >> p.lg)) * (p.H * 64) + (h + (row & gm)) * 64;
+            o[j] = __ldg(reinterpret_cast<const uint4*>(p.out + off) + c8);
+            a[j] = __ldg(reinterpret_cast<const uint4*>(p.dout + off) + c8);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float part = bf16_lo(a[j].x) * bf16_lo(o[j].x) + bf16_hi(a[j].x) * bf16_hi(o[j].x) + bf16_lo(a[j].y) * bf16_lo(o[j].y) +
+                       bf16_hi(a[j].y) * bf16_hi(o[j].y) + bf16_lo(a[j].z) * bf16_lo(o[j].z) + bf16_hi(a[j].z) * bf16_hi(o[j].z) +
+                       bf16_lo(a[j].w) * bf16_lo(o[j].w) + bf16_hi(a[j].w) * bf16_hi(o[j].w);
+          part += __shfl_xor_sync(0xffffffffu, part, 1);
+          part += __shfl_xor_sync(0xffffffffu, part, 2);
+          part += __shfl_xor_sync(0xffffffffu, part, 4);
+          if (c8 == j) dv[i] = part;
+        }
+      }
+      mbar_wait(&qdo_empty[w], (use & 1) ^ 1);                  // the slot's previous use (and its readers of dl) is over
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dl[(8 * i + c8) * 4 + sub] = make_float2(dv[i], lv[i] * 1.44269504088896341f);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&d_full[w]);
+    }
   }
 
   tc_fence_before();
@@ -1271,10 +1310,11 @@ int attention_bwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v,
   p.nqt = (p.rows + kTile - 1) / kTile; p.nkt = p.nqt;
   p.items = B * p.HG;
   p.scale = scale; p.scale_log2e = scale * 1.44269504088896341f;
-  p.key_len = key_len; p.lse = lse; p.out = reinterpret_cast<const __nv_bfloat16*>(out);
+  p.key_len = key_len; p.lse = lse; p.out = reinterpret_cast<const __nv_bfloat16*>(out); p.dout = reinterpret_cast<const __nv_bfloat16*>(dout);
   p.dq = reinterpret_cast<__nv_bfloat16*>(dq); p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dv = reinterpret_cast<__nv_bfloat16*>(dv);
   p.sb = sb; p.ss = ss; p.sh = sh;
-  const int smem_bytes = 1024 + 8 * kTileBytes + 2 * kPBytes + 256 + kAbEwWarps * 2048 + 1024;   // + per-warp drain staging + D exchange
+  // alignment slack (768: the kernel traps if the base needs more) + tiles + P / dS + barriers + per-warp drain staging + {D, lse} rows
+  const int smem_bytes = 768 + 8 * kTileBytes + 2 * kPBytes + 256 + kAbEwWarps * 2048 + 2 * kTile * 8;
   static bool attr_set = false;
   if (!attr_set) {
     SIMSEG_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
