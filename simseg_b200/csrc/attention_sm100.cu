@@ -42,6 +42,7 @@ struct AttnBwdParams {
   const __nv_bfloat16* dout;        // [B,S,H*64]
   __nv_bfloat16 *dq, *dk, *dv;      // strides as q/k/v
   int64_t sb, ss, sh;
+  int32_t dbg;                      // timing knock-outs (SIMSEG_ATTN_DBG, results wrong): see tools/attn_knockout.py
 };
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1,
@@ -66,34 +67,26 @@ __device__ int g_attn_trace_on = 0;
 // one") and written out once at the end of the kernel — no memory traffic inside the loops.
 #ifdef SIMSEG_ATTN_TRACE
 struct Tracer {
-  uint32_t acc[kTraceIds], cnt[kTraceIds], last;
+  // one clock register per traced thread; deltas leave through fire-and-forget global reductions (RED, no return value, no
+  // register arrays: the first version kept 48 accumulators per thread, spilled, and measured mostly its own reloads)
+  uint32_t last;
   int slot;
   __device__ __forceinline__ Tracer(int slot_, bool active) : last(0), slot(-1) {
     if (active && g_attn_trace_on && blockIdx.x == 0 && slot_ >= 0) slot = slot_;
-#pragma unroll
-    for (int i = 0; i < kTraceIds; ++i) { acc[i] = 0; cnt[i] = 0; }
     last = static_cast<uint32_t>(clock64());
   }
   __device__ __forceinline__ void operator()(int id) {       // id must be a compile-time constant at every call site
     if (slot >= 0) {
       const uint32_t now = static_cast<uint32_t>(clock64());
-      acc[id] += now - last;
-      cnt[id] += 1;
-      last = now;
+      atomicAdd(&g_attn_trace[slot * kTraceLen + id], static_cast<unsigned long long>(now - last));
+      atomicAdd(&g_attn_trace[slot * kTraceLen + kTraceIds + id], 1ull);
+      last = static_cast<uint32_t>(clock64());
     }
   }
-  __device__ __forceinline__ void flush() {
-    if (slot >= 0) {
-#pragma unroll
-      for (int i = 0; i < kTraceIds; ++i) {
-        g_attn_trace[slot * kTraceLen + i] = acc[i];
-        g_attn_trace[slot * kTraceLen + kTraceIds + i] = cnt[i];
-      }
-    }
-  }
+  __device__ __forceinline__ void flush() {}
 };
 #else
-struct Tracer {                                              // compiled out: the accumulators cost ~48 registers per thread
+struct Tracer {                                              // compiled out: no code
   __device__ __forceinline__ Tracer(int, bool) {}
   __device__ __forceinline__ void operator()(int) {}
   __device__ __forceinline__ void flush() {}
@@ -235,7 +228,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           const uint32_t aQ = smem_u32(sQ + slot_of(c) * kTileBytes) >> 4, aK = smem_u32(sK + buf * kTileBytes) >> 4;
           const uint32_t id = idesc_sdp(c);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_f16(tS, kd + aQ + 2 * kk, kd + aK + 2 * kk, id, kk > 0 ? 1u : 0u);
+          if (!(p.dbg & 32))
+            for (int kk = 0; kk < 4; ++kk) umma_f16(tS, kd + aQ + 2 * kk, kd + aK + 2 * kk, id, kk > 0 ? 1u : 0u);
           umma_commit(s_full);
         }
         __syncwarp();
@@ -246,7 +240,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           const uint32_t adO = smem_u32(sdO + slot_of(c) * kTileBytes) >> 4, aV = smem_u32(sV + buf * kTileBytes) >> 4;
           const uint32_t id = idesc_sdp(c);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_f16(tdP, kd + adO + 2 * kk, kd + aV + 2 * kk, id, kk > 0 ? 1u : 0u);
+          if (!(p.dbg & 32))
+            for (int kk = 0; kk < 4; ++kk) umma_f16(tdP, kd + adO + 2 * kk, kd + aV + 2 * kk, id, kk > 0 ? 1u : 0u);
           umma_commit(dp_full);
         }
         __syncwarp();
@@ -271,7 +266,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         tc_fence_after();
         if (elect_one()) {
           // dV += P^T dO      (A MN-major: key atoms 16 KB apart; K-step = 16 q rows = 2048 B)
-          for (int ks = 0; ks < qsteps; ++ks)
+          for (int ks = 0; ks < ((p.dbg & 16) ? 0 : qsteps); ++ks)
             umma_f16(tdV, md + aP + 128 * ks, md + adO + 128 * ks, id_dkv, (c.qt > 0 || ks > 0) ? 1u : 0u);
           umma_commit(p_free);
         }
@@ -287,10 +282,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         if (valid(n)) { issue_dp(n); advance(n); }                           // ahead of dK / dQ: phase B of the next block waits for it
         if (elect_one()) {
           // dK += dS^T Q
-          for (int ks = 0; ks < qsteps; ++ks)
+          for (int ks = 0; ks < ((p.dbg & 16) ? 0 : qsteps); ++ks)
             umma_f16(tdK, md + adS + 128 * ks, md + aQ + 128 * ks, id_dkv, (c.qt > 0 || ks > 0) ? 1u : 0u);
           // dQ += dS K        (A K-major: 4 K-steps per 64-key atom; B MN-major: K-step = 16 key rows)
-          for (int ks = 0; ks < ksteps; ++ks)
+          for (int ks = 0; ks < ((p.dbg & 16) ? 0 : ksteps); ++ks)
             umma_f16(tdQ + 64 * c.qt, kd + adS + (ks >> 2) * (kTileBytes >> 4) + (ks & 3) * 2, md + aK + 128 * ks, id_dq,
                      (c.kt > 0 || ks > 0) ? 1u : 0u);
           umma_commit(ds_free);
@@ -343,7 +338,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         const int rr = (lane >> 2) + 8 * i;
         const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4));
         const int row = tile_row0 + rr;
-        if (row < p.rows)
+        if (row < p.rows && !(p.dbg & 8))
           *reinterpret_cast<uint4*>(dst + base_b + static_cast<int64_t>(row >> p.lg) * p.ss +
                                     static_cast<int64_t>(sh0 + (row & gm0)) * p.sh + dcol0 + (lane & 3) * 8) = val;
       }
@@ -430,10 +425,15 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           const float Dq = dl.x, Lq = dl.y;
           tr(12);
           uint32_t pp[16];
-          if (chunk_live && rows_live) {
+          if (chunk_live && rows_live && !(p.dbg & 128)) {
             uint32_t sr[32];
-            tmem_ld_32x32(tS + lane_off + col0, sr);
-            tmem_ld_wait();
+            if (!(p.dbg & 64)) {
+              tmem_ld_32x32(tS + lane_off + col0, sr);
+              tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sr[j] = 0;
+            }
             if (need_mask || kt * kTile + col0 + 32 > p.rows) {    // padding keys: exp2(-lse) could overflow, mask them
 #pragma unroll
               for (int j = 0; j < 32; j += 2) {
@@ -452,7 +452,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
               for (int j = 0; j < 32; j += 2) {
                 float e0, e1;
                 f2_unpack(f2_fma(f2_pack(__uint_as_float(sr[j]), __uint_as_float(sr[j + 1])), sc2, nl2), e0, e1);
-                pp[j >> 1] = pack_bf16(ex2_approx(e0), ex2_approx(e1));
+                pp[j >> 1] = (p.dbg & 1) ? pack_bf16(e0, e1) : pack_bf16(ex2_approx(e0), ex2_approx(e1));
               }
             }
           }
@@ -462,7 +462,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           // 32 keys = four 16-byte chunks of this row inside key atom (col0 / 64)
           const uint32_t rowoff = (col0 >> 6) * kTileBytes + r * 128;
           const int ch0 = (col0 & 63) >> 3;
-          if (chunk_live && rows_live) {
+          if (chunk_live && rows_live && !(p.dbg & 4)) {
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4)
               *reinterpret_cast<uint4*>(sP + rowoff + (((ch0 + q4) ^ sw) << 4)) =
@@ -482,10 +482,15 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           if (g > 0) mbar_wait(ds_free, (g - 1) & 1);
           tr(17);                  // dK / dQ of the previous block have read sdS (issued a
                                                                        // whole phase A ago: this wait does not stall)
-          if (chunk_live && rows_live) {
+          if (chunk_live && rows_live && !(p.dbg & 2)) {
             uint32_t dr[32], dd[16];
-            tmem_ld_32x32(tdP + lane_off + col0, dr);
-            tmem_ld_wait();
+            if (!(p.dbg & 64)) {
+              tmem_ld_32x32(tdP + lane_off + col0, dr);
+              tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) dr[j] = 0;
+            }
             const f32x2 nd2 = f2_splat(-Dq);
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
@@ -495,6 +500,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                                f2_add(f2_pack(__uint_as_float(dr[j]), __uint_as_float(dr[j + 1])), nd2)), d0, d1);
               dd[j >> 1] = pack_bf16(d0, d1);
             }
+            if (!(p.dbg & 4))
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4)
               *reinterpret_cast<uint4*>(sdS + rowoff + (((ch0 + q4) ^ sw) << 4)) =
@@ -1313,6 +1319,7 @@ int attention_bwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v,
   p.key_len = key_len; p.lse = lse; p.out = reinterpret_cast<const __nv_bfloat16*>(out); p.dout = reinterpret_cast<const __nv_bfloat16*>(dout);
   p.dq = reinterpret_cast<__nv_bfloat16*>(dq); p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dv = reinterpret_cast<__nv_bfloat16*>(dv);
   p.sb = sb; p.ss = ss; p.sh = sh;
+  { const char* d = getenv("SIMSEG_ATTN_DBG"); p.dbg = d ? atoi(d) : 0; }
   // alignment slack (768: the kernel traps if the base needs more) + tiles + P / dS + barriers + per-warp drain staging + {D, lse} rows
   const int smem_bytes = 768 + 8 * kTileBytes + 2 * kPBytes + 256 + kAbEwWarps * 2048 + 2 * kTile * 8;
   static bool attr_set = false;

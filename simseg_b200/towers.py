@@ -3,7 +3,8 @@
 Precision contract (= the reference under bf16 autocast, ``simseg/tasks/clip/clip_runner.py:226-228``):
 fp32 master weights, bf16 tensor-core GEMM operands with fp32 accumulation, fp32 residual stream,
 fp32 LayerNorm / softmax statistics.  LayerNorm outputs and MLP pre-activations are stored for backward (bf16);
-GELU outputs are re-emitted by the dGELU epilogue of the fc2 dgrad GEMM; what is stored per block is listed in ``_Blk``.
+GELU outputs are kept when they are a small part of the device's memory and otherwise re-emitted by the dGELU epilogue of the
+fc2 dgrad GEMM (``keep_gelu_output``); what is stored per block is listed in ``_Blk``.
 
 Gradients are accumulated (fp32) by the wgrad GEMMs into the buffer ``grad_of(param)`` names: ``param.grad`` itself
 under ``train.Trainer`` (flat buffers), a scratch buffer handed back to autograd otherwise (``pipeline._VitFn``).
@@ -19,6 +20,20 @@ from . import ops
 from ._lib import EPI_BIAS_GELU, EPI_DGELU, EPI_NONE
 
 Tensor = torch.Tensor
+
+
+def keep_gelu_output(extra_bytes: int, device) -> bool:
+    """Backward needs BOTH the fc1 pre-activation h (for gelu'(h)) and gelu(h) (operand of the fc2 wgrad).  Saving both costs
+    ``extra_bytes`` (layers x tokens x 4D x 2 B); saving only h makes the dGELU epilogue of the fc2 dgrad GEMM re-emit
+    gelu(h) — one more bf16 [M,4D] write per layer on a kernel that is HBM-bound (ViT-S at b = 4096: 8.0 GB -> 5.6 GB per
+    launch without it).  Keep gelu(h) whenever that is a small part of the device: up to 12 % of its memory per tower
+    (ViT-S: per-GPU batch <= 2900, i.e. every shard of the global batch 4096 on >= 2 GPUs; at b = 4096 on ONE GPU the step
+    already peaks at 147 of 180 GB and re-emits).  ``SIMSEG_KEEP_GELU=0|1`` overrides."""
+    import os
+    f = os.environ.get("SIMSEG_KEEP_GELU")
+    if f is not None and f != "auto":
+        return f not in ("0", "")
+    return extra_bytes <= 0.12 * torch.cuda.get_device_properties(device).total_memory
 
 
 def param_grad(p: Tensor) -> Tensor:
@@ -207,6 +222,7 @@ class _Blk:
     h: Tensor = None          # bf16 [M,4D] fc1 pre-activation
     y: Tensor = None          # bf16 [M,D]  LN1 output (wgrad operand; 0.6 GB/layer at b=4096 is cheaper than re-reading x)
     y2: Tensor = None         # bf16 [M,D]  LN2 output
+    a: Tensor = None          # bf16 [M,4D] gelu(h) when kept (keep_gelu_output), else re-emitted in backward
 
 
 @dataclass
@@ -238,6 +254,7 @@ def vit_forward(m, image: Tensor, wc: Bf16Weights, save: bool):
     # bf16 output (+bias) through the coalesced TMA-store epilogue, exactly the tensor the reference's autocast produces,
     # and the fp32 residual stream is updated where it is read anyway.
     f = None                                      # bf16 output of the previous block's fc2, not yet added to x
+    keep_a = save and keep_gelu_output(len(m.blocks) * M * 4 * D * 2, x.device)
     for blk in m.blocks:
         if f is None:
             y, _, mean1, rstd1 = ops.layernorm_fwd(x, blk.norm1.weight, blk.norm1.bias, 1e-6)
@@ -253,9 +270,9 @@ def vit_forward(m, image: Tensor, wc: Bf16Weights, save: bool):
         h = torch.empty((M, 4 * D), device=x.device, dtype=torch.bfloat16) if save else None
         a = ops.linear_fwd(y2, wc.get(blk.mlp.fc1.weight), blk.mlp.fc1.bias, epilogue=EPI_BIAS_GELU, aux=h)
         f = ops.linear_fwd(a, wc.get(blk.mlp.fc2.weight), blk.mlp.fc2.bias)
-        del a
         if save:
-            sv.blocks.append(_Blk(x, mean1, rstd1, qkv, o, lse, x1, mean2, rstd2, h, y, y2))
+            sv.blocks.append(_Blk(x, mean1, rstd1, qkv, o, lse, x1, mean2, rstd2, h, y, y2, a if keep_a else None))
+        del a
         x = x1
     if f is None:
         tok_bf16, tok_f32, mean_n, rstd_n = ops.layernorm_fwd(x, m.norm.weight, m.norm.bias, 1e-6, want_f32=True)
@@ -287,10 +304,10 @@ def vit_backward(m, sv: VitSaved, dtok: Tensor, wc: Bf16Weights, dtok2: Optional
         blk, s = m.blocks[i], sv.blocks[i]
         # ---- MLP branch: x2 = x1 + fc2(gelu(fc1(LN2(x1))))
         # dgrad first: its epilogue multiplies by gelu'(h) AND emits a = gelu(h), which the fc2 wgrad then consumes
-        a = torch.empty_like(s.h)
-        dh = ops.linear_dgrad(g, wc.get_t(blk.mlp.fc2.weight), epilogue=EPI_DGELU, aux=s.h, aux2=a,
+        a = s.a if s.a is not None else torch.empty_like(s.h)
+        dh = ops.linear_dgrad(g, wc.get_t(blk.mlp.fc2.weight), epilogue=EPI_DGELU, aux=s.h, aux2=None if s.a is not None else a,
                               col_sum=_grad_of(blk.mlp.fc1.bias))
-        s.h = None
+        s.h = s.a = None
         ops.linear_wgrad(g, a, _grad_of(blk.mlp.fc2.weight), accumulate=True)
         del a
         ops.linear_wgrad(dh, s.y2, _grad_of(blk.mlp.fc1.weight), accumulate=True)
@@ -342,6 +359,7 @@ class _Lyr:
     s2: Tensor = None         # fp32 [M,D] output pre-LN sum
     mean2: Tensor = None
     rstd2: Tensor = None
+    act: Tensor = None        # bf16 [M,F] gelu(pre) when kept (keep_gelu_output), else re-emitted in backward
 
 
 @dataclass
@@ -379,6 +397,7 @@ def bert_forward(m, input_ids: Tensor, attention_mask: Tensor, wc: Bf16Weights, 
     if save:
         sv.e, sv.mean0, sv.rstd0 = e, mean0, rstd0
     strides = (T * 3 * D, 3 * D, 64)
+    keep_a = save and keep_gelu_output(len(m.encoder.layer) * M * m.encoder.layer[0].intermediate.dense.weight.shape[0] * 2, e.device)
     for li, layer in enumerate(m.encoder.layer):
         qp = _qkv_params(layer)
         wqkv = wc.packed(f"bert.qkv.{li}", [p.weight for p in qp])
@@ -396,12 +415,13 @@ def bert_forward(m, input_ids: Tensor, attention_mask: Tensor, wc: Bf16Weights, 
         f = ops.linear_fwd(h1b, wc.get(layer.intermediate.dense.weight), layer.intermediate.dense.bias,
                            epilogue=EPI_BIAS_GELU, aux=pre)
         d2 = ops.linear_fwd(f, wc.get(layer.output.dense.weight), layer.output.dense.bias)
+        act = f if keep_a else None
         del f
         s2, h2b, h2f, mean2, rstd2 = ops.add_layernorm_fwd(h1f, d2, layer.output.LayerNorm.weight, layer.output.LayerNorm.bias,
                                                            1e-12, want_f32=True)
         del d2
         if save:
-            sv.layers.append(_Lyr(hb, qkv, c, lse, s1, mean1, rstd1, pre, h1b, s2, mean2, rstd2))
+            sv.layers.append(_Lyr(hb, qkv, c, lse, s1, mean1, rstd1, pre, h1b, s2, mean2, rstd2, act))
         hb, hf = h2b, h2f
     return hf.view(B, T, D), hb.view(B, T, D), sv
 
@@ -428,9 +448,10 @@ def bert_backward(m, sv: BertSaved, dh: Tensor, wc: Bf16Weights, dh2: Optional[T
         ops.layernorm_bwd(dy, s.s2, layer.output.LayerNorm.weight, s.mean2, s.rstd2, dy2=dres, dx=ds2, dx_bf16=g2,
                           dgamma=_grad_of(layer.output.LayerNorm.weight), dbeta=_grad_of(layer.output.LayerNorm.bias),
                           dx_colsum=_grad_of(layer.output.dense.bias))
-        f = torch.empty_like(s.pre)
-        dpre = ops.linear_dgrad(g2, wc.get_t(layer.output.dense.weight), epilogue=EPI_DGELU, aux=s.pre, aux2=f,
-                                col_sum=_grad_of(layer.intermediate.dense.bias))
+        f = s.act if s.act is not None else torch.empty_like(s.pre)
+        dpre = ops.linear_dgrad(g2, wc.get_t(layer.output.dense.weight), epilogue=EPI_DGELU, aux=s.pre,
+                                aux2=None if s.act is not None else f, col_sum=_grad_of(layer.intermediate.dense.bias))
+        s.act = None
         ops.linear_wgrad(g2, f, _grad_of(layer.output.dense.weight), accumulate=True)
         del f
         ops.linear_wgrad(dpre, s.h1b, _grad_of(layer.intermediate.dense.weight), accumulate=True)

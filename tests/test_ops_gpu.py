@@ -156,6 +156,12 @@ def test_gemm_tma_epilogue_bf16(cuda, M, N, K, tile_n, mode):
     dh8 = ops.gemm(a, b, M=M, N=N, K=K, epilogue=EPI_DGELU, aux=aux, aux2=a28, col_sum=cs8, tile_n=tile_n, _dbg=mode | 64)
     assert torch.equal(dh8, dh) and torch.equal(a28, a2)
     assert _rel(cs8, cs) < 1e-5
+    # without the gelu(pre) re-emit (towers.keep_gelu_output: the forward's activation was kept): same gradient, same sums
+    for extra in (0, 64):
+        csn = torch.zeros(N, device=cuda)
+        dhn = ops.gemm(a, b, M=M, N=N, K=K, epilogue=EPI_DGELU, aux=aux, col_sum=csn, tile_n=tile_n, _dbg=mode | extra)
+        assert torch.equal(dhn, dh)
+        assert _rel(csn, cs) < 1e-5
 
 
 @pytest.mark.parametrize("D", [384, 768])

@@ -334,3 +334,28 @@ def test_cuda_graph_step_equals_eager_steps(cuda):
     print(f"eager-vs-eager: loss {noise_l:.2e}, weight deltas {noise_w:.2e}; graph-vs-eager: loss {diff_l:.2e}, weight deltas {diff_w:.2e}")
     assert diff_l <= 3 * noise_l + 5e-3
     assert diff_w <= 3 * noise_w + 2e-2
+
+
+def test_keep_gelu_output_policy(cuda, monkeypatch):
+    """``towers.keep_gelu_output``: keeping gelu(h) from the forward (small shards) and re-emitting it from the dGELU epilogue
+    (b = 4096 on one GPU) are the same backward — the two activations differ by at most a bf16 rounding of two fp32-grade
+    evaluations of the same function."""
+    from oracle import simseg_oracle as O
+    from simseg_b200 import towers
+    sd = O.make_state_dict(384, 6, seed=0)
+    gb = {k: v.to(cuda) for k, v in O.make_batch(8, 25, seed=77).items()}
+    assert towers.keep_gelu_output(1 << 30, cuda) and not towers.keep_gelu_output(1 << 36, cuda)
+    grads = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SIMSEG_KEEP_GELU", flag)
+        model, _ = _build(cuda)
+        model.load_state_dict(sd)
+        model.zero_grad(set_to_none=True)
+        loss = model(gb)[0]["nce_loss"]
+        loss.backward()
+        torch.cuda.synchronize()
+        grads[flag] = (loss.item(), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None})
+    assert grads["0"][0] == grads["1"][0]                       # the forward is the same code
+    assert len(grads["0"][1]) == len(grads["1"][1]) > 300
+    for n, g0 in grads["0"][1].items():
+        assert _rel(grads["1"][1][n], g0) < 3e-3, n

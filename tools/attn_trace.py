@@ -23,8 +23,8 @@ NID = 24
 buf = np.zeros(5 * 2 * NID, dtype=np.uint64)
 lib.simseg_debug_trace_read(buf.ctypes.data_as(C.c_void_p), buf.size)
 lib.simseg_debug_trace_enable(0)
-names = {1: "loop top", 2: "wait p_ready", 3: "wait dkv_free", 4: "issue dV", 5: "issue S(n)", 6: "wait ds_ready", 7: "issue dP(n),dK,dQ",
-         8: "loop back-edge", 10: "issue O/lse loads", 11: "wait s_full", 12: "D (dO.O) + exchange", 13: "phase A math", 14: "wait p_free",
+names = {0: "?", 1: "loop top", 2: "wait p_ready", 3: "wait dkv_free", 4: "issue dV", 5: "issue S(n)", 6: "wait ds_ready", 7: "issue dP(n),dK,dQ",
+         10: "loop back-edge", 11: "wait s_full", 12: "wait d_full + D/L read", 13: "phase A math", 14: "wait p_free",
          15: "P store+fence+arrive", 16: "wait dp_full", 17: "wait ds_free", 18: "phase B math+store+arrive", 19: "wait dkv_full",
          20: "drain dK/dV", 21: "wait dq_full", 22: "drain dQ"}
 items = B * H / 148.0
