@@ -53,6 +53,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 4-D tiled store shared -> global (bulk async group); elements outside the tensor are clipped
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 __device__ __forceinline__ int ceil16(int x) { return (x + 15) & ~15; }
 
 // ---- debug: per-warp phase timing of CTA 0, read back with simseg_debug_trace_read (tools/attn_trace.py) ----------------
@@ -96,7 +103,8 @@ struct Tracer {                                              // compiled out: no
 __global__ void __launch_bounds__(kAbThreads, 1)
 attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                         const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
-                        const AttnBwdParams p) {
+                        const __grid_constant__ CUtensorMap tm_dq, const __grid_constant__ CUtensorMap tm_dk,
+                        const __grid_constant__ CUtensorMap tm_dv, const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* sQ = smem;                          // [2][16 KB]
@@ -105,7 +113,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   uint8_t* sV = sK + 2 * kTileBytes;           // [2 buffers][16 KB]
   uint8_t* sP = sV + 2 * kTileBytes;           // 32 KB
   uint8_t* sdS = sP + kPBytes;                 // 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + kPBytes);
+  uint8_t* sStg = sdS + kPBytes;               // [16 warps][2 KB] drain staging (1024-byte aligned: SWIZZLE_64B TMA stores)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + kAbEwWarps * 2048);
   uint64_t* qdo_full = bars;          // [2]
   uint64_t* qdo_empty = bars + 2;     // [2]
   uint64_t* kv_full = bars + 4;       // [2]
@@ -124,7 +133,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   // per Q / dO slot and tile row: {D, lse * log2 e}, written by the producer warp (it has the dO tile in smem and 31 idle
   // lanes) one item ahead of the elementwise warps — their only global loads and a 4-warp exchange used to sit here
-  float2* sDL = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 256 + kAbEwWarps * 2048);   // [2 slots][128 rows]
+  float2* sDL = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2 slots][128 rows]
   if (threadIdx.x == 0 && static_cast<uint32_t>(smem - smem_raw) > 768u) {
     printf("simseg: attention_bwd dynamic shared memory base is not 256-byte aligned\n");
     __trap();
@@ -135,6 +144,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_q); prefetch_tmap(&tm_k); prefetch_tmap(&tm_v); prefetch_tmap(&tm_do);
+    prefetch_tmap(&tm_dq); prefetch_tmap(&tm_dk); prefetch_tmap(&tm_dv);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1);
       mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
@@ -317,32 +327,28 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const int sw = r & 7;
     const int col0 = cq * 32;
-    // drain staging: a thread owns a tile ROW, so storing straight from registers makes every store instruction touch 32
-    // different 128-byte lines (16 bytes each) — the L1 store path, not HBM, then paces the drains.  The warp's 32 rows x 64
-    // bytes go through a swizzled 2 KB block instead and leave as 8 rows x 64 contiguous bytes per instruction.
-    uint8_t* stg = reinterpret_cast<uint8_t*>(bars) + 256 + ew * 2048;
+    // drain staging: a thread owns a tile ROW (32 of its 64 d-columns = 64 bytes); stored straight from registers every
+    // instruction would touch 32 different 128-byte lines.  The warp's 32 rows go through a SWIZZLE_64B 2 KB block and leave
+    // as ONE 4-D TMA store {32 d, G heads, 32/G tokens, 1 batch}: no address arithmetic, rows past S are clipped by the
+    // tensor map, and — unlike st.global — the stores are not waited for by the MEMBAR of the next fence.proxy.async.
+    uint8_t* stg = sStg + ew * 2048;
     uint32_t it = 0, g = 0, drains = 0;
     Tracer tr(warp == 2 ? 1 : warp == 3 ? 2 : warp == 6 ? 3 : warp == 10 ? 4 : -1, lane == 0);
-    const int gm0 = p.G - 1;
-    // w[16] = this thread's row (32 bf16 of d-columns dcol0..dcol0+31) -> rows tile_row0 .. +32 of `dst` of item (sb, sh0)
-    auto store_rows = [&](const uint32_t (&w)[16], __nv_bfloat16* dst, int sb_idx, int sh0, int tile_row0, int dcol0) {
+    // w[16] = this thread's row (32 bf16 of d-columns dcol0..dcol0+31) -> rows tile_row0 .. +32 of the tensor behind `tm`
+    auto store_rows = [&](const uint32_t (&w)[16], const CUtensorMap* tm, int sb_idx, int sh0, int tile_row0, int dcol0) {
+      if (lane == 0) tma_store_wait_read<0>();                  // the block's previous store has been read (long ago)
+      __syncwarp();
       uint8_t* mine = stg + lane * 64;
       const int swz = (lane >> 1) & 3;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         *reinterpret_cast<uint4*>(mine + ((j ^ swz) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+      fence_proxy_async_smem();
       __syncwarp();
-      const int64_t base_b = static_cast<int64_t>(sb_idx) * p.sb;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int rr = (lane >> 2) + 8 * i;
-        const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4));
-        const int row = tile_row0 + rr;
-        if (row < p.rows && !(p.dbg & 8))
-          *reinterpret_cast<uint4*>(dst + base_b + static_cast<int64_t>(row >> p.lg) * p.ss +
-                                    static_cast<int64_t>(sh0 + (row & gm0)) * p.sh + dcol0 + (lane & 3) * 8) = val;
+      if (lane == 0 && tile_row0 < p.rows && !(p.dbg & 8)) {
+        tma_store_4d(tm, stg, dcol0, sh0, tile_row0 >> p.lg, sb_idx);
+        tma_store_commit();
       }
-      __syncwarp();
     };
     // Deferred drains: the accumulators of a key tile (dK / dV) and of an item (dQ) complete ~a block's worth of MMAs after
     // this warp's last contribution; draining right away would idle the elementwise warps for that long (20 % of their
@@ -370,7 +376,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         uint32_t w[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) w[j] = pack_bf16(__uint_as_float(a[2 * j]) * sc, __uint_as_float(a[2 * j + 1]) * sc);
-        store_rows(w, is_dk ? p.dk : p.dv, pend_b, pend_h0, pend_kt * kTile + quarter * 32, dcol0);
+        store_rows(w, is_dk ? &tm_dk : &tm_dv, pend_b, pend_h0, pend_kt * kTile + quarter * 32, dcol0);
         ++drains;
         pend_kv = false;
         tr(20);
@@ -392,7 +398,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(dq_free);
-        if (dqt < p.nqt) store_rows(w, p.dq, pend_b, pend_h0, dqt * kTile + quarter * 32, dcol0);
+        if (dqt < p.nqt) store_rows(w, &tm_dq, pend_b, pend_h0, dqt * kTile + quarter * 32, dcol0);
         pend_q = false;
         tr(22);
       }
@@ -520,6 +526,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       }
     }
     drain_pending();
+    if (lane == 0) tma_store_wait<0>();
     tr.flush();
   } else {
     // =============================== D / lse rows (warps 18, 19) ===============================
@@ -1242,7 +1249,9 @@ typedef CUresult (*EncodeTiledFn4)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 
 // {64 d, H heads, S tokens, B batch} bf16 view of a (batch, token, head)-strided tensor; box = 128 tokens of one head
 // G > 1: one box = {64 d, G heads, all S tokens} of one batch element (row = token * G + head in shared memory)
-static int make_tmap_bshd(CUtensorMap* m, const void* ptr, int B, int H, int S, int64_t sb, int64_t ss, int64_t sh, int G = 1) {
+// store = true: box {32 d, G heads, 32 / G tokens, 1 batch}, SWIZZLE_64B — one elementwise warp's 32 rows x 64 bytes of dQ / dK / dV
+static int make_tmap_bshd(CUtensorMap* m, const void* ptr, int B, int H, int S, int64_t sb, int64_t ss, int64_t sh, int G = 1,
+                          bool store = false) {
   static EncodeTiledFn4 enc = nullptr;
   if (!enc) {
     void* f = nullptr;
@@ -1256,10 +1265,11 @@ static int make_tmap_bshd(CUtensorMap* m, const void* ptr, int B, int H, int S, 
   cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(B)};
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(sh) * 2, static_cast<cuuint64_t>(ss) * 2, static_cast<cuuint64_t>(sb) * 2};
   cuuint32_t box[4] = {64, static_cast<cuuint32_t>(G), static_cast<cuuint32_t>(G > 1 ? S : kTile), 1};
+  if (store) { box[0] = 32; box[2] = static_cast<cuuint32_t>(32 / G); }
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, store ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(4d) failed (%d): ptr=%p B=%d H=%d S=%d sb=%lld ss=%lld sh=%lld", static_cast<int>(r), ptr, B, H, S,
               static_cast<long long>(sb), static_cast<long long>(ss), static_cast<long long>(sh));
@@ -1308,6 +1318,10 @@ int attention_bwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v,
   if ((rc = make_tmap_bshd(&tk, k, B, H, S, sb, ss, sh, G))) return rc;
   if ((rc = make_tmap_bshd(&tv, v, B, H, S, sb, ss, sh, G))) return rc;
   if ((rc = make_tmap_bshd(&tdo, dout, B, H, S, static_cast<int64_t>(S) * H * 64, static_cast<int64_t>(H) * 64, 64, G))) return rc;
+  CUtensorMap tdq, tdk, tdv;
+  if ((rc = make_tmap_bshd(&tdq, dq, B, H, S, sb, ss, sh, G, true))) return rc;
+  if ((rc = make_tmap_bshd(&tdk, dk, B, H, S, sb, ss, sh, G, true))) return rc;
+  if ((rc = make_tmap_bshd(&tdv, dv, B, H, S, sb, ss, sh, G, true))) return rc;
   AttnBwdParams p{};
   p.B = B; p.H = H; p.S = S;
   p.G = G; p.HG = H / G; p.rows = S * G;
@@ -1328,7 +1342,7 @@ int attention_bwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v,
     attr_set = true;
   }
   const int grid = p.items < ctx->num_sms ? p.items : ctx->num_sms;
-  attention_bwd_tc_kernel<<<grid, kAbThreads, smem_bytes, st>>>(tq, tk, tv, tdo, p);
+  attention_bwd_tc_kernel<<<grid, kAbThreads, smem_bytes, st>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
   ctx->launches++;
   SIMSEG_LAUNCH_CHECK();
   return SIMSEG_OK;
