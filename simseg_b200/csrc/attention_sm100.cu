@@ -26,6 +26,11 @@ namespace simseg {
 
 using namespace sm100;
 
+// Drain of dK / dV (dQ) parked until after phase B of the NEXT block, with S(n) issued ahead of the accumulator wait: right after
+// phase A the accumulators are still being written (the drain waited ~540 clk for dkv_full), a phase later they have landed.
+// (A/B on the ViT-S layer: 2.23 -> 2.12 ms.)
+// Single-block items (BERT, T = 77) keep the early drain: there every block ends a key tile, and the late drain would make the
+// next block's dV wait for it (1.51 -> 1.75 ms).  The host picks the instantiation (nqt > 1).
 constexpr int kAbEwWarps = 16;                       // elementwise warps: four per TMEM lane quarter
 constexpr int kAbThreads = 32 * (2 + kAbEwWarps + 2);   // + two D / lse warps
 constexpr int kTile = 128;                 // query rows / key rows per tile
@@ -100,6 +105,7 @@ struct Tracer {                                              // compiled out: no
 };
 #endif
 
+template <bool kLateDrain>
 __global__ void __launch_bounds__(kAbThreads, 1)
 attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                         const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
@@ -271,6 +277,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         // ---- phase A of block c is done: P is in smem, the S buffer is free
         mbar_wait(p_ready, c.g & 1);
         tr(2);
+        if (kLateDrain && valid(n)) { tc_fence_after(); issue_s(n); }           // S buffer is free: ahead of the accumulator wait
         if (c.qt == 0 && drains > 0) mbar_wait(dkv_free, (drains - 1) & 1);  // dV/dK accumulators drained (first MMA overwrites)
         tr(3);
         tc_fence_after();
@@ -282,7 +289,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         }
         __syncwarp();
         tr(4);
-        if (valid(n)) issue_s(n);                                            // runs under phase B of block c
+        if (!kLateDrain && valid(n)) issue_s(n);                             // runs under phase B of block c
         tr(5);
         // ---- phase B of block c is done: dS is in smem, the dP buffer is free
         mbar_wait(ds_ready, c.g & 1);
@@ -479,7 +486,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           __syncwarp();
           if (lane == 0) mbar_arrive(p_ready);
           tr(15);
-          drain_pending();                                             // accumulators of the previous key tile / item
+          if (!kLateDrain) drain_pending();                              // accumulators of the previous key tile / item
 
           // ---- phase B: dP -> dS = P * (dP - D), dS into smem
           mbar_wait(dp_full, g & 1);
@@ -517,6 +524,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           __syncwarp();
           if (lane == 0) mbar_arrive(ds_ready);
           tr(18);
+          if (kLateDrain) drain_pending();
 
           if (qt == p.nqt - 1) {                                      // park the drains (see drain_pending)
             pend_kv = true; pend_b = b; pend_h0 = h0; pend_kt = kt;
@@ -546,6 +554,26 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       const uint32_t use = (p.nqt == 1) ? (it >> 1) : it;
       const int b = item / p.HG, h = (item - b * p.HG) * p.G;
       const int nrows = min(kTile, p.rows - qt * kTile);
+#ifndef SIMSEG_ATTN_NO_D_PREFETCH
+      {
+        // pull the O / dO rows of this warp's NEXT tile into L2 now: its loads (a whole item later) then see L2 latency, and so
+        // does the TMA load of that dO tile
+        const int nitem = item + static_cast<int>(gridDim.x) * (p.nqt == 1 ? 2 : 1);
+        if (nitem < p.items) {
+          const int nb = nitem / p.HG, nh = (nitem - nb * p.HG) * p.G;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = lane + 32 * i;
+            if (r < nrows) {
+              const int row = qt * kTile + r;
+              const int64_t off = (static_cast<int64_t>(nb) * p.S + (row >> p.lg)) * (p.H * 64) + (nh + (row & gm)) * 64;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.out + off));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dout + off));
+            }
+          }
+        }
+      }
+#endif
       float dv[4], lv[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {                              // this lane keeps rows (8 i + c8) * 4 + sub
@@ -1338,11 +1366,13 @@ int attention_bwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v,
   const int smem_bytes = 768 + 8 * kTileBytes + 2 * kPBytes + 256 + kAbEwWarps * 2048 + 2 * kTile * 8;
   static bool attr_set = false;
   if (!attr_set) {
-    SIMSEG_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    SIMSEG_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    SIMSEG_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
   }
   const int grid = p.items < ctx->num_sms ? p.items : ctx->num_sms;
-  attention_bwd_tc_kernel<<<grid, kAbThreads, smem_bytes, st>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
+  if (p.nqt > 1) attention_bwd_tc_kernel<true><<<grid, kAbThreads, smem_bytes, st>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
+  else attention_bwd_tc_kernel<false><<<grid, kAbThreads, smem_bytes, st>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
   ctx->launches++;
   SIMSEG_LAUNCH_CHECK();
   return SIMSEG_OK;

@@ -18,7 +18,7 @@ def run(B, H, S, masked):
     dqkv = torch.empty_like(qkv)
     out, lse = ops.attention_fwd(q, k, v, B, H, S, strides, klen, 0.125)
     res = []
-    for dbg in (0, 1, 2, 4, 8, 16, 32, 48, 64, 128, 130, 130 + 48, 255):
+    for dbg in (0, 1, 2, 4, 8, 16, 32, 48, 64, 128, 130, 178, 255):
         os.environ["SIMSEG_ATTN_DBG"] = str(dbg)
         fn = lambda: ops.attention_bwd(q, k, v, out, dout, lse, B, H, S, strides, klen, 0.125, dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2])
         fn(); fn()
