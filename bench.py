@@ -24,6 +24,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "image-text pairs/sec (train)"
 UNIT = "pairs/s"
+BERT_DROPOUT = 0.1        # bert-base-uncased hidden_dropout_prob = attention_probs_dropout_prob, active in every timed train step
 MODELS = {"vit-s": dict(yaml="simseg.vit-s.yaml", dim=384, heads=6, fwd_gf_img=9.20),
           "vit-b": dict(yaml="simseg.vit-b.yaml", dim=768, heads=12, fwd_gf_img=35.1)}
 
@@ -144,7 +145,8 @@ def cpu_pairs_per_s(a, pairs: int, steps: int = 1, warmup: int = 0):
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
-        loss, _, _ = O.clip_train_forward(params, batch, m["heads"])
+        # train mode, as the reference runs it: BERT's hidden / attention-probability dropout (0.1) is part of the step
+        loss, _, _ = O.clip_train_forward(params, batch, m["heads"], dropout=O.TorchDropout(BERT_DROPOUT, BERT_DROPOUT))
         loss.backward()
         opt.step()
         if i >= warmup:
@@ -300,6 +302,9 @@ def run_ours(a):
             "config": {"workload": workload_name(a), "global_batch": a.global_batch, "per_gpu_batch": b,
                        "seq_len": a.seq_len, "parallelism": f"dp{world}", "micro_batch": a.micro_batch or b,
                        "cuda_graph": graph_note,
+                       "bert_dropout": {"hidden": model.text_encoder.model.hidden_dropout_prob,
+                                        "attention_probs": model.text_encoder.model.attention_probs_dropout_prob,
+                                        "mode": "model.train(): masks drawn in-kernel (Philox), fresh every replay"},
                        "l2": "per-step working set (>10 GB of activations) is far larger than the 126 MB L2"},
             "clocks": cs.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": 4 * world,
@@ -378,7 +383,13 @@ def dp_check(trainer, dev, world, rank, T, pairs=64):
     gb = make_batch(pairs, T, seed=4242)                         # the same global batch on every rank, whatever N is
     b = pairs // world
     mine = {k: v[rank * b:(rank + 1) * b].to(dev) for k, v in gb.items()}
-    loss, i2t, t2i = trainer.backward_only(mine)
+    # eval mode for this block only: BERT's dropout masks are drawn per rank-local row, so a train-mode loss is not comparable
+    # across N (the timed steps below run in train mode, dropout on, as the reference trains)
+    trainer.model.eval()
+    try:
+        loss, i2t, t2i = trainer.backward_only(mine)
+    finally:
+        trainer.model.train()
     stats = torch.stack([loss.float(), i2t.float(), t2i.float()])
     if world > 1:
         dist.all_reduce(stats)

@@ -145,6 +145,45 @@ int simseg_attention_bwd(simseg_ctx* ctx, const void* q, const void* k, const vo
                          int B, int H, int S, const int32_t* key_len, float scale, void* dq, void* dk, void* dv,
                          void* stream);
 
+/* ---- train-mode dropout of the BERT tower ------------------------------------------------------
+ * HF BertModel under model.train() (huggingface_builder.py:16-17 wraps it; hidden_dropout_prob =
+ * attention_probs_dropout_prob = 0.1 in bert-base-uncased): dropout after the embedding LayerNorm, on the attention
+ * probabilities, and on the two dense outputs before their residual add + LayerNorm.
+ * A keep bit is a pure function of (seed, step, site, element) — Philox4x32-10, csrc/philox.cuh — so backward regenerates
+ * the forward's mask.  drop_rng is a DEVICE pointer to {seed, step}: kernels read it at run time, a replayed CUDA graph
+ * draws new masks once the host (or a captured add) bumps step.  drop_site separates the dropout layers of one step.
+ * Kept values are scaled by 1 / (1 - drop_p); drop_p = 0 reduces every call to its plain counterpart. */
+/* add_bf16 != NULL: y = LayerNorm(x + dropout(add))            (BertSelfOutput / BertOutput), sum_out = x + dropout(add)
+ * add_bf16 == NULL: y = dropout(LayerNorm(x))                  (BertEmbeddings) */
+int simseg_layernorm_fwd_dropout(simseg_ctx* ctx, const float* x, const void* add_bf16, const float* gamma,
+                                 const float* beta, float eps, int64_t M, int D, float* sum_out, void* y_bf16, float* y_f32,
+                                 float* mean, float* rstd, float drop_p, const uint64_t* drop_rng, uint32_t drop_site,
+                                 void* stream);
+/* simseg_layernorm_bwd with the matching mask.  drop_mode 1 (forward had add_bf16): dx_bf16 and dx_colsum — the gradient of
+ * the dropped summand and of its Linear's bias — carry the mask, dx (residual path) does not.  drop_mode 2 (forward
+ * dropped the outputs): dy (+ dy2) is masked before the LayerNorm backward. */
+int simseg_layernorm_bwd_dropout(simseg_ctx* ctx, const void* dy, int dy_dtype, const float* dy2, const float* x,
+                                 const float* gamma, const float* mean, const float* rstd, int64_t M, int D, float* dx,
+                                 int dx_accumulate, void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum,
+                                 int drop_mode, float drop_p, const uint64_t* drop_rng, uint32_t drop_site, void* stream);
+/* Keep bits of one attention layer: keep(b,h,q,k) = word (k & 3) of philox(seed; {k >> 2, (b H + h) S + q, site, step})
+ * >= round(p 2^32), stored in the tile coordinates of the tcgen05 attention kernels (G = largest power of two <= 8 with
+ * G S <= 128 dividing H heads share a tile; tile row r = q G + (h mod G); word [((b H/G + h/G) S G + r) ceil(S G / 32) + w]
+ * bit j = tile column 32 w + j = key (32 w + j) / G of head (32 w + j) mod G).  simseg_attn_dropout_mask_words gives the
+ * buffer size in 32-bit words (0: shape unsupported, S > 256). */
+int64_t simseg_attn_dropout_mask_words(int B, int H, int S);
+int simseg_attn_dropout_mask(simseg_ctx* ctx, int B, int H, int S, float drop_p, const uint64_t* drop_rng,
+                             uint32_t drop_site, uint32_t* mask, int64_t mask_words, void* stream);
+/* simseg_attention_fwd / _bwd with dropout(softmax(..)) (HF BertSelfAttention): out = dropout(P) V; lse is that of the
+ * undropped softmax.  tcgen05 kernels only (S <= 224); other shapes return SIMSEG_ERR_UNSUPPORTED — there is no fallback. */
+int simseg_attention_fwd_dropout(simseg_ctx* ctx, const void* q, const void* k, const void* v, int64_t stride_b,
+                                 int64_t stride_s, int64_t stride_h, int B, int H, int S, const int32_t* key_len,
+                                 float scale, void* out, float* lse, const uint32_t* drop_mask, float drop_p, void* stream);
+int simseg_attention_bwd_dropout(simseg_ctx* ctx, const void* q, const void* k, const void* v, const void* out,
+                                 const void* dout, const float* lse, int64_t stride_b, int64_t stride_s, int64_t stride_h,
+                                 int B, int H, int S, const int32_t* key_len, float scale, void* dq, void* dk, void* dv,
+                                 const uint32_t* drop_mask, float drop_p, void* stream);
+
 /* ---- ViT / BERT embedding stages ------------------------------------------------------------ */
 /* image [B,3,Hi,Wi] f32 NCHW -> patches bf16 [B*N, 768] (k = c*256 + py*16 + px), the im2col of the
  * stride-16 conv in timm PatchEmbed (vit_builder.py:14). */

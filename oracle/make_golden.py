@@ -195,6 +195,71 @@ def encoders_cross_check():
     return out
 
 
+def bert_dropout():
+    """Pins WHERE the oracle applies BERT's train-mode dropout (sites and order, oracle/simseg_oracle.py) against the installed
+    ``transformers`` BertModel in train() mode: ``torch.nn.functional.dropout`` is replaced for the duration of one forward +
+    backward by a function that serves the oracle's own Philox masks in call order, so both sides drop the same elements and
+    the outputs / gradients must agree.  (The reference reaches this code as ``huggingface_builder.py:16-17`` under
+    ``model.train()``; bert-base-uncased: hidden_dropout_prob = attention_probs_dropout_prob = 0.1.)"""
+    print("[BERT train-mode dropout placement vs transformers BertModel.train()]")
+    from transformers import BertConfig, BertModel
+    seed, step, B, T = 20260117, 3, 3, 25
+    sd_all = O.make_state_dict(384, 6, seed=0)
+    bsd = {k[len(O.TXT_PREFIX):]: v for k, v in sd_all.items() if k.startswith(O.TXT_PREFIX)}
+    try:
+        bm = BertModel(BertConfig(hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, attn_implementation="eager"),
+                       add_pooling_layer=False)
+    except TypeError:
+        bm = BertModel(BertConfig(hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1), add_pooling_layer=False)
+    missing, unexpected = bm.load_state_dict(bsd, strict=False)
+    assert not unexpected and all("position_ids" in m or "token_type_ids" in m for m in missing), (missing, unexpected)
+    bm.train()
+    batch = O.make_batch(B, T, seed=5)
+    drop = O.PhiloxDropout(seed, step, 0.1, 0.1)
+    calls = []
+    real = F.dropout
+
+    def served(x, p=0.5, training=True, inplace=False):
+        if not training or p == 0.0:
+            return x
+        site = len(calls)
+        calls.append(tuple(x.shape))
+        assert abs(p - 0.1) < 1e-12
+        return drop.attn(site, x) if x.dim() == 4 else drop.hidden(site, x)
+
+    torch.nn.functional.dropout = served
+    try:
+        r = bm(input_ids=batch["input_ids"], attention_mask=batch["attention_mask"]).last_hidden_state
+        g = torch.randn(r.shape, generator=torch.Generator().manual_seed(9))
+        (r * g).sum().backward()
+    finally:
+        torch.nn.functional.dropout = real
+    want = [(B, T, 768)]
+    for _ in range(12):
+        want += [(B, 12, T, T), (B, T, 768), (B, T, 768)]
+    assert calls == want, "HF's dropout call order differs from the oracle's site numbering"
+    print("  dropout call order: embeddings, then 12 x (attention probs, attention.output, output)  [ok]")
+    sdg = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in bsd.items()}
+    o = O.bert_forward(sdg, batch["input_ids"], batch["attention_mask"], dropout=drop)
+    (o * g).sum().backward()
+    _check("BERT train() last_hidden_state, served masks", o, r, 2e-4)
+    named = dict(bm.named_parameters())
+    for k in ("encoder.layer.0.attention.self.query.weight", "encoder.layer.5.attention.output.dense.bias",
+              "encoder.layer.11.output.dense.weight", "embeddings.word_embeddings.weight", "embeddings.LayerNorm.weight"):
+        rg, og = named[k].grad, sdg[k].grad
+        sc = rg.abs().max().item() + 1e-12
+        _check(f"grad {k[-44:]}", og / sc, rg / sc, 2e-3)
+    # eval-mode output differs (the masks really act), and the p = 0 oracle reproduces it
+    bm.eval()
+    with torch.no_grad():
+        r0 = bm(input_ids=batch["input_ids"], attention_mask=batch["attention_mask"]).last_hidden_state
+    assert (r0 - r).abs().max().item() > 0.1
+    return dict(bd_seed=np.array(seed), bd_step=np.array(step), bd_hidden=r.detach()[:, :, :96].contiguous().numpy(),
+                bd_grad_g=g[:, :, :8].contiguous().numpy(),
+                bd_dq0_norm=np.array(named["encoder.layer.0.attention.self.query.weight"].grad.norm().item()),
+                bd_keep_rate_site1=np.array(O.attn_keep_mask(seed, step, 1, B, 12, T, 0.1).float().mean().item()))
+
+
 def full_model():
     print("[reference CLIPModel (ViT-S + BERT-base) vs oracle, same weights]")
     import simseg.core  # noqa: F401
@@ -401,11 +466,14 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "global_reduce.npz"), **global_reduce_two_ranks())
     np.savez_compressed(os.path.join(GOLD, "clip_vit_s.npz"), **full_model())
     np.savez_compressed(os.path.join(GOLD, "seg_glue.npz"), **seg_glue())
+    np.savez_compressed(os.path.join(GOLD, "bert_dropout.npz"), **bert_dropout())
     print("golden vectors written to", GOLD)
 
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "seg_glue":          # regenerate this fixture alone
         np.savez_compressed(os.path.join(GOLD, "seg_glue.npz"), **seg_glue())
+    elif len(sys.argv) > 1 and sys.argv[1] == "bert_dropout":
+        np.savez_compressed(os.path.join(GOLD, "bert_dropout.npz"), **bert_dropout())
     else:
         main()

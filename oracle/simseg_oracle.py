@@ -89,19 +89,112 @@ def vit_forward(sd: Dict[str, Tensor], image: Tensor, heads: int, prefix: str = 
     return layer_norm(x, p("norm.weight"), p("norm.bias"), eps)
 
 
+# ---- train-mode dropout of the BERT tower ----------------------------------------------------------------------------
+# HF ``BertModel`` under ``model.train()`` (the reference trains it so: ``huggingface_builder.py:16-17`` inside
+# ``CLIPModel``; bert-base-uncased config: hidden_dropout_prob = attention_probs_dropout_prob = 0.1) applies dropout
+#   site 0          after the embedding LayerNorm                       (BertEmbeddings)
+#   site 1 + 3 l    to the attention probabilities, after the softmax   (BertSelfAttention)
+#   site 2 + 3 l    to attention.output.dense before the residual add   (BertSelfOutput)
+#   site 3 + 3 l    to output.dense before the residual add             (BertOutput)
+# — the order HF calls them in; ``make_golden.py:bert_dropout`` pins the placement against the installed BertModel by serving
+# it these very masks.  WHICH elements drop is each framework's own random stream (torch's CUDA Philox offsets depend on its
+# kernel launch geometry), so the product defines its stream as below and the tests compare against it bit for bit.
+_PHILOX_M0, _PHILOX_M1 = 0xD2511F53, 0xCD9E8D57
+_PHILOX_W0, _PHILOX_W1 = 0x9E3779B9, 0xBB67AE85
+
+
+def philox4x32_10(ctr, key):
+    """Philox4x32-10 (Salmon et al., SC'11; the Random123 reference algorithm).  ``ctr``: uint32 array [..., 4],
+    ``key``: two uint32.  Returns uint32 [..., 4].  Known answers: tests/test_oracle_cpu.py::test_philox_known_answers."""
+    import numpy as np
+    c = [np.asarray(ctr[..., i], dtype=np.uint64) for i in range(4)]
+    k0, k1 = int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(_PHILOX_M0) * c[0]
+        p1 = np.uint64(_PHILOX_M1) * c[2]
+        hi0, lo0 = p0 >> np.uint64(32), p0 & mask
+        hi1, lo1 = p1 >> np.uint64(32), p1 & mask
+        c = [hi1 ^ c[1] ^ np.uint64(k0), lo1, hi0 ^ c[3] ^ np.uint64(k1), lo0]
+        k0 = (k0 + _PHILOX_W0) & 0xFFFFFFFF
+        k1 = (k1 + _PHILOX_W1) & 0xFFFFFFFF
+    return np.stack(c, axis=-1).astype(np.uint32)
+
+
+def dropout_threshold(p: float) -> int:
+    """An element is dropped iff its 32-bit word < round(p * 2**32) (csrc/philox.cuh:make_drop_spec)."""
+    t = float(p) * 4294967296.0
+    return 0xFFFFFFFF if t >= 4294967295.0 else int(t + 0.5)
+
+
+def hidden_keep_mask(seed: int, step: int, site: int, M: int, D: int, p: float) -> Tensor:
+    """bool [M, D]: element (row, col) is word (col & 3) of philox(key = seed, counter = {col >> 2, row, site, step})."""
+    import numpy as np
+    assert D % 4 == 0
+    rows, grp = np.meshgrid(np.arange(M, dtype=np.uint32), np.arange(D // 4, dtype=np.uint32), indexing="ij")
+    ctr = np.stack([grp, rows, np.full_like(rows, site), np.full_like(rows, step & 0xFFFFFFFF)], axis=-1)
+    w = philox4x32_10(ctr, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)).reshape(M, D)
+    return torch.from_numpy(w >= np.uint32(dropout_threshold(p)))
+
+
+def attn_keep_mask(seed: int, step: int, site: int, B: int, H: int, S: int, p: float) -> Tensor:
+    """bool [B, H, S, S]: (b, h, q, k) is word (k & 3) of philox(key = seed, counter = {k >> 2, (b H + h) S + q, site, step})."""
+    import numpy as np
+    ng = (S + 3) // 4
+    rows, grp = np.meshgrid(np.arange(B * H * S, dtype=np.uint32), np.arange(ng, dtype=np.uint32), indexing="ij")
+    ctr = np.stack([grp, rows, np.full_like(rows, site), np.full_like(rows, step & 0xFFFFFFFF)], axis=-1)
+    w = philox4x32_10(ctr, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)).reshape(B * H * S, ng * 4)[:, :S]
+    return torch.from_numpy(w >= np.uint32(dropout_threshold(p))).reshape(B, H, S, S)
+
+
+class PhiloxDropout:
+    """The product's dropout stream for one forward: ``hidden(site, x)`` / ``attn(site, probs)`` return the dropped tensor."""
+
+    def __init__(self, seed: int, step: int, p_hidden: float = 0.1, p_attn: float = 0.1):
+        self.seed, self.step, self.p_hidden, self.p_attn = seed, step, p_hidden, p_attn
+
+    def hidden(self, site: int, x: Tensor) -> Tensor:
+        if self.p_hidden <= 0:
+            return x
+        keep = hidden_keep_mask(self.seed, self.step, site, x.numel() // x.shape[-1], x.shape[-1], self.p_hidden)
+        return x * keep.reshape(x.shape).to(x.dtype) * (1.0 / (1.0 - self.p_hidden))
+
+    def attn(self, site: int, a: Tensor) -> Tensor:
+        if self.p_attn <= 0:
+            return a
+        B, H, S, _ = a.shape
+        return a * attn_keep_mask(self.seed, self.step, site, B, H, S, self.p_attn).to(a.dtype) * (1.0 / (1.0 - self.p_attn))
+
+
+class TorchDropout:
+    """``F.dropout`` from torch's global generator — the CPU baseline's stand-in when only the WORK matters (bench.py)."""
+
+    def __init__(self, p_hidden: float = 0.1, p_attn: float = 0.1):
+        self.p_hidden, self.p_attn = p_hidden, p_attn
+
+    def hidden(self, site: int, x: Tensor) -> Tensor:
+        return F.dropout(x, self.p_hidden, True)
+
+    def attn(self, site: int, a: Tensor) -> Tensor:
+        return F.dropout(a, self.p_attn, True)
+
+
 def bert_forward(sd: Dict[str, Tensor], input_ids: Tensor, attention_mask: Tensor,
-                 heads: int = 12, prefix: str = "", depth: int = 12, eps: float = 1e-12) -> Tensor:
-    """BERT encoder ``last_hidden_state`` (dropout p = 0), HF state-dict names.
+                 heads: int = 12, prefix: str = "", depth: int = 12, eps: float = 1e-12, dropout=None) -> Tensor:
+    """BERT encoder ``last_hidden_state``, HF state-dict names.  ``dropout`` = None (eval mode / p = 0) or an object with
+    ``hidden(site, x)`` / ``attn(site, probs)`` (train mode, sites as listed above).
 
     Call site: ``simseg/models/pipelines/clip.py:220-223`` through
     ``huggingface_builder.py:16-17``; internals per SURVEY.md appendix B.2.
     """
+    dh = (lambda site, x: x) if dropout is None else dropout.hidden
+    da = (lambda site, x: x) if dropout is None else dropout.attn
     p = lambda k: sd[prefix + k]
     B, T = input_ids.shape
     e = (p("embeddings.word_embeddings.weight")[input_ids]
          + p("embeddings.token_type_embeddings.weight")[0]
          + p("embeddings.position_embeddings.weight")[:T])
-    h = layer_norm(e, p("embeddings.LayerNorm.weight"), p("embeddings.LayerNorm.bias"), eps)
+    h = dh(0, layer_norm(e, p("embeddings.LayerNorm.weight"), p("embeddings.LayerNorm.bias"), eps))
     D = h.shape[-1]
     hd = D // heads
     bias = (1.0 - attention_mask.to(h.dtype))[:, None, None, :] * torch.finfo(h.dtype).min
@@ -110,12 +203,12 @@ def bert_forward(sd: Dict[str, Tensor], input_ids: Tensor, attention_mask: Tenso
         lin = lambda t, name: t @ p(l + name + ".weight").T + p(l + name + ".bias")
         sh = lambda t: t.reshape(B, T, heads, hd).transpose(1, 2)
         q, k, v = sh(lin(h, "attention.self.query")), sh(lin(h, "attention.self.key")), sh(lin(h, "attention.self.value"))
-        a = torch.softmax(q @ k.transpose(-2, -1) / math.sqrt(hd) + bias, dim=-1)
+        a = da(1 + 3 * i, torch.softmax(q @ k.transpose(-2, -1) / math.sqrt(hd) + bias, dim=-1))
         c = (a @ v).transpose(1, 2).reshape(B, T, D)
-        h = layer_norm(lin(c, "attention.output.dense") + h,
+        h = layer_norm(dh(2 + 3 * i, lin(c, "attention.output.dense")) + h,
                        p(l + "attention.output.LayerNorm.weight"), p(l + "attention.output.LayerNorm.bias"), eps)
         f = gelu_erf(lin(h, "intermediate.dense"))
-        h = layer_norm(lin(f, "output.dense") + h,
+        h = layer_norm(dh(3 + 3 * i, lin(f, "output.dense")) + h,
                        p(l + "output.LayerNorm.weight"), p(l + "output.LayerNorm.bias"), eps)
     return h
 
@@ -308,19 +401,19 @@ TXT_PREFIX = "text_encoder.model.model."
 
 
 def clip_embeddings(sd: Dict[str, Tensor], batch: Dict[str, Tensor], vit_heads: int,
-                    image_k: int = 5, text_k: int = 1) -> Tuple[Tensor, Tensor]:
-    """``CLIPModel.forward(batch, embeddings='all')`` — ``clip.py:152-168``."""
+                    image_k: int = 5, text_k: int = 1, dropout=None) -> Tuple[Tensor, Tensor]:
+    """``CLIPModel.forward(batch, embeddings='all')`` — ``clip.py:152-168``.  ``dropout``: BERT train mode (``bert_forward``)."""
     it = vit_forward(sd, batch["image"], vit_heads, IMG_PREFIX)
-    tt = bert_forward(sd, batch["input_ids"], batch["attention_mask"], 12, TXT_PREFIX)
+    tt = bert_forward(sd, batch["input_ids"], batch["attention_mask"], 12, TXT_PREFIX, dropout=dropout)
     img = image_embed(it, sd["image_projection.linear.weight"], image_k)
     txt = text_embed(tt, sd["text_projection.linear.weight"], batch["attention_mask"], text_k)
     return img, txt
 
 
 def clip_train_forward(sd: Dict[str, Tensor], batch: Dict[str, Tensor], vit_heads: int,
-                       image_k: int = 5, text_k: int = 1):
+                       image_k: int = 5, text_k: int = 1, dropout=None):
     """``CLIPModel.forward(batch)`` at world size 1 — ``clip.py:152-176``."""
-    img, txt = clip_embeddings(sd, batch, vit_heads, image_k, text_k)
+    img, txt = clip_embeddings(sd, batch, vit_heads, image_k, text_k, dropout)
     return clip_loss(img, txt, img, txt, sd["loss.temperature"], 0)
 
 

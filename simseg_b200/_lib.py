@@ -19,7 +19,7 @@ F32, BF16 = 0, 1
 EPI_NONE, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU, EPI_ROWSCALE = range(5)
 PREC_FP32, PREC_TF32, PREC_SPLIT_BF16 = 0, 1, 2     # PREC_SPLIT_BF16: host-side selector of the fused tcgen05 entry points
 
-vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+vp, i32, i64, f32, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint32
 
 
 class GemmArgs(C.Structure):
@@ -48,6 +48,12 @@ PROTOTYPES = {
     "simseg_layernorm_bwd": (i32, [vp, vp, i32, vp, vp, i32, vp, vp, vp, i64, i32, vp, i32, vp, vp, vp, vp, vp]),
     "simseg_attention_fwd": (i32, [vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp, f32, vp, vp, vp]),
     "simseg_attention_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp, f32, vp, vp, vp, vp]),
+    "simseg_layernorm_fwd_dropout": (i32, [vp, vp, vp, vp, vp, f32, i64, i32, vp, vp, vp, vp, vp, f32, vp, u32, vp]),
+    "simseg_layernorm_bwd_dropout": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, i64, i32, vp, i32, vp, vp, vp, vp, i32, f32, vp, u32, vp]),
+    "simseg_attn_dropout_mask_words": (i64, [i32, i32, i32]),
+    "simseg_attn_dropout_mask": (i32, [vp, i32, i32, i32, f32, vp, u32, vp, i64, vp]),
+    "simseg_attention_fwd_dropout": (i32, [vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp, f32, vp, vp, vp, f32, vp]),
+    "simseg_attention_bwd_dropout": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp, f32, vp, vp, vp, vp, f32, vp]),
     "simseg_im2col16": (i32, [vp, vp, i32, i32, i32, vp, vp]),
     "simseg_vit_tokens_fwd": (i32, [vp, vp, i32, vp, vp, i32, i32, i32, vp, vp]),
     "simseg_vit_tokens_bwd": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp]),

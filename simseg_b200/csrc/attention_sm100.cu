@@ -19,6 +19,7 @@
 // nothing is ever re-read from HBM and S x S never exists outside TMEM/smem.
 #include "common.cuh"
 #include "sm100.cuh"
+#include "philox.cuh"
 
 #include <cstdlib>
 
@@ -48,6 +49,9 @@ struct AttnBwdParams {
   __nv_bfloat16 *dq, *dk, *dv;      // strides as q/k/v
   int64_t sb, ss, sh;
   int32_t dbg;                      // timing knock-outs (SIMSEG_ATTN_DBG, results wrong): see tools/attn_knockout.py
+  const uint32_t* drop_mask;        // dropout keep bits, layout as in AttnFwdParams (kDrop instantiations only)
+  int32_t mask_nw;
+  float inv_keep;
 };
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1,
@@ -105,7 +109,10 @@ struct Tracer {                                              // compiled out: no
 };
 #endif
 
-template <bool kLateDrain>
+// kDrop (dropout on the probabilities, BERT under model.train()): with keep bits m and c = 1 / (1 - p) the forward was
+// O = c (m o P) V, so dV = c (m o P)^T dO (m o P goes to smem, c is applied in the dV drain), dP = c m o (dO V^T) and
+// dS = P o (dP - D) with D = rowsum(dO o O) unchanged — P itself stays unmasked in registers between the two phases.
+template <bool kLateDrain, bool kDrop>
 __global__ void __launch_bounds__(kAbThreads, 1)
 attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                         const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
@@ -379,7 +386,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(dkv_free);
-        const float sc = is_dk ? p.scale : 1.0f;
+        const float sc = is_dk ? p.scale : (kDrop ? p.inv_keep : 1.0f);
         uint32_t w[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) w[j] = pack_bf16(__uint_as_float(a[2 * j]) * sc, __uint_as_float(a[2 * j + 1]) * sc);
@@ -428,6 +435,9 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           const int qslot = (p.nqt == 1) ? static_cast<int>(it & 1) : qt;     // Q / dO slot (single-tile items alternate slots)
           const uint32_t quse = (p.nqt == 1) ? (it >> 1) : it;
           // ---- phase A: S -> P (kept as packed bf16 in registers for phase B), P into smem
+          uint32_t keep = 0xffffffffu;                                 // requested before the wait below, used after it
+          if (kDrop && chunk_live && rows_live)
+            keep = __ldg(p.drop_mask + (static_cast<int64_t>(item) * p.rows + min(qrow, p.rows - 1)) * p.mask_nw + kt * 4 + cq);
           tr(10);
           mbar_wait(s_full, g & 1);                                    // implies the Q / dO tiles of this qt have landed
           tr(11);
@@ -476,10 +486,20 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           const uint32_t rowoff = (col0 >> 6) * kTileBytes + r * 128;
           const int ch0 = (col0 & 63) >> 3;
           if (chunk_live && rows_live && !(p.dbg & 4)) {
+            if (kDrop) {
+              auto pm = [&](int i) {                                   // pair i = keys 2 i, 2 i + 1 of the chunk
+                return pp[i] & (((0u - ((keep >> (2 * i)) & 1u)) & 0xffffu) | ((0u - ((keep >> (2 * i + 1)) & 1u)) & 0xffff0000u));
+              };
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4)
-              *reinterpret_cast<uint4*>(sP + rowoff + (((ch0 + q4) ^ sw) << 4)) =
-                  make_uint4(pp[4 * q4], pp[4 * q4 + 1], pp[4 * q4 + 2], pp[4 * q4 + 3]);
+              for (int q4 = 0; q4 < 4; ++q4)
+                *reinterpret_cast<uint4*>(sP + rowoff + (((ch0 + q4) ^ sw) << 4)) =
+                    make_uint4(pm(4 * q4), pm(4 * q4 + 1), pm(4 * q4 + 2), pm(4 * q4 + 3));
+            } else {
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4)
+                *reinterpret_cast<uint4*>(sP + rowoff + (((ch0 + q4) ^ sw) << 4)) =
+                    make_uint4(pp[4 * q4], pp[4 * q4 + 1], pp[4 * q4 + 2], pp[4 * q4 + 3]);
+            }
           }
           tc_fence_before();
           fence_proxy_async_smem();
@@ -509,8 +529,14 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             for (int j = 0; j < 32; j += 2) {
               const uint32_t pk = pp[j >> 1];                          // masked entries are exactly 0 -> dS = 0
               float d0, d1;
-              f2_unpack(f2_mul(f2_pack(bf16_lo(pk), bf16_hi(pk)),
-                               f2_add(f2_pack(__uint_as_float(dr[j]), __uint_as_float(dr[j + 1])), nd2)), d0, d1);
+              if (kDrop) {
+                const f32x2 mk = f2_pack((keep >> j) & 1u ? p.inv_keep : 0.f, (keep >> (j + 1)) & 1u ? p.inv_keep : 0.f);
+                f2_unpack(f2_mul(f2_pack(bf16_lo(pk), bf16_hi(pk)),
+                                 f2_fma(f2_pack(__uint_as_float(dr[j]), __uint_as_float(dr[j + 1])), mk, nd2)), d0, d1);
+              } else {
+                f2_unpack(f2_mul(f2_pack(bf16_lo(pk), bf16_hi(pk)),
+                                 f2_add(f2_pack(__uint_as_float(dr[j]), __uint_as_float(dr[j + 1])), nd2)), d0, d1);
+              }
               dd[j >> 1] = pack_bf16(d0, d1);
             }
             if (!(p.dbg & 4))
@@ -656,6 +682,12 @@ struct AttnFwdParams {
   const int32_t* key_len;
   float* lse;                 // [B,H,S]
   __nv_bfloat16* out;         // [B,S,H*64]
+  // dropout on the probabilities (HF BertSelfAttention under model.train()): keep bits of tile row r = token * G + head,
+  // 32 tile columns per word — mask[(item * rows + r) * mask_nw + chunk], written by attn_dropout_mask_kernel; kept P are
+  // scaled by inv_keep = 1 / (1 - p) (folded into the output normalisation)
+  const uint32_t* drop_mask;
+  int32_t mask_nw;
+  float inv_keep;
 };
 
 __global__ void __launch_bounds__(kAfThreads, 1)
@@ -991,6 +1023,9 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 // alternate units completely independently; only the MUFU rate couples them.
 //   warp 0      TMA (as above)          warp 1   MMA issue: QK^T of unit u+1, then P V of unit u
 //   warps 2-5   softmax + output of even units      warps 6-9   the same for odd units
+// kDrop: the probabilities are dropped (keep bits from p.drop_mask) AFTER the row sum — softmax, then dropout, as
+// BertSelfAttention does; log-sum-exp stays that of the undropped softmax.
+template <bool kDrop>
 __global__ void __launch_bounds__(kAfThreads, 1)
 attention_fwd_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                         const __grid_constant__ CUtensorMap tm_v, const AttnFwdParams p) {
@@ -1138,6 +1173,8 @@ attention_fwd_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         mbar_wait(&s_full[g], (u >> 1) & 1);
         tc_fence_after();
         float m = -INFINITY, sum = 0.f;
+        const uint32_t* mrow = nullptr;
+        if (kDrop) mrow = p.drop_mask + (static_cast<int64_t>(item) * p.rows + (q_ok ? qrow : 0)) * p.mask_nw;
         if (warp_live) {
           // ---- pass 1: row max
           for (int c = 0; c < nch; ++c) {
@@ -1166,6 +1203,8 @@ attention_fwd_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             uint32_t pp[16];
             if (c < nch) {
               uint32_t x[32];
+              uint32_t keep = 0xffffffffu;
+              if (kDrop) keep = __ldg(mrow + c);
               tmem_ld_32x32(tS + c * 32, x);
               tmem_ld_wait();
               if (dense && c * 32 + 32 <= klen) {
@@ -1177,8 +1216,13 @@ attention_fwd_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                   const float p2 = ex2_approx(fmaf(__uint_as_float(x[j + 2]), p.scale_log2e, -ms));
                   const float p3 = ex2_approx(fmaf(__uint_as_float(x[j + 3]), p.scale_log2e, -ms));
                   s0 += p0; s1 += p1; s2 += p2; s3 += p3;
-                  pp[j >> 1] = pack_bf16(p0, p1);
-                  pp[(j >> 1) + 1] = pack_bf16(p2, p3);
+                  if (kDrop) {
+                    pp[j >> 1] = pack_bf16((keep >> j) & 1u ? p0 : 0.f, (keep >> (j + 1)) & 1u ? p1 : 0.f);
+                    pp[(j >> 1) + 1] = pack_bf16((keep >> (j + 2)) & 1u ? p2 : 0.f, (keep >> (j + 3)) & 1u ? p3 : 0.f);
+                  } else {
+                    pp[j >> 1] = pack_bf16(p0, p1);
+                    pp[(j >> 1) + 1] = pack_bf16(p2, p3);
+                  }
                 }
                 sum += (s0 + s1) + (s2 + s3);
               } else {
@@ -1189,6 +1233,10 @@ attention_fwd_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                   p0 = (c * 32 + j < klen && ((c * 32 + j) & gm) == rg) ? p0 : 0.f;
                   p1 = (c * 32 + j + 1 < klen && ((c * 32 + j + 1) & gm) == rg) ? p1 : 0.f;
                   sum += p0 + p1;
+                  if (kDrop) {
+                    p0 = (keep >> j) & 1u ? p0 : 0.f;
+                    p1 = (keep >> (j + 1)) & 1u ? p1 : 0.f;
+                  }
                   pp[j >> 1] = pack_bf16(p0, p1);
                 }
               }
@@ -1219,7 +1267,7 @@ attention_fwd_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             // a thread owns a query ROW: stored straight from registers, every instruction would touch 32 different lines
             // (16 bytes each).  The warp's 32 rows x 128 bytes go through a swizzled 4 KB block and leave as 4 full
             // 128-byte rows per instruction.
-            const float inv = q_ok ? 1.0f / sum : 0.f;
+            const float inv = q_ok ? (kDrop ? p.inv_keep / sum : 1.0f / sum) : 0.f;
             uint8_t* mine = stg + lane * 128;
             const int swz = lane & 7;
 #pragma unroll
@@ -1329,10 +1377,65 @@ static int pack_factor(int H, int S) {
   return G;
 }
 
+// ---- dropout keep bits for the probabilities, in the tile coordinates the two kernels above walk ---------------------------------
+// Logical definition (oracle/simseg_oracle.py:attn_keep_mask): keep(b, h, q, k) = word (k & 3) of
+// philox4x32_10(key = seed, counter = {k >> 2, (b H + h) S + q, site, step}) >= thr.  One thread per tile row r = q * G + head
+// writes that row's ceil(rows / 32) words: bit j of word w = tile column 32 w + j = key token (32 w + j) >> lg of the head
+// (32 w + j) & (G - 1); bits of other heads' columns and of columns >= rows are never read and stay 0.
+__global__ void __launch_bounds__(256) attn_dropout_mask_kernel(uint32_t* __restrict__ mask, int B, int H, int S, int G, int lg,
+                                                                const DropSpec ds) {
+  const int rows = S * G, nw = (rows + 31) >> 5, HG = H / G;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<int64_t>(B) * HG * rows) return;
+  const int r = static_cast<int>(t % rows);
+  const int item = static_cast<int>(t / rows);
+  const int b = item / HG, h = (item - b * HG) * G + (r & (G - 1)), q = r >> lg;
+  const DropKey dk = load_drop_key(ds);
+  const uint32_t row = static_cast<uint32_t>((b * H + h) * S + q);
+  uint32_t* out = mask + t * nw;
+  const int kpw = 32 >> lg;                                   // key tokens per word
+  for (int w = 0; w < nw; ++w) {
+    uint32_t bits = 0;
+    for (int k0 = w * kpw; k0 < (w + 1) * kpw && k0 < S; k0 += 4) {       // kpw is 32, 16, 8 or 4: groups of four stay aligned
+      const uint4 x = drop_words(ds, dk, static_cast<uint32_t>(k0 >> 2), row);
+      const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = k0 + i;
+        if (k < S && xs[i] >= ds.thr) bits |= 1u << ((k * G + (r & (G - 1))) & 31);
+      }
+    }
+    out[w] = bits;
+  }
+}
+
+int64_t attn_dropout_mask_words_impl(int B, int H, int S) {
+  if (B < 1 || H < 1 || S < 1 || S > 256) return 0;
+  const int G = pack_factor(H, S);
+  const int rows = S * G;
+  return static_cast<int64_t>(B) * (H / G) * rows * ((rows + 31) / 32);
+}
+
+int attn_dropout_mask_impl(Ctx* ctx, int B, int H, int S, float drop_p, const void* rng, uint32_t site, uint32_t* mask,
+                           int64_t mask_words, cudaStream_t st) {
+  const int64_t need = attn_dropout_mask_words_impl(B, H, S);
+  SIMSEG_CHECK_ARG(need > 0 && mask_words >= need, "attn_dropout_mask: B=%d H=%d S=%d needs %lld words (S <= 256), buffer has %lld", B, H, S,
+                   static_cast<long long>(need), static_cast<long long>(mask_words));
+  SIMSEG_CHECK_ARG(static_cast<int64_t>(B) * H * S < (int64_t(1) << 32), "attn_dropout_mask: B*H*S exceeds the 32-bit row counter");
+  const int G = pack_factor(H, S);
+  const int lg = G == 1 ? 0 : (G == 2 ? 1 : (G == 4 ? 2 : 3));
+  const int64_t threads = static_cast<int64_t>(B) * (H / G) * S * G;
+  attn_dropout_mask_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(mask, B, H, S, G, lg,
+                                                                                        make_drop_spec(drop_p, rng, site));
+  ctx->launches++;
+  SIMSEG_LAUNCH_CHECK();
+  return SIMSEG_OK;
+}
+
 // SIMSEG_ERR_UNSUPPORTED => caller uses the mma.sync kernel (S > 256, unaligned pointers, H == 1 with odd strides ...)
 int attention_bwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v, const void* out, const void* dout,
                           const float* lse, int64_t sb, int64_t ss, int64_t sh, int B, int H, int S, const int32_t* key_len,
-                          float scale, void* dq, void* dk, void* dv, cudaStream_t st) {
+                          float scale, void* dq, void* dk, void* dv, const uint32_t* drop_mask, float drop_p, cudaStream_t st) {
   if (S > 256 || S < 1) return SIMSEG_ERR_UNSUPPORTED;
   const uintptr_t al = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
                        reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dq) |
@@ -1362,17 +1465,23 @@ int attention_bwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v,
   p.dq = reinterpret_cast<__nv_bfloat16*>(dq); p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dv = reinterpret_cast<__nv_bfloat16*>(dv);
   p.sb = sb; p.ss = ss; p.sh = sh;
   { const char* d = getenv("SIMSEG_ATTN_DBG"); p.dbg = d ? atoi(d) : 0; }
+  p.drop_mask = drop_mask; p.mask_nw = (p.rows + 31) / 32; p.inv_keep = drop_mask ? 1.0f / (1.0f - drop_p) : 1.0f;
   // alignment slack (768: the kernel traps if the base needs more) + tiles + P / dS + barriers + per-warp drain staging + {D, lse} rows
   const int smem_bytes = 768 + 8 * kTileBytes + 2 * kPBytes + 256 + kAbEwWarps * 2048 + 2 * kTile * 8;
   static bool attr_set = false;
   if (!attr_set) {
-    SIMSEG_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    SIMSEG_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    SIMSEG_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    SIMSEG_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    SIMSEG_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    SIMSEG_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
   }
   const int grid = p.items < ctx->num_sms ? p.items : ctx->num_sms;
-  if (p.nqt > 1) attention_bwd_tc_kernel<true><<<grid, kAbThreads, smem_bytes, st>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
-  else attention_bwd_tc_kernel<false><<<grid, kAbThreads, smem_bytes, st>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
+  if (drop_mask) {
+    if (p.nqt > 1) attention_bwd_tc_kernel<true, true><<<grid, kAbThreads, smem_bytes, st>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
+    else attention_bwd_tc_kernel<false, true><<<grid, kAbThreads, smem_bytes, st>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
+  } else if (p.nqt > 1) attention_bwd_tc_kernel<true, false><<<grid, kAbThreads, smem_bytes, st>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
+  else attention_bwd_tc_kernel<false, false><<<grid, kAbThreads, smem_bytes, st>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
   ctx->launches++;
   SIMSEG_LAUNCH_CHECK();
   return SIMSEG_OK;
@@ -1383,10 +1492,11 @@ int attention_bwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v,
 // images = 325 tokens, configs/clip/simseg.vit-s.yaml:70-77): the shared-memory-P variant with ONE S accumulator (up to 384
 // columns + 64 for O), all keys of a sequence in smem (3 K + 3 V tiles, single stage) and two MMAs per S = Q K^T (N <= 256 each).
 int attention_fwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v, int64_t sb, int64_t ss, int64_t sh, int B, int H,
-                          int S, const int32_t* key_len, float scale, void* out, float* lse, cudaStream_t st) {
+                          int S, const int32_t* key_len, float scale, void* out, float* lse, const uint32_t* drop_mask, float drop_p,
+                          cudaStream_t st) {
   if (S > 384 || S < 1) return SIMSEG_ERR_UNSUPPORTED;
   const int G = pack_factor(H, S);
-  if (G == 1 && S < 48 && getenv("SIMSEG_ATTN_FWD") == nullptr) return SIMSEG_ERR_UNSUPPORTED;   // mostly padding: mma.sync kernel
+  if (G == 1 && S < 48 && getenv("SIMSEG_ATTN_FWD") == nullptr && !drop_mask) return SIMSEG_ERR_UNSUPPORTED;   // mostly padding: mma.sync kernel
   const uintptr_t al = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
                        reinterpret_cast<uintptr_t>(out);
   if ((al & 15) || sb % 8 || ss % 8 || sh % 8) return SIMSEG_ERR_UNSUPPORTED;
@@ -1411,18 +1521,22 @@ int attention_fwd_tc_impl(Ctx* ctx, const void* q, const void* k, const void* v,
   p.p_atoms = (p.nkc + 63) / 64 < 4 ? 4 : (p.nkc + 63) / 64;
   p.scale_log2e = scale * 1.44269504088896341f;
   p.key_len = key_len; p.lse = lse; p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.drop_mask = drop_mask; p.mask_nw = (p.rows + 31) / 32; p.inv_keep = drop_mask ? 1.0f / (1.0f - drop_p) : 1.0f;
+  if (drop_mask && p.nbuf != 2) return SIMSEG_ERR_UNSUPPORTED;             // dropout lives in the "ts" variant only (S <= 224)
   // default: the "ts" variant (P stays in tensor memory; measured 0.895 vs 0.974 ms on 4096 x 6 x 197 and 0.174 vs 0.214 ms on
   // the packed 4096 x 12 x 25 case); SIMSEG_ATTN_FWD=tc selects the shared-memory-P variant below
   const char* var = getenv("SIMSEG_ATTN_FWD");
-  if (p.nbuf == 2 && !(var != nullptr && var[0] == 't' && var[1] == 'c')) {
+  if (p.nbuf == 2 && (drop_mask || !(var != nullptr && var[0] == 't' && var[1] == 'c'))) {
     const int smem_ts = 1024 + 10 * kTileBytes + 256 + 8 * 4096;                  // + per-warp output staging
     static bool ts_set = false;
     if (!ts_set) {
-      SIMSEG_CUDA(cudaFuncSetAttribute(attention_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ts));
+      SIMSEG_CUDA(cudaFuncSetAttribute(attention_fwd_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ts));
+      SIMSEG_CUDA(cudaFuncSetAttribute(attention_fwd_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ts));
       ts_set = true;
     }
     const int grid_ts = p.items < ctx->num_sms ? p.items : ctx->num_sms;
-    attention_fwd_ts_kernel<<<grid_ts, kAfThreads, smem_ts, st>>>(tq, tk, tv, p);
+    if (drop_mask) attention_fwd_ts_kernel<true><<<grid_ts, kAfThreads, smem_ts, st>>>(tq, tk, tv, p);
+    else attention_fwd_ts_kernel<false><<<grid_ts, kAfThreads, smem_ts, st>>>(tq, tk, tv, p);
     ctx->launches++;
     SIMSEG_LAUNCH_CHECK();
     return SIMSEG_OK;

@@ -20,8 +20,8 @@ int cast_bf16_impl(Ctx*, const float*, void*, void*, int64_t, int64_t, cudaStrea
 int cast_bf16_multi_impl(Ctx*, const simseg_cast_item*, int, int64_t, cudaStream_t);
 int colsum_impl(Ctx*, const void*, int, int64_t, int64_t, int64_t, float*, int, cudaStream_t);
 int gelu_fwd_impl(Ctx*, const void*, void*, int64_t, cudaStream_t);
-int layernorm_fwd_impl(Ctx*, const void*, int, const float*, const float*, float, int64_t, int, void*, float*, float*, float*, const void*, float*, cudaStream_t);
-int layernorm_bwd_impl(Ctx*, const void*, int, const float*, const void*, int, const float*, const float*, const float*, int64_t, int, float*, int, void*, float*, float*, float*, cudaStream_t);
+int layernorm_fwd_impl(Ctx*, const void*, int, const float*, const float*, float, int64_t, int, void*, float*, float*, float*, const void*, float*, float, const void*, uint32_t, cudaStream_t);
+int layernorm_bwd_impl(Ctx*, const void*, int, const float*, const void*, int, const float*, const float*, const float*, int64_t, int, float*, int, void*, float*, float*, float*, int, float, const void*, uint32_t, cudaStream_t);
 int attention_fwd_impl(Ctx*, const void*, const void*, const void*, int64_t, int64_t, int64_t, int, int, int, const int32_t*, float, void*, float*, cudaStream_t);
 int attention_bwd_impl(Ctx*, const void*, const void*, const void*, const void*, const void*, const float*, int64_t, int64_t, int64_t, int, int, int, const int32_t*, float, void*, void*, void*, cudaStream_t);
 int im2col16_impl(Ctx*, const float*, int, int, int, void*, cudaStream_t);
@@ -39,8 +39,10 @@ int nce_rows_bwd_impl(Ctx*, float*, int, int, int64_t, const float*, int, const 
 int row_inv_norm_impl(Ctx*, const void*, int, int64_t, int, float*, cudaStream_t);
 int row_argmax_impl(Ctx*, const float*, int64_t, int, int32_t*, cudaStream_t);
 int retrieval_rank_impl(Ctx*, const float*, int, int, const int64_t*, const int64_t*, int32_t*, cudaStream_t);
-int attention_bwd_tc_impl(Ctx*, const void*, const void*, const void*, const void*, const void*, const float*, int64_t, int64_t, int64_t, int, int, int, const int32_t*, float, void*, void*, void*, cudaStream_t);
-int attention_fwd_tc_impl(Ctx*, const void*, const void*, const void*, int64_t, int64_t, int64_t, int, int, int, const int32_t*, float, void*, float*, cudaStream_t);
+int attention_bwd_tc_impl(Ctx*, const void*, const void*, const void*, const void*, const void*, const float*, int64_t, int64_t, int64_t, int, int, int, const int32_t*, float, void*, void*, void*, const uint32_t*, float, cudaStream_t);
+int attention_fwd_tc_impl(Ctx*, const void*, const void*, const void*, int64_t, int64_t, int64_t, int, int, int, const int32_t*, float, void*, float*, const uint32_t*, float, cudaStream_t);
+int64_t attn_dropout_mask_words_impl(int, int, int);
+int attn_dropout_mask_impl(Ctx*, int, int, int, float, const void*, uint32_t, uint32_t*, int64_t, cudaStream_t);
 int seg_class_embed_impl(Ctx*, const float*, int, int, int, float*, cudaStream_t);
 int seg_select_impl(Ctx*, const float*, const float*, int, int, int, int, int, float*, int32_t*, float*, cudaStream_t);
 int seg_upsample_norm_impl(Ctx*, const float*, const int32_t*, int, int, int, int, int, int, int, float*, cudaStream_t);
@@ -133,21 +135,39 @@ int simseg_gelu_fwd(simseg_ctx* ctx, const void* h, void* a, int64_t n, void* st
 int simseg_layernorm_fwd(simseg_ctx* ctx, const void* x, int x_dtype, const float* gamma, const float* beta, float eps,
                          int64_t M, int D, void* y_bf16, float* y_f32, float* mean, float* rstd, void* stream) {
   CTX_OR_FAIL();
-  return layernorm_fwd_impl(c, x, x_dtype, gamma, beta, eps, M, D, y_bf16, y_f32, mean, rstd, nullptr, nullptr, st);
+  return layernorm_fwd_impl(c, x, x_dtype, gamma, beta, eps, M, D, y_bf16, y_f32, mean, rstd, nullptr, nullptr, 0.f, nullptr, 0u, st);
 }
 int simseg_add_layernorm_fwd(simseg_ctx* ctx, const float* x, const void* add_bf16, const float* gamma, const float* beta,
                              float eps, int64_t M, int D, float* sum_out, void* y_bf16, float* y_f32, float* mean, float* rstd,
                              void* stream) {
   CTX_OR_FAIL();
   SIMSEG_CHECK_ARG(x != nullptr && add_bf16 != nullptr, "add_layernorm_fwd: x and add are required");
-  return layernorm_fwd_impl(c, x, SIMSEG_F32, gamma, beta, eps, M, D, y_bf16, y_f32, mean, rstd, add_bf16, sum_out, st);
+  return layernorm_fwd_impl(c, x, SIMSEG_F32, gamma, beta, eps, M, D, y_bf16, y_f32, mean, rstd, add_bf16, sum_out, 0.f, nullptr, 0u, st);
+}
+int simseg_layernorm_fwd_dropout(simseg_ctx* ctx, const float* x, const void* add_bf16, const float* gamma, const float* beta,
+                                 float eps, int64_t M, int D, float* sum_out, void* y_bf16, float* y_f32, float* mean,
+                                 float* rstd, float drop_p, const uint64_t* drop_rng, uint32_t drop_site, void* stream) {
+  CTX_OR_FAIL();
+  SIMSEG_CHECK_ARG(x != nullptr, "layernorm_fwd_dropout: x is required");
+  SIMSEG_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "layernorm_fwd_dropout: p=%g outside [0,1)", drop_p);
+  return layernorm_fwd_impl(c, x, SIMSEG_F32, gamma, beta, eps, M, D, y_bf16, y_f32, mean, rstd, add_bf16, sum_out, drop_p,
+                            drop_rng, drop_site, st);
 }
 int simseg_layernorm_bwd(simseg_ctx* ctx, const void* dy, int dy_dtype, const float* dy2, const void* x, int x_dtype,
                          const float* gamma, const float* mean, const float* rstd, int64_t M, int D, float* dx,
                          int dx_accumulate, void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, void* stream) {
   CTX_OR_FAIL();
   return layernorm_bwd_impl(c, dy, dy_dtype, dy2, x, x_dtype, gamma, mean, rstd, M, D, dx, dx_accumulate, dx_bf16, dgamma,
-                            dbeta, dx_colsum, st);
+                            dbeta, dx_colsum, 0, 0.f, nullptr, 0u, st);
+}
+int simseg_layernorm_bwd_dropout(simseg_ctx* ctx, const void* dy, int dy_dtype, const float* dy2, const float* x,
+                                 const float* gamma, const float* mean, const float* rstd, int64_t M, int D, float* dx,
+                                 int dx_accumulate, void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, int drop_mode,
+                                 float drop_p, const uint64_t* drop_rng, uint32_t drop_site, void* stream) {
+  CTX_OR_FAIL();
+  SIMSEG_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "layernorm_bwd_dropout: p=%g outside [0,1)", drop_p);
+  return layernorm_bwd_impl(c, dy, dy_dtype, dy2, x, SIMSEG_F32, gamma, mean, rstd, M, D, dx, dx_accumulate, dx_bf16, dgamma,
+                            dbeta, dx_colsum, drop_mode, drop_p, drop_rng, drop_site, st);
 }
 int simseg_attention_fwd(simseg_ctx* ctx, const void* q, const void* k, const void* v, int64_t stride_b, int64_t stride_s,
                          int64_t stride_h, int B, int H, int S, const int32_t* key_len, float scale, void* out, float* lse,
@@ -158,7 +178,7 @@ int simseg_attention_fwd(simseg_ctx* ctx, const void* q, const void* k, const vo
   const char* force = getenv("SIMSEG_ATTN_FWD");
   const bool want_tc = force ? (force[0] == 't') : true;       // short sequences are packed several heads per tile
   if (want_tc) {
-    const int rc = attention_fwd_tc_impl(c, q, k, v, stride_b, stride_s, stride_h, B, H, S, key_len, scale, out, lse, st);
+    const int rc = attention_fwd_tc_impl(c, q, k, v, stride_b, stride_s, stride_h, B, H, S, key_len, scale, out, lse, nullptr, 0.f, st);
     if (rc != SIMSEG_ERR_UNSUPPORTED) return rc;
   }
   return attention_fwd_impl(c, q, k, v, stride_b, stride_s, stride_h, B, H, S, key_len, scale, out, lse, st);
@@ -172,10 +192,39 @@ int simseg_attention_bwd(simseg_ctx* ctx, const void* q, const void* k, const vo
   const char* force = getenv("SIMSEG_ATTN_BWD");
   const bool want_tc = force ? (force[0] == 't') : true;       // short sequences are packed several heads per tile
   if (want_tc) {
-    const int rc = attention_bwd_tc_impl(c, q, k, v, out, dout, lse, stride_b, stride_s, stride_h, B, H, S, key_len, scale, dq, dk, dv, st);
+    const int rc = attention_bwd_tc_impl(c, q, k, v, out, dout, lse, stride_b, stride_s, stride_h, B, H, S, key_len, scale, dq, dk, dv, nullptr, 0.f, st);
     if (rc != SIMSEG_ERR_UNSUPPORTED) return rc;
   }
   return attention_bwd_impl(c, q, k, v, out, dout, lse, stride_b, stride_s, stride_h, B, H, S, key_len, scale, dq, dk, dv, st);
+}
+int64_t simseg_attn_dropout_mask_words(int B, int H, int S) { return attn_dropout_mask_words_impl(B, H, S); }
+int simseg_attn_dropout_mask(simseg_ctx* ctx, int B, int H, int S, float drop_p, const uint64_t* drop_rng, uint32_t drop_site,
+                             uint32_t* mask, int64_t mask_words, void* stream) {
+  CTX_OR_FAIL();
+  SIMSEG_CHECK_ARG(drop_p > 0.f && drop_p < 1.f && drop_rng != nullptr && mask != nullptr,
+                   "attn_dropout_mask: needs 0 < p < 1, a device {seed, step} pair and a mask buffer");
+  return attn_dropout_mask_impl(c, B, H, S, drop_p, drop_rng, drop_site, mask, mask_words, st);
+}
+// Attention with dropout on the probabilities runs on the tcgen05 kernels only (S <= 224 forward, <= 256 backward, 16-byte
+// aligned head rows): there is no fallback, shapes they reject are an error.
+int simseg_attention_fwd_dropout(simseg_ctx* ctx, const void* q, const void* k, const void* v, int64_t stride_b,
+                                 int64_t stride_s, int64_t stride_h, int B, int H, int S, const int32_t* key_len, float scale,
+                                 void* out, float* lse, const uint32_t* drop_mask, float drop_p, void* stream) {
+  CTX_OR_FAIL();
+  SIMSEG_CHECK_ARG(drop_mask != nullptr && drop_p > 0.f && drop_p < 1.f, "attention_fwd_dropout: needs a mask and 0 < p < 1");
+  const int rc = attention_fwd_tc_impl(c, q, k, v, stride_b, stride_s, stride_h, B, H, S, key_len, scale, out, lse, drop_mask, drop_p, st);
+  if (rc == SIMSEG_ERR_UNSUPPORTED) set_error("attention_fwd_dropout: shape B=%d H=%d S=%d not supported with dropout (S <= 224, aligned strides)", B, H, S);
+  return rc;
+}
+int simseg_attention_bwd_dropout(simseg_ctx* ctx, const void* q, const void* k, const void* v, const void* out,
+                                 const void* dout, const float* lse, int64_t stride_b, int64_t stride_s, int64_t stride_h, int B,
+                                 int H, int S, const int32_t* key_len, float scale, void* dq, void* dk, void* dv,
+                                 const uint32_t* drop_mask, float drop_p, void* stream) {
+  CTX_OR_FAIL();
+  SIMSEG_CHECK_ARG(drop_mask != nullptr && drop_p > 0.f && drop_p < 1.f, "attention_bwd_dropout: needs a mask and 0 < p < 1");
+  const int rc = attention_bwd_tc_impl(c, q, k, v, out, dout, lse, stride_b, stride_s, stride_h, B, H, S, key_len, scale, dq, dk, dv, drop_mask, drop_p, st);
+  if (rc == SIMSEG_ERR_UNSUPPORTED) set_error("attention_bwd_dropout: shape B=%d H=%d S=%d not supported with dropout (S <= 224, aligned strides)", B, H, S);
+  return rc;
 }
 int simseg_im2col16(simseg_ctx* ctx, const float* image, int B, int Hi, int Wi, void* patches, void* stream) {
   CTX_OR_FAIL();

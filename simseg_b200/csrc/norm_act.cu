@@ -1,6 +1,7 @@
 // Bandwidth-bound row / elementwise kernels: casts, column sums, GELU recompute, LayerNorm fwd/bwd.
 // All use 128-bit global accesses; LayerNorm keeps a whole row in the registers of one warp.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace simseg {
 
@@ -214,16 +215,21 @@ __device__ __forceinline__ void load_row(const void* x, int64_t row, int D, int 
   }
 }
 
-template <int V, bool XBF16>
+// DROP (train-mode BERT dropout, philox.cuh): 0 none; 1 the `add` summand is dropped (BertSelfOutput / BertOutput:
+// LayerNorm(dropout(dense(..)) + input)); 2 the outputs are dropped (BertEmbeddings: dropout(LayerNorm(e))).
+template <int V, bool XBF16, int DROP>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps, int64_t M,
                                                             __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32,
                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                            const __nv_bfloat16* __restrict__ add, float* __restrict__ sum_out) {
+                                                            const __nv_bfloat16* __restrict__ add, float* __restrict__ sum_out,
+                                                            const DropSpec ds) {
   constexpr int D = V * 128;
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  DropKey dk{};
+  if (DROP) dk = load_drop_key(ds);
   float g[V][4], b[V][4];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
@@ -241,7 +247,15 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const void* __restri
       for (int i = 0; i < V; ++i) {
         const int c = (i * 32 + lane) * 4;
         const uint2 u = *reinterpret_cast<const uint2*>(add + row * D + c);
-        v[i][0] += bf16_lo(u.x); v[i][1] += bf16_hi(u.x); v[i][2] += bf16_lo(u.y); v[i][3] += bf16_hi(u.y);
+        if (DROP == 1) {
+          const uint4 w = drop_words(ds, dk, static_cast<uint32_t>(i * 32 + lane), static_cast<uint32_t>(row));
+          v[i][0] += w.x >= ds.thr ? bf16_lo(u.x) * ds.inv_keep : 0.f;
+          v[i][1] += w.y >= ds.thr ? bf16_hi(u.x) * ds.inv_keep : 0.f;
+          v[i][2] += w.z >= ds.thr ? bf16_lo(u.y) * ds.inv_keep : 0.f;
+          v[i][3] += w.w >= ds.thr ? bf16_hi(u.y) * ds.inv_keep : 0.f;
+        } else {
+          v[i][0] += bf16_lo(u.x); v[i][1] += bf16_hi(u.x); v[i][2] += bf16_lo(u.y); v[i][3] += bf16_hi(u.y);
+        }
         if (sum_out) *reinterpret_cast<float4*>(sum_out + row * D + c) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
       }
     }
@@ -265,6 +279,13 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const void* __restri
       float o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[j] = (v[i][j] - mu) * rstd * g[i][j] + b[i][j];
+      if (DROP == 2) {
+        const uint4 w = drop_words(ds, dk, static_cast<uint32_t>(i * 32 + lane), static_cast<uint32_t>(row));
+        o[0] = w.x >= ds.thr ? o[0] * ds.inv_keep : 0.f;
+        o[1] = w.y >= ds.thr ? o[1] * ds.inv_keep : 0.f;
+        o[2] = w.z >= ds.thr ? o[2] * ds.inv_keep : 0.f;
+        o[3] = w.w >= ds.thr ? o[3] * ds.inv_keep : 0.f;
+      }
       if (y_bf16) {
         uint2 u; u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]);
         *reinterpret_cast<uint2*>(y_bf16 + row * D + c) = u;
@@ -274,14 +295,19 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const void* __restri
   }
 }
 
-template <int V, bool XBF16, bool DYBF16>
+// DROP as in the forward: 1 -> dx_bf16 and dx_colsum (gradient of the dropped summand and of its Linear's bias) carry the
+// mask, dx (the residual path) does not; 2 -> the incoming gradient dy (+ dy2) is masked first.
+template <int V, bool XBF16, bool DYBF16, int DROP>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
     const void* __restrict__ dy, const float* __restrict__ dy2, const void* __restrict__ x, const float* __restrict__ gamma,
     const float* __restrict__ mean, const float* __restrict__ rstd, int64_t M, float* __restrict__ dx, int dx_accumulate,
-    __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dx_colsum) {
+    __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dx_colsum,
+    const DropSpec ds) {
   constexpr int D = V * 128;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  DropKey dk{};
+  if (DROP) dk = load_drop_key(ds);
   const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   float g[V][4];
@@ -312,6 +338,16 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
         dv[i][0] += f.x; dv[i][1] += f.y; dv[i][2] += f.z; dv[i][3] += f.w;
       }
     }
+    if (DROP == 2) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const uint4 w = drop_words(ds, dk, static_cast<uint32_t>(i * 32 + lane), static_cast<uint32_t>(row));
+        dv[i][0] = w.x >= ds.thr ? dv[i][0] * ds.inv_keep : 0.f;
+        dv[i][1] = w.y >= ds.thr ? dv[i][1] * ds.inv_keep : 0.f;
+        dv[i][2] = w.z >= ds.thr ? dv[i][2] * ds.inv_keep : 0.f;
+        dv[i][3] = w.w >= ds.thr ? dv[i][3] * ds.inv_keep : 0.f;
+      }
+    }
     const float mu = mean[row], rs = rstd[row];
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
@@ -335,6 +371,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[j] = rs * (dv[i][j] - c1 - xv[i][j] * c2) + pv[i][j];
       if (dx) *reinterpret_cast<float4*>(dx + row * D + c) = make_float4(o[0], o[1], o[2], o[3]);
+      if (DROP == 1) {
+        const uint4 w = drop_words(ds, dk, static_cast<uint32_t>(i * 32 + lane), static_cast<uint32_t>(row));
+        o[0] = w.x >= ds.thr ? o[0] * ds.inv_keep : 0.f;
+        o[1] = w.y >= ds.thr ? o[1] * ds.inv_keep : 0.f;
+        o[2] = w.z >= ds.thr ? o[2] * ds.inv_keep : 0.f;
+        o[3] = w.w >= ds.thr ? o[3] * ds.inv_keep : 0.f;
+      }
       if (dx_bf16) {
         uint2 u; u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]);
         *reinterpret_cast<uint2*>(dx_bf16 + row * D + c) = u;
@@ -373,15 +416,21 @@ static int ln_grid(Ctx* ctx, int64_t M) {
 
 int layernorm_fwd_impl(Ctx* ctx, const void* x, int x_dtype, const float* gamma, const float* beta, float eps, int64_t M,
                        int D, void* y_bf16, float* y_f32, float* mean, float* rstd, const void* add_v, float* sum_out,
-                       cudaStream_t st) {
+                       float drop_p, const void* drop_rng, uint32_t drop_site, cudaStream_t st) {
   const __nv_bfloat16* add = reinterpret_cast<const __nv_bfloat16*>(add_v);
   SIMSEG_CHECK_ARG(M > 0, "layernorm_fwd: empty");
   SIMSEG_CHECK_ARG(D == 384 || D == 768 || D == 512 || D == 128 || D == 256, "layernorm: D=%d unsupported (128/256/384/512/768)", D);
   const int grid = ln_grid(ctx, M);
   auto* yb = reinterpret_cast<__nv_bfloat16*>(y_bf16);
+  const bool drop = drop_p > 0.f;
+  SIMSEG_CHECK_ARG(!drop || (drop_p < 1.f && drop_rng != nullptr && x_dtype == SIMSEG_F32 && M < (int64_t(1) << 32)),
+                   "layernorm_fwd: dropout needs 0 < p < 1, a device {seed, step} pair and an fp32 x");
+  const DropSpec ds = make_drop_spec(drop ? drop_p : 0.f, drop_rng, drop_site);
 #define LN_FWD(V)                                                                                             \
-  if (x_dtype == SIMSEG_BF16) layernorm_fwd_kernel<V, true><<<grid, 256, 0, st>>>(x, gamma, beta, eps, M, yb, y_f32, mean, rstd, add, sum_out); \
-  else layernorm_fwd_kernel<V, false><<<grid, 256, 0, st>>>(x, gamma, beta, eps, M, yb, y_f32, mean, rstd, add, sum_out)
+  if (drop && add) layernorm_fwd_kernel<V, false, 1><<<grid, 256, 0, st>>>(x, gamma, beta, eps, M, yb, y_f32, mean, rstd, add, sum_out, ds); \
+  else if (drop) layernorm_fwd_kernel<V, false, 2><<<grid, 256, 0, st>>>(x, gamma, beta, eps, M, yb, y_f32, mean, rstd, add, sum_out, ds); \
+  else if (x_dtype == SIMSEG_BF16) layernorm_fwd_kernel<V, true, 0><<<grid, 256, 0, st>>>(x, gamma, beta, eps, M, yb, y_f32, mean, rstd, add, sum_out, ds); \
+  else layernorm_fwd_kernel<V, false, 0><<<grid, 256, 0, st>>>(x, gamma, beta, eps, M, yb, y_f32, mean, rstd, add, sum_out, ds)
   switch (D / 128) {
     case 1: LN_FWD(1); break;
     case 2: LN_FWD(2); break;
@@ -397,30 +446,34 @@ int layernorm_fwd_impl(Ctx* ctx, const void* x, int x_dtype, const float* gamma,
 
 int layernorm_bwd_impl(Ctx* ctx, const void* dy, int dy_dtype, const float* dy2, const void* x, int x_dtype,
                        const float* gamma, const float* mean, const float* rstd, int64_t M, int D, float* dx,
-                       int dx_accumulate, void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, cudaStream_t st) {
+                       int dx_accumulate, void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, int drop_mode,
+                       float drop_p, const void* drop_rng, uint32_t drop_site, cudaStream_t st) {
   SIMSEG_CHECK_ARG(M > 0, "layernorm_bwd: empty");
   SIMSEG_CHECK_ARG(D == 384 || D == 768 || D == 512 || D == 128 || D == 256, "layernorm: D=%d unsupported", D);
   SIMSEG_CHECK_ARG(!(dx_accumulate && dx == nullptr), "layernorm_bwd: dx_accumulate needs dx");
   const int grid = ln_grid(ctx, M);
   auto* db = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
+  if (!(drop_p > 0.f)) drop_mode = 0;
+  SIMSEG_CHECK_ARG(drop_mode == 0 || ((drop_mode == 1 || drop_mode == 2) && drop_p < 1.f && drop_rng != nullptr &&
+                                      x_dtype == SIMSEG_F32 && M < (int64_t(1) << 32)),
+                   "layernorm_bwd: dropout needs mode 1|2, 0 < p < 1, a device {seed, step} pair and an fp32 x");
+  const DropSpec ds = make_drop_spec(drop_mode ? drop_p : 0.f, drop_rng, drop_site);
+#define LN_BWD_K(V, XB, DB, DR) \
+  layernorm_bwd_kernel<V, XB, DB, DR><<<grid, 256, 0, st>>>(dy, dy2, x, gamma, mean, rstd, M, dx, dx_accumulate, db, dgamma, dbeta, dx_colsum, ds)
 #define LN_BWD(V)                                                                                                   \
   do {                                                                                                              \
-    if (x_dtype == SIMSEG_BF16) {                                                                                   \
-      if (dy_dtype == SIMSEG_BF16) layernorm_bwd_kernel<V, true, true><<<grid, 256, 0, st>>>(dy, dy2, x, gamma, mean, rstd, M, dx, dx_accumulate, db, dgamma, dbeta, dx_colsum); \
-      else layernorm_bwd_kernel<V, true, false><<<grid, 256, 0, st>>>(dy, dy2, x, gamma, mean, rstd, M, dx, dx_accumulate, db, dgamma, dbeta, dx_colsum); \
+    if (drop_mode == 1) {                                                                                           \
+      if (dy_dtype == SIMSEG_BF16) LN_BWD_K(V, false, true, 1); else LN_BWD_K(V, false, false, 1);                 \
+    } else if (drop_mode == 2) {                                                                                    \
+      if (dy_dtype == SIMSEG_BF16) LN_BWD_K(V, false, true, 2); else LN_BWD_K(V, false, false, 2);                 \
+    } else if (x_dtype == SIMSEG_BF16) {                                                                            \
+      if (dy_dtype == SIMSEG_BF16) LN_BWD_K(V, true, true, 0); else LN_BWD_K(V, true, false, 0);                   \
     } else {                                                                                                        \
-      if (dy_dtype == SIMSEG_BF16) layernorm_bwd_kernel<V, false, true><<<grid, 256, 0, st>>>(dy, dy2, x, gamma, mean, rstd, M, dx, dx_accumulate, db, dgamma, dbeta, dx_colsum); \
-      else layernorm_bwd_kernel<V, false, false><<<grid, 256, 0, st>>>(dy, dy2, x, gamma, mean, rstd, M, dx, dx_accumulate, db, dgamma, dbeta, dx_colsum); \
+      if (dy_dtype == SIMSEG_BF16) LN_BWD_K(V, false, true, 0); else LN_BWD_K(V, false, false, 0);                 \
     }                                                                                                               \
   } while (0)
-  switch (D / 128) {
-    case 1: LN_BWD(1); break;
-    case 2: LN_BWD(2); break;
-    case 3: LN_BWD(3); break;
-    case 4: LN_BWD(4); break;
-    default: LN_BWD(6); break;
-  }
 #undef LN_BWD
+#undef LN_BWD_K
   ctx->launches++;
   SIMSEG_LAUNCH_CHECK();
   return SIMSEG_OK;

@@ -143,22 +143,40 @@ def gelu_fwd(h: Tensor, out: Optional[Tensor] = None) -> Tensor:
     return out
 
 
+class Drop:
+    """One train-mode dropout site (HF BertModel: hidden / attention-probability dropout): probability ``p``, the DEVICE
+    int64 pair ``rng`` = {seed, step} the kernels read, and the ``site`` number that separates the dropout layers of a step."""
+    __slots__ = ("p", "rng", "site")
+
+    def __init__(self, p: float, rng: Tensor, site: int):
+        assert 0.0 < p < 1.0 and rng.dtype == torch.int64 and rng.numel() == 2 and rng.is_cuda
+        self.p, self.rng, self.site = float(p), rng, int(site)
+
+
 def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, *, want_bf16=True, want_f32=False,
-                  want_stats=True):
+                  want_stats=True, drop: Optional[Drop] = None):
+    """``drop``: the OUTPUTS are dropped (HF BertEmbeddings: dropout(LayerNorm(e)))."""
     M, D = x.shape
     assert x.is_contiguous()
     yb = torch.empty((M, D), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
     yf = torch.empty((M, D), device=x.device, dtype=torch.float32) if want_f32 else None
     mean = torch.empty(M, device=x.device, dtype=torch.float32) if want_stats else None
     rstd = torch.empty(M, device=x.device, dtype=torch.float32) if want_stats else None
+    if drop is not None:
+        assert x.dtype == torch.float32
+        check(_lib.load().simseg_layernorm_fwd_dropout(ctx(), _p(x), None, _p(gamma), _p(beta), eps, M, D, None, _p(yb), _p(yf),
+                                                       _p(mean), _p(rstd), drop.p, _p(drop.rng), drop.site, _stream()),
+              "layernorm_fwd_dropout")
+        return yb, yf, mean, rstd
     check(_lib.load().simseg_layernorm_fwd(ctx(), _p(x), _dt(x), _p(gamma), _p(beta), eps, M, D, _p(yb), _p(yf),
                                            _p(mean), _p(rstd), _stream()), "layernorm_fwd")
     return yb, yf, mean, rstd
 
 
 def add_layernorm_fwd(x: Tensor, add: Tensor, gamma: Tensor, beta: Tensor, eps: float, *, want_sum=True, want_bf16=True,
-                      want_f32=False, want_stats=True):
-    """s = x (f32) + add (bf16); returns (s, LN(s) bf16, LN(s) f32, mean, rstd) — residual add fused into the LayerNorm."""
+                      want_f32=False, want_stats=True, drop: Optional[Drop] = None):
+    """s = x (f32) + add (bf16); returns (s, LN(s) bf16, LN(s) f32, mean, rstd) — residual add fused into the LayerNorm.
+    ``drop``: s = x + dropout(add) (HF BertSelfOutput / BertOutput)."""
     M, D = x.shape
     assert x.is_contiguous() and add.is_contiguous() and x.dtype == torch.float32 and add.dtype == torch.bfloat16
     sm = torch.empty((M, D), device=x.device, dtype=torch.float32) if want_sum else None
@@ -166,6 +184,11 @@ def add_layernorm_fwd(x: Tensor, add: Tensor, gamma: Tensor, beta: Tensor, eps: 
     yf = torch.empty((M, D), device=x.device, dtype=torch.float32) if want_f32 else None
     mean = torch.empty(M, device=x.device, dtype=torch.float32) if want_stats else None
     rstd = torch.empty(M, device=x.device, dtype=torch.float32) if want_stats else None
+    if drop is not None:
+        check(_lib.load().simseg_layernorm_fwd_dropout(ctx(), _p(x), _p(add), _p(gamma), _p(beta), eps, M, D, _p(sm), _p(yb),
+                                                       _p(yf), _p(mean), _p(rstd), drop.p, _p(drop.rng), drop.site, _stream()),
+              "layernorm_fwd_dropout")
+        return sm, yb, yf, mean, rstd
     check(_lib.load().simseg_add_layernorm_fwd(ctx(), _p(x), _p(add), _p(gamma), _p(beta), eps, M, D, _p(sm), _p(yb), _p(yf),
                                                _p(mean), _p(rstd), _stream()), "add_layernorm_fwd")
     return sm, yb, yf, mean, rstd
@@ -174,9 +197,18 @@ def add_layernorm_fwd(x: Tensor, add: Tensor, gamma: Tensor, beta: Tensor, eps: 
 def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, *, dy2: Optional[Tensor] = None,
                   dx: Optional[Tensor] = None, dx_accumulate: bool = False, dx_bf16: Optional[Tensor] = None,
                   dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None,
-                  dx_colsum: Optional[Tensor] = None):
+                  dx_colsum: Optional[Tensor] = None, drop: Optional[Drop] = None, drop_mode: int = 0):
+    """``drop`` + ``drop_mode``: 1 = backward of ``add_layernorm_fwd(drop=)`` (dx_bf16 / dx_colsum carry the mask),
+    2 = backward of ``layernorm_fwd(drop=)`` (dy + dy2 is masked first)."""
     M, D = x.shape
     assert dy.is_contiguous() and x.is_contiguous()
+    if drop is not None:
+        assert drop_mode in (1, 2) and x.dtype == torch.float32
+        check(_lib.load().simseg_layernorm_bwd_dropout(ctx(), _p(dy), _dt(dy), _p(dy2), _p(x), _p(gamma), _p(mean), _p(rstd), M, D,
+                                                       _p(dx), 1 if dx_accumulate else 0, _p(dx_bf16), _p(dgamma), _p(dbeta),
+                                                       _p(dx_colsum), drop_mode, drop.p, _p(drop.rng), drop.site, _stream()),
+              "layernorm_bwd_dropout")
+        return
     check(_lib.load().simseg_layernorm_bwd(ctx(), _p(dy), _dt(dy), _p(dy2), _p(x), _dt(x), _p(gamma), _p(mean),
                                            _p(rstd), M, D, _p(dx), 1 if dx_accumulate else 0, _p(dx_bf16),
                                            _p(dgamma), _p(dbeta), _p(dx_colsum), _stream()), "layernorm_bwd")
@@ -184,17 +216,40 @@ def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tens
 
 # --------------------------------------------------------------------------------------- attention
 def attention_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, H: int, S: int, strides, key_len: Optional[Tensor],
-                  scale: float, out: Optional[Tensor] = None, lse: Optional[Tensor] = None):
+                  scale: float, out: Optional[Tensor] = None, lse: Optional[Tensor] = None,
+                  drop_mask: Optional[Tensor] = None, drop_p: float = 0.0):
+    """``drop_mask`` (from ``attn_dropout_mask``) + ``drop_p``: out = dropout(softmax(..)) V (HF BertSelfAttention, train mode)."""
     sb, ss, sh = strides
     out = torch.empty((B, S, H * 64), device=q.device, dtype=torch.bfloat16) if out is None else out
     lse = torch.empty((B, H, S), device=q.device, dtype=torch.float32) if lse is None else lse
+    if drop_mask is not None:
+        check(_lib.load().simseg_attention_fwd_dropout(ctx(), _p(q), _p(k), _p(v), sb, ss, sh, B, H, S, _p(key_len), scale,
+                                                       _p(out), _p(lse), _p(drop_mask), drop_p, _stream()), "attention_fwd_dropout")
+        return out, lse
     check(_lib.load().simseg_attention_fwd(ctx(), _p(q), _p(k), _p(v), sb, ss, sh, B, H, S, _p(key_len), scale,
                                            _p(out), _p(lse), _stream()), "attention_fwd")
     return out, lse
 
 
-def attention_bwd(q, k, v, out, dout, lse, B, H, S, strides, key_len, scale, dq, dk, dv):
+def attn_dropout_mask(B: int, H: int, S: int, drop: Drop, out: Optional[Tensor] = None) -> Tensor:
+    """Keep bits of one attention layer's probability dropout, in the attention kernels' tile coordinates (int32 words)."""
+    n = _lib.load().simseg_attn_dropout_mask_words(B, H, S)
+    if n <= 0:
+        raise _lib.SimsegError(f"attention dropout: B={B} H={H} S={S} unsupported (S <= 224)")
+    mask = torch.empty(n, device=drop.rng.device, dtype=torch.int32) if out is None else out
+    assert mask.numel() >= n and mask.dtype == torch.int32
+    check(_lib.load().simseg_attn_dropout_mask(ctx(), B, H, S, drop.p, _p(drop.rng), drop.site, _p(mask), mask.numel(), _stream()),
+          "attn_dropout_mask")
+    return mask
+
+
+def attention_bwd(q, k, v, out, dout, lse, B, H, S, strides, key_len, scale, dq, dk, dv, drop_mask=None, drop_p=0.0):
     sb, ss, sh = strides
+    if drop_mask is not None:
+        check(_lib.load().simseg_attention_bwd_dropout(ctx(), _p(q), _p(k), _p(v), _p(out), _p(dout), _p(lse), sb, ss, sh, B, H, S,
+                                                       _p(key_len), scale, _p(dq), _p(dk), _p(dv), _p(drop_mask), drop_p,
+                                                       _stream()), "attention_bwd_dropout")
+        return
     check(_lib.load().simseg_attention_bwd(ctx(), _p(q), _p(k), _p(v), _p(out), _p(dout), _p(lse), sb, ss, sh, B, H, S,
                                            _p(key_len), scale, _p(dq), _p(dk), _p(dv), _stream()), "attention_bwd")
 

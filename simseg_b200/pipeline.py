@@ -10,6 +10,7 @@ sees five coarse ``torch.autograd.Function`` nodes whose backward passes are han
 """
 from __future__ import annotations
 
+import os
 import warnings
 import weakref
 from typing import Dict, Optional
@@ -218,8 +219,8 @@ class _VitFn(torch.autograd.Function):
 
 class _BertFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, input_ids, attention_mask, bert, shared, save, *params):
-        h_f32, h_bf16, sv = towers.bert_forward(bert, input_ids, attention_mask, shared.wc, save)
+    def forward(ctx, input_ids, attention_mask, bert, shared, save, drop, *params):
+        h_f32, h_bf16, sv = towers.bert_forward(bert, input_ids, attention_mask, shared.wc, save, drop)
         ctx.bert, ctx.shared, ctx.sv, ctx.params = bert, shared, sv, params
         shared.stash["bert"] = h_bf16
         return h_f32
@@ -233,7 +234,7 @@ class _BertFn(torch.autograd.Function):
         if ctx.shared.tower_done is not None:
             ctx.shared.tower_done("bert")
         pg = sink.as_tuple() if sink is not None else (None,) * len(ctx.params)
-        return (None, None, None, None, None) + pg
+        return (None, None, None, None, None, None) + pg
 
 
 def _bf16_tokens(x: Tensor):
@@ -545,25 +546,45 @@ class HuggingFaceModel(nn.Module):
             raise RuntimeError("pretrained HF weights cannot be downloaded here: load a checkpoint with load_state_dict")
         self.model = BertModel()
         self._shared = shared
-        # bert-base-uncased ships hidden_dropout_prob = attention_probs_dropout_prob = 0.1, active under model.train() in
-        # the reference.  The B200 kernels implement p = 0 only (parity is defined at p = 0, SURVEY 8d "Dropout p forced to
-        # 0"): a deliberate, documented deviation — train() warns once instead of silently differing.
-        self.hidden_dropout_prob = 0.0
-        self.attention_probs_dropout_prob = 0.0
-        self._warned_dropout = False
+        # bert-base-uncased ships hidden_dropout_prob = attention_probs_dropout_prob = 0.1 (its HF config.json), active under
+        # model.train() in the reference: after the embedding LayerNorm, on the attention probabilities and on both dense
+        # outputs of every layer.  Same here (towers.BertDropout; masks from a counter-based Philox stream, regenerated in
+        # backward).  SIMSEG_BERT_DROPOUT=<p> overrides both probabilities at construction (0 = the p = 0 parity configuration
+        # of oracle/make_golden.py); the attributes can also be set afterwards, as on an HF config.
+        p_env = os.environ.get("SIMSEG_BERT_DROPOUT")
+        self.hidden_dropout_prob = 0.1 if p_env in (None, "") else float(p_env)
+        self.attention_probs_dropout_prob = 0.1 if p_env in (None, "") else float(p_env)
+        # {seed, step} read by the dropout kernels ON THE DEVICE: every train-mode forward bumps step with an in-place add, which
+        # a captured CUDA graph replays, so each replay draws fresh masks
+        self.register_buffer("drop_rng", torch.zeros(2, dtype=torch.int64), persistent=False)
+        self._drop_seeded = False
 
-    def train(self, mode: bool = True):
-        if mode and not self._warned_dropout and any(p.requires_grad for p in self.parameters()):
-            warnings.warn("simseg_b200: the text tower trains WITHOUT BERT's dropout (reference: hidden / attention-probability "
-                          "dropout 0.1 under model.train()); see INTEGRATION.md section 3", stacklevel=2)
-            self._warned_dropout = True
-        return super().train(mode)
+    def seed_dropout(self, seed: int, step: int = 0):
+        """Fix the dropout stream: masks are a pure function of (seed, step, site, element); the next train-mode forward
+        uses step + 1.  Without a call, the seed is ``torch.initial_seed() + rank`` at the first train-mode forward."""
+        self.drop_rng.copy_(torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, step], dtype=torch.int64))
+        self._drop_seeded = True
+
+    def dropout_state(self) -> Tensor:
+        """The device {seed, step} pair (seeded on first use).  ``train.Trainer`` snapshots / restores it around the two passes
+        of the micro-batched step so that pass 2 re-draws pass 1's masks."""
+        if not self._drop_seeded:
+            rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
+            self.seed_dropout(torch.initial_seed() + 0x9E3779B97F4A7C15 * rank)
+        return self.drop_rng
+
+    def _dropout(self):
+        if not self.training or (self.hidden_dropout_prob <= 0 and self.attention_probs_dropout_prob <= 0):
+            return None
+        self.dropout_state()
+        self.drop_rng[1] += 1
+        return towers.BertDropout(float(self.hidden_dropout_prob), float(self.attention_probs_dropout_prob), self.drop_rng.clone())
 
     def forward(self, input_ids, attention_mask, **kwargs):
         _check_text(input_ids, attention_mask, self.model)
         params = tuple(self.model.parameters())
         save = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        out = _BertFn.apply(input_ids, attention_mask, self.model, self._shared, save, *params)
+        out = _BertFn.apply(input_ids, attention_mask, self.model, self._shared, save, self._dropout(), *params)
         out._simseg_bf16 = self._shared.stash.pop("bert")
         out._simseg_tok_begin = 0
         return out

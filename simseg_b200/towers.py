@@ -363,11 +363,30 @@ class _Lyr:
 
 
 @dataclass
+class BertDropout:
+    """Train-mode dropout of HF ``BertModel`` (``hidden_dropout_prob`` / ``attention_probs_dropout_prob``, 0.1 each in
+    bert-base-uncased; active under ``model.train()`` in the reference, ``huggingface_builder.py:16-17``).  ``rng`` is the
+    DEVICE int64 pair {seed, step} the kernels read; a forward works on its own copy, which backward reuses, so the masks of
+    the two passes agree whatever happens to the model's counter in between.  Sites: 0 = embeddings, then per layer l:
+    1 + 3l attention probabilities, 2 + 3l attention.output dense, 3 + 3l output dense (the order HF calls them in)."""
+    p_hidden: float = 0.0
+    p_attn: float = 0.0
+    rng: Tensor = None
+
+    def hidden(self, site: int):
+        return ops.Drop(self.p_hidden, self.rng, site) if self.p_hidden > 0 else None
+
+    def attn(self, site: int):
+        return ops.Drop(self.p_attn, self.rng, site) if self.p_attn > 0 else None
+
+
+@dataclass
 class BertSaved:
     B: int = 0
     T: int = 0
     ids: Tensor = None
     key_len: Tensor = None
+    drop: Optional[BertDropout] = None
     e: Tensor = None
     mean0: Tensor = None
     rstd0: Tensor = None
@@ -379,8 +398,12 @@ def _qkv_params(layer):
     return [a.query, a.key, a.value]
 
 
-def bert_forward(m, input_ids: Tensor, attention_mask: Tensor, wc: Bf16Weights, save: bool):
-    """HF ``BertModel(...).last_hidden_state`` as called by ``huggingface_builder.py:16-17`` (dropout p = 0).
+def bert_forward(m, input_ids: Tensor, attention_mask: Tensor, wc: Bf16Weights, save: bool,
+                 drop: Optional[BertDropout] = None):
+    """HF ``BertModel(...).last_hidden_state`` as called by ``huggingface_builder.py:16-17``; ``drop`` = train-mode dropout
+    (None in eval mode / p = 0): after the embedding LayerNorm, on the attention probabilities (keep bits drawn once per
+    layer by ``ops.attn_dropout_mask``, applied inside the attention kernel after the softmax), and on the two dense
+    outputs inside the residual-add LayerNorm kernels.
 
     The additive ``finfo.min`` key mask of a left-aligned ``attention_mask`` is applied as a per-sample key
     length inside the attention kernel."""
@@ -390,10 +413,14 @@ def bert_forward(m, input_ids: Tensor, attention_mask: Tensor, wc: Bf16Weights, 
     H = m.num_heads
     M = B * T
     key_len = attention_mask.sum(1).to(torch.int32).contiguous()
-    sv = BertSaved(B=B, T=T, ids=input_ids.contiguous(), key_len=key_len) if save else None
+    if drop is not None and drop.p_hidden <= 0 and drop.p_attn <= 0:
+        drop = None
+    sv = BertSaved(B=B, T=T, ids=input_ids.contiguous(), key_len=key_len, drop=drop) if save else None
+    hid = (lambda site: drop.hidden(site)) if drop is not None else (lambda site: None)
+    amask = None
     e = ops.bert_embed_fwd(input_ids.contiguous(), emb.word_embeddings.weight, emb.position_embeddings.weight,
                            emb.token_type_embeddings.weight).view(M, D)
-    hb, hf, mean0, rstd0 = ops.layernorm_fwd(e, emb.LayerNorm.weight, emb.LayerNorm.bias, 1e-12, want_f32=True)
+    hb, hf, mean0, rstd0 = ops.layernorm_fwd(e, emb.LayerNorm.weight, emb.LayerNorm.bias, 1e-12, want_f32=True, drop=hid(0))
     if save:
         sv.e, sv.mean0, sv.rstd0 = e, mean0, rstd0
     strides = (T * 3 * D, 3 * D, 64)
@@ -404,11 +431,17 @@ def bert_forward(m, input_ids: Tensor, attention_mask: Tensor, wc: Bf16Weights, 
         bqkv = torch.cat([p.bias.detach() for p in qp])
         qkv = ops.linear_fwd(hb, wqkv, bqkv)
         q5 = qkv.view(B, T, 3, H, 64)
-        c, lse = ops.attention_fwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], B, H, T, strides, key_len, 0.125)
+        if drop is not None and drop.p_attn > 0:
+            amask = ops.attn_dropout_mask(B, H, T, drop.attn(1 + 3 * li), out=amask)      # one buffer, redrawn per layer
+            c, lse = ops.attention_fwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], B, H, T, strides, key_len, 0.125,
+                                       drop_mask=amask, drop_p=drop.p_attn)
+        else:
+            c, lse = ops.attention_fwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], B, H, T, strides, key_len, 0.125)
         c = c.view(M, D)
         ao = layer.attention.output
         d1 = ops.linear_fwd(c, wc.get(ao.dense.weight), ao.dense.bias)
-        s1, h1b, h1f, mean1, rstd1 = ops.add_layernorm_fwd(hf, d1, ao.LayerNorm.weight, ao.LayerNorm.bias, 1e-12, want_f32=True)
+        s1, h1b, h1f, mean1, rstd1 = ops.add_layernorm_fwd(hf, d1, ao.LayerNorm.weight, ao.LayerNorm.bias, 1e-12, want_f32=True,
+                                                           drop=hid(2 + 3 * li))
         del d1
         F = layer.intermediate.dense.weight.shape[0]
         pre = torch.empty((M, F), device=e.device, dtype=torch.bfloat16) if save else None
@@ -418,7 +451,7 @@ def bert_forward(m, input_ids: Tensor, attention_mask: Tensor, wc: Bf16Weights, 
         act = f if keep_a else None
         del f
         s2, h2b, h2f, mean2, rstd2 = ops.add_layernorm_fwd(h1f, d2, layer.output.LayerNorm.weight, layer.output.LayerNorm.bias,
-                                                           1e-12, want_f32=True)
+                                                           1e-12, want_f32=True, drop=hid(3 + 3 * li))
         del d2
         if save:
             sv.layers.append(_Lyr(hb, qkv, c, lse, s1, mean1, rstd1, pre, h1b, s2, mean2, rstd2, act))
@@ -439,6 +472,9 @@ def bert_backward(m, sv: BertSaved, dh: Tensor, wc: Bf16Weights, dh2: Optional[T
     strides = (T * 3 * D, 3 * D, 64)
     dy = dh.reshape(M, D)
     dres = None if dh2 is None else dh2.reshape(M, D)     # fp32 residual-path gradient added to dy
+    drop = sv.drop                                        # the forward's {seed, step}: every mask is regenerated from it
+    hid = (lambda site: drop.hidden(site)) if drop is not None else (lambda site: None)
+    amask = None
     for li in range(len(m.encoder.layer) - 1, -1, -1):
         layer, s = m.encoder.layer[li], sv.layers[li]
         ao = layer.attention.output
@@ -447,7 +483,7 @@ def bert_backward(m, sv: BertSaved, dh: Tensor, wc: Bf16Weights, dh2: Optional[T
         g2 = torch.empty((M, D), device=dev, dtype=torch.bfloat16)
         ops.layernorm_bwd(dy, s.s2, layer.output.LayerNorm.weight, s.mean2, s.rstd2, dy2=dres, dx=ds2, dx_bf16=g2,
                           dgamma=_grad_of(layer.output.LayerNorm.weight), dbeta=_grad_of(layer.output.LayerNorm.bias),
-                          dx_colsum=_grad_of(layer.output.dense.bias))
+                          dx_colsum=_grad_of(layer.output.dense.bias), drop=hid(3 + 3 * li), drop_mode=1)
         f = s.act if s.act is not None else torch.empty_like(s.pre)
         dpre = ops.linear_dgrad(g2, wc.get_t(layer.output.dense.weight), epilogue=EPI_DGELU, aux=s.pre,
                                 aux2=None if s.act is not None else f, col_sum=_grad_of(layer.intermediate.dense.bias))
@@ -462,14 +498,19 @@ def bert_backward(m, sv: BertSaved, dh: Tensor, wc: Bf16Weights, dh2: Optional[T
         g1 = g2
         ops.layernorm_bwd(dh1, s.s1, ao.LayerNorm.weight, s.mean1, s.rstd1, dy2=ds2, dx=ds1, dx_bf16=g1,
                           dgamma=_grad_of(ao.LayerNorm.weight), dbeta=_grad_of(ao.LayerNorm.bias),
-                          dx_colsum=_grad_of(ao.dense.bias))
+                          dx_colsum=_grad_of(ao.dense.bias), drop=hid(2 + 3 * li), drop_mode=1)
         del dh1, ds2
         ops.linear_wgrad(g1, s.c, _grad_of(ao.dense.weight), accumulate=True)
         dc = ops.linear_dgrad(g1, wc.get_t(ao.dense.weight))
         dqkv = torch.empty_like(s.qkv)
         q5, d5 = s.qkv.view(B, T, 3, H, 64), dqkv.view(B, T, 3, H, 64)
-        ops.attention_bwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], s.c, dc, s.lse, B, H, T, strides, sv.key_len, 0.125,
-                          d5[:, :, 0], d5[:, :, 1], d5[:, :, 2])
+        if drop is not None and drop.p_attn > 0:
+            amask = ops.attn_dropout_mask(B, H, T, drop.attn(1 + 3 * li), out=amask)
+            ops.attention_bwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], s.c, dc, s.lse, B, H, T, strides, sv.key_len, 0.125,
+                              d5[:, :, 0], d5[:, :, 1], d5[:, :, 2], drop_mask=amask, drop_p=drop.p_attn)
+        else:
+            ops.attention_bwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], s.c, dc, s.lse, B, H, T, strides, sv.key_len, 0.125,
+                              d5[:, :, 0], d5[:, :, 1], d5[:, :, 2])
         del dc
         qp = _qkv_params(layer)
         bsum = ops.colsum(dqkv)
@@ -481,6 +522,6 @@ def bert_backward(m, sv: BertSaved, dh: Tensor, wc: Bf16Weights, dh2: Optional[T
         sv.layers[li] = None
     de = torch.empty((M, D), device=dev, dtype=torch.float32)
     ops.layernorm_bwd(dy, sv.e, emb.LayerNorm.weight, sv.mean0, sv.rstd0, dy2=dres, dx=de,
-                      dgamma=_grad_of(emb.LayerNorm.weight), dbeta=_grad_of(emb.LayerNorm.bias))
+                      dgamma=_grad_of(emb.LayerNorm.weight), dbeta=_grad_of(emb.LayerNorm.bias), drop=hid(0), drop_mode=2)
     ops.bert_embed_bwd(sv.ids, de, _grad_of(emb.word_embeddings.weight), _grad_of(emb.position_embeddings.weight),
                        _grad_of(emb.token_type_embeddings.weight)[0])

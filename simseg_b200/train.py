@@ -11,8 +11,10 @@
 * optional micro-batching with an embedding cache (the reference's BSGS idea, ``tasks/clip/clip_bsgs_runner.py:
   309-451``): pass 1 embeds micro-batches without saving activations, the loss and the embedding gradients are
   computed on the full (gathered) batch, pass 2 re-runs each micro-batch with activations and back-propagates the
-  cached embedding gradient.  Mathematically identical to the single pass (the text top-k clamp of
-  ``pooling.py:61-63`` is taken over the whole batch, as the single pass does); trades 1 extra forward for memory.
+  cached embedding gradient.  Mathematically identical to the single pass at dropout p = 0 (the text top-k clamp of
+  ``pooling.py:61-63`` is taken over the whole batch, as the single pass does); with BERT's train-mode dropout the two
+  passes draw the SAME masks (the {seed, step} pair is restored in between — the reference's BSGS re-draws them, so its
+  pass-2 activations do not match the embeddings its loss saw); trades 1 extra forward for memory.
 """
 from __future__ import annotations
 
@@ -138,6 +140,8 @@ class Trainer:
             te = m.forward_text_project(m.forward_text_feature(sub["input_ids"], sub["attention_mask"]),
                                         sub["attention_mask"], k=tk)
             return ie, te
+        hf = m.text_encoder.model
+        rng0 = hf.dropout_state().clone()                 # BERT dropout: pass 2 must re-draw the masks of pass 1
         with torch.no_grad():
             embs = [embed(c) for c in chunks]
         img = torch.cat([e[0] for e in embs]).requires_grad_(True)
@@ -145,6 +149,7 @@ class Trainer:
         loss_dict, i2t, t2i = m.forward_loss(img, txt)
         loss = loss_dict["nce_loss"]
         loss.backward()                                   # -> img.grad, txt.grad, temperature.grad
+        hf.drop_rng.copy_(rng0)                           # micro-batch n sees the same {seed, step} in both passes
         self._defer_reduce = True
         try:
             for n, c in enumerate(chunks):

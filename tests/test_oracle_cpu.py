@@ -210,3 +210,38 @@ def test_seg_glue_vs_reference_fixture():
                 assert _max(maps[b, 0], O.upsample_nearest(torch.tensor(z[f"sel{k}_map0_{b}"]), 16)) < 1e-6
             seen.update(c for c in cand[b].tolist() if c >= 0)
     assert 0 not in seen and 255 not in seen and len(seen) >= 8
+
+
+def test_philox_known_answers():
+    """Random123's published known-answer vectors for philox4x32-10 (kat_vectors: zeros, all ones, digits of pi)."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = O.philox4x32_10(np.array([ctr], dtype=np.uint32), key)[0]
+        assert tuple(int(x) for x in got) == want
+    assert O.dropout_threshold(0.1) == 429496730 and O.dropout_threshold(0.0) == 0
+    keep = O.hidden_keep_mask(7, 1, 0, 512, 768, 0.1)
+    assert abs(keep.float().mean().item() - 0.9) < 3e-3
+    assert not torch.equal(keep, O.hidden_keep_mask(7, 2, 0, 512, 768, 0.1))      # step, site and seed all move the stream
+    assert not torch.equal(keep, O.hidden_keep_mask(7, 1, 1, 512, 768, 0.1))
+    assert not torch.equal(keep, O.hidden_keep_mask(8, 1, 0, 512, 768, 0.1))
+
+
+def test_bert_train_mode_dropout_vs_transformers_fixture():
+    """tests/golden/bert_dropout.npz holds the output of the installed transformers BertModel in train() mode when its
+    F.dropout calls are served the oracle's Philox masks in call order (make_golden.py:bert_dropout, which also checks the
+    call order itself and five parameter gradients): the oracle must place its dropouts where HF does."""
+    z = np.load(os.path.join(GOLD, "bert_dropout.npz"))
+    seed, step = int(z["bd_seed"]), int(z["bd_step"])
+    sd = O.make_state_dict(384, 6, seed=0)
+    batch = O.make_batch(3, 25, seed=5)
+    drop = O.PhiloxDropout(seed, step, 0.1, 0.1)
+    with torch.no_grad():
+        h = O.bert_forward(sd, batch["input_ids"], batch["attention_mask"], 12, O.TXT_PREFIX, dropout=drop)
+        h0 = O.bert_forward(sd, batch["input_ids"], batch["attention_mask"], 12, O.TXT_PREFIX)
+    ref = torch.from_numpy(z["bd_hidden"])
+    assert (h[:, :, :96] - ref).abs().max().item() < 2e-4
+    assert (h0[:, :, :96] - ref).abs().max().item() > 0.1                      # the masks act
+    assert abs(float(z["bd_keep_rate_site1"]) - O.attn_keep_mask(seed, step, 1, 3, 12, 25, 0.1).float().mean().item()) < 1e-7
