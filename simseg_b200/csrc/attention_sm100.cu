@@ -435,9 +435,14 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           const int qslot = (p.nqt == 1) ? static_cast<int>(it & 1) : qt;     // Q / dO slot (single-tile items alternate slots)
           const uint32_t quse = (p.nqt == 1) ? (it >> 1) : it;
           // ---- phase A: S -> P (kept as packed bf16 in registers for phase B), P into smem
-          uint32_t keep = 0xffffffffu;                                 // requested before the wait below, used after it
-          if (kDrop && chunk_live && rows_live)
-            keep = __ldg(p.drop_mask + (static_cast<int64_t>(item) * p.rows + min(qrow, p.rows - 1)) * p.mask_nw + kt * 4 + cq);
+          // keep bits of this thread's (row, 32-key chunk): requested before the wait below, used after it; read again for
+          // phase B (an L1 / L2 hit) instead of being held in a register across the drain
+          const uint32_t* keep_ptr = nullptr;
+          uint32_t keep = 0xffffffffu;
+          if (kDrop && chunk_live && rows_live) {
+            keep_ptr = p.drop_mask + (static_cast<int64_t>(item) * p.rows + min(qrow, p.rows - 1)) * p.mask_nw + kt * 4 + cq;
+            keep = __ldg(keep_ptr);
+          }
           tr(10);
           mbar_wait(s_full, g & 1);                                    // implies the Q / dO tiles of this qt have landed
           tr(11);
@@ -509,6 +514,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           if (!kLateDrain) drain_pending();                              // accumulators of the previous key tile / item
 
           // ---- phase B: dP -> dS = P * (dP - D), dS into smem
+          if (kDrop && keep_ptr != nullptr) keep = __ldg(keep_ptr);
           mbar_wait(dp_full, g & 1);
           tr(16);
           tc_fence_after();

@@ -472,6 +472,13 @@ int layernorm_bwd_impl(Ctx* ctx, const void* dy, int dy_dtype, const float* dy2,
       if (dy_dtype == SIMSEG_BF16) LN_BWD_K(V, false, true, 0); else LN_BWD_K(V, false, false, 0);                 \
     }                                                                                                               \
   } while (0)
+  switch (D / 128) {
+    case 1: LN_BWD(1); break;
+    case 2: LN_BWD(2); break;
+    case 3: LN_BWD(3); break;
+    case 4: LN_BWD(4); break;
+    default: LN_BWD(6); break;
+  }
 #undef LN_BWD
 #undef LN_BWD_K
   ctx->launches++;

@@ -222,10 +222,12 @@ def test_bert_tower_train_mode_vs_oracle_same_stream(cuda, T):
     for k, p in model.named_parameters():
         if not k.startswith(O.TXT_PREFIX) or sdg[k].grad is None or sdg[k].grad.norm().item() <= 1e-7:
             continue
+        if k.endswith("attention.self.key.bias"):       # exactly zero in theory (rows of dS sum to 0, dropout or not): noise / noise
+            continue
         gq, gr = p.grad.cpu(), sdg[k].grad
         rows.append((k, _cos(gq, gr), ((gq - gr).norm() / gr.norm()).item()))
     bad = sorted(rows, key=lambda r: r[1])[:6]
-    assert len(rows) > 190
+    assert len(rows) > 180
     assert all(r[1] > 0.98 and r[2] < 0.2 for r in rows), bad
     # same seed / step again -> bit-identical tokens; next step -> different masks
     hf.seed_dropout(SEED, 41)
