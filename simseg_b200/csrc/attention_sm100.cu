@@ -462,7 +462,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 #pragma unroll
               for (int j = 0; j < 32; ++j) sr[j] = 0;
             }
-            if (need_mask || kt * kTile + col0 + 32 > p.rows) {    // padding keys: exp2(-lse) could overflow, mask them
+            if (need_mask) {                                       // padding keys: exp2(-lse) could overflow, mask them
 #pragma unroll
               for (int j = 0; j < 32; j += 2) {
                 const int key = kt * kTile + col0 + j;
@@ -470,6 +470,19 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                 float p1 = ex2_approx(fmaf(__uint_as_float(sr[j + 1]), p.scale_log2e, -Lq));
                 p0 = (q_ok && key < klen && (key & gm) == rg) ? p0 : 0.f;
                 p1 = (q_ok && key + 1 < klen && ((key + 1) & gm) == rg) ? p1 : 0.f;
+                pp[j >> 1] = pack_bf16(p0, p1);
+              }
+            } else if (kt * kTile + col0 + 32 > p.rows) {
+              // last, partial chunk of an unmasked, unpacked sequence (ViT: key 197 of 208): only its live keys, warp-uniform
+              // early exit; dead query rows as in the dense path below
+              const int rem = p.rows - (kt * kTile + col0);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pp[j] = 0u;
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                if (j >= rem) break;
+                const float p0 = ex2_approx(fmaf(__uint_as_float(sr[j]), p.scale_log2e, -Lq));
+                const float p1 = j + 1 < rem ? ex2_approx(fmaf(__uint_as_float(sr[j + 1]), p.scale_log2e, -Lq)) : 0.f;
                 pp[j >> 1] = pack_bf16(p0, p1);
               }
             } else {
@@ -1188,14 +1201,24 @@ attention_fwd_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             tmem_ld_32x32(tS + c * 32, x);
             tmem_ld_wait();
             if (dense && c * 32 + 32 <= klen) {
-              float m0 = fmaxf(__uint_as_float(x[0]), __uint_as_float(x[1]));
+              // three-input max (FMNMX3): 16 instructions per 32 keys on two independent chains
+              float m0 = fmax3(m, __uint_as_float(x[0]), __uint_as_float(x[1]));
               float m1 = fmaxf(__uint_as_float(x[2]), __uint_as_float(x[3]));
 #pragma unroll
-              for (int j = 4; j < 32; j += 2) {
-                m0 = fmaxf(m0, __uint_as_float(x[j]));
-                m1 = fmaxf(m1, __uint_as_float(x[j + 1]));
+              for (int j = 4; j < 32; j += 4) {
+                m0 = fmax3(m0, __uint_as_float(x[j]), __uint_as_float(x[j + 1]));
+                m1 = fmax3(m1, __uint_as_float(x[j + 2]), __uint_as_float(x[j + 3]));
               }
-              m = fmaxf(m, fmaxf(m0, m1));
+              m = fmaxf(m0, m1);
+            } else if (dense) {
+              // last, partial chunk of an unpacked sequence (ViT: 197 = 6 x 32 + 5): only the live keys, warp-uniform early exit
+              // (the per-element predicates of the general path cost more than the whole dense chunk for these 5 keys)
+              const int rem = klen - c * 32;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (j >= rem) break;
+                m = fmaxf(m, __uint_as_float(x[j]));
+              }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
@@ -1214,14 +1237,17 @@ attention_fwd_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
               tmem_ld_32x32(tS + c * 32, x);
               tmem_ld_wait();
               if (dense && c * 32 + 32 <= klen) {
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                // packed f32x2 for the scale / subtract and the row sums: 10 instead of 14 issue slots per four keys
+                const f32x2 sc2 = f2_splat(p.scale_log2e), nm2 = f2_splat(-ms);
+                f32x2 acc0 = f2_splat(0.f), acc1 = f2_splat(0.f);
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                  const float p0 = ex2_approx(fmaf(__uint_as_float(x[j]), p.scale_log2e, -ms));
-                  const float p1 = ex2_approx(fmaf(__uint_as_float(x[j + 1]), p.scale_log2e, -ms));
-                  const float p2 = ex2_approx(fmaf(__uint_as_float(x[j + 2]), p.scale_log2e, -ms));
-                  const float p3 = ex2_approx(fmaf(__uint_as_float(x[j + 3]), p.scale_log2e, -ms));
-                  s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+                  float e0, e1, e2, e3;
+                  f2_unpack(f2_fma(f2_pack(__uint_as_float(x[j]), __uint_as_float(x[j + 1])), sc2, nm2), e0, e1);
+                  f2_unpack(f2_fma(f2_pack(__uint_as_float(x[j + 2]), __uint_as_float(x[j + 3])), sc2, nm2), e2, e3);
+                  const float p0 = ex2_approx(e0), p1 = ex2_approx(e1), p2 = ex2_approx(e2), p3 = ex2_approx(e3);
+                  acc0 = f2_add(acc0, f2_pack(p0, p1));
+                  acc1 = f2_add(acc1, f2_pack(p2, p3));
                   if (kDrop) {
                     pp[j >> 1] = pack_bf16((keep >> j) & 1u ? p0 : 0.f, (keep >> (j + 1)) & 1u ? p1 : 0.f);
                     pp[(j >> 1) + 1] = pack_bf16((keep >> (j + 2)) & 1u ? p2 : 0.f, (keep >> (j + 3)) & 1u ? p3 : 0.f);
@@ -1230,7 +1256,22 @@ attention_fwd_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                     pp[(j >> 1) + 1] = pack_bf16(p2, p3);
                   }
                 }
+                float s0, s1, s2, s3;
+                f2_unpack(acc0, s0, s1);
+                f2_unpack(acc1, s2, s3);
                 sum += (s0 + s1) + (s2 + s3);
+              } else if (dense && !kDrop) {
+                const int rem = klen - c * 32;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) pp[j] = 0u;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                  if (j >= rem) break;
+                  const float p0 = ex2_approx(fmaf(__uint_as_float(x[j]), p.scale_log2e, -ms));
+                  const float p1 = j + 1 < rem ? ex2_approx(fmaf(__uint_as_float(x[j + 1]), p.scale_log2e, -ms)) : 0.f;
+                  sum += p0 + p1;
+                  pp[j >> 1] = pack_bf16(p0, p1);
+                }
               } else {
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {

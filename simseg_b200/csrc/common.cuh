@@ -124,6 +124,13 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 // ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 — one issue slot and one FMA-pipe pass for two lanes) ------
 // The GELU epilogues are issue-bound: evaluating two adjacent columns per instruction halves the
 // FMA-pipe instruction count.  A value is two fp32 in one 64-bit register pair (.x = low word).
+// three-input maximum (FMNMX3 on sm_100)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
   f32x2 r;
