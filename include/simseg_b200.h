@@ -93,7 +93,7 @@ int simseg_gemm(simseg_ctx* ctx, const simseg_gemm_args* args, void* stream);
 int simseg_cast_bf16(simseg_ctx* ctx, const float* src, void* dst, void* dst_t, int64_t rows, int64_t cols,
                      void* stream);
 /* The same cast for many weights in one launch (the per-optimizer-step bf16 refresh of every Linear weight).  `items` is a
- * DEVICE array; item i covers blocks [first_block, first_block + ceil(rows/32)*ceil(cols/32)) of the 1-D grid of
+ * DEVICE array; item i covers blocks [first_block, first_block + ceil(rows/32)*ceil(cols/128)) of the 1-D grid of
  * `total_blocks` blocks (first_block ascending).  dst rows have pitch `ld` (>= cols), dst_t rows pitch `ld_t` (>= rows) so
  * several weights can land side by side in one packed matrix (BERT q/k/v); dst or dst_t may be NULL. */
 typedef struct simseg_cast_item {

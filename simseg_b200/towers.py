@@ -123,7 +123,7 @@ class Bf16Weights:
             host[i, 5] = it["ld"] or it["cols"]
             host[i, 6] = it["ld_t"] or it["rows"]
             host[i, 7] = fb
-            fb += ((it["rows"] + 31) // 32) * ((it["cols"] + 31) // 32)
+            fb += ((it["rows"] + 31) // 32) * ((it["cols"] + 127) // 128)     # one block = 32 rows x 128 columns
         dev = next(iter(items))["p"].device
         table = host.to(dev)
         self._keep = [table]
