@@ -398,6 +398,45 @@ def _qkv_params(layer):
     return [a.query, a.key, a.value]
 
 
+def qkv_adjacent_order(named_params):
+    """Parameters of the BERT tower in an order that puts each layer's query / key / value weights next to each other (and
+    their biases likewise).  ``dist.FlatGrads`` lays gradients out in the order it is given, so with this order the three
+    weight gradients of a layer are ONE contiguous [3D, D] matrix and ``bert_backward`` fills it with a single wgrad GEMM
+    (and one column-sum launch for the biases) instead of three of each."""
+    named = list(named_params)
+    by_name = dict(named)
+    out, done = [], set()
+    for name, p in named:
+        if name in done:
+            continue
+        if name.endswith("attention.self.query.weight"):
+            base = name[:-len("query.weight")]
+            for suffix in ("query.weight", "key.weight", "value.weight", "query.bias", "key.bias", "value.bias"):
+                if base + suffix in by_name:
+                    out.append(by_name[base + suffix])
+                    done.add(base + suffix)
+            continue
+        out.append(p)
+        done.add(name)
+    return out
+
+
+def _adjacent(ts: List[Tensor]) -> Optional[Tensor]:
+    """One tensor over ``ts`` stacked along dim 0 if they sit back to back in one fp32 buffer (see ``qkv_adjacent_order``)."""
+    t0 = ts[0]
+    end = t0.data_ptr() + t0.numel() * 4
+    for t in ts[1:]:
+        if (t.dtype != torch.float32 or not t.is_contiguous() or t.shape[1:] != t0.shape[1:] or t.data_ptr() != end
+                or t.untyped_storage().data_ptr() != t0.untyped_storage().data_ptr()):
+            return None
+        end += t.numel() * 4
+    if t0.dtype != torch.float32 or not t0.is_contiguous():
+        return None
+    rows = sum(t.shape[0] for t in ts)
+    size = (rows,) + tuple(t0.shape[1:])
+    return torch.as_strided(t0, size, t0.stride())
+
+
 def bert_forward(m, input_ids: Tensor, attention_mask: Tensor, wc: Bf16Weights, save: bool,
                  drop: Optional[BertDropout] = None):
     """HF ``BertModel(...).last_hidden_state`` as called by ``huggingface_builder.py:16-17``; ``drop`` = train-mode dropout
@@ -513,10 +552,19 @@ def bert_backward(m, sv: BertSaved, dh: Tensor, wc: Bf16Weights, dh2: Optional[T
                               d5[:, :, 0], d5[:, :, 1], d5[:, :, 2])
         del dc
         qp = _qkv_params(layer)
-        bsum = ops.colsum(dqkv)
-        for j, p in enumerate(qp):
-            _grad_of(p.bias).add_(bsum[j * D:(j + 1) * D])
-            ops.linear_wgrad(dqkv[:, j * D:(j + 1) * D], s.h_in, _grad_of(p.weight), accumulate=True)
+        gw, gb = [_grad_of(p.weight) for p in qp], [_grad_of(p.bias) for p in qp]
+        gw_all, gb_all = _adjacent(gw), _adjacent(gb)
+        if gb_all is not None:
+            ops.colsum(dqkv, gb_all, accumulate=True)
+        else:
+            bsum = ops.colsum(dqkv)
+            for j in range(3):
+                gb[j].add_(bsum[j * D:(j + 1) * D])
+        if gw_all is not None:                            # the three weight gradients are one [3D, D] matrix: one GEMM
+            ops.linear_wgrad(dqkv, s.h_in, gw_all, accumulate=True)
+        else:
+            for j in range(3):
+                ops.linear_wgrad(dqkv[:, j * D:(j + 1) * D], s.h_in, gw[j], accumulate=True)
         dy = ops.linear_dgrad(dqkv, wc.packed_t(f"bert.qkv.{li}", [p.weight for p in qp]))
         dres = ds1
         sv.layers[li] = None

@@ -25,6 +25,7 @@ from typing import Dict, Optional
 import torch
 
 from . import dist as sdist
+from . import towers
 from .pipeline import CLIPModel
 
 Tensor = torch.Tensor
@@ -73,7 +74,7 @@ class Trainer:
     def __init__(self, model: CLIPModel, cfg, micro_batch: Optional[int] = None, capturable: bool = False):
         self.model, self.cfg, self.micro_batch = model, cfg, micro_batch
         vit = list(model.image_encoder.parameters())
-        bert = list(model.text_encoder.parameters())
+        bert = towers.qkv_adjacent_order(model.text_encoder.named_parameters())   # q/k/v gradients of a layer back to back
         heads = [p for n, p in model.named_parameters() if not n.startswith(("image_encoder.", "text_encoder."))]
         # a frozen tower (image_encoder.trainable / text_encoder.trainable = False) simply has no buffer
         self.flat = {name: sdist.FlatGrads(ps) for name, ps in (("vit", vit), ("bert", bert), ("heads", heads))

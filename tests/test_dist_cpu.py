@@ -92,3 +92,30 @@ def test_single_process_paths_are_identity():
     assert sdist.all_gather_rows(x, None) is x
     assert sdist.reduce_scatter_rows(x, 0, 4, None) is x
     assert sdist.rank() == 0 and sdist.world_size() == 1
+
+
+def test_qkv_gradients_are_one_matrix_under_flatgrads():
+    """``towers.qkv_adjacent_order`` + ``dist.FlatGrads``: a BERT layer's query / key / value weight gradients form ONE
+    contiguous [3D, D] matrix (one wgrad GEMM in ``bert_backward``), the biases one [3D] vector; every parameter appears
+    exactly once and the packed view aliases the per-parameter ``.grad`` tensors."""
+    import torch
+    from simseg_b200 import towers
+    from simseg_b200.dist import FlatGrads
+    from simseg_b200.pipeline import BertModel
+    bert = BertModel(vocab=100, dim=64, heads=1, ffn=128, depth=2, max_pos=16)
+    params = list(bert.parameters())
+    order = towers.qkv_adjacent_order(bert.named_parameters())
+    assert len(order) == len(params) and {id(p) for p in order} == {id(p) for p in params}
+    FlatGrads(order)
+    for layer in bert.encoder.layer:
+        qp = towers._qkv_params(layer)
+        w = towers._adjacent([p.weight.grad for p in qp])
+        b = towers._adjacent([p.bias.grad for p in qp])
+        assert w is not None and w.shape == (192, 64) and b is not None and b.shape == (192,)
+        w[64:128].fill_(2.0)
+        b[128:].fill_(3.0)
+        assert qp[1].weight.grad.eq(2.0).all() and qp[0].weight.grad.eq(0.0).all() and qp[2].weight.grad.eq(0.0).all()
+        assert qp[2].bias.grad.eq(3.0).all() and qp[1].bias.grad.eq(0.0).all()
+    # module order (weight, bias interleaved) is not adjacent: bert_backward then keeps three GEMMs
+    FlatGrads(params)
+    assert towers._adjacent([p.weight.grad for p in towers._qkv_params(bert.encoder.layer[0])]) is None
