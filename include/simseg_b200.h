@@ -106,7 +106,8 @@ int simseg_cast_bf16_multi(simseg_ctx* ctx, const simseg_cast_item* items, int n
 /* bf16/f32 column sums: out[n] (+)= sum_m x[m,n]   (bias gradients) */
 int simseg_colsum(simseg_ctx* ctx, const void* x, int dtype, int64_t M, int64_t N, int64_t ldx, float* out,
                   int accumulate, void* stream);
-/* a = gelu_erf(h)  (recomputed in backward instead of being stored) */
+/* a = gelu_erf(h), bf16 -> bf16 (timm Mlp / HF BertIntermediate activation as a standalone pass; the towers do not use it:
+ * forward applies GELU in the fc1 GEMM epilogue, backward gets gelu(h) kept from the forward or re-emitted by the dGELU epilogue) */
 int simseg_gelu_fwd(simseg_ctx* ctx, const void* h, void* a, int64_t n, void* stream);
 
 /* LayerNorm over the last dim (timm LayerNorm eps 1e-6, HF BERT LayerNorm eps 1e-12).
