@@ -561,7 +561,8 @@ class HuggingFaceModel(nn.Module):
 
     def seed_dropout(self, seed: int, step: int = 0):
         """Fix the dropout stream: masks are a pure function of (seed, step, site, element); the next train-mode forward
-        uses step + 1.  Without a call, the seed is ``torch.initial_seed() + rank`` at the first train-mode forward."""
+        uses step + 1.  Without a call, the seed is ``torch.initial_seed()`` at the first train-mode forward; rank r adds a
+        fixed multiple of r to the key it uses."""
         self.drop_rng.copy_(torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, step], dtype=torch.int64))
         self._drop_seeded = True
 
@@ -569,8 +570,7 @@ class HuggingFaceModel(nn.Module):
         """The device {seed, step} pair (seeded on first use).  ``train.Trainer`` snapshots / restores it around the two passes
         of the micro-batched step so that pass 2 re-draws pass 1's masks."""
         if not self._drop_seeded:
-            rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
-            self.seed_dropout(torch.initial_seed() + 0x9E3779B97F4A7C15 * rank)
+            self.seed_dropout(torch.initial_seed())
         return self.drop_rng
 
     def _dropout(self):
@@ -578,7 +578,13 @@ class HuggingFaceModel(nn.Module):
             return None
         self.dropout_state()
         self.drop_rng[1] += 1
-        return towers.BertDropout(float(self.hidden_dropout_prob), float(self.attention_probs_dropout_prob), self.drop_rng.clone())
+        rng = self.drop_rng.clone()
+        # ranks draw different masks: the rank enters the key of THIS forward's copy, not the buffer (a torch DDP wrap broadcasts
+        # module buffers from rank 0, which would otherwise hand every rank the same stream)
+        rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
+        if rank:
+            rng[0] += (rank * 0x9E3779B97F4A7C15) & 0x3FFFFFFFFFFFFFFF
+        return towers.BertDropout(float(self.hidden_dropout_prob), float(self.attention_probs_dropout_prob), rng)
 
     def forward(self, input_ids, attention_mask, **kwargs):
         _check_text(input_ids, attention_mask, self.model)

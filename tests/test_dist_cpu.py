@@ -63,6 +63,28 @@ def _worker(rank, world, port, q):
         fg.zero()
         out["reattach_ok"] = ps[0].grad is not None and ps[0].grad.data_ptr() == fg.flat.data_ptr()
         out["rank_world"] = (sdist.rank(), sdist.world_size())
+        # ---- BERT dropout stream: same {seed, step} buffer on every rank (a DDP wrap broadcasts buffers), rank-specific key
+        from simseg_b200.config import load_cfg
+        from simseg_b200.pipeline import HuggingFaceModel, _Shared
+        cfg = load_cfg("simseg.vit-s.yaml", ["model.image_encoder.pretrained=False", "model.text_encoder.pretrained=False"])
+        real = HuggingFaceModel.__init__
+
+        def light(self, cfg_, shared, **kw):               # the stream logic without allocating BERT-base on two CPU ranks
+            torch.nn.Module.__init__(self)
+            self.hidden_dropout_prob = self.attention_probs_dropout_prob = 0.1
+            self.register_buffer("drop_rng", torch.zeros(2, dtype=torch.int64), persistent=False)
+            self._drop_seeded = False
+        HuggingFaceModel.__init__ = light
+        try:
+            hf = HuggingFaceModel(cfg, _Shared())
+        finally:
+            HuggingFaceModel.__init__ = real
+        hf.seed_dropout(1234, 7)
+        d = hf._dropout()
+        out["drop_buf"] = hf.drop_rng.tolist()
+        out["drop_key"] = d.rng.tolist()
+        hf.eval()
+        out["drop_eval_none"] = hf._dropout() is None
         q.put((rank, out))
         dist.barrier()
     finally:
@@ -84,6 +106,9 @@ def test_two_rank_gather_reduce_scatter_and_flat_grads():
         assert o["gather_ok"] and o["flat_ok"] and o["reattach_ok"]
         assert o["rank_world"] == (r, 2)
         assert o["loss_err"] < 1e-5 and o["dimg_err"] < 1e-5 and o["dtxt_err"] < 1e-5, o
+        assert o["drop_buf"] == [1234, 8] and o["drop_eval_none"]           # the forward bumped step; eval draws nothing
+        assert o["drop_key"] == [1234 + ((r * 0x9E3779B97F4A7C15) & 0x3FFFFFFFFFFFFFFF), 8]
+    assert res[0]["drop_key"] != res[1]["drop_key"]
 
 
 def test_single_process_paths_are_identity():
