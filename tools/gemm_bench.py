@@ -87,11 +87,11 @@ if __name__ == "__main__":
         sys.exit(0)
     if which == "prof":     # one launch per configuration, for `ncu --set full -k regex:gemm_kernel`
         f32 = torch.float32
-        bench("vit-b fc1 dgrad (pair 256x256)", 201728, 768, 3072, reps=1, tile_ns=(0,), dbg=64)
-        bench("vit-s fc2 fwd (pair 256x192)", 806912, 384, 1536, reps=1, tile_ns=(0,), dbg=64)
-        bench("vit-s fc1 fwd gelu+aux", 806912, 1536, 384, epi=EPI_BIAS_GELU, reps=1, tile_ns=(0,), dbg=64)
-        bench("vit-s fc2 dgrad dgelu+colsum", 806912, 1536, 384, epi=EPI_DGELU, reps=1, tile_ns=(0,), dbg=64)
-        bench("vit-s fc2 wgrad (pair 256x384, dW^T)", 384, 1536, 806912, a_major=1, b_major=1, out_dtype=f32, reps=1, tile_ns=(0,), accumulate=True, dbg=64)
+        bench("vit-b fc1 dgrad (pair 256x256)", 201728, 768, 3072, reps=1, tile_ns=(0,))
+        bench("vit-s fc2 fwd (pair 256x192)", 806912, 384, 1536, reps=1, tile_ns=(0,))
+        bench("vit-s fc1 fwd gelu+aux", 806912, 1536, 384, epi=EPI_BIAS_GELU, reps=1, tile_ns=(0,))
+        bench("vit-s fc2 dgrad dgelu+colsum", 806912, 1536, 384, epi=EPI_DGELU, reps=1, tile_ns=(0,))
+        bench("vit-s fc2 wgrad (pair 256x384, dW^T)", 384, 1536, 806912, a_major=1, b_major=1, out_dtype=f32, reps=1, tile_ns=(0,), accumulate=True)
         sys.exit(0)
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
     if which == "layouts":
