@@ -383,6 +383,17 @@ __device__ __forceinline__ void epilogue_act16(const GemmParams& p, const CUtens
 #pragma unroll
     for (int j = 0; j < kCw; ++j, ++f) {
       const int col = n0 + (grp + kG * j) * 32;
+      // dGELU with gelu(h) kept from the forward (aux2 == NULL): the pre-activation box of the NEXT chunk is requested now, a
+      // whole chunk ahead — its slot was last read (generic proxy, fenced) in chunk f - 1.  With the re-emit the slot is the
+      // source of chunk f - 1's gelu(h) store and can only be refilled once that store has read it (below).
+      const bool early_aux = EPI == SIMSEG_EPI_DGELU && p.aux2 == nullptr && !(p.dbg & 4);
+      if (early_aux && lane == 0) {
+        int r2, c2;
+        if (coords(f + 1, r2, c2)) {
+          mbar_arrive_expect_tx(&aux_full[(f + 1) & 1], kEpiBoxBytes);
+          tma_load_2d(stg + ((f + 1) & 1) * kEpiBoxBytes, &tmap_x, &aux_full[(f + 1) & 1], c2, r2);
+        }
+      }
       uint32_t r[32];
       tmem_ld_32x32(t_row + (grp + kG * j) * 32, r);
       tmem_ld_wait();
@@ -459,7 +470,7 @@ __device__ __forceinline__ void epilogue_act16(const GemmParams& p, const CUtens
       // ---- the boxes written below must have been read by the bulk group of the previous chunk
       if (lane == 0) {
         tma_store_wait_read<0>();
-        if (EPI == SIMSEG_EPI_DGELU) {
+        if (EPI == SIMSEG_EPI_DGELU && !early_aux) {
           int r2, c2;
           if (coords(f + 1, r2, c2)) {                               // slot (f+1)&1 == (f-1)&1: its aux2 store has been read
             mbar_arrive_expect_tx(&aux_full[(f + 1) & 1], kEpiBoxBytes);
@@ -1209,7 +1220,8 @@ int gemm_impl(Ctx* ctx, const simseg_gemm_args* a, cudaStream_t st) { return gem
 
 // `reserved` bits (bench / debug only): 1 = no TMA, 2 = no MMA, 4 = 2-D boxes for MN-major operands, 8 = direct-store
 // epilogue, 16 = force single-CTA tiles, 32 = force CTA pairs, 64 = activation epilogues on 8 warps (the round-1 version),
-// 128 = no wide (256 x 384|512) split-K tiles, 256 = 16-warp GELU epilogue regardless of K.
+// 128 = no wide (256 x 384|512) split-K tiles, 256 = 16-warp GELU epilogue regardless of K, 512 = dGELU pre-activation
+// boxes requested late (after the chunk's math, the order the gelu(h) re-emit needs) even when gelu(h) was kept.
 // `sim` != NULL: split-bf16 operands (a / b are the hi halves, sim->a_lo / b_lo the lo halves, K counts ONE segment) and
 // optionally one of the similarity epilogues (sim->epi = 0 keeps a->epilogue).
 int gemm_sim_impl(Ctx* ctx, const simseg_gemm_args* a, const GemmSim* sim, cudaStream_t st) {
@@ -1362,7 +1374,7 @@ int gemm_sim_impl(Ctx* ctx, const simseg_gemm_args* a, const GemmSim* sim, cudaS
   if (a->aux) vec = vec && (a->ld_aux * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0;
   if (a->bias) vec = vec && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0;
   p.vec_ok = vec ? 1 : 0;
-  p.dbg = a->reserved & 3;
+  p.dbg = (a->reserved & 3) | ((a->reserved & 512) ? 4 : 0);          // 4 = late pre-activation prefetch (A/B)
 
   if ((p.splits > 1 || wide_bn) && !a->accumulate) {
     // partial sums are reduced with atomics: start from zero (D is stored [N, M] when d_trans)
