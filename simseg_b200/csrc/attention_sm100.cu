@@ -71,6 +71,13 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
 
 __device__ __forceinline__ int ceil16(int x) { return (x + 15) & ~15; }
 
+// 0 or 0xffffffff from bit `pos` of `word` (signed one-bit field extract)
+__device__ __forceinline__ uint32_t bit_mask(uint32_t word, int pos) {
+  int32_t r;
+  asm("bfe.s32 %0, %1, %2, 1;" : "=r"(r) : "r"(static_cast<int32_t>(word)), "r"(pos));
+  return static_cast<uint32_t>(r);
+}
+
 // ---- debug: per-warp phase timing of CTA 0, read back with simseg_debug_trace_read (tools/attn_trace.py) ----------------
 // Only in builds with -DSIMSEG_ATTN_TRACE (the register cost perturbs the kernel: use for RELATIVE shares only), armed with
 // simseg_debug_trace_enable(1).  Slot 0 = MMA warp, slots 1.. = elementwise warps 2, 3, 6, 10.
@@ -417,6 +424,16 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         tr(22);
       }
     };
+    // dropout keep word of (item, key tile, query tile) for this thread's row and 32-key chunk; all-ones where the chunk or the
+    // row quarter is not live (never used there)
+    auto load_keep = [&](int item_, int kt_, int qt_) -> uint32_t {
+      const int nkc_ = min(kTile, ceil16(p.rows - kt_ * kTile));
+      if (!(col0 < nkc_ && qt_ * kTile + quarter * 32 < ceil16(p.rows))) return 0xffffffffu;
+      const int qrow_ = qt_ * kTile + r;
+      return __ldg(p.drop_mask + (static_cast<int64_t>(item_) * p.rows + min(qrow_, p.rows - 1)) * p.mask_nw + kt_ * 4 + cq);
+    };
+    uint32_t keep_next = 0xffffffffu;
+    if (kDrop && static_cast<int>(blockIdx.x) < p.items) keep_next = load_keep(blockIdx.x, 0, 0);
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
       const int b = item / p.HG, h0 = (item - b * p.HG) * p.G;
       // klen = live key COLUMNS (packed: key tokens * G, column = token * G + head); a column is live for a row iff it
@@ -435,13 +452,14 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           const int qslot = (p.nqt == 1) ? static_cast<int>(it & 1) : qt;     // Q / dO slot (single-tile items alternate slots)
           const uint32_t quse = (p.nqt == 1) ? (it >> 1) : it;
           // ---- phase A: S -> P (kept as packed bf16 in registers for phase B), P into smem
-          // keep bits of this thread's (row, 32-key chunk): requested before the wait below, used after it; read again for
-          // phase B (an L1 / L2 hit) instead of being held in a register across the drain
-          const uint32_t* keep_ptr = nullptr;
+          // keep bits of this thread's (row, 32-key chunk): the word was requested a whole block ago (keep_next), the word of
+          // the NEXT block — same item or the CTA's next item — is requested now, so the global load is never waited for
           uint32_t keep = 0xffffffffu;
-          if (kDrop && chunk_live && rows_live) {
-            keep_ptr = p.drop_mask + (static_cast<int64_t>(item) * p.rows + min(qrow, p.rows - 1)) * p.mask_nw + kt * 4 + cq;
-            keep = __ldg(keep_ptr);
+          if (kDrop) {
+            keep = keep_next;
+            int n_item = item, n_kt = kt, n_qt = qt + 1;
+            if (n_qt == p.nqt) { n_qt = 0; if (++n_kt == p.nkt) { n_kt = 0; n_item += gridDim.x; } }
+            if (n_item < p.items) keep_next = load_keep(n_item, n_kt, n_qt);
           }
           tr(10);
           mbar_wait(s_full, g & 1);                                    // implies the Q / dO tiles of this qt have landed
@@ -506,7 +524,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           if (chunk_live && rows_live && !(p.dbg & 4)) {
             if (kDrop) {
               auto pm = [&](int i) {                                   // pair i = keys 2 i, 2 i + 1 of the chunk
-                return pp[i] & (((0u - ((keep >> (2 * i)) & 1u)) & 0xffffu) | ((0u - ((keep >> (2 * i + 1)) & 1u)) & 0xffff0000u));
+                // bfe.s32 of one bit = 0 or ~0: two field extracts, one select-by-constant (LOP3), one AND — no predicates
+                return pp[i] & ((bit_mask(keep, 2 * i) & 0xffffu) | (bit_mask(keep, 2 * i + 1) & 0xffff0000u));
               };
 #pragma unroll
               for (int q4 = 0; q4 < 4; ++q4)
@@ -527,7 +546,6 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           if (!kLateDrain) drain_pending();                              // accumulators of the previous key tile / item
 
           // ---- phase B: dP -> dS = P * (dP - D), dS into smem
-          if (kDrop && keep_ptr != nullptr) keep = __ldg(keep_ptr);
           mbar_wait(dp_full, g & 1);
           tr(16);
           tc_fence_after();
@@ -544,14 +562,16 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
               for (int j = 0; j < 32; ++j) dr[j] = 0;
             }
             const f32x2 nd2 = f2_splat(-Dq);
+            const f32x2 ik2 = f2_splat(p.inv_keep);
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               const uint32_t pk = pp[j >> 1];                          // masked entries are exactly 0 -> dS = 0
               float d0, d1;
               if (kDrop) {
-                const f32x2 mk = f2_pack((keep >> j) & 1u ? p.inv_keep : 0.f, (keep >> (j + 1)) & 1u ? p.inv_keep : 0.f);
+                // dropped keys: dP := 0 by masking its bits, then one packed FMA with the splat 1 / (1 - p)
                 f2_unpack(f2_mul(f2_pack(bf16_lo(pk), bf16_hi(pk)),
-                                 f2_fma(f2_pack(__uint_as_float(dr[j]), __uint_as_float(dr[j + 1])), mk, nd2)), d0, d1);
+                                 f2_fma(f2_pack(__uint_as_float(dr[j] & bit_mask(keep, j)), __uint_as_float(dr[j + 1] & bit_mask(keep, j + 1))),
+                                        ik2, nd2)), d0, d1);
               } else {
                 f2_unpack(f2_mul(f2_pack(bf16_lo(pk), bf16_hi(pk)),
                                  f2_add(f2_pack(__uint_as_float(dr[j]), __uint_as_float(dr[j + 1])), nd2)), d0, d1);
@@ -1193,7 +1213,18 @@ attention_fwd_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         tc_fence_after();
         float m = -INFINITY, sum = 0.f;
         const uint32_t* mrow = nullptr;
-        if (kDrop) mrow = p.drop_mask + (static_cast<int64_t>(item) * p.rows + (q_ok ? qrow : 0)) * p.mask_nw;
+        uint32_t kw0 = 0xffffffffu, kw1 = 0xffffffffu, kw2 = 0xffffffffu, kw3 = 0xffffffffu;
+        if (kDrop) {
+          // the row's first four keep words (128 key columns: every packed case and T <= 128) are requested before pass 1 and
+          // used in pass 2; longer rows read the remaining words in place
+          mrow = p.drop_mask + (static_cast<int64_t>(item) * p.rows + (q_ok ? qrow : 0)) * p.mask_nw;
+          if (warp_live) {
+            kw0 = __ldg(mrow);
+            if (nch > 1) kw1 = __ldg(mrow + 1);
+            if (nch > 2) kw2 = __ldg(mrow + 2);
+            if (nch > 3) kw3 = __ldg(mrow + 3);
+          }
+        }
         if (warp_live) {
           // ---- pass 1: row max
           for (int c = 0; c < nch; ++c) {
@@ -1233,7 +1264,7 @@ attention_fwd_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             if (c < nch) {
               uint32_t x[32];
               uint32_t keep = 0xffffffffu;
-              if (kDrop) keep = __ldg(mrow + c);
+              if (kDrop) keep = c == 0 ? kw0 : c == 1 ? kw1 : c == 2 ? kw2 : c == 3 ? kw3 : __ldg(mrow + c);
               tmem_ld_32x32(tS + c * 32, x);
               tmem_ld_wait();
               if (dense && c * 32 + 32 <= klen) {
@@ -1249,8 +1280,8 @@ attention_fwd_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                   acc0 = f2_add(acc0, f2_pack(p0, p1));
                   acc1 = f2_add(acc1, f2_pack(p2, p3));
                   if (kDrop) {
-                    pp[j >> 1] = pack_bf16((keep >> j) & 1u ? p0 : 0.f, (keep >> (j + 1)) & 1u ? p1 : 0.f);
-                    pp[(j >> 1) + 1] = pack_bf16((keep >> (j + 2)) & 1u ? p2 : 0.f, (keep >> (j + 3)) & 1u ? p3 : 0.f);
+                    pp[j >> 1] = pack_bf16(p0, p1) & ((bit_mask(keep, j) & 0xffffu) | (bit_mask(keep, j + 1) & 0xffff0000u));
+                    pp[(j >> 1) + 1] = pack_bf16(p2, p3) & ((bit_mask(keep, j + 2) & 0xffffu) | (bit_mask(keep, j + 3) & 0xffff0000u));
                   } else {
                     pp[j >> 1] = pack_bf16(p0, p1);
                     pp[(j >> 1) + 1] = pack_bf16(p2, p3);
@@ -1280,11 +1311,8 @@ attention_fwd_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                   p0 = (c * 32 + j < klen && ((c * 32 + j) & gm) == rg) ? p0 : 0.f;
                   p1 = (c * 32 + j + 1 < klen && ((c * 32 + j + 1) & gm) == rg) ? p1 : 0.f;
                   sum += p0 + p1;
-                  if (kDrop) {
-                    p0 = (keep >> j) & 1u ? p0 : 0.f;
-                    p1 = (keep >> (j + 1)) & 1u ? p1 : 0.f;
-                  }
                   pp[j >> 1] = pack_bf16(p0, p1);
+                  if (kDrop) pp[j >> 1] &= (bit_mask(keep, j) & 0xffffu) | (bit_mask(keep, j + 1) & 0xffff0000u);
                 }
               }
             } else {
