@@ -33,7 +33,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         path = os.path.join(CSRC, src)
         if force or _stale(obj, [path] + headers):
-            cmd = [nvcc] + FLAGS + ["-c", path, "-o", obj]
+            # SIMSEG_NVCC_DEFINES="-DSIMSEG_ATTN_KNOCKOUT -DSIMSEG_ATTN_TRACE": instrumented builds for tools/attn_knockout.py /
+            # tools/attn_trace.py (use with --force; the product build carries neither)
+            cmd = [nvcc] + FLAGS + os.environ.get("SIMSEG_NVCC_DEFINES", "").split() + ["-c", path, "-o", obj]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if verbose or r.returncode:
                 sys.stderr.write(r.stdout + r.stderr)

@@ -69,6 +69,15 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
                : "memory");
 }
 
+// Timing knock-outs of the backward (SIMSEG_ATTN_DBG bits, results wrong: tools/attn_knockout.py) exist only in builds with
+// -DSIMSEG_ATTN_KNOCKOUT: tested at run time they cost a predicate / select per element in the unrolled elementwise loops of the
+// production kernel, whose instruction footprint is its second largest stall reason (no_inst, profiles/r02_ncu_attention.txt).
+#ifdef SIMSEG_ATTN_KNOCKOUT
+#define KO(bit) ((p.dbg & (bit)) != 0)
+#else
+#define KO(bit) false
+#endif
+
 __device__ __forceinline__ int ceil16(int x) { return (x + 15) & ~15; }
 
 // 0 or 0xffffffff from bit `pos` of `word` (signed one-bit field extract)
@@ -258,7 +267,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           const uint32_t aQ = smem_u32(sQ + slot_of(c) * kTileBytes) >> 4, aK = smem_u32(sK + buf * kTileBytes) >> 4;
           const uint32_t id = idesc_sdp(c);
 #pragma unroll
-          if (!(p.dbg & 32))
+          if (!KO(32))
             for (int kk = 0; kk < 4; ++kk) umma_f16(tS, kd + aQ + 2 * kk, kd + aK + 2 * kk, id, kk > 0 ? 1u : 0u);
           umma_commit(s_full);
         }
@@ -270,7 +279,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           const uint32_t adO = smem_u32(sdO + slot_of(c) * kTileBytes) >> 4, aV = smem_u32(sV + buf * kTileBytes) >> 4;
           const uint32_t id = idesc_sdp(c);
 #pragma unroll
-          if (!(p.dbg & 32))
+          if (!KO(32))
             for (int kk = 0; kk < 4; ++kk) umma_f16(tdP, kd + adO + 2 * kk, kd + aV + 2 * kk, id, kk > 0 ? 1u : 0u);
           umma_commit(dp_full);
         }
@@ -297,7 +306,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         tc_fence_after();
         if (elect_one()) {
           // dV += P^T dO      (A MN-major: key atoms 16 KB apart; K-step = 16 q rows = 2048 B)
-          for (int ks = 0; ks < ((p.dbg & 16) ? 0 : qsteps); ++ks)
+          for (int ks = 0; ks < (KO(16) ? 0 : qsteps); ++ks)
             umma_f16(tdV, md + aP + 128 * ks, md + adO + 128 * ks, id_dkv, (c.qt > 0 || ks > 0) ? 1u : 0u);
           umma_commit(p_free);
         }
@@ -313,10 +322,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         if (valid(n)) { issue_dp(n); advance(n); }                           // ahead of dK / dQ: phase B of the next block waits for it
         if (elect_one()) {
           // dK += dS^T Q
-          for (int ks = 0; ks < ((p.dbg & 16) ? 0 : qsteps); ++ks)
+          for (int ks = 0; ks < (KO(16) ? 0 : qsteps); ++ks)
             umma_f16(tdK, md + adS + 128 * ks, md + aQ + 128 * ks, id_dkv, (c.qt > 0 || ks > 0) ? 1u : 0u);
           // dQ += dS K        (A K-major: 4 K-steps per 64-key atom; B MN-major: K-step = 16 key rows)
-          for (int ks = 0; ks < ((p.dbg & 16) ? 0 : ksteps); ++ks)
+          for (int ks = 0; ks < (KO(16) ? 0 : ksteps); ++ks)
             umma_f16(tdQ + 64 * c.qt, kd + adS + (ks >> 2) * (kTileBytes >> 4) + (ks & 3) * 2, md + aK + 128 * ks, id_dq,
                      (c.kt > 0 || ks > 0) ? 1u : 0u);
           umma_commit(ds_free);
@@ -366,7 +375,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         *reinterpret_cast<uint4*>(mine + ((j ^ swz) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0 && tile_row0 < p.rows && !(p.dbg & 8)) {
+      if (lane == 0 && tile_row0 < p.rows && !KO(8)) {
         tma_store_4d(tm, stg, dcol0, sh0, tile_row0 >> p.lg, sb_idx);
         tma_store_commit();
       }
@@ -471,9 +480,9 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           const float Dq = dl.x, Lq = dl.y;
           tr(12);
           uint32_t pp[16];
-          if (chunk_live && rows_live && !(p.dbg & 128)) {
+          if (chunk_live && rows_live && !KO(128)) {
             uint32_t sr[32];
-            if (!(p.dbg & 64)) {
+            if (!KO(64)) {
               tmem_ld_32x32(tS + lane_off + col0, sr);
               tmem_ld_wait();
             } else {
@@ -511,7 +520,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
               for (int j = 0; j < 32; j += 2) {
                 float e0, e1;
                 f2_unpack(f2_fma(f2_pack(__uint_as_float(sr[j]), __uint_as_float(sr[j + 1])), sc2, nl2), e0, e1);
-                pp[j >> 1] = (p.dbg & 1) ? pack_bf16(e0, e1) : pack_bf16(ex2_approx(e0), ex2_approx(e1));
+                pp[j >> 1] = KO(1) ? pack_bf16(e0, e1) : pack_bf16(ex2_approx(e0), ex2_approx(e1));
               }
             }
           }
@@ -521,7 +530,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           // 32 keys = four 16-byte chunks of this row inside key atom (col0 / 64)
           const uint32_t rowoff = (col0 >> 6) * kTileBytes + r * 128;
           const int ch0 = (col0 & 63) >> 3;
-          if (chunk_live && rows_live && !(p.dbg & 4)) {
+          if (chunk_live && rows_live && !KO(4)) {
             if (kDrop) {
               auto pm = [&](int i) {                                   // pair i = keys 2 i, 2 i + 1 of the chunk
                 // bfe.s32 of one bit = 0 or ~0: two field extracts, one select-by-constant (LOP3), one AND — no predicates
@@ -552,9 +561,9 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           if (g > 0) mbar_wait(ds_free, (g - 1) & 1);
           tr(17);                  // dK / dQ of the previous block have read sdS (issued a
                                                                        // whole phase A ago: this wait does not stall)
-          if (chunk_live && rows_live && !(p.dbg & 2)) {
+          if (chunk_live && rows_live && !KO(2)) {
             uint32_t dr[32], dd[16];
-            if (!(p.dbg & 64)) {
+            if (!KO(64)) {
               tmem_ld_32x32(tdP + lane_off + col0, dr);
               tmem_ld_wait();
             } else {
@@ -578,7 +587,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
               }
               dd[j >> 1] = pack_bf16(d0, d1);
             }
-            if (!(p.dbg & 4))
+            if (!KO(4))
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4)
               *reinterpret_cast<uint4*>(sdS + rowoff + (((ch0 + q4) ^ sw) << 4)) =

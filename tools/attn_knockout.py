@@ -1,4 +1,6 @@
 """attention_bwd_tc_kernel timed with pieces knocked out (SIMSEG_ATTN_DBG bits; results are WRONG, timing only).
+Needs an instrumented library: SIMSEG_NVCC_DEFINES=-DSIMSEG_ATTN_KNOCKOUT python -m simseg_b200.build --force
+(the run-time tests of these bits cost the production kernel 10 %: 1.92 -> 1.73 ms on the ViT-S layer once compiled out).
 bits: 1 no MUFU in phase A | 2 no phase B at all (ld dP, math, dS stores) | 4 no P / dS smem stores | 8 no global stores in drains
       16 no gradient MMAs (dV, dK, dQ) | 32 no S / dP MMAs | 64 no tcgen05.ld of S / dP | 128 no phase A at all"""
 import os, sys
