@@ -86,6 +86,19 @@ __device__ __forceinline__ uint32_t bit_mask(uint32_t word, int pos) {
   asm("bfe.s32 %0, %1, %2, 1;" : "=r"(r) : "r"(static_cast<int32_t>(word)), "r"(pos));
   return static_cast<uint32_t>(r);
 }
+// mask of a packed bf16 pair from bits pos (low half) and pos + 1 (high half)
+__device__ __forceinline__ uint32_t pair_mask(uint32_t word, int pos) {
+  return (bit_mask(word, pos) & 0xffffu) | (bit_mask(word, pos + 1) & 0xffff0000u);
+}
+// Live key columns of a 32-column chunk as ONE word per thread instead of three compares per element: a column is live for a
+// row iff it belongs to the row's head (packed tiles: column = token * G + head -> every G-th bit, `pat`) and lies below the
+// caption's key length (`nlive` = live columns counted from the chunk's first column).
+__device__ __forceinline__ uint32_t head_pattern(int G, int rg) {
+  return (G == 1 ? 0xffffffffu : G == 2 ? 0x55555555u : G == 4 ? 0x11111111u : 0x01010101u) << rg;
+}
+__device__ __forceinline__ uint32_t live_mask(int nlive, uint32_t pat) {
+  return nlive >= 32 ? pat : (nlive <= 0 ? 0u : (pat & ((1u << nlive) - 1u)));
+}
 
 // ---- debug: per-warp phase timing of CTA 0, read back with simseg_debug_trace_read (tools/attn_trace.py) ----------------
 // Only in builds with -DSIMSEG_ATTN_TRACE (the register cost perturbs the kernel: use for RELATIVE shares only), armed with
@@ -490,14 +503,12 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
               for (int j = 0; j < 32; ++j) sr[j] = 0;
             }
             if (need_mask) {                                       // padding keys: exp2(-lse) could overflow, mask them
+              const uint32_t live = q_ok ? live_mask(klen - (kt * kTile + col0), head_pattern(p.G, rg)) : 0u;
 #pragma unroll
               for (int j = 0; j < 32; j += 2) {
-                const int key = kt * kTile + col0 + j;
-                float p0 = ex2_approx(fmaf(__uint_as_float(sr[j]), p.scale_log2e, -Lq));
-                float p1 = ex2_approx(fmaf(__uint_as_float(sr[j + 1]), p.scale_log2e, -Lq));
-                p0 = (q_ok && key < klen && (key & gm) == rg) ? p0 : 0.f;
-                p1 = (q_ok && key + 1 < klen && ((key + 1) & gm) == rg) ? p1 : 0.f;
-                pp[j >> 1] = pack_bf16(p0, p1);
+                const float p0 = ex2_approx(fmaf(__uint_as_float(sr[j]), p.scale_log2e, -Lq));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(sr[j + 1]), p.scale_log2e, -Lq));
+                pp[j >> 1] = pack_bf16(p0, p1) & pair_mask(live, j);       // dead keys (possibly inf) -> exactly 0
               }
             } else if (kt * kTile + col0 + 32 > p.rows) {
               // last, partial chunk of an unmasked, unpacked sequence (ViT: key 197 of 208): only its live keys, warp-uniform
@@ -1260,9 +1271,12 @@ attention_fwd_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                 m = fmaxf(m, __uint_as_float(x[j]));
               }
             } else {
+              const uint32_t live = live_mask(klen - c * 32, head_pattern(p.G, rg));
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                m = (c * 32 + j < klen && ((c * 32 + j) & gm) == rg) ? fmaxf(m, __uint_as_float(x[j])) : m;
+              for (int j = 0; j < 32; ++j) {
+                const uint32_t bm = bit_mask(live, j);                        // dead keys enter the max as -inf
+                m = fmaxf(m, __uint_as_float((x[j] & bm) | (0xff800000u & ~bm)));
+              }
             }
           }
           const float ms = m * p.scale_log2e;
@@ -1313,15 +1327,16 @@ attention_fwd_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                   pp[j >> 1] = pack_bf16(p0, p1);
                 }
               } else {
+                const uint32_t live = live_mask(klen - c * 32, head_pattern(p.G, rg));
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
                   float p0 = ex2_approx(fmaf(__uint_as_float(x[j]), p.scale_log2e, -ms));
                   float p1 = ex2_approx(fmaf(__uint_as_float(x[j + 1]), p.scale_log2e, -ms));
-                  p0 = (c * 32 + j < klen && ((c * 32 + j) & gm) == rg) ? p0 : 0.f;
-                  p1 = (c * 32 + j + 1 < klen && ((c * 32 + j + 1) & gm) == rg) ? p1 : 0.f;
+                  p0 = __uint_as_float(__float_as_uint(p0) & bit_mask(live, j));
+                  p1 = __uint_as_float(__float_as_uint(p1) & bit_mask(live, j + 1));
                   sum += p0 + p1;
                   pp[j >> 1] = pack_bf16(p0, p1);
-                  if (kDrop) pp[j >> 1] &= (bit_mask(keep, j) & 0xffffu) | (bit_mask(keep, j + 1) & 0xffff0000u);
+                  if (kDrop) pp[j >> 1] &= pair_mask(keep, j);
                 }
               }
             } else {
